@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE ONLY -- runs the *reference's own* FrustumProposerOG on the CPU.
+
+Only usable where /root/reference exists (the build container).  Nothing is copied: the
+reference modules are imported from where they lie, behind bare namespace stubs so the
+heavy package __init__ files (spconv, clip, kornia ...) never run.  The head hard-codes
+device='cuda' (frustum_proposals_v1.py:240-303), so its source text is loaded with the
+substitutions  device='cuda' -> device='cpu'  and  .cuda() -> .cpu()  (nothing else).
+
+Documented deviations from an unmodified GPU run:
+  1. roiaware_pool3d_utils.points_in_boxes_gpu is emulated by the oracle's restatement of
+     the GPU kernel predicate (no GPU here);
+  2. iou3d_nms_utils.nms_normal_gpu is emulated with a *stable* descending sort and the
+     oracle's iou_normal greedy scan (the reference's unstable sort leaves ties undefined);
+  3. PreprocessedGLIP is replaced by a feeder returning the synthetic detections;
+  4. capture hooks record intermediates.
+"""
+import importlib
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("FNP_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+import oracle as O  # noqa: E402
+
+
+class AttrDict(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+_CAPTURE = None
+
+
+def _pkg(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    m.__package__ = name
+    sys.modules[name] = m
+    return m
+
+
+def _emul_points_in_boxes_gpu(points, boxes):
+    out = O.points_in_boxes_gpu(points.detach().cpu().numpy(), boxes.detach().cpu().numpy())
+    if _CAPTURE is not None:
+        _CAPTURE["pib_calls"].append((boxes.detach().cpu().numpy().reshape(-1, 7).copy(), int((out >= 0).sum())))
+        _CAPTURE["last_points"] = points.detach().cpu().numpy().reshape(-1, 3)
+    return torch.from_numpy(out)
+
+
+def _emul_nms_normal_gpu(boxes, scores, thresh, **kw):
+    b = boxes.detach().cpu().numpy()
+    s = scores.detach().cpu().numpy()
+    keep = O.nms_normal(b, s, thresh)
+    if _CAPTURE is not None:
+        calls = _CAPTURE["pib_calls"]
+        n = b.shape[0]
+        _CAPTURE["frustums"].append(dict(
+            boxes=b.copy(), scores=s.copy(), keep=keep.copy(),
+            counts=np.array([c for _, c in calls[-n:]], np.int32),
+            points=_CAPTURE.get("last_points", np.zeros((0, 3), np.float32)).copy()))
+        _CAPTURE["pib_calls"] = []
+    return torch.from_numpy(keep), None
+
+
+def load():
+    """Import the reference head (CPU-patched source) and return its module."""
+    if "fnp_ref_head" in sys.modules:
+        return sys.modules["fnp_ref_head"]
+    P = os.path.join(REF, "pcdet")
+    for n, p in [("pcdet", P), ("pcdet.models", P + "/models"),
+                 ("pcdet.models.dense_heads", P + "/models/dense_heads"),
+                 ("pcdet.models.dense_heads.target_assigner", P + "/models/dense_heads/target_assigner"),
+                 ("pcdet.models.model_utils", P + "/models/model_utils"), ("pcdet.utils", P + "/utils"),
+                 ("pcdet.ops", P + "/ops"), ("pcdet.ops.roiaware_pool3d", P + "/ops/roiaware_pool3d"),
+                 ("pcdet.ops.iou3d_nms", P + "/ops/iou3d_nms")]:
+        _pkg(n, p)
+    sys.modules.setdefault("SharedArray", types.ModuleType("SharedArray"))
+    # the compiled reference extension modules (oracle/_ref), importable by name
+    import build_ref
+    for pk, name in (("pcdet.ops.iou3d_nms", "iou3d_nms_cuda"), ("pcdet.ops.roiaware_pool3d", "roiaware_pool3d_cuda")):
+        try:
+            ext = build_ref.load(name)
+        except ImportError:
+            ext = types.ModuleType(name)
+        sys.modules[pk + "." + name] = ext
+        setattr(sys.modules[pk], name, ext)
+    # native op wrappers -> emulations (no GPU in this container)
+    rp = types.ModuleType("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
+    rp.points_in_boxes_gpu = _emul_points_in_boxes_gpu
+    rp.points_in_boxes_cpu = lambda p, b: O.points_in_boxes_cpu(np.asarray(p), np.asarray(b))
+    sys.modules[rp.__name__] = rp
+    sys.modules["pcdet.ops.roiaware_pool3d"].roiaware_pool3d_utils = rp
+    iu = types.ModuleType("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    iu.nms_normal_gpu = _emul_nms_normal_gpu
+    iu.boxes_iou3d_gpu = lambda a, b: torch.from_numpy(O.boxes_iou3d(a.cpu().numpy(), b.cpu().numpy()))
+    iu.boxes_bev_iou_cpu = lambda a, b: O.boxes_iou_bev(np.asarray(a), np.asarray(b))
+    sys.modules[iu.__name__] = iu
+    sys.modules["pcdet.ops.iou3d_nms"].iou3d_nms_utils = iu
+
+    path = os.path.join(P, "models/dense_heads/frustum_proposals_v1.py")
+    src = open(path).read()
+    src = src.replace("device='cuda'", "device='cpu'").replace(".cuda()", ".cpu()")
+    assert "cuda" not in re.sub(r"#.*", "", src).replace("torch.cuda", ""), "unpatched cuda use"
+    mod = types.ModuleType("pcdet.models.dense_heads.frustum_proposals_v1")
+    mod.__file__ = path
+    mod.__package__ = "pcdet.models.dense_heads"
+    sys.modules[mod.__name__] = mod
+    sys.modules["fnp_ref_head"] = mod
+    exec(compile(src, path, "exec"), mod.__dict__)
+    return mod
+
+
+class SyntheticFeeder:
+    """Stands in for PreprocessedGLIP (preprocessed_detector.py:104): same 5-tensor return."""
+
+    def __init__(self, frames):
+        self.frames = frames
+
+    def __call__(self, batch_dict):
+        boxes, labels, scores, idx, cam = [], [], [], [], []
+        for b, f in enumerate(self.frames):
+            boxes.append(torch.from_numpy(f.det_boxes))
+            labels.append(torch.from_numpy(f.det_labels))
+            scores.append(torch.from_numpy(f.det_scores))
+            idx.extend([b] * len(f.det_boxes))
+            cam.append(torch.from_numpy(f.det_cam_idx))
+        return (torch.cat(boxes), torch.cat(labels), torch.cat(scores), torch.tensor(idx, dtype=torch.long),
+                torch.cat(cam))
+
+
+def build_head(params, frames):
+    mod = load()
+    mod.PreprocessedGLIP = lambda class_names=None: SyntheticFeeder(frames)
+    cfg = AttrDict(PARAMS=dict(params), PREDS_PATH="PreprocessedGLIP", BOX_FORMAT="xyxy")
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        head = mod.FrustumProposerOG(model_cfg=cfg, class_names=None)
+    head.eval()
+    return head
+
+
+def run(frames, params, capture=True):
+    """Run reference get_proposals over `frames` (one call, batch_size=len(frames)).
+    Returns (boxes (K,7), labels (K), scores (K), batch_idx (K), capture dict, head)."""
+    global _CAPTURE
+    from findnpropagate_b200 import synth
+    head = build_head(params, frames)
+    head.image_detector = SyntheticFeeder(frames)
+    bd = synth.collate(frames)
+    for k, v in list(bd.items()):
+        if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+            bd[k] = torch.from_numpy(v).float()
+    _CAPTURE = dict(pib_calls=[], frustums=[]) if capture else None
+    with torch.no_grad():
+        boxes, labels, scores, bidx = head.get_proposals(bd)
+    cap, _CAPTURE = _CAPTURE, None
+    return (boxes.numpy().astype(np.float32), labels.numpy(), scores.numpy().astype(np.float32),
+            bidx.numpy(), cap, head)

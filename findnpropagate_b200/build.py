@@ -1,0 +1,42 @@
+"""Builds libfnp_sm100.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m findnpropagate_b200.build [--force] [--verbose]
+
+-fmad=false: every fused multiply-add in the library is written explicitly (__fmaf_rn), so
+the results are bit-reproducible against the reference kernels' compiled arithmetic.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libfnp_sm100.so")
+SOURCES = ["fnp_ops.cu", "fnp_seeker.cu"]
+HEADERS = ["fnp_common.cuh", os.path.join("..", "..", "include", "fnp.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libfnp_sm100.so")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,790 @@
+// Fused Greedy Box Seeker stages for sm_100a (B200).  See include/fnp.h for the C ABI and
+// DESIGN.md for the data layout and the roofline of each kernel.
+//
+// What these kernels replace (reference: pcdet/models/dense_heads/frustum_proposals_v1.py):
+//   stage 1   :590-613,:812-815   project_to_camera x6 + boolean-mask compaction per 2D box
+//   stage 1b  :616-662,:817-845   torch.quantile x3, get_cam_frustum, unprojection, clamp,
+//                                 centre line
+//   stage 2a  :851-911,:1392-1411 hypothesis grid, softmin front shift, distance/IoU filters
+//   stage 2b  :930-932            one points_in_boxes_gpu launch + sum + D2H per hypothesis
+//   stage 3   :994-1053           density+IoU score, sort, nms_normal(thresh 1), top-1
+#include "fnp_common.cuh"
+
+namespace fnp {
+
+constexpr int kCullThreads = FNP_CULL_TILE;  // one point per thread
+constexpr int kCullWarps = kCullThreads / 32;
+constexpr int kStatsFloats = 40;
+
+// ======================================================================================
+// Stage 1: projection + frustum cull (+ ordered compaction when WRITE)
+// ======================================================================================
+struct CullSmem {
+    float cam[6][24];
+    int cam_lo[6], cam_hi[6];  // candidate range (local index) per camera
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kCullThreads) cull_kernel(const fnp_seeker_batch b, const float img_w,
+                                                            const float img_h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
+    float4 *s_box = reinterpret_cast<float4 *>(smem_raw + sizeof(CullSmem));       // [Cmax]
+    int *s_cnt = reinterpret_cast<int *>(s_box + b.max_cands_per_frame);            // [Cmax][warps]
+    float *s_pts = reinterpret_cast<float *>(s_cnt + b.max_cands_per_frame * kCullWarps);  // tile rows
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = b.tile_frame[tile];
+    const int row0 = b.tile_row0[tile];
+    const int64_t frow = b.frame_row_start[frame];
+    const int n_rows = (int)min((int64_t)kCullThreads, b.frame_row_start[frame + 1] - frow - row0);
+    const int c0 = b.frame_cand_start[frame];
+    const int nc = b.frame_cand_start[frame + 1] - c0;
+    if (nc == 0) return;
+
+    // ---- per-block setup: camera matrices, candidate boxes, per-camera candidate ranges
+    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
+    for (int j = tid; j < nc; j += kCullThreads)
+        s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
+    for (int i = tid; i < nc * kCullWarps; i += kCullThreads) s_cnt[i] = 0;
+    if (tid < 6) {
+        // candidates of one frame are grouped by camera (reference order), find my group
+        int lo = nc, hi = 0;
+        for (int j = 0; j < nc; j++)
+            if (b.cand_cam[c0 + j] == tid) { lo = min(lo, j); hi = max(hi, j + 1); }
+        S.cam_lo[tid] = lo;
+        S.cam_hi[tid] = (hi > lo) ? hi : lo;
+    }
+
+    // ---- stage the tile's rows in shared memory with coalesced 128-bit loads
+    const int stride = b.point_stride;
+    const float *gsrc = b.points + (size_t)(frow + row0) * stride;
+    const int n_floats = n_rows * stride;
+    if ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) {
+        const int n4 = n_floats >> 2;
+        const float4 *g4 = reinterpret_cast<const float4 *>(gsrc);
+        float4 *s4 = reinterpret_cast<float4 *>(s_pts);
+        for (int i = tid; i < n4; i += kCullThreads) s4[i] = __ldg(g4 + i);
+        for (int i = (n4 << 2) + tid; i < n_floats; i += kCullThreads) s_pts[i] = __ldg(gsrc + i);
+    } else {
+        for (int i = tid; i < n_floats; i += kCullThreads) s_pts[i] = __ldg(gsrc + i);
+    }
+    __syncthreads();
+
+    const bool live = tid < n_rows;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+        const float *p = s_pts + tid * stride + b.xyz_offset;
+        x = p[0]; y = p[1]; z = p[2];
+    }
+
+    // ---- project into every camera that has candidates
+    float u[6], v[6], d[6];
+    unsigned on_mask = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        u[c] = v[c] = d[c] = 0.f;
+        if (S.cam_hi[c] > S.cam_lo[c] && live) {
+            if (project(S.cam[c], x, y, z, img_w, img_h, u[c], v[c], d[c])) on_mask |= 1u << c;
+        }
+    }
+
+    // ---- phase A: per-warp population of every candidate
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        const bool on = (on_mask >> c) & 1u;
+        if (!__any_sync(0xffffffffu, on)) continue;
+        for (int j = S.cam_lo[c]; j < S.cam_hi[c]; j++) {
+            const float4 bx = s_box[j];
+            const bool in = on && (v[c] < bx.w) && (v[c] >= bx.y) && (u[c] < bx.z) && (u[c] >= bx.x);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (lane == 0 && m) s_cnt[j * kCullWarps + warp] = __popc(m);
+        }
+    }
+    __syncthreads();
+
+    if (!WRITE) {
+        for (int j = tid; j < nc; j += kCullThreads) {
+            int s = 0;
+#pragma unroll
+            for (int w = 0; w < kCullWarps; w++) s += s_cnt[j * kCullWarps + w];
+            b.tile_counts[(size_t)tile * b.max_cands_per_frame + j] = s;
+        }
+        return;
+    }
+
+    // ---- phase B (WRITE): ordered scatter of (x,y,z,depth) of the unprojected points
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        const bool on = (on_mask >> c) & 1u;
+        if (!__any_sync(0xffffffffu, on)) continue;
+        float X = 0.f, Y = 0.f, Z = 0.f;
+        if (on) unproject(S.cam[c] + 12, S.cam[c] + 21, u[c], v[c], d[c], X, Y, Z);
+        for (int j = S.cam_lo[c]; j < S.cam_hi[c]; j++) {
+            const float4 bx = s_box[j];
+            const bool in = on && (v[c] < bx.w) && (v[c] >= bx.y) && (u[c] < bx.z) && (u[c] >= bx.x);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (!in) continue;
+            int base = b.cand_pt_start[c0 + j] + b.tile_counts[(size_t)tile * b.max_cands_per_frame + j];
+            for (int w = 0; w < warp; w++) base += s_cnt[j * kCullWarps + w];
+            const int64_t pos = (int64_t)base + __popc(m & lt);
+            if (pos < b.pts_capacity) {
+                reinterpret_cast<float4 *>(b.frustum_pts)[pos] = make_float4(X, Y, Z, d[c]);
+                if (b.frustum_idx) b.frustum_idx[pos] = row0 + tid;
+            }
+        }
+    }
+}
+
+// exclusive prefix of one candidate's tile counts (one warp per candidate)
+__global__ void __launch_bounds__(128) scan_tiles_kernel(const fnp_seeker_batch b)
+{
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= b.n_cands) return;
+    const int frame = b.cand_frame[f];
+    const int j = f - b.frame_cand_start[frame];
+    const int t0 = b.frame_tile_start[frame], t1 = b.frame_tile_start[frame + 1];
+    int carry = 0;
+    for (int t = t0; t < t1; t += 32) {
+        const int i = t + lane;
+        int *cell = b.tile_counts + (size_t)i * b.max_cands_per_frame + j;
+        const int val = (i < t1) ? *cell : 0;
+        int inc = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (i < t1) *cell = carry + inc - val;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) b.cand_npts[f] = carry;
+}
+
+// exclusive prefix over candidates -> cand_pt_start, capacity check
+__global__ void __launch_bounds__(1024) scan_cands_kernel(const fnp_seeker_batch b)
+{
+    __shared__ int s_warp[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < b.n_cands; base += 1024) {
+        const int i = base + tid;
+        const int val = (i < b.n_cands) ? b.cand_npts[i] : 0;
+        int inc = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long excl = carry + (warp ? s_warp[warp - 1] : 0) + inc - val;
+        if (i < b.n_cands) b.cand_pt_start[i] = (int)min(excl, (long long)0x7fffffff);
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const long long total = s_carry;
+        b.cand_pt_start[b.n_cands] = (int)min(total, (long long)0x7fffffff);
+        b.status[0] = (total > b.pts_capacity) ? 1 : 0;
+        b.status[1] = (int)min(total, (long long)0x7fffffff);
+    }
+}
+
+// ======================================================================================
+// Stage 1b: per-frustum statistics and centre line
+// ======================================================================================
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// k-th smallest (0-based) and (k+1)-th smallest depth of a frustum: MSD radix select on the
+// float bit patterns (depths are >= 1e-5 > 0, so the patterns order like the values).
+// All threads of the block call this; results are block-uniform.
+__device__ void select_pair(const float4 *__restrict__ pts, int n, int k, unsigned *s_hist, unsigned *s_misc,
+                            float &v_lo, float &v_hi)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    unsigned prefix = 0, mask = 0;
+    int rank = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            const unsigned key = __float_as_uint(pts[i].w);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned acc = 0;
+            int bin = 0;
+            for (; bin < 256; bin++) {
+                const unsigned c = s_hist[bin];
+                if (acc + c > (unsigned)rank) break;
+                acc += c;
+            }
+            s_misc[0] = (unsigned)bin;
+            s_misc[1] = acc;
+        }
+        __syncthreads();
+        prefix |= s_misc[0] << shift;
+        mask |= 255u << shift;
+        rank -= (int)s_misc[1];
+        __syncthreads();
+    }
+    v_lo = __uint_as_float(prefix);
+    // neighbour: count of keys <= v_lo and the smallest key above it
+    if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0xffffffffu; }
+    __syncthreads();
+    unsigned c_le = 0, nxt = 0xffffffffu;
+    for (int i = tid; i < n; i += nt) {
+        const unsigned key = __float_as_uint(pts[i].w);
+        if (key <= prefix) c_le++;
+        else nxt = min(nxt, key);
+    }
+    atomicAdd(&s_misc[2], c_le);
+    atomicMin(&s_misc[3], nxt);
+    __syncthreads();
+    v_hi = ((int)s_misc[2] >= k + 2 || s_misc[3] == 0xffffffffu) ? v_lo : __uint_as_float(s_misc[3]);
+    __syncthreads();
+}
+
+// torch.quantile(depth, q), linear interpolation (ATen Sorting.cpp quantile_compute + lerp)
+__device__ float block_quantile(const float4 *__restrict__ pts, int n, float q, float dmin, float dmax,
+                                unsigned *s_hist, unsigned *s_misc)
+{
+    const float pos = __fmul_rn(q, (float)(n - 1));
+    const float lo = floorf(pos), hi = ceilf(pos);
+    const float w = __fsub_rn(pos, lo);
+    const int klo = (int)lo, khi = (int)hi;
+    float a, bv;
+    if (khi == 0) { a = dmin; bv = dmin; }
+    else if (klo == n - 1) { a = dmax; bv = dmax; }
+    else {
+        select_pair(pts, n, klo, s_hist, s_misc, a, bv);
+        if (khi == klo) bv = a;
+    }
+    const float diff = __fsub_rn(bv, a);
+    return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), bv);
+}
+
+__global__ void __launch_bounds__(256) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+{
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_misc[4];
+    __shared__ float s_red[8][8];
+    __shared__ float s_geo[16];  // close[3], vec[3]
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = b.cand_npts[f];
+    float *st = b.cand_stats + (size_t)f * kStatsFloats;
+    if (n <= 0 || b.status[0] != 0) {
+        if (tid == 0) { st[9] = 0.f; }
+        return;
+    }
+    const float4 *pts = reinterpret_cast<const float4 *>(b.frustum_pts) + b.cand_pt_start[f];
+
+    // ---- min / max of depth and of x, y, z
+    const float INF = __int_as_float(0x7f800000);
+    float mn[4] = {INF, INF, INF, INF}, mx[4] = {-INF, -INF, -INF, -INF};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float4 p = pts[i];
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+        mn[3] = fminf(mn[3], p.w); mx[3] = fmaxf(mx[3], p.w);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        mn[a] = warp_min(mn[a]);
+        mx[a] = warp_max(mx[a]);
+        if (lane == 0) { s_red[warp][a] = mn[a]; s_red[warp][4 + a] = mx[a]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        float m0 = INF, m1 = -INF;
+        for (int w = 0; w < 8; w++) { m0 = fminf(m0, s_red[w][a]); m1 = fmaxf(m1, s_red[w][4 + a]); }
+        mn[a] = m0; mx[a] = m1;
+    }
+    __syncthreads();
+
+    // ---- depth quantiles (frustum_proposals_v1.py:616-648)
+    const float qmin = block_quantile(pts, n, cfg.lq, mn[3], mx[3], s_hist, s_misc);
+    const float qmax = block_quantile(pts, n, cfg.uq, mn[3], mx[3], s_hist, s_misc);
+    const float qc = block_quantile(pts, n, cfg.cq, mn[3], mx[3], s_hist, s_misc);
+    const float dmax = fminf(qmax, cfg.max_dist);
+    const float dmin = fmaxf(qmin, cfg.frustum_min);
+
+    if (tid == 0) {
+        const int frame = b.cand_frame[f];
+        const float *cm = b.cam_mats + ((size_t)frame * 6 + b.cand_cam[f]) * 24;
+        const float *bx = b.cand_box2d + (size_t)f * 4;
+        const float lo[3] = {bx[0], bx[1], dmin}, hi[3] = {bx[2], bx[3], dmax};
+        const float tpl[8][3] = {{1, 1, -1}, {1, -1, -1}, {-1, -1, -1}, {-1, 1, -1},
+                                 {1, 1, 1}, {1, -1, 1}, {-1, -1, 1}, {-1, 1, 1}};
+        float c[8][3];
+        for (int k = 0; k < 8; k++) {
+            float uvd[3];
+            for (int a = 0; a < 3; a++) {
+                const float whl = __fsub_rn(hi[a], lo[a]);
+                const float cen = __fmul_rn(__fadd_rn(hi[a], lo[a]), 0.5f);
+                uvd[a] = __fadd_rn(__fmul_rn(whl, tpl[k][a] * 0.5f), cen);
+            }
+            unproject(cm + 12, cm + 21, uvd[0], uvd[1], uvd[2], c[k][0], c[k][1], c[k][2]);
+        }
+        if (cfg.clamp_bottom > 0) {
+            for (int a = 0; a < 3; a++) {
+                float cmin = c[0][a], cmax = c[0][a];
+                for (int k = 1; k < 8; k++) { cmin = fminf(cmin, c[k][a]); cmax = fmaxf(cmax, c[k][a]); }
+                const float f1 = fmaxf(mn[a], cmin), f2 = fminf(mx[a], cmax);
+                for (int k = 0; k < 8; k++) c[k][a] = fminf(fmaxf(c[k][a], f1), f2);
+            }
+        }
+        for (int a = 0; a < 3; a++) {
+            float bev[4];
+            for (int i = 0; i < 4; i++) bev[i] = __fmul_rn(__fadd_rn(c[2 * i][a], c[2 * i + 1][a]), 0.5f);
+            const float close = __fmul_rn(__fadd_rn(bev[0], bev[1]), 0.5f);
+            const float far = __fmul_rn(__fadd_rn(bev[2], bev[3]), 0.5f);
+            s_geo[a] = close;
+            s_geo[3 + a] = __fsub_rn(far, close);
+        }
+        st[0] = dmin; st[1] = dmax; st[2] = qc;
+        for (int a = 0; a < 3; a++) { st[3 + a] = mn[a]; st[6 + a] = mx[a]; }
+        st[9] = (float)n;
+        for (int k = 0; k < 8; k++)
+            for (int a = 0; a < 3; a++) st[16 + k * 3 + a] = c[k][a];
+    }
+    __syncthreads();
+    const int M = cfg.num_mags;
+    for (int i = tid; i < M * 3; i += blockDim.x) {
+        const int m = i / 3, a = i % 3;
+        b.centres[((size_t)f * M + m) * 3 + a] = __fadd_rn(s_geo[a], __fmul_rn(s_geo[3 + a], b.mags[m]));
+    }
+}
+
+// ======================================================================================
+// Stage 2a: hypotheses
+// ======================================================================================
+__global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+{
+    __shared__ int s_wcnt[4];
+    __shared__ int s_base;
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int J = cfg.num_yaw_size, M = cfg.num_mags, H = J * M;
+    const bool empty = (b.cand_npts[f] <= 0) || (b.status[0] != 0);
+    if (empty) {
+        if (tid == 0) b.hyp_nvalid[f] = 0;
+        if (b.hyp_valid_dbg)
+            for (int h = tid; h < H; h += blockDim.x) b.hyp_valid_dbg[(size_t)f * H + h] = 0;
+        return;
+    }
+    const int frame = b.cand_frame[f];
+    const int label = b.cand_label[f];
+    const float *L = b.cam_mats + ((size_t)frame * 6 + b.cand_cam[f]) * 24;
+    const float4 box2d = reinterpret_cast<const float4 *>(b.cand_box2d)[f];
+    const float area2 = __fmul_rn(__fsub_rn(box2d.z, box2d.x), __fsub_rn(box2d.w, box2d.y));
+    const float *bb_tab = b.base_boxes + (size_t)(label - 1) * J * 7;
+    const float *bc_tab = b.base_corners + (size_t)(label - 1) * J * 24;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+
+    for (int h0 = 0; h0 < H; h0 += blockDim.x) {
+        const int h = h0 + tid;
+        bool valid = false;
+        float box[7] = {0, 0, 0, 0, 0, 0, 0};
+        float iou = 0.f;
+        if (h < H) {
+            const int m = h / J, j = h - m * J;
+            const float *ct = b.centres + ((size_t)f * M + m) * 3;
+            const float *bc = bc_tab + (size_t)j * 24;
+            const float *bb = bb_tab + (size_t)j * 7;
+            const float ctr[3] = {ct[0], ct[1], ct[2]};
+            float cor[8][3], e[8];
+            float mxn = -__int_as_float(0x7f800000);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) cor[k][a] = __fadd_rn(__ldg(bc + k * 3 + a), ctr[a]);
+                e[k] = -norm3(cor[k][0], cor[k][1], cor[k][2]);
+                mxn = fmaxf(mxn, e[k]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { e[k] = fnp_exp(__fsub_rn(e[k], mxn)); sum = __fadd_rn(sum, e[k]); }
+            float front[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float w = __fdiv_rn(e[k], sum);
+#pragma unroll
+                for (int a = 0; a < 3; a++) front[a] = __fadd_rn(front[a], __fmul_rn(w, cor[k][a]));
+            }
+            float shift[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float cc = __fadd_rn(__ldg(bb + a), ctr[a]);
+                shift[a] = __fsub_rn(cc, front[a]);
+                box[a] = __fadd_rn(cc, shift[a]);
+            }
+#pragma unroll
+            for (int a = 3; a < 7; a++) box[a] = __ldg(bb + a);
+            const bool near_enough = norm3(front[0], front[1], front[2]) < cfg.max_dist;
+            const float INF = __int_as_float(0x7f800000);
+            float x1 = INF, y1 = INF, x2 = -INF, y2 = -INF;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float u, v, d;
+                project(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]),
+                        __fadd_rn(cor[k][2], shift[2]), cfg.img_w, cfg.img_h, u, v, d);
+                u = fminf(fmaxf(u, 0.f), cfg.img_w);
+                v = fminf(fmaxf(v, 0.f), cfg.img_h);
+                x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+            }
+            const float area1 = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+            const float lx = fmaxf(x1, box2d.x), ly = fmaxf(y1, box2d.y);
+            const float rx = fminf(x2, box2d.z), ry = fminf(y2, box2d.w);
+            const float iw = fmaxf(__fsub_rn(rx, lx), 0.f), ih = fmaxf(__fsub_rn(ry, ly), 0.f);
+            const float inter = __fmul_rn(iw, ih);
+            const float uni = __fsub_rn(__fadd_rn(area1, area2), inter);
+            iou = __fdiv_rn(inter, uni);
+            valid = near_enough && (iou > cfg.min_cam_iou);
+            if (b.hyp_boxes_dbg) {
+                float *o = b.hyp_boxes_dbg + ((size_t)f * H + h) * 7;
+#pragma unroll
+                for (int a = 0; a < 7; a++) o[a] = box[a];
+            }
+            if (b.hyp_iou_dbg) b.hyp_iou_dbg[(size_t)f * H + h] = iou;
+            if (b.hyp_valid_dbg) b.hyp_valid_dbg[(size_t)f * H + h] = valid ? 1 : 0;
+        }
+        // ordered compaction of the valid hypotheses
+        const unsigned mk = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) s_wcnt[warp] = __popc(mk);
+        __syncthreads();
+        int base = s_base;
+        for (int w = 0; w < warp; w++) base += s_wcnt[w];
+        if (valid) {
+            const int r = base + __popc(mk & ((1u << lane) - 1u));
+            const BoxPrep p = prep_box(box);
+            float4 *dst = reinterpret_cast<float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
+            dst[0] = make_float4(p.cx, p.cy, p.cz, p.hz);
+            dst[1] = make_float4(p.cosa, p.sina, p.tx, p.ty);
+            b.hyp_index[(size_t)f * H + r] = h;
+            b.hyp_iou[(size_t)f * H + r] = iou;
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+        __syncthreads();
+    }
+    if (tid == 0) b.hyp_nvalid[f] = s_base;
+}
+
+// ======================================================================================
+// Stage 2b: scoring -- per-hypothesis point counts
+// ======================================================================================
+constexpr int kScoreThreads = 128;
+constexpr int kScoreTile = 512;  // points per TMA stage (8 KB)
+
+__host__ __device__ inline int n_splits(int npts, int s_max, int split_points)
+{
+    int s = (npts + split_points - 1) / split_points;
+    s = s < 1 ? 1 : s;
+    return s > s_max ? s_max : s;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_batch b, const int H)
+{
+    __shared__ __align__(128) float4 s_tile[2][kScoreTile];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int f = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const int split = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int nv = b.hyp_nvalid[f];
+    const int h_base = chunk * (kScoreThreads * K);
+    if (h_base >= nv) return;
+    const int npts = b.cand_npts[f];
+    const int S = n_splits(npts, b.score_splits, b.split_points);
+    if (split >= S) return;
+    const int len = (npts + S - 1) / S;
+    const int p0 = split * len;
+    const int p1 = min(npts, p0 + len);
+    const float4 *gpts = reinterpret_cast<const float4 *>(b.frustum_pts) + b.cand_pt_start[f] + p0;
+    const int n = p1 - p0;
+    const int n_tiles = (n + kScoreTile - 1) / kScoreTile;
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < 2 && t < n_tiles; t++) {
+            const uint32_t bytes = (uint32_t)min(kScoreTile, n - t * kScoreTile) * 16u;
+            mbar_expect_tx(&s_bar[t], bytes);
+            tma_load_1d(s_tile[t], gpts + (size_t)t * kScoreTile, bytes, &s_bar[t]);
+        }
+    }
+
+    // hypotheses of this thread live in registers for the whole CTA lifetime
+    BoxPrep hp[K];
+    int cnt[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = h_base + k * kScoreThreads + tid;
+        cnt[k] = 0;
+        if (r < nv) {
+            const float4 *src = reinterpret_cast<const float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
+            const float4 a = __ldg(src), c = __ldg(src + 1);
+            hp[k].cx = a.x; hp[k].cy = a.y; hp[k].cz = a.z; hp[k].hz = a.w;
+            hp[k].cosa = c.x; hp[k].sina = c.y; hp[k].tx = c.z; hp[k].ty = c.w;
+        } else {
+            hp[k].cx = hp[k].cy = hp[k].cz = 0.f; hp[k].hz = -1.f;   // never inside
+            hp[k].cosa = 1.f; hp[k].sina = 0.f; hp[k].tx = hp[k].ty = -1.f;
+        }
+    }
+
+    for (int t = 0; t < n_tiles; t++) {
+        const int s = t & 1;
+        mbar_wait(&s_bar[s], (uint32_t)((t >> 1) & 1));
+        const int m = min(kScoreTile, n - t * kScoreTile);
+        const float4 *tp = s_tile[s];
+        int i = 0;
+        for (; i + 4 <= m; i += 4) {
+            const float4 q0 = tp[i], q1 = tp[i + 1], q2 = tp[i + 2], q3 = tp[i + 3];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                count_if(cnt[k], in_box(q0.x, q0.y, q0.z, hp[k]));
+                count_if(cnt[k], in_box(q1.x, q1.y, q1.z, hp[k]));
+                count_if(cnt[k], in_box(q2.x, q2.y, q2.z, hp[k]));
+                count_if(cnt[k], in_box(q3.x, q3.y, q3.z, hp[k]));
+            }
+        }
+        for (; i < m; i++) {
+            const float4 q = tp[i];
+#pragma unroll
+            for (int k = 0; k < K; k++) count_if(cnt[k], in_box(q.x, q.y, q.z, hp[k]));
+        }
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && t + 2 < n_tiles) {
+            const uint32_t bytes = (uint32_t)min(kScoreTile, n - (t + 2) * kScoreTile) * 16u;
+            mbar_expect_tx(&s_bar[s], bytes);
+            tma_load_1d(s_tile[s], gpts + (size_t)(t + 2) * kScoreTile, bytes, &s_bar[s]);
+        }
+    }
+
+    int *out = b.counts + ((size_t)f * b.score_splits + split) * H;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = h_base + k * kScoreThreads + tid;
+        if (r < nv) out[r] = cnt[k];
+    }
+}
+
+// ======================================================================================
+// Stage 3: score + greedy argmax
+// ======================================================================================
+__global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+{
+    __shared__ float s_f[4];
+    __shared__ int s_i[4];
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int J = cfg.num_yaw_size, H = J * cfg.num_mags;
+    const int nv = b.hyp_nvalid[f];
+    if (nv <= 0) {
+        if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
+        return;
+    }
+    const int npts = b.cand_npts[f];
+    const int S = n_splits(npts, b.score_splits, b.split_points);
+    int *cbase = b.counts + (size_t)f * b.score_splits * H;
+    // total counts (plane 0 receives the sum), block max
+    int mx = 0;
+    for (int r = tid; r < nv; r += blockDim.x) {
+        int c = cbase[r];
+        for (int s = 1; s < S; s++) c += cbase[(size_t)s * H + r];
+        cbase[r] = c;
+        mx = max(mx, c);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_i[warp] = mx;
+    __syncthreads();
+    mx = max(max(s_i[0], s_i[1]), max(s_i[2], s_i[3]));
+    __syncthreads();
+    const float den = __fadd_rn((float)mx, 1e-8f);
+    // argmax of score, lowest index wins ties (stable descending sort + top-1)
+    float best = -__int_as_float(0x7f800000);
+    int besti = 0x7fffffff;
+    for (int r = tid; r < nv; r += blockDim.x) {
+        const float dens = __fdiv_rn((float)cbase[r], den);
+        const float sc = __fadd_rn(__fmul_rn(dens, cfg.dns_w), __fmul_rn(b.hyp_iou[(size_t)f * H + r], cfg.iou_w));
+        if (sc > best || besti == 0x7fffffff) { best = sc; besti = r; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    if (lane == 0) { s_f[warp] = best; s_i[warp] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 4; w++) {
+            const float ob = s_f[w];
+            const int oi = s_i[w];
+            if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+        }
+        const int h = b.hyp_index[(size_t)f * H + besti];
+        const int j = h % J;
+        const float *pp = b.hyp_prep + ((size_t)f * H + besti) * 8;
+        const float *bb = b.base_boxes + ((size_t)(b.cand_label[f] - 1) * J + j) * 7;
+        float *o = b.out_boxes + (size_t)f * 7;
+        o[0] = pp[0]; o[1] = pp[1]; o[2] = pp[2];
+        o[3] = bb[3]; o[4] = bb[4]; o[5] = bb[5]; o[6] = bb[6];
+        b.out_best[f] = besti;
+        b.out_score[f] = best;
+        b.out_count[f] = cbase[besti];
+    }
+}
+
+}  // namespace fnp
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+using namespace fnp;
+
+static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
+{
+    if (!cfg || !b) return FNP_EINVAL;
+    if (b->n_frames < 0 || b->n_cands < 0 || b->n_tiles < 0) return FNP_EINVAL;
+    if (cfg->num_mags < 1 || cfg->num_yaw_size < 1) return FNP_EINVAL;
+    if (b->score_splits < 1 || b->split_points < 1) return FNP_EINVAL;
+    return FNP_OK;
+}
+
+static size_t cull_smem_bytes(const fnp_seeker_batch *b)
+{
+    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullWarps) +
+           (size_t)kCullThreads * b->point_stride * 4 + 16;
+}
+
+extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->n_cands == 0 || b->n_tiles == 0) {
+        cudaMemsetAsync(b->status, 0, 4 * sizeof(int32_t), st);
+        cudaMemsetAsync(b->cand_pt_start, 0, sizeof(int32_t) * (size_t)(b->n_cands + 1), st);
+        if (b->n_cands) cudaMemsetAsync(b->cand_npts, 0, sizeof(int32_t) * (size_t)b->n_cands, st);
+        FNP_LAUNCH_CHECK();
+        return FNP_OK;
+    }
+    if (!b->points || !b->tile_counts || !b->frustum_pts || b->point_stride < 3 ||
+        b->xyz_offset < 0 || b->xyz_offset + 3 > b->point_stride)
+        return FNP_EINVAL;
+    const size_t smem = cull_smem_bytes(b);
+    if (smem > 200 * 1024) return FNP_EINVAL;
+    cudaFuncSetAttribute(cull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cull_kernel<false><<<b->n_tiles, kCullThreads, smem, st>>>(*b, cfg->img_w, cfg->img_h);
+    scan_tiles_kernel<<<divup(b->n_cands, 4), 128, 0, st>>>(*b);
+    scan_cands_kernel<<<1, 1024, 0, st>>>(*b);
+    cull_kernel<true><<<b->n_tiles, kCullThreads, smem, st>>>(*b, cfg->img_w, cfg->img_h);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    if (b->n_cands == 0) return FNP_OK;
+    stats_kernel<<<b->n_cands, 256, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    if (b->n_cands == 0) return FNP_OK;
+    hypotheses_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    if (b->n_cands == 0) return FNP_OK;
+    const int H = cfg->num_mags * cfg->num_yaw_size;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H <= 128) {
+        dim3 g(b->n_cands, divup(H, kScoreThreads), b->score_splits);
+        score_kernel<1><<<g, kScoreThreads, 0, st>>>(*b, H);
+    } else if (H <= 512) {
+        dim3 g(b->n_cands, divup(H, kScoreThreads * 2), b->score_splits);
+        score_kernel<2><<<g, kScoreThreads, 0, st>>>(*b, H);
+    } else {
+        dim3 g(b->n_cands, divup(H, kScoreThreads * 4), b->score_splits);
+        score_kernel<4><<<g, kScoreThreads, 0, st>>>(*b, H);
+    }
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    if (b->n_cands == 0) return FNP_OK;
+    select_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_run(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc;
+    if ((rc = fnp_seeker_cull(cfg, b, stream))) return rc;
+    if ((rc = fnp_seeker_frustum_stats(cfg, b, stream))) return rc;
+    if ((rc = fnp_seeker_hypotheses(cfg, b, stream))) return rc;
+    if ((rc = fnp_seeker_score(cfg, b, stream))) return rc;
+    return fnp_seeker_select(cfg, b, stream);
+}

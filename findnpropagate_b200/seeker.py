@@ -1,0 +1,433 @@
+"""Greedy Box Seeker, B200-native.
+
+Host-side mirror of ``FrustumProposerOG`` (reference:
+pcdet/models/dense_heads/frustum_proposals_v1.py:142-1573) for the option set of
+tools/cfgs/nuscenes_box_seeker_proposals.yaml: same constructor arguments / PARAMS keys,
+same ``get_proposals`` / ``get_bboxes`` / ``forward`` contract and output format, with the
+per-frame Python loop replaced by five fused CUDA stages over a *batch* of frames
+(libfnp_sm100.so, include/fnp.h):
+
+    host  : 2D NMS + score threshold (nms2d.py), camera matrices, tile/candidate tables
+    GPU 1 : projection x cameras + per-2D-box frustum cull + ordered compaction
+    GPU 1b: depth quantiles, point AABB, frustum corners, centre line
+    GPU 2a: hypothesis grid, softmin front shift, distance + 2D-IoU filters
+    GPU 2b: points-in-boxes scoring (TMA-staged point tiles)
+    GPU 3 : density + IoU score, greedy argmax
+    GPU 4 : (optional) rotated-BEV NMS of the frame's proposals, recall counters
+
+There is no CPU compute path: the engine raises if CUDA or the extension is missing.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, nms2d
+
+ANCHORS = [[4.63, 1.97, 1.74], [6.93, 2.51, 2.84], [6.37, 2.85, 3.19], [10.5, 2.94, 3.47],
+           [12.29, 2.90, 3.87], [0.50, 2.53, 0.98], [2.11, 0.77, 1.47], [1.70, 0.60, 1.28],
+           [0.73, 0.67, 1.77], [0.41, 0.41, 1.07]]          # frustum_proposals_v1.py:270-281
+IMAGE_SIZE = (900, 1600)                                     # frustum_proposals_v1.py:203
+FRUSTUM_MIN = 2.0                                            # frustum_proposals_v1.py:240
+
+# constructor defaults, frustum_proposals_v1.py:146-148
+DEFAULTS = dict(lq=0.336, uq=0.356, iou_w=0.95, dst_w=0.226, dns_w=0.05, min_cam_iou=0.3,
+                size_min=0.957, size_max=1.2, ry_min=0.0, ry_max=float(torch.pi), cq=0.46, num_mags=6,
+                max_dist=50, num_sizes=4, num_rotations=10, topk=1, nms_2d=0.7, nms_3d=1.0,
+                score_thr=0.1, nms_normal=0.7, clamp_bottom=0)
+
+RECALL_KEYS = ["gt", "num_3known", "num_6known", "num_4unknown", "num_7unknown"]
+RECALL_PER_THRESH = ["rcnn", "rcnn_3known", "rcnn_6known", "rcnn_4unknown", "rcnn_7unknown"]
+
+
+def resolve_params(params: Optional[dict]) -> dict:
+    p = dict(DEFAULTS)
+    if params:
+        p.update(params)
+    unsupported = []
+    if p["topk"] != 1:
+        unsupported.append("topk != 1")
+    if p["nms_3d"] != 0:
+        unsupported.append("nms_3d != 0 (the reference asserts it too, :209)")
+    if p["dst_w"] != 0:
+        unsupported.append("dst_w != 0")
+    for k in ("aln_w", "ego_w", "occl_w", "rand_center", "search_depth"):
+        if p.get(k):
+            unsupported.append(k)
+    if unsupported:
+        raise NotImplementedError("Box Seeker options outside the shipped config: " + ", ".join(unsupported))
+    return p
+
+
+def build_tables(p: dict):
+    """base_boxes (A,J,7), base_corners (A,J,8,3) -- the constructor tables of
+    frustum_proposals_v1.py:282-298 (+ box_utils.boxes_to_corners_3d, box_utils.py:28-52),
+    built with the same torch calls on the host."""
+    anchors = torch.tensor(ANCHORS, dtype=torch.float32)
+    A, R, S = anchors.shape[0], int(p["num_rotations"]), int(p["num_sizes"])
+    size_variations = torch.linspace(p["size_min"], p["size_max"], steps=S)
+    base_rotations = torch.linspace(p["ry_min"], p["ry_max"], steps=R)
+    base = torch.zeros((A, R, S, 7))
+    base[..., 3:6] = anchors[:, None, None, :]
+    base[..., 6] = base_rotations[None, :, None]
+    base[..., 3:6] = base[..., 3:6] * size_variations[None, None, :, None]
+    flat = base.reshape(-1, 7)
+    template = flat.new_tensor(([1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1],
+                                [1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, 1])) / 2
+    corners = flat[:, None, 3:6].repeat(1, 8, 1) * template[None, :, :]
+    cosa, sina = torch.cos(flat[:, 6]), torch.sin(flat[:, 6])
+    zeros, ones = torch.zeros_like(cosa), torch.ones_like(cosa)
+    rot = torch.stack((cosa, sina, zeros, -sina, cosa, zeros, zeros, zeros, ones), dim=1).view(-1, 3, 3)
+    corners = torch.matmul(corners, rot) + flat[:, None, 0:3]
+    return base.reshape(A, R * S, 7).contiguous(), corners.reshape(A, R * S, 8, 3).contiguous()
+
+
+def camera_matrices(lidar2image, camera2lidar, camera_intrinsics):
+    """(B,6,24) f32: lidar2image rows 0..2 | combine = cam2lidar_R @ inverse(K) | cam2lidar_t
+    (frustum_proposals_v1.py:1442-1452 and :1512-1535), computed with torch on the host."""
+    l2i = torch.as_tensor(np.asarray(lidar2image), dtype=torch.float32)
+    c2l = torch.as_tensor(np.asarray(camera2lidar), dtype=torch.float32)
+    K = torch.as_tensor(np.asarray(camera_intrinsics), dtype=torch.float32)[..., :3, :3]
+    combine = c2l[..., :3, :3].matmul(torch.inverse(K))
+    out = torch.cat([l2i[..., :3, :].reshape(*l2i.shape[:-2], 12), combine.reshape(*combine.shape[:-2], 9),
+                     c2l[..., :3, 3]], dim=-1)
+    return out.numpy()
+
+
+@dataclass
+class FrameInput:
+    """What the engine needs of one frame (host memory)."""
+    points: np.ndarray            # (N, C>=3) f32, xyz in columns xyz_offset..+3
+    lidar2image: np.ndarray       # (6,4,4)
+    camera2lidar: np.ndarray      # (6,4,4)
+    camera_intrinsics: np.ndarray  # (6,4,4)
+    det_boxes: np.ndarray         # (D,4) xyxy
+    det_labels: np.ndarray        # (D,) 1..10
+    det_scores: np.ndarray        # (D,)
+    det_cam_idx: np.ndarray       # (D,) 0..5
+    gt_boxes: Optional[np.ndarray] = None   # (G,>=8): box7 ... class label last
+
+
+class _Arena:
+    """Grow-only device/pinned scratch so that steady-state batches allocate nothing."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, nbytes, pinned=False):
+        nbytes = int(max(nbytes, 256))
+        t = self.bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            cap = int(nbytes * 1.25) + 256
+            if pinned:
+                t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            else:
+                t = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self.bufs[name] = t
+        return t
+
+
+def _align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+class SeekerEngine:
+    """Batched Box Seeker on one GPU."""
+
+    def __init__(self, params=None, device=None, debug=False, score_splits=None, split_points=2048):
+        if not torch.cuda.is_available():
+            raise RuntimeError("findnpropagate_b200.SeekerEngine needs a CUDA device (no CPU fallback)")
+        self.p = resolve_params(params)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.debug = debug
+        self.M = max(int(self.p["num_mags"]), 1)
+        self.J = int(self.p["num_rotations"]) * int(self.p["num_sizes"])
+        self.H = self.M * self.J
+        bb, bc = build_tables(self.p)
+        self.base_boxes_host, self.base_corners_host = bb, bc
+        self.base_boxes = bb.to(self.device)
+        self.base_corners = bc.to(self.device)
+        mags = torch.linspace(0.0, 1.0, self.p["num_mags"]) if self.p["num_mags"] > 0 else torch.zeros(1)
+        self.mags = mags.to(self.device)
+        self.cfg = _lib.SeekerCfg(
+            num_mags=self.M, num_yaw_size=self.J, n_classes=bb.shape[0], clamp_bottom=int(self.p["clamp_bottom"]),
+            img_w=float(IMAGE_SIZE[1]), img_h=float(IMAGE_SIZE[0]), lq=float(self.p["lq"]), uq=float(self.p["uq"]),
+            cq=float(self.p["cq"]), frustum_min=FRUSTUM_MIN, max_dist=float(self.p["max_dist"]),
+            min_cam_iou=float(self.p["min_cam_iou"]), dns_w=float(self.p["dns_w"]), iou_w=float(self.p["iou_w"]))
+        self.arena = _Arena(self.device)
+        self.fixed_splits = score_splits
+        self.split_points = int(split_points)
+        self.pts_factor = 2.0
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.launches = 0          # kernels of ours launched (bench bookkeeping)
+
+    # ------------------------------------------------------------------ host planning
+    def plan(self, frames: List[FrameInput], xyz_offset=0):
+        """Everything the host contributes to a batch, as numpy arrays."""
+        B = len(frames)
+        n_rows = np.array([f.points.shape[0] for f in frames], dtype=np.int64)
+        frame_row_start = np.zeros(B + 1, np.int64)
+        np.cumsum(n_rows, out=frame_row_start[1:])
+        stride = int(frames[0].points.shape[1]) if B else 5
+        det_frame = np.concatenate([np.full(len(f.det_scores), b, np.int64) for b, f in enumerate(frames)]) if B else np.zeros(0, np.int64)
+        det_boxes = np.concatenate([np.asarray(f.det_boxes, np.float32).reshape(-1, 4) for f in frames]) if B else np.zeros((0, 4), np.float32)
+        det_labels = np.concatenate([np.asarray(f.det_labels, np.int64) for f in frames]) if B else np.zeros(0, np.int64)
+        det_scores = np.concatenate([np.asarray(f.det_scores, np.float32) for f in frames]) if B else np.zeros(0, np.float32)
+        det_cam = np.concatenate([np.asarray(f.det_cam_idx, np.int64) for f in frames]) if B else np.zeros(0, np.int64)
+        cam_mats = camera_matrices(np.stack([f.lidar2image for f in frames]), np.stack([f.camera2lidar for f in frames]),
+                                   np.stack([f.camera_intrinsics for f in frames])) if B else np.zeros((0, 6, 24), np.float32)
+        return self.plan_arrays(frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
+                                det_frame, det_cam)
+
+    def plan_arrays(self, frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
+                    det_frame, det_cam):
+        B = frame_row_start.shape[0] - 1
+        sel = nms2d.frustum_candidates(det_boxes, det_labels, det_scores, det_frame, det_cam,
+                                       self.p["nms_2d"], self.p["score_thr"])
+        cand_frame = det_frame[sel].astype(np.int32)
+        F = int(sel.shape[0])
+        frame_cand_start = np.zeros(B + 1, np.int32)
+        np.cumsum(np.bincount(cand_frame, minlength=B), out=frame_cand_start[1:])
+        n_rows = np.diff(frame_row_start)
+        tiles_per_frame = (n_rows + _lib.CULL_TILE - 1) // _lib.CULL_TILE
+        frame_tile_start = np.zeros(B + 1, np.int32)
+        np.cumsum(tiles_per_frame, out=frame_tile_start[1:])
+        n_tiles = int(frame_tile_start[-1])
+        tile_frame = np.repeat(np.arange(B, dtype=np.int32), tiles_per_frame)
+        tile_row0 = ((np.arange(n_tiles, dtype=np.int64) - np.repeat(frame_tile_start[:-1].astype(np.int64), tiles_per_frame))
+                     * _lib.CULL_TILE).astype(np.int32)
+        return dict(
+            B=B, F=F, n_tiles=n_tiles, stride=int(stride), xyz_offset=int(xyz_offset),
+            total_rows=int(frame_row_start[-1]),
+            max_cands=int(np.diff(frame_cand_start).max()) if B else 0,
+            frame_row_start=frame_row_start.astype(np.int64), tile_frame=tile_frame, tile_row0=tile_row0,
+            frame_tile_start=frame_tile_start, cam_mats=np.ascontiguousarray(cam_mats, np.float32),
+            frame_cand_start=frame_cand_start, cand_frame=cand_frame,
+            cand_cam=det_cam[sel].astype(np.int32), cand_label=det_labels[sel].astype(np.int32),
+            cand_box2d=np.ascontiguousarray(det_boxes[sel], np.float32),
+            cand_score=np.ascontiguousarray(det_scores[sel], np.float32), cand_det=sel)
+
+    # ------------------------------------------------------------------ device execution
+    _META = ["frame_row_start", "tile_frame", "tile_row0", "frame_tile_start", "cam_mats", "frame_cand_start",
+             "cand_frame", "cand_cam", "cand_label", "cand_box2d"]
+
+    def _upload_meta(self, plan, stream, slot=0):
+        offs, total = {}, 0
+        for k in self._META:
+            offs[k] = total
+            total = _align(total + plan[k].nbytes)
+        host = self.arena.get("meta_host%d" % slot, total, pinned=True)
+        hv = host.numpy()
+        for k in self._META:
+            a = plan[k]
+            hv[offs[k]:offs[k] + a.nbytes] = a.reshape(-1).view(np.uint8)
+        dev = self.arena.get("meta_dev%d" % slot, total)
+        dev[:total].copy_(host[:total], non_blocking=True)
+        base = dev.data_ptr()
+        return {k: base + o for k, o in offs.items()}
+
+    def execute(self, plan, points_dev, nms_thresh=None, gt=None, recall_thresh=(0.3, 0.5, 0.7), slot=0):
+        """Enqueue the whole batch on the current stream.  points_dev: CUDA float32 tensor
+        holding the rows of all frames back to back.  Returns a handle for `finish`."""
+        _lib.require_cuda(points_dev)
+        assert points_dev.dtype == torch.float32 and points_dev.is_contiguous()
+        F, B, H, M = plan["F"], plan["B"], self.H, self.M
+        dev = self.device
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            meta = self._upload_meta(plan, stream, slot)
+            chunks = -(-H // (128 * (1 if H <= 128 else 2 if H <= 512 else 4)))
+            if self.fixed_splits is not None:
+                S = int(self.fixed_splits)
+            else:
+                want = 8 * self.n_sms
+                S = int(min(16, max(1, -(-want // max(F * chunks, 1)))))
+            cap = int(max(plan["total_rows"] * self.pts_factor, 4096))
+            Cmax = max(plan["max_cands"], 1)
+            sizes = dict(
+                tile_counts=4 * plan["n_tiles"] * Cmax, frustum_pts=16 * cap,
+                cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
+                hyp_iou=4 * H * F, counts=4 * H * F * S,
+                # outputs, one D2H: boxes(7) score best count npts nvalid per candidate + status
+                )
+            sizes["out"] = 4 * (12 * F + 8)
+            if self.debug:
+                sizes.update(frustum_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
+            ptr = {k: self.arena.get(k, v).data_ptr() for k, v in sizes.items() if k != "out"}
+            out_dev = self.arena.get("out%d" % slot, sizes["out"])
+            ob = out_dev.data_ptr()
+            o_boxes, o_score, o_best, o_count = ob, ob + 28 * F, ob + 32 * F, ob + 36 * F
+            o_npts, o_nvalid, o_status = ob + 40 * F, ob + 44 * F, ob + 48 * F
+            o_ptstart = self.arena.get("cand_pt_start", 4 * (F + 1)).data_ptr()
+            b = _lib.SeekerBatch(
+                n_frames=B, n_cands=F, n_tiles=plan["n_tiles"], max_cands_per_frame=Cmax,
+                points=points_dev.data_ptr(), point_stride=plan["stride"], xyz_offset=plan["xyz_offset"],
+                frame_row_start=meta["frame_row_start"], tile_frame=meta["tile_frame"], tile_row0=meta["tile_row0"],
+                frame_tile_start=meta["frame_tile_start"], cam_mats=meta["cam_mats"],
+                frame_cand_start=meta["frame_cand_start"], cand_frame=meta["cand_frame"], cand_cam=meta["cand_cam"],
+                cand_label=meta["cand_label"], cand_box2d=meta["cand_box2d"],
+                base_boxes=self.base_boxes.data_ptr(), base_corners=self.base_corners.data_ptr(),
+                mags=self.mags.data_ptr(),
+                tile_counts=ptr["tile_counts"], cand_npts=o_npts, cand_pt_start=o_ptstart,
+                frustum_pts=ptr["frustum_pts"], frustum_idx=ptr.get("frustum_idx"), pts_capacity=cap,
+                cand_stats=ptr["cand_stats"], centres=ptr["centres"], hyp_prep=ptr["hyp_prep"],
+                hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
+                hyp_boxes_dbg=ptr.get("hyp_boxes_dbg"), hyp_iou_dbg=ptr.get("hyp_iou_dbg"),
+                hyp_valid_dbg=ptr.get("hyp_valid_dbg"),
+                score_splits=S, split_points=self.split_points, counts=ptr["counts"],
+                out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
+            rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
+            _lib.check(rc, "fnp_seeker_run")
+            self.launches += 8 if F and plan["n_tiles"] else 0
+            handle = dict(plan=plan, batch=b, S=S, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta)
+            if nms_thresh is not None and F:
+                handle["nms_keep"] = self._stage4_nms(plan, meta, o_boxes, o_best, float(nms_thresh), stream)
+            if gt is not None and F:
+                handle["recall"] = self._recall(plan, meta, o_boxes, o_best, gt, recall_thresh, stream)
+            host = self.arena.get("out_host%d" % slot, sizes["out"], pinned=True)
+            host[:sizes["out"]].copy_(out_dev[:sizes["out"]], non_blocking=True)
+            handle["out_host"] = host
+            handle["event"] = torch.cuda.Event()
+            handle["event"].record()
+        return handle
+
+    def _stage4_nms(self, plan, meta, o_boxes, o_best, thresh, stream):
+        """Rotated-BEV NMS of each frame's proposals in 2D-score order (the dedup
+        PseudoLoader applies later on the CPU, pseudo_loader.py:29-55,755)."""
+        F, B = plan["F"], plan["B"]
+        fcs = plan["frame_cand_start"]
+        # priority order inside each frame: descending 2D score, stable
+        order = np.lexsort((np.arange(F), -plan["cand_score"].astype(np.float64), plan["cand_frame"])).astype(np.int32)
+        order_dev = torch.from_numpy(order).to(self.device, non_blocking=True)
+        keep = torch.empty(F, dtype=torch.uint8, device=self.device)
+        rc = _lib.lib.fnp_seg_nms_rotated(o_boxes, None, order_dev.data_ptr(), o_best, meta["frame_cand_start"], B,
+                                          int(min(max(plan["max_cands"], 1), _lib.SEG_NMS_MAX)), thresh,
+                                          keep.data_ptr(), stream)
+        _lib.check(rc, "fnp_seg_nms_rotated")
+        self.launches += 1
+        self._keepalive = order_dev
+        return keep
+
+    def _recall(self, plan, meta, o_boxes, o_best, gt, thresh, stream):
+        gt_boxes, gt_start = gt
+        counters = torch.zeros(5 + 5 * len(thresh), dtype=torch.int64, device=self.device)
+        th = (C.c_float * len(thresh))(*[float(t) for t in thresh])
+        rc = _lib.lib.fnp_recall_counters(o_boxes, o_best, meta["frame_cand_start"], gt_boxes.data_ptr(),
+                                          gt_start.data_ptr(), plan["B"], th, len(thresh), counters.data_ptr(), stream)
+        _lib.check(rc, "fnp_recall_counters")
+        self.launches += 1
+        return counters
+
+    def finish(self, handle):
+        """Wait for the batch and assemble per-frame results (reference output format)."""
+        handle["event"].synchronize()
+        plan = handle["plan"]
+        F, B = plan["F"], plan["B"]
+        raw = handle["out_host"].numpy()[:handle["out_bytes"]]
+        f32 = raw.view(np.float32)
+        i32 = raw.view(np.int32)
+        boxes = f32[0:7 * F].reshape(F, 7)
+        score = f32[7 * F:8 * F]
+        best = i32[8 * F:9 * F]
+        count = i32[9 * F:10 * F]
+        npts = i32[10 * F:11 * F]
+        nvalid = i32[11 * F:12 * F]
+        status = i32[12 * F:12 * F + 4]
+        if status[0] != 0:
+            raise OverflowError(int(status[1]))
+        ok = best >= 0
+        fcs = plan["frame_cand_start"]
+        keep = handle["nms_keep"].cpu().numpy().astype(bool) if "nms_keep" in handle else None
+        frames = []
+        for b in range(B):
+            s = slice(fcs[b], fcs[b + 1])
+            m = ok[s]
+            d = dict(pred_boxes=boxes[s][m].copy(), pred_scores=plan["cand_score"][s][m].copy(),
+                     pred_labels=plan["cand_label"][s][m].astype(np.int32))
+            if keep is not None:
+                d["nms_keep"] = keep[s][m]
+            frames.append(d)
+        res = dict(frames=frames, cand_valid=ok.copy(), cand_best=best.copy(), cand_score2=score.copy(),
+                   cand_count=count.copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),
+                   cand_boxes=boxes.copy())
+        if "recall" in handle:
+            res["recall"] = self.recall_dict(handle["recall"].cpu().numpy())
+        return res
+
+    @staticmethod
+    def recall_dict(counters, thresh=(0.3, 0.5, 0.7)):
+        d = {k: int(counters[i]) for i, k in enumerate(RECALL_KEYS)}
+        for t, th in enumerate(thresh):
+            for j, k in enumerate(RECALL_PER_THRESH):
+                d["%s_%s" % (k, th)] = int(counters[5 + 5 * t + j])
+        return d
+
+    def run(self, frames: List[FrameInput], points_dev=None, nms_thresh=None, with_recall=False, xyz_offset=0):
+        """Plan + H2D + execute + finish for a list of frames; grows the frustum-point
+        buffer and retries on overflow."""
+        plan = self.plan(frames, xyz_offset=xyz_offset)
+        if points_dev is None:
+            points_dev = self.upload_points(frames)
+        gt = self.upload_gt(frames) if with_recall else None
+        while True:
+            h = self.execute(plan, points_dev, nms_thresh=nms_thresh, gt=gt)
+            try:
+                return self.finish(h)
+            except OverflowError as e:
+                need = int(e.args[0])
+                self.pts_factor = max(self.pts_factor * 1.5, 1.25 * need / max(plan["total_rows"], 1))
+
+    def upload_points(self, frames):
+        rows = sum(f.points.shape[0] for f in frames)
+        stride = frames[0].points.shape[1] if frames else 5
+        buf = self.arena.get("points", 4 * rows * stride)
+        pts = buf[:4 * rows * stride].view(torch.float32).view(rows, stride)
+        r = 0
+        for f in frames:
+            n = f.points.shape[0]
+            src = f.points if isinstance(f.points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(f.points, np.float32))
+            pts[r:r + n].copy_(src, non_blocking=True)
+            r += n
+        return pts
+
+    def upload_gt(self, frames):
+        g, start = [], [0]
+        for f in frames:
+            gb = np.zeros((0, 8), np.float32) if f.gt_boxes is None else np.asarray(f.gt_boxes, np.float32)
+            if gb.shape[0]:
+                gb = np.concatenate([gb[:, :7], gb[:, -1:]], 1)
+            g.append(gb.reshape(-1, 8))
+            start.append(start[-1] + gb.shape[0])
+        gt = torch.from_numpy(np.ascontiguousarray(np.concatenate(g) if g else np.zeros((0, 8), np.float32)))
+        return gt.to(self.device), torch.tensor(start, dtype=torch.int32).to(self.device)
+
+    # ------------------------------------------------------------------ debug views
+    def debug_views(self, handle):
+        """Intermediate tensors of the last batch (only with debug=True): per candidate the
+        frustum points, source rows, stats, centres, hypothesis boxes / iou / valid, counts."""
+        assert self.debug
+        torch.cuda.synchronize(self.device)
+        plan, F, H, M = handle["plan"], handle["plan"]["F"], self.H, self.M
+        S = handle["S"]
+
+        def view(name, dtype, shape):
+            n = int(np.prod(shape)) * torch.tensor([], dtype=dtype).element_size()
+            return self.arena.bufs[name][:n].view(dtype).view(*shape).cpu().numpy()
+        pt_start = view("cand_pt_start", torch.int32, (F + 1,))
+        total = int(pt_start[-1])
+        return dict(
+            pt_start=pt_start,
+            frustum_pts=view("frustum_pts", torch.float32, (total, 4)),
+            frustum_idx=view("frustum_idx", torch.int32, (total,)),
+            stats=view("cand_stats", torch.float32, (F, _lib.STATS_FLOATS)),
+            centres=view("centres", torch.float32, (F, M, 3)),
+            hyp_boxes=view("hyp_boxes_dbg", torch.float32, (F, H, 7)),
+            hyp_iou=view("hyp_iou_dbg", torch.float32, (F, H)),
+            hyp_valid=view("hyp_valid_dbg", torch.uint8, (F, H)).astype(bool),
+            hyp_index=view("hyp_index", torch.int32, (F, H)),
+            hyp_prep=view("hyp_prep", torch.float32, (F, H, 8)),
+            counts=view("counts", torch.int32, (F, S, H))[:, 0, :],
+        )

@@ -1,0 +1,198 @@
+/*
+ * fnp.h -- C ABI of libfnp_sm100.so, the B200-native (sm_100a) Greedy Box Seeker path.
+ *
+ * Drop-in boundary for the native side of findnpropagate's pcdet.ops on this path
+ * (reference paths relative to the reference tree):
+ *
+ *   reference pybind symbol (file:line)                     replaced by
+ *   ------------------------------------------------------  ---------------------------
+ *   roiaware_pool3d_cuda.points_in_boxes_gpu
+ *     (roiaware_pool3d/src/roiaware_pool3d.cpp:98,175)       fnp_points_in_boxes
+ *   iou3d_nms_cuda.boxes_overlap_bev_gpu
+ *     (iou3d_nms/src/iou3d_nms.cpp:49, iou3d_nms_api.cpp:12) fnp_boxes_overlap_bev
+ *   iou3d_nms_cuda.boxes_aligned_overlap_bev_gpu
+ *     (iou3d_nms.cpp:71, iou3d_nms_api.cpp:13)               fnp_boxes_aligned_overlap_bev
+ *   iou3d_nms_cuda.boxes_iou_bev_gpu
+ *     (iou3d_nms.cpp:93, iou3d_nms_api.cpp:14)               fnp_boxes_iou_bev
+ *   iou3d_nms_cuda.nms_gpu
+ *     (iou3d_nms.cpp:113, iou3d_nms_api.cpp:15)              fnp_nms_rotated
+ *   iou3d_nms_cuda.nms_normal_gpu
+ *     (iou3d_nms.cpp:162, iou3d_nms_api.cpp:16)              fnp_nms_normal
+ *   the per-hypothesis loop of FrustumProposerOG.get_proposals
+ *     (models/dense_heads/frustum_proposals_v1.py:582-1053)  fnp_seeker_* (fused stages)
+ *
+ * Conventions (differences from the reference are deliberate):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - the caller owns all memory, including workspaces (no cudaMalloc in any call);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, and no call
+ *     synchronises the device or the stream (the reference uses the legacy default
+ *     stream and a blocking cudaMemcpy inside NMS);
+ *   - return value: 0 on success, otherwise a cudaError_t (> 0) or an FNP_E* code (< 0).
+ *     Nothing ever calls exit() (the reference does, roiaware_pool3d_kernel.cu:350-354).
+ *   - all floating point data is fp32, boxes are [x, y, z, dx, dy, dz, heading] (7 floats).
+ */
+#ifndef FNP_H_
+#define FNP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNP_OK 0
+#define FNP_EINVAL (-1)   /* bad argument (null pointer, negative size, misalignment) */
+#define FNP_EWORKSPACE (-2) /* workspace too small */
+
+/* Library / build identification: returns e.g. "fnp-sm100a 0.1". */
+const char *fnp_version(void);
+
+/* ------------------------------------------------------------------ op-level API */
+
+/* First containing box per point (k ascending) or -1.
+ * boxes (B,T,7), pts (B,M,3) contiguous, out (B,M) int32 -- every entry is written. */
+int fnp_points_in_boxes(const float *boxes, const float *pts, int32_t *out, int B, int T, int M,
+                        void *stream);
+
+/* Per-box point counts over packed segments: for segment s (one frustum), points
+ * pts4[pt_start[s] .. pt_start[s+1]) (float4 x,y,z,_) are tested against boxes
+ * boxes[box_start[s] .. box_start[s+1]) (7 floats each); counts[] is indexed like boxes.
+ * Same predicate as fnp_points_in_boxes; count = what the reference obtains with one
+ * points_in_boxes_gpu call + (idx >= 0).sum() per box (frustum_proposals_v1.py:930-932). */
+int fnp_count_in_boxes(const float *pts4, const int32_t *pt_start, const float *boxes,
+                       const int32_t *box_start, int n_segments, int32_t *counts, void *stream);
+
+/* Rotated BEV overlap area / IoU, (N,7) x (M,7) -> (N,M). */
+int fnp_boxes_overlap_bev(const float *boxes_a, const float *boxes_b, float *out, int N, int M,
+                          void *stream);
+int fnp_boxes_iou_bev(const float *boxes_a, const float *boxes_b, float *out, int N, int M,
+                      void *stream);
+/* Aligned pairs, (N,7),(N,7) -> (N). */
+int fnp_boxes_aligned_overlap_bev(const float *boxes_a, const float *boxes_b, float *out, int N,
+                                  void *stream);
+
+/* NMS over boxes already sorted by descending score.  keep (N) int64 and num_keep (1) int32
+ * are written on the device; entries keep[*num_keep..N) are left untouched.
+ * workspace: fnp_nms_workspace_bytes(N) bytes, 8-byte aligned. */
+size_t fnp_nms_workspace_bytes(int N);
+int fnp_nms_rotated(const float *boxes_sorted, int N, float thresh, int64_t *keep,
+                    int32_t *num_keep, void *workspace, size_t workspace_bytes, void *stream);
+int fnp_nms_normal(const float *boxes_sorted, int N, float thresh, int64_t *keep,
+                   int32_t *num_keep, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------- fused seeker stages
+ *
+ * One call sequence processes a BATCH of frames.  Units: `cand` = one candidate frustum
+ * (a 2D box that survived the 2D NMS and the score threshold, in reference order:
+ * frame, then camera order [2,0,1,5,3,4], then 2D-NMS order); F = total candidates.
+ */
+
+typedef struct fnp_seeker_cfg {
+    int32_t num_mags;        /* M depth steps                    (PARAMS num_mags)      */
+    int32_t num_yaw_size;    /* J = num_rotations * num_sizes                           */
+    int32_t n_classes;       /* A rows of the prior tables                               */
+    int32_t clamp_bottom;    /* PARAMS clamp_bottom                                      */
+    float img_w, img_h;      /* 1600, 900  (frustum_proposals_v1.py:203)                 */
+    float lq, uq, cq;        /* depth quantiles                                          */
+    float frustum_min;       /* 2.0       (frustum_proposals_v1.py:240)                  */
+    float max_dist;          /* 50                                                       */
+    float min_cam_iou;       /* 0.3                                                      */
+    float dns_w, iou_w;      /* score weights                                            */
+} fnp_seeker_cfg;
+
+typedef struct fnp_seeker_batch {
+    /* ---- inputs ---- */
+    int32_t n_frames;
+    int32_t n_cands;                 /* F */
+    int32_t n_tiles;                 /* point tiles over all frames (FNP_CULL_TILE rows each) */
+    int32_t max_cands_per_frame;
+    const float *points;             /* rows of point_stride floats, xyz at xyz_offset     */
+    int32_t point_stride, xyz_offset;
+    const int64_t *frame_row_start;  /* (n_frames+1) first row of each frame               */
+    const int32_t *tile_frame;       /* (n_tiles) frame of each tile                       */
+    const int32_t *tile_row0;        /* (n_tiles) first row (within the frame) of each tile */
+    const int32_t *frame_tile_start; /* (n_frames+1) first tile of each frame              */
+    const float *cam_mats;           /* (n_frames,6,24): lidar2image rows 0..2 (12),
+                                        combine = cam2lidar_R inv(K) (9), cam2lidar_t (3)  */
+    const int32_t *frame_cand_start; /* (n_frames+1) first candidate of each frame         */
+    const int32_t *cand_frame;       /* (F) */
+    const int32_t *cand_cam;         /* (F) 0..5 */
+    const int32_t *cand_label;       /* (F) 1..A */
+    const float *cand_box2d;         /* (F,4) x1,y1,x2,y2 */
+    const float *base_boxes;         /* (A,J,7)   constructor tables                       */
+    const float *base_corners;       /* (A,J,8,3)                                          */
+    const float *mags;               /* (M) linspace(0,1,M)                                */
+    /* ---- workspaces / intermediates (caller allocated) ---- */
+    int32_t *tile_counts;            /* (n_tiles, max_cands_per_frame)                     */
+    int32_t *cand_npts;              /* (F)   P_f                                          */
+    int32_t *cand_pt_start;          /* (F+1) start of each frustum in frustum_pts         */
+    float *frustum_pts;              /* (pts_capacity,4) x,y,z,depth of the frustum points */
+    int32_t *frustum_idx;            /* (pts_capacity) source row within the frame, or NULL */
+    int64_t pts_capacity;
+    float *cand_stats;               /* (F,40): [0]dmin [1]dmax [2]dcentre [3..5]pmin [6..8]pmax
+                                        [9]n_points [16..39] clamped frustum corners (8,3)  */
+    float *centres;                  /* (F,M,3) */
+    float *hyp_prep;                 /* (F,H,8) compacted valid hypotheses, H = M*J:
+                                        cx,cy,cz,hz, cosa,sina,tx,ty                       */
+    int32_t *hyp_index;              /* (F,H) original hypothesis index of each compacted one */
+    float *hyp_iou;                  /* (F,H) its 2D IoU                                   */
+    int32_t *hyp_nvalid;             /* (F)                                                */
+    float *hyp_boxes_dbg;            /* (F,H,7) all hypothesis boxes by original index, or NULL */
+    float *hyp_iou_dbg;              /* (F,H) or NULL                                      */
+    uint8_t *hyp_valid_dbg;          /* (F,H) or NULL                                      */
+    int32_t score_splits;            /* S_max >= 1: max point splits per frustum           */
+    int32_t split_points;            /* target points per split                            */
+    int32_t *counts;                 /* (F,S_max,H) per-split partial counts               */
+    /* ---- outputs ---- */
+    float *out_boxes;                /* (F,7) selected box per candidate                   */
+    float *out_score;                /* (F)   its second-stage score                       */
+    int32_t *out_best;               /* (F)   compacted index of the winner, -1 if none    */
+    int32_t *out_count;              /* (F)   point count of the winner                    */
+    int32_t *status;                 /* (4)   [0] != 0: frustum_pts overflow (needed pts in [1]) */
+} fnp_seeker_batch;
+
+#define FNP_CULL_TILE 256
+
+/* Stage 1: fused LiDAR->camera projection + per-2D-box frustum cull + ordered compaction.
+ * count pass, scan, write pass (three launches, no host sync). */
+int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* Stage 1b: per-frustum depth quantiles, point AABB, frustum corners, centre line. */
+int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* Stage 2a: hypothesis grid, softmin front shift, distance + 2D-IoU filters, compaction. */
+int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* Stage 2b: points-in-boxes scoring (TMA-staged point tiles, register-resident hypotheses). */
+int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* Stage 3: density + IoU score and greedy argmax per frustum. */
+int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* All five stages back to back on `stream`. */
+int fnp_seeker_run(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+
+/* Stage 4: batched rotated-BEV bitmask NMS in shared memory.  Segment s covers boxes
+ * [seg_start[s], seg_start[s+1]) (<= max_seg_boxes <= FNP_SEG_NMS_MAX each, in priority order: an earlier
+ * kept box suppresses later ones with IoU > thresh, and if label != NULL only boxes of the
+ * same label interact).  order (n_boxes, nullable): entry i of a segment is box order[i]
+ * (gather; lets the caller impose a score order without moving boxes).  valid (nullable,
+ * indexed like boxes): entries < 0 are not boxes (never kept, never suppress).
+ * keep_mask (n_boxes) uint8, indexed like boxes, is written. */
+#define FNP_SEG_NMS_MAX 1024
+int fnp_seg_nms_rotated(const float *boxes, const int32_t *label, const int32_t *order,
+                        const int32_t *valid, const int32_t *seg_start, int n_segments,
+                        int max_seg_boxes, float thresh, uint8_t *keep_mask, void *stream);
+
+/* Recall counters (Detector3DTemplate.generate_recall_record): per frame, IoU3D of the
+ * proposals vs GT, per-GT max, thresholded.  pred (sum K,7) with pred_start (n_frames+1),
+ * pred_valid (nullable): rows with pred_valid[i] < 0 are skipped;
+ * gt (sum G,8) = box7 + class label with gt_start (n_frames+1); thresh (n_thresh<=8).
+ * counters (int64): [0]=gt, [1]=num_3known, [2]=num_6known, [3]=num_4unknown,
+ * [4]=num_7unknown, then per threshold t: [5+5t+0]=rcnn, +1 = 3known, +2 = 6known,
+ * +3 = 4unknown, +4 = 7unknown.  Counters are ACCUMULATED (caller zeroes them). */
+int fnp_recall_counters(const float *pred, const int32_t *pred_valid, const int32_t *pred_start, const float *gt,
+                        const int32_t *gt_start, int n_frames, const float *thresh_host,
+                        int n_thresh, long long *counters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNP_H_ */

@@ -1,0 +1,105 @@
+"""CPU tests of the host-side logic and of the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from findnpropagate_b200 import nms2d, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from findnpropagate_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
+    declared = set(re.findall(r"\b(fnp_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"fnp_seeker_cfg", "fnp_seeker_batch"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), "libfnp_sm100.so does not export %s" % name
+    assert set(_lib.EXPORTED) == declared
+    assert _lib.lib.fnp_version().startswith(b"fnp-sm100a")
+    assert _lib.lib.fnp_nms_workspace_bytes(1000) >= 1000 * 16 * 8
+
+
+def test_struct_layout_matches_header():
+    from findnpropagate_b200 import _lib
+    # 14 x 4-byte fields
+    assert ctypes.sizeof(_lib.SeekerCfg) == 56
+    hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
+    body = hdr[hdr.index("typedef struct fnp_seeker_batch"):hdr.index("} fnp_seeker_batch;")]
+    names = re.findall(r"[\*\s]([a-z_0-9]+)(?:,\s*([a-z_0-9]+))?;", body)
+    flat = [n for pair in names for n in pair if n]
+    assert flat == [f[0] for f in _lib.SeekerBatch._fields_]
+
+
+def test_ops_refuse_cpu_tensors():
+    from findnpropagate_b200.pcdet_ops import iou3d_nms_utils, roiaware_pool3d_utils
+    with pytest.raises(RuntimeError):
+        roiaware_pool3d_utils.points_in_boxes_gpu(torch.zeros(1, 4, 3), torch.zeros(1, 2, 7))
+    with pytest.raises(RuntimeError):
+        iou3d_nms_utils.boxes_iou_bev(torch.zeros(2, 7), torch.zeros(2, 7))
+    from findnpropagate_b200.seeker import SeekerEngine
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            SeekerEngine(synth.seeker_params(synth.CONFIGS["tiny"]))
+
+
+def test_nms2d_matches_torchvision():
+    from torchvision.ops import batched_nms
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        D = int(rng.integers(0, 40))
+        b = rng.uniform(0, 1500, (D, 2)).astype(np.float32)
+        boxes = np.concatenate([b, b + rng.uniform(2, 400, (D, 2)).astype(np.float32)], 1)
+        for _ in range(D // 3):
+            i, j = rng.integers(0, D, 2)
+            boxes[j] = boxes[i] + rng.normal(0, 3, 4).astype(np.float32)
+        scores = rng.uniform(0, 1, D).astype(np.float32)
+        if D > 4:
+            scores[1] = scores[3]
+        labels = rng.integers(1, 4, D)
+        cam = rng.integers(0, 6, D)
+        frame = rng.integers(0, 3, D)
+        got = list(nms2d.frustum_candidates(boxes, labels, scores, frame, cam, 0.4, 0.45))
+        ref = []
+        for f in range(3):
+            for c in nms2d.IMAGE_ORDER:
+                m = np.flatnonzero((cam == c) & (frame == f))
+                if len(m) == 0:
+                    continue
+                sel = batched_nms(torch.from_numpy(boxes[m]), torch.from_numpy(scores[m]),
+                                  torch.from_numpy(labels[m]), 0.4).numpy()
+                ref += [m[s] for s in sel if not (scores[m][s] < np.float32(0.45))]
+        assert got == ref
+
+
+def test_tables_match_reference_constructor(golden_dir):
+    from findnpropagate_b200 import seeker
+    g = np.load(os.path.join(golden_dir, "seeker_cfg1_0.npz"))
+    bb, bc = seeker.build_tables(seeker.resolve_params(synth.seeker_params(synth.CONFIGS["cfg1"])))
+    assert np.array_equal(bb.numpy(), g["base_boxes"])
+    assert np.array_equal(bc.numpy(), g["base_corners"])
+
+
+def test_synth_frame_is_deterministic_and_well_formed(golden_dir):
+    g = np.load(os.path.join(golden_dir, "seeker_tiny_0.npz"))
+    f = synth.make_frame(0, synth.CONFIGS["tiny"])
+    assert f.points.dtype == np.float32 and f.points.shape[1] == 5
+    assert f.lidar2image.shape == (6, 4, 4) and f.det_boxes.shape[1] == 4
+    assert np.allclose(f.points, g["points"], atol=1e-4)
+    assert np.array_equal(f.det_labels, g["det_labels"])
+    bd = synth.collate([f, f])
+    assert bd["points"].shape == (2 * f.points.shape[0], 6) and bd["batch_size"] == 2
+    assert set(np.unique(bd["points"][:, 0])) == {0.0, 1.0}
+
+
+def test_unsupported_options_raise():
+    from findnpropagate_b200 import seeker
+    with pytest.raises(NotImplementedError):
+        seeker.resolve_params(dict(topk=2, nms_3d=0, dst_w=0))
+    with pytest.raises(NotImplementedError):
+        seeker.resolve_params(dict(nms_3d=0, dst_w=0.2))

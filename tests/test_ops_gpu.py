@@ -1,0 +1,261 @@
+"""GPU parity tests of the op-level C ABI (through the pcdet_ops drop-in wrappers) against
+(i) the reference's own kernels compiled for sm_100a (oracle/_ref) and (ii) the C oracle.
+Bit-exact for indices, counts and keep sets; IoU values are compared bit for bit as well."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _boxes(rng, n, centre=(14.0, 0.0, -0.5), spread=8.0, yaw="rand"):
+    from findnpropagate_b200.synth import PRIORS
+    b = np.zeros((n, 7), np.float32)
+    b[:, 0:3] = rng.uniform(-0.5, 0.5, (n, 3)) * [spread, spread, 1.0] + centre
+    b[:, 3:6] = PRIORS[rng.integers(0, 10, n)] * rng.uniform(0.8, 1.2, (n, 3))
+    b[:, 6] = rng.uniform(-2 * np.pi, 2 * np.pi, n) if yaw == "rand" else np.linspace(0, np.pi, n)
+    return b
+
+
+def test_device_trig_matches_oracle_restatement():
+    # torch's CUDA sin/cos/atan2 call the same libdevice routines the reference kernels use
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 50000),
+                        rng.uniform(-1e9, 1e9, 20000), np.linspace(0, np.pi, 97)]).astype(np.float32)
+    xs = torch.from_numpy(x).to(DEV)
+    s, c = torch.sin(xs).cpu().numpy(), torch.cos(xs).cpu().numpy()
+    idx = rng.choice(x.shape[0], 20000, replace=False)
+    idx = np.concatenate([idx, np.arange(x.shape[0] - 97, x.shape[0])])
+    for i in idx:
+        assert O.sinf(x[i]).tobytes() == s[i].tobytes(), (x[i], O.sinf(x[i]), s[i])
+        assert O.cosf(x[i]).tobytes() == c[i].tobytes(), (x[i], O.cosf(x[i]), c[i])
+    y = rng.normal(size=20000).astype(np.float32)
+    z = rng.normal(size=20000).astype(np.float32)
+    a = torch.atan2(torch.from_numpy(y).to(DEV), torch.from_numpy(z).to(DEV)).cpu().numpy()
+    for i in range(0, 20000, 4):
+        assert O.atan2f(y[i], z[i]).tobytes() == a[i].tobytes()
+
+
+def test_points_in_boxes_vs_reference_kernel_and_oracle(ref_ops):
+    from findnpropagate_b200.pcdet_ops import roiaware_pool3d_utils as RP
+    ref_rp, _ = ref_ops
+    rng = np.random.default_rng(1)
+    total = 0
+    for (B, M, T) in [(1, 200000, 64), (3, 50001, 17), (2, 1000, 300), (1, 7, 1), (1, 1, 0 + 1)]:
+        pts = (rng.uniform(-0.5, 0.5, (B, M, 3)) * [10, 10, 3] + [14, 0, -0.5]).astype(np.float32)
+        boxes = np.stack([_boxes(rng, T) for _ in range(B)])
+        tp, tb = torch.from_numpy(pts).to(DEV), torch.from_numpy(boxes).to(DEV)
+        mine = RP.points_in_boxes_gpu(tp, tb)
+        assert mine.dtype == torch.int32 and mine.shape == (B, M)
+        ref = torch.full((B, M), -1, dtype=torch.int32, device=DEV)
+        ref_rp.points_in_boxes_gpu(tb, tp, ref)
+        torch.cuda.synchronize()
+        assert torch.equal(mine, ref)
+        if M <= 50001:
+            assert np.array_equal(mine.cpu().numpy(), O.points_in_boxes_gpu(pts, boxes))
+        total += B * M * T
+    assert total > 1e7
+
+
+def test_points_in_boxes_boundary_stress(ref_ops):
+    """Points placed within a few ulp of the box faces (fma shape / f64 compare stress)."""
+    from findnpropagate_b200.pcdet_ops import roiaware_pool3d_utils as RP
+    ref_rp, _ = ref_ops
+    rng = np.random.default_rng(2)
+    boxes = _boxes(rng, 256)
+    n = 0
+    for b in boxes:
+        k = 4096
+        t = rng.uniform(-1, 1, k)
+        lx = np.where(np.arange(k) % 2 == 0, (b[3] / 2 + 1e-5) * np.sign(t), t * b[3] / 2)
+        ly = np.where(np.arange(k) % 2 == 1, (b[4] / 2 + 1e-5) * np.sign(t), t * b[4] / 2)
+        c, s = np.cos(b[6]), np.sin(b[6])
+        x = b[0] + lx * c - ly * s + rng.integers(-3, 4, k) * 2e-6
+        y = b[1] + lx * s + ly * c
+        z = np.where(np.arange(k) % 3 == 0, b[2] + np.sign(t) * b[5] / 2, b[2])
+        pts = np.stack([x, y, z], 1).astype(np.float32)[None]
+        tp, tb = torch.from_numpy(pts).to(DEV), torch.from_numpy(b[None, None]).to(DEV)
+        mine = RP.points_in_boxes_gpu(tp, tb)
+        ref = torch.full((1, k), -1, dtype=torch.int32, device=DEV)
+        ref_rp.points_in_boxes_gpu(tb, tp, ref)
+        assert torch.equal(mine, ref)
+        assert np.array_equal(mine.cpu().numpy(), O.points_in_boxes_gpu(pts, b[None, None]))
+        n += k
+    assert n == 256 * 4096
+
+
+def test_points_in_boxes_edge_cases():
+    from findnpropagate_b200.pcdet_ops import roiaware_pool3d_utils as RP
+    out = RP.points_in_boxes_gpu(torch.zeros(2, 0, 3, device=DEV), torch.zeros(2, 3, 7, device=DEV))
+    assert out.shape == (2, 0)
+    out = RP.points_in_boxes_gpu(torch.zeros(1, 5, 3, device=DEV), torch.zeros(1, 0, 7, device=DEV))
+    assert torch.equal(out, torch.full((1, 5), -1, dtype=torch.int32, device=DEV))
+    nanp = torch.tensor([[[float("nan"), 0, 0], [0, 0, float("nan")], [0, 0, 0]]], device=DEV)
+    box = torch.tensor([[[0, 0, 0, 2, 2, 2, 0.1]]], device=DEV)
+    assert RP.points_in_boxes_gpu(nanp, box).cpu().tolist() == [[-1, -1, 0]]
+    with pytest.raises(ValueError):
+        RP.points_in_boxes_gpu(torch.zeros(1, 5, 3, device=DEV, dtype=torch.float64), box)
+    cpu_like = RP.points_in_boxes_cpu(np.zeros((5, 3), np.float32), np.array([[0, 0, 0, 1, 1, 1, 0]], np.float32))
+    assert isinstance(cpu_like, np.ndarray) and cpu_like.shape == (1, 5) and cpu_like.sum() == 5
+
+
+def test_count_in_boxes_op(ref_ops):
+    """Segmented counts == per-hypothesis reference launches (frustum_proposals_v1.py:930-932)."""
+    import ctypes as C
+    from findnpropagate_b200 import _lib
+    ref_rp, _ = ref_ops
+    rng = np.random.default_rng(4)
+    seg_pts = [3000, 1, 0, 777]
+    seg_box = [60, 5, 9, 130]
+    pts = [(rng.uniform(-0.5, 0.5, (n, 3)) * [10, 10, 3] + [14, 0, -0.5]).astype(np.float32) for n in seg_pts]
+    boxes = [_boxes(rng, n) for n in seg_box]
+    p4 = np.concatenate([np.concatenate([p, np.zeros((p.shape[0], 1), np.float32)], 1) for p in pts])
+    ps = np.cumsum([0] + seg_pts).astype(np.int32)
+    bs = np.cumsum([0] + seg_box).astype(np.int32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    tp, tps, tb, tbs = d(p4), d(ps), d(np.concatenate(boxes)), d(bs)
+    counts = torch.full((int(bs[-1]),), -7, dtype=torch.int32, device=DEV)
+    rc = _lib.lib.fnp_count_in_boxes(tp.data_ptr(), tps.data_ptr(), tb.data_ptr(), tbs.data_ptr(), 4,
+                                     counts.data_ptr(), _lib.current_stream())
+    assert rc == 0
+    got = counts.cpu().numpy()
+    for s in range(4):
+        exp = O.count_in_boxes(pts[s], boxes[s]) if seg_pts[s] else np.zeros(seg_box[s], np.int32)
+        assert np.array_equal(got[bs[s]:bs[s + 1]], exp)
+        if seg_pts[s]:
+            # the reference's own way: one launch per hypothesis
+            tpp = torch.from_numpy(pts[s][None]).to(DEV)
+            for h in range(0, seg_box[s], 7):
+                idx = torch.full((1, seg_pts[s]), -1, dtype=torch.int32, device=DEV)
+                ref_rp.points_in_boxes_gpu(torch.from_numpy(boxes[s][h][None, None]).to(DEV), tpp, idx)
+                assert int((idx >= 0).sum()) == got[bs[s] + h]
+
+
+def _pair_boxes(rng, n):
+    a = _boxes(rng, n, spread=10.0)
+    b = _boxes(rng, n, spread=10.0)
+    b[: n // 8] = a[: n // 8]                                   # identical
+    b[n // 8: n // 4, :2] = a[n // 8: n // 4, :2] + rng.normal(0, 0.05, (n // 4 - n // 8, 2))
+    b[n // 8: n // 4, 3:7] = a[n // 8: n // 4, 3:7]             # same size+yaw, shifted
+    a[n // 4: n // 4 + 8, 6] = 0.0                              # axis-aligned
+    b[n // 4: n // 4 + 8, 6] = np.pi / 2
+    return a.astype(np.float32), b.astype(np.float32)
+
+
+def test_rotated_iou_and_overlap_vs_reference_kernels(ref_ops):
+    from findnpropagate_b200.pcdet_ops import iou3d_nms_cuda as mine, iou3d_nms_utils as IU
+    _, ref_iou = ref_ops
+    rng = np.random.default_rng(5)
+    for n, m in [(768, 768), (60, 200), (1, 1), (17, 33)]:
+        a, b = _pair_boxes(rng, max(n, m, 16))
+        a, b = a[:n], b[:m]
+        ta, tb = torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)
+        for fn_m, fn_r in [(mine.boxes_iou_bev_gpu, ref_iou.boxes_iou_bev_gpu),
+                           (mine.boxes_overlap_bev_gpu, ref_iou.boxes_overlap_bev_gpu)]:
+            o1 = torch.zeros(n, m, device=DEV)
+            o2 = torch.zeros(n, m, device=DEV)
+            fn_m(ta, tb, o1)
+            fn_r(ta, tb, o2)
+            torch.cuda.synchronize()
+            neq = int((o1 != o2).sum())
+            assert neq == 0, "%d of %d values differ, max abs %g" % (neq, n * m, float((o1 - o2).abs().max()))
+        if n * m <= 4000:
+            assert np.array_equal(IU.boxes_iou_bev(ta, tb).cpu().numpy(), O.boxes_iou_bev(a, b))
+    # aligned + iou3d wrappers
+    a, b = _pair_boxes(rng, 500)
+    ta, tb = torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)
+    o1, o2 = torch.zeros(500, 1, device=DEV), torch.zeros(500, 1, device=DEV)
+    mine.boxes_aligned_overlap_bev_gpu(ta, tb, o1)
+    ref_iou.boxes_aligned_overlap_bev_gpu(ta, tb, o2)
+    assert torch.equal(o1, o2)
+    i3 = IU.boxes_iou3d_gpu(ta[:50], tb[:60]).cpu().numpy()
+    assert np.allclose(i3, O.boxes_iou3d(a[:50], b[:60]), rtol=1e-6, atol=1e-7)
+    assert IU.boxes_aligned_iou3d_gpu(ta, tb).shape == (500, 1)
+    assert IU.boxes_iou_bev(ta[:0], tb).shape == (0, 500)
+    cpu_like = IU.boxes_bev_iou_cpu(a[:5], b[:6])
+    assert isinstance(cpu_like, np.ndarray) and cpu_like.shape == (5, 6)
+
+
+@pytest.mark.parametrize("rotated", [True, False])
+def test_nms_keep_indices_vs_reference(ref_ops, rotated):
+    from findnpropagate_b200.pcdet_ops import iou3d_nms_utils as IU
+    _, ref_iou = ref_ops
+    rng = np.random.default_rng(6 + rotated)
+    for n, thr in [(60, 0.1), (200, 0.3), (768, 0.5), (3072, 0.7), (65, 0.01), (64, 1.0), (1, 0.5)]:
+        boxes = _boxes(rng, n, spread=12.0 if n < 1000 else 40.0)
+        boxes[n // 2:n // 2 + n // 10] = boxes[:n // 10]          # exact duplicates
+        scores = rng.uniform(0, 1, n).astype(np.float32)
+        tb, ts = torch.from_numpy(boxes).to(DEV), torch.from_numpy(scores).to(DEV)
+        fn = IU.nms_gpu if rotated else IU.nms_normal_gpu
+        keep, _ = fn(tb, ts, thr)
+        assert keep.dtype == torch.int64 and keep.is_cuda
+        order = ts.sort(0, descending=True, stable=True)[1]
+        sb = tb[order].contiguous()
+        k_ref = torch.zeros(n, dtype=torch.int64)
+        n_ref = (ref_iou.nms_gpu if rotated else ref_iou.nms_normal_gpu)(sb, k_ref, thr)
+        exp = order[k_ref[:n_ref].to(DEV)]
+        assert torch.equal(keep, exp), (n, thr, keep.numel(), n_ref)
+        if n <= 768:
+            o = (O.nms_rotated if rotated else O.nms_normal)(boxes, scores, thr)
+            assert np.array_equal(keep.cpu().numpy(), o)
+        # scores on the CPU (as the seeker passes them, frustum_proposals_v1.py:994-1030)
+        keep2, _ = fn(tb, ts.cpu(), thr)
+        assert torch.equal(keep2, keep.cpu())
+    keep, _ = IU.nms_gpu(torch.zeros(0, 7, device=DEV), torch.zeros(0, device=DEV), 0.5)
+    assert keep.numel() == 0
+    keep, _ = IU.nms_gpu(tb, ts, 0.5, pre_maxsize=1)
+    assert keep.numel() == 1
+
+
+def test_seg_nms_and_recall_counters():
+    import ctypes as C
+    from findnpropagate_b200 import _lib
+    import seeker_oracle as SO
+    rng = np.random.default_rng(9)
+    segs = [40, 0, 130, 1]
+    boxes = np.concatenate([_boxes(rng, n, spread=6.0) for n in segs if n] or [np.zeros((0, 7), np.float32)])
+    start = np.cumsum([0] + segs).astype(np.int32)
+    valid = np.where(rng.uniform(size=boxes.shape[0]) < 0.15, -1, 3).astype(np.int32)
+    scores = rng.uniform(size=boxes.shape[0]).astype(np.float32)
+    order = np.concatenate([start[s] + np.argsort(-scores[start[s]:start[s + 1]], kind="stable") for s in range(4)]).astype(np.int32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    tb, to, tv, ts = d(boxes), d(order), d(valid), d(start)
+    keep = torch.full((boxes.shape[0],), 9, dtype=torch.uint8, device=DEV)
+    rc = _lib.lib.fnp_seg_nms_rotated(tb.data_ptr(), None, to.data_ptr(), tv.data_ptr(), ts.data_ptr(), 4, 130,
+                                      C.c_float(0.1), keep.data_ptr(), _lib.current_stream())
+    assert rc == 0
+    got = keep.cpu().numpy()
+    for s in range(4):
+        sl = slice(start[s], start[s + 1])
+        ok = valid[sl] >= 0
+        exp = np.zeros(segs[s], bool)
+        if ok.any():
+            kept = O.nms_rotated(boxes[sl][ok], scores[sl][ok], 0.1)
+            exp[np.flatnonzero(ok)[kept]] = True
+        assert np.array_equal(got[sl].astype(bool), exp)
+    # recall counters vs the restated generate_recall_record
+    gts, gstart, exp = [], [0], None
+    for s in range(4):
+        g = np.zeros((12, 8), np.float32)
+        g[:9, :7] = _boxes(rng, 9, spread=6.0)
+        if segs[s]:
+            g[:4, :7] = boxes[start[s]:start[s] + 4] * [1, 1, 1, 1.05, 0.95, 1, 1]
+        g[:9, 7] = rng.integers(1, 11, 9)
+        gts.append(g)
+        gstart.append(gstart[-1] + 12)
+        sl = slice(start[s], start[s + 1])
+        rd = SO.recall_record(boxes[sl][valid[sl] >= 0], np.concatenate([g[:, :7], np.zeros((12, 2), np.float32), g[:, 7:]], 1))
+        exp = rd if exp is None else {k: exp[k] + rd[k] for k in rd}
+    tg, tgs = d(np.concatenate(gts)), d(np.array(gstart, np.int32))
+    counters = torch.zeros(20, dtype=torch.int64, device=DEV)
+    th = (C.c_float * 3)(0.3, 0.5, 0.7)
+    rc = _lib.lib.fnp_recall_counters(tb.data_ptr(), tv.data_ptr(), ts.data_ptr(), tg.data_ptr(), tgs.data_ptr(), 4,
+                                      th, 3, counters.data_ptr(), _lib.current_stream())
+    assert rc == 0
+    from findnpropagate_b200.seeker import SeekerEngine
+    got = SeekerEngine.recall_dict(counters.cpu().numpy())
+    assert got == exp, (got, exp)

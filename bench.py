@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Headline benchmark: Greedy Box Seeker frames/s (and hypotheses/s) on synthetic
+nuScenes-shaped frames -- BASELINE.json configs[1] frames (10 sweeps ~300k points, 6
+cameras, ~60 GLIP boxes, 64 depths x 12 yaws = 768 hypotheses per frustum), a batch of
+such frames per step.
+
+    python bench.py --gpus N --steps K --warmup W          # ours (CUDA, sm_100a)
+    python bench.py --impl reference ...                    # reference CPU path on host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every
+field.  Nothing here reads /root/reference; the CPU arms use oracle/_ref (the reference's
+own ops, prebuilt) and the oracle restatement of the seeker loop.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--frames", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated per rank")
+    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]          # samples under load = upper half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- data
+def make_frames(cfg_name, first_index, n, device):
+    from findnpropagate_b200 import synth
+    from findnpropagate_b200.seeker import FrameInput
+    cfg = synth.CONFIGS[cfg_name]
+    out = []
+    for i in range(n):
+        f = synth.make_frame(first_index + i, cfg, device=device)
+        out.append(FrameInput(points=f.points, lidar2image=f.lidar2image, camera2lidar=f.camera2lidar,
+                              camera_intrinsics=f.camera_intrinsics, det_boxes=f.det_boxes, det_labels=f.det_labels,
+                              det_scores=f.det_scores, det_cam_idx=f.det_cam_idx, gt_boxes=f.gt_boxes))
+    return out, synth.seeker_params(cfg)
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _cpu_frame(args):
+    """Reference CPU path for one frame: the seeker loop restated with numpy/torch-CPU
+    calling the reference-compiled points_in_boxes_cpu for the per-hypothesis counts."""
+    fi, params, kind = args
+    import oracle as O
+    import seeker_oracle as SO
+    if kind == "reference":
+        import build_ref
+        import torch
+        rp = build_ref.load("roiaware_pool3d_cuda")
+
+        def count(points, boxes):
+            out = torch.zeros((boxes.shape[0], points.shape[0]), dtype=torch.int32)
+            rp.points_in_boxes_cpu(torch.from_numpy(np.ascontiguousarray(boxes, np.float32)),
+                                   torch.from_numpy(np.ascontiguousarray(points[:, :3], np.float32)), out)
+            return out.sum(1).numpy().astype(np.int32)
+        O_count, O.count_in_boxes = O.count_in_boxes, count
+    try:
+        r = SO.seek_frame(fi.points, fi.lidar2image, fi.camera2lidar, fi.camera_intrinsics,
+                          (fi.det_boxes, fi.det_labels, fi.det_scores, fi.det_cam_idx), params)
+    finally:
+        if kind == "reference":
+            O.count_in_boxes = O_count
+    return r["pred_boxes"].shape[0]
+
+
+def cpu_kind():
+    try:
+        import build_ref
+        build_ref.load("roiaware_pool3d_cuda")
+        return "reference"
+    except Exception:
+        return "port"
+
+
+def cpu_baseline(frames, params, n_frames):
+    kind = cpu_kind()
+    import oracle as O
+    O.lib()
+    t = time.perf_counter()
+    for fi in frames[:n_frames]:
+        _cpu_frame((fi, params, kind))
+    dt = time.perf_counter() - t
+    return {"value": n_frames / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+            "sample": "%d frame(s) of the same workload, single thread: seeker loop restated on the host + "
+                      "reference points_in_boxes_cpu (oracle/_ref)" % n_frames if kind == "reference" else
+                      "%d frame(s), single thread, oracle port" % n_frames}
+
+
+def run_reference_arm(a):
+    """bench.py --impl reference: the reference's CPU implementation of the path on all host
+    cores (frame-parallel, one frame per process)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    kind = cpu_kind()
+    frames, params = make_frames(a.config, 0, min(a.distinct, max(2, cores)), "cpu")
+    per_step = max(1, min(cores, 8))
+    jobs = [(frames[i % len(frames)], params, kind) for i in range(per_step)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=min(cores, per_step)) as pool:
+        for _ in range(max(a.warmup, 1) if a.warmup else 0):
+            pool.map(_cpu_frame, jobs[:min(len(jobs), 2)])
+        t = time.perf_counter()
+        for _ in range(a.steps):
+            pool.map(_cpu_frame, jobs)
+        dt = time.perf_counter() - t
+    fps = per_step * a.steps / dt
+    H = params["num_mags"] * params["num_rotations"] * params["num_sizes"]
+    line = {
+        "impl": "reference", "metric": "box_seeker_frames_per_s", "value": fps, "unit": "frames/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s frames (BASELINE.json configs[1] shape), %d hypotheses/frustum; bounded sample: "
+                               "%d frames per step" % (a.config, H, per_step)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": min(cores, per_step), "kind": kind,
+                         "sample": "%d frames per step, frame-parallel over %d processes" % (per_step, min(cores, per_step))},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from findnpropagate_b200 import _lib
+    from findnpropagate_b200.seeker import SeekerEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    frames_d, params = make_frames(a.config, rank * a.distinct, a.distinct, str(dev))
+    B = a.frames
+    batch = [frames_d[i % a.distinct] for i in range(B)]
+    eng = SeekerEngine(params, device=dev)
+    H = eng.H
+    # two input sets (A/B) so that consecutive steps never touch the same HBM lines; each is
+    # B x ~7.7 MB of points, well above the 126 MB L2 for the default B
+    pinned = []
+    for s in range(2):
+        rows = sum(f.points.shape[0] for f in batch)
+        t = torch.empty((rows, batch[0].points.shape[1]), dtype=torch.float32, pin_memory=True)
+        r = 0
+        for f in batch:
+            t[r:r + f.points.shape[0]] = torch.from_numpy(f.points)
+            r += f.points.shape[0]
+        pinned.append(t)
+    dev_pts = [p.to(dev) for p in pinned]
+    gt = eng.upload_gt(batch)
+    in_bytes = pinned[0].numel() * 4
+
+    Kmax = 0
+    copy_stream = torch.cuda.Stream(device=dev)
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in consumed:
+        e.record()
+
+    def step(k, resident, prev):
+        """One pass of the hot path over one batch; returns the new handle."""
+        nonlocal Kmax
+        pts = dev_pts[k % 2]
+        if not resident:
+            # H2D of this step's points from pinned host memory, inside the timed region, on a
+            # copy stream so that it overlaps the previous step's kernels
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[k % 2])
+                pts.copy_(pinned[k % 2], non_blocking=True)
+                ready[k % 2].record(copy_stream)
+        plan = eng.plan(batch)
+        if not resident:
+            torch.cuda.current_stream(dev).wait_event(ready[k % 2])
+        h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2)
+        consumed[k % 2].record()
+        res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
+        if res is not None and world > 1:
+            gather_results(res, plan)
+        return h, res
+
+    def gather_results(res, plan):
+        # frame-sharded run: one all_gather of fixed-stride packed proposals + one
+        # all_reduce of the recall counters per step (NCCL over NVLink)
+        nonlocal Kmax
+        Kmax = max(Kmax, plan["max_cands"], 1)
+        pack = np.zeros((B, Kmax, 9), np.float32)
+        cnt = np.zeros((B,), np.int32)
+        for b, fr in enumerate(res["frames"]):
+            k = fr["pred_boxes"].shape[0]
+            pack[b, :k, :7] = fr["pred_boxes"]; pack[b, :k, 7] = fr["pred_scores"]; pack[b, :k, 8] = fr["pred_labels"]
+            cnt[b] = k
+        tp = torch.from_numpy(pack).to(dev)
+        tc = torch.from_numpy(cnt).to(dev)
+        allp = torch.empty((world,) + tuple(tp.shape), dtype=tp.dtype, device=dev)
+        allc = torch.empty((world, B), dtype=tc.dtype, device=dev)
+        dist.all_gather_into_tensor(allp, tp)
+        dist.all_gather_into_tensor(allc, tc)
+        rc = torch.tensor([res["recall"][k] for k in sorted(res["recall"])], dtype=torch.int64, device=dev)
+        dist.all_reduce(rc)
+
+    def timed(resident, steps, warmup):
+        prev = None
+        for k in range(warmup):
+            prev, _ = step(k, resident, prev)
+        if prev is not None:
+            eng.finish(prev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launches
+        e0.record()
+        prev, last = None, None
+        for k in range(steps):
+            prev, r = step(k, resident, prev)
+            last = r or last
+        last = eng.finish(prev)
+        if world > 1:
+            gather_results(last, prev["plan"])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, last, eng.launches - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, last, launches = timed(True, a.steps, a.warmup)
+    ms_e2e, _, _ = timed(False, a.steps, a.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel (scoring) in isolation, CUDA events on the launching stream
+    plan = eng.plan(batch)
+    h = eng.execute(plan, dev_pts[0])
+    res = eng.finish(h)
+    stream = _lib.current_stream(dev)
+    import ctypes as C
+    for _ in range(3):
+        _lib.lib.fnp_seeker_score(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+    iters = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scr = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = 0.0
+    for _ in range(iters):
+        scr.zero_()                                   # flush L2 (256 MB > 126 MB)
+        e0.record()
+        _lib.lib.fnp_seeker_score(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    score_ms = tot / iters
+    npts = res["cand_npts"].astype(np.int64)
+    nval = res["cand_nvalid"].astype(np.int64)
+    alg_bytes = float(16 * npts[nval > 0].sum() + 36 * nval.sum())
+    tests = float((npts * nval).sum())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (score_ms * 1e-3) / 1e9
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak_tests = eng.n_sms * 4 * 32 * sm_clock * 1e6 / 11.0   # 11 issue slots per point-box test
+
+    if rank == 0:
+        n_frames = B * world
+        F_step = plan["F"]
+        cpu = None if (a.no_cpu_baseline or world > 1) else cpu_baseline(batch, params, a.cpu_sample_frames)
+        line = {
+            "metric": "box_seeker_frames_per_s", "value": n_frames * a.steps / (ms_res * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_res / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "%s frames (BASELINE.json configs[1] shape: 10 sweeps ~%dk points, 6 cameras, ~%d 2D boxes, "
+                            "%d depths x %d yaws = %d hypotheses/frustum), batch of %d frames per step per GPU"
+                            % (a.config, int(np.mean([f.points.shape[0] for f in batch]) / 1000), F_step // B,
+                               params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B),
+                "frames_per_step_per_gpu": B, "distinct_frames": a.distinct,
+                "l2_policy": "inputs larger than L2: %.0f MB of points per step, two alternating input sets" % (in_bytes / 1e6),
+                "sharding": "frame-wise, no data-path collective; per step one all_gather of packed proposals + one "
+                            "all_reduce of recall counters" if world > 1 else "single GPU"},
+            "hypotheses_per_s": F_step * H * world * a.steps / (ms_res * 1e-3),
+            "point_box_tests_per_s_scoring_kernel": tests / (score_ms * 1e-3),
+            "e2e": {"value": n_frames * a.steps / (ms_e2e * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(in_bytes + sum(plan[k].nbytes for k in eng._META)),
+                    "d2h_bytes_per_step": int(4 * (12 * plan["F"] + 8) + plan["F"]),
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "fnp::score_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "the scoring kernel is FP32-issue-bound, not HBM-bound (DESIGN.md): "
+                                 "issue_frac = tests/s over n_SM*4*32*clk/11",
+                         "issue_frac": tests / (score_ms * 1e-3) / issue_peak_tests},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

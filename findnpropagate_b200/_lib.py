@@ -42,7 +42,8 @@ class SeekerBatch(C.Structure):
         ("frustum_idx", _vp), ("pts_capacity", C.c_int64), ("cand_stats", _vp), ("centres", _vp),
         ("hyp_prep", _vp), ("hyp_index", _vp), ("hyp_iou", _vp), ("hyp_nvalid", _vp),
         ("hyp_boxes_dbg", _vp), ("hyp_iou_dbg", _vp), ("hyp_valid_dbg", _vp),
-        ("score_splits", C.c_int32), ("split_points", C.c_int32), ("counts", _vp),
+        ("split_points", C.c_int32), ("max_items", C.c_int32), ("max_count_rows", C.c_int32),
+        ("cand_item_start", _vp), ("cand_split_row", _vp), ("items", _vp), ("counts", _vp),
         ("out_boxes", _vp), ("out_score", _vp), ("out_best", _vp), ("out_count", _vp),
         ("status", _vp),
     ]
@@ -77,7 +78,11 @@ lib.fnp_seg_nms_rotated.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _v
 lib.fnp_recall_counters.restype = _i
 lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _vp, _vp]
 
+lib.fnp_dbg_math.restype = _i
+lib.fnp_dbg_math.argtypes = [_vp, _vp, _vp, _i, _vp]
+
 EXPORTED = [
+    "fnp_dbg_math",
     "fnp_version", "fnp_points_in_boxes", "fnp_count_in_boxes", "fnp_boxes_overlap_bev",
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",

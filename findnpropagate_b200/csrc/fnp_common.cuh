@@ -78,6 +78,13 @@ __device__ __forceinline__ float dot3(const float *__restrict__ a, float x, floa
     return __fmaf_rn(a[2], z, __fmaf_rn(a[1], y, __fmul_rn(a[0], x)));
 }
 
+// 3-term dot product in the order torch's batched (L,3,3)@(L,3,1) matmul uses on B200
+// (measured, tools/probe_gpu.py): rn(fma(a1,y, rn(a0*x)) + rn(a2*z)).
+__device__ __forceinline__ float dot3_bmm(const float *__restrict__ a, float x, float y, float z)
+{
+    return __fadd_rn(__fmaf_rn(a[1], y, __fmul_rn(a[0], x)), __fmul_rn(a[2], z));
+}
+
 __device__ __forceinline__ float norm3(float x, float y, float z)
 {
     return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
@@ -122,9 +129,9 @@ __device__ __forceinline__ void unproject(const float *__restrict__ C, const flo
                                           float u, float v, float d, float &x, float &y, float &z)
 {
     const float px = __fmul_rn(u, d), py = __fmul_rn(v, d);
-    x = __fadd_rn(dot3(C + 0, px, py, d), t[0]);
-    y = __fadd_rn(dot3(C + 3, px, py, d), t[1]);
-    z = __fadd_rn(dot3(C + 6, px, py, d), t[2]);
+    x = __fadd_rn(dot3_bmm(C + 0, px, py, d), t[0]);
+    y = __fadd_rn(dot3_bmm(C + 3, px, py, d), t[1]);
+    z = __fadd_rn(dot3_bmm(C + 6, px, py, d), t[2]);
 }
 
 // ---------------------------------------------------------------------------------------

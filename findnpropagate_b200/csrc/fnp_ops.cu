@@ -461,9 +461,28 @@ __global__ void __launch_bounds__(128) recall_kernel(const float *__restrict__ p
     }
 }
 
+// test hook: the device math routines exactly as this library's kernels see them
+__global__ void dbg_math_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = sinf(x[i]);
+    out[n + i] = cosf(x[i]);
+    out[2 * n + i] = atan2f(y[i], x[i]);
+    out[3 * n + i] = fnp_exp(x[i]);
+}
+
 }  // namespace fnp
 
 using namespace fnp;
+
+extern "C" int fnp_dbg_math(const float *x, const float *y, float *out, int n, void *stream)
+{
+    if (n <= 0) return FNP_OK;
+    dbg_math_kernel<<<divup(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, out, n);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
 
 extern "C" const char *fnp_version(void) { return "fnp-sm100a 0.1"; }
 

@@ -512,11 +512,79 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
 constexpr int kScoreThreads = 128;
 constexpr int kScoreTile = 512;  // points per TMA stage (8 KB)
 
-__host__ __device__ inline int n_splits(int npts, int s_max, int split_points)
+__host__ __device__ inline int hyps_per_cta(int H) { return kScoreThreads * (H <= 128 ? 1 : (H <= 512 ? 2 : 4)); }
+
+// Work items of the scoring stage.  Frustum f with P_f points and nv_f valid hypotheses is cut
+// into S_f = ceil(P_f / split_points) point splits x ceil(nv_f / hyps_per_cta) hypothesis
+// chunks; every (split, chunk) pair is one CTA-sized item, so the largest frustums no longer
+// set the kernel's duration.  Split s of frustum f writes its partial counts to row
+// split_row[f] + s of `counts`; select_kernel adds the S_f rows (a fixed-order integer
+// reduction, no atomics).
+__global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch b, const int H)
 {
-    int s = (npts + split_points - 1) / split_points;
-    s = s < 1 ? 1 : s;
-    return s > s_max ? s_max : s;
+    __shared__ int s_warp_i[32], s_warp_r[32];
+    __shared__ int s_carry_i, s_carry_r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hpc = hyps_per_cta(H);
+    if (tid == 0) { s_carry_i = 0; s_carry_r = 0; }
+    __syncthreads();
+    for (int base = 0; base < b.n_cands; base += 1024) {
+        const int f = base + tid;
+        int rows = 0, items = 0;
+        if (f < b.n_cands) {
+            const int np = b.cand_npts[f], nv = b.hyp_nvalid[f];
+            if (np > 0 && nv > 0) {
+                rows = (np + b.split_points - 1) / b.split_points;
+                items = rows * ((nv + hpc - 1) / hpc);
+            }
+        }
+        int inc_i = items, inc_r = rows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, inc_i, o);
+            const int c = __shfl_up_sync(0xffffffffu, inc_r, o);
+            if (lane >= o) { inc_i += a; inc_r += c; }
+        }
+        if (lane == 31) { s_warp_i[warp] = inc_i; s_warp_r[warp] = inc_r; }
+        __syncthreads();
+        if (warp == 0) {
+            int wi = s_warp_i[lane], wr = s_warp_r[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, wi, o);
+                const int c = __shfl_up_sync(0xffffffffu, wr, o);
+                if (lane >= o) { wi += a; wr += c; }
+            }
+            s_warp_i[lane] = wi; s_warp_r[lane] = wr;
+        }
+        __syncthreads();
+        const int ci = s_carry_i, cr = s_carry_r;
+        if (f < b.n_cands) {
+            b.cand_item_start[f] = ci + (warp ? s_warp_i[warp - 1] : 0) + inc_i - items;
+            b.cand_split_row[f] = cr + (warp ? s_warp_r[warp - 1] : 0) + inc_r - rows;
+        }
+        __syncthreads();
+        if (tid == 1023) { s_carry_i = ci + s_warp_i[31]; s_carry_r = cr + s_warp_r[31]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        b.cand_item_start[b.n_cands] = s_carry_i;
+        b.cand_split_row[b.n_cands] = s_carry_r;
+        b.status[2] = s_carry_i;
+        b.status[3] = s_carry_r;
+        if (s_carry_i > b.max_items || s_carry_r > b.max_count_rows) b.status[0] |= 2;
+    }
+}
+
+__global__ void __launch_bounds__(128) write_items_kernel(const fnp_seeker_batch b, const int H)
+{
+    const int f = blockIdx.x;
+    const int i0 = b.cand_item_start[f], n = b.cand_item_start[f + 1] - i0;
+    if (n <= 0 || (b.status[0] & 2)) return;
+    const int hpc = hyps_per_cta(H);
+    const int nchunks = (b.hyp_nvalid[f] + hpc - 1) / hpc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)   // split-major: neighbours share a point tile
+        reinterpret_cast<int4 *>(b.items)[i0 + i] = make_int4(f, i % nchunks, i / nchunks, 0);
 }
 
 template <int K>
@@ -525,19 +593,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_b
     __shared__ __align__(128) float4 s_tile[2][kScoreTile];
     __shared__ __align__(8) uint64_t s_bar[2];
 
-    const int f = blockIdx.x;
-    const int chunk = blockIdx.y;
-    const int split = blockIdx.z;
+    if ((int)blockIdx.x >= b.status[2] || (b.status[0] & 2)) return;
+    const int4 item = reinterpret_cast<const int4 *>(b.items)[blockIdx.x];
+    const int f = item.x;
+    const int chunk = item.y;
+    const int split = item.z;
     const int tid = threadIdx.x;
     const int nv = b.hyp_nvalid[f];
     const int h_base = chunk * (kScoreThreads * K);
-    if (h_base >= nv) return;
     const int npts = b.cand_npts[f];
-    const int S = n_splits(npts, b.score_splits, b.split_points);
-    if (split >= S) return;
-    const int len = (npts + S - 1) / S;
-    const int p0 = split * len;
-    const int p1 = min(npts, p0 + len);
+    const int p0 = split * b.split_points;
+    const int p1 = min(npts, p0 + b.split_points);
     const float4 *gpts = reinterpret_cast<const float4 *>(b.frustum_pts) + b.cand_pt_start[f] + p0;
     const int n = p1 - p0;
     const int n_tiles = (n + kScoreTile - 1) / kScoreTile;
@@ -603,7 +669,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_b
         }
     }
 
-    int *out = b.counts + ((size_t)f * b.score_splits + split) * H;
+    int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int r = h_base + k * kScoreThreads + tid;
@@ -626,9 +692,12 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
         if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
         return;
     }
-    const int npts = b.cand_npts[f];
-    const int S = n_splits(npts, b.score_splits, b.split_points);
-    int *cbase = b.counts + (size_t)f * b.score_splits * H;
+    const int S = b.cand_split_row[f + 1] - b.cand_split_row[f];
+    if (S <= 0 || (b.status[0] & 2)) {
+        if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
+        return;
+    }
+    int *cbase = b.counts + (size_t)b.cand_split_row[f] * H;
     // total counts (plane 0 receives the sum), block max
     int mx = 0;
     for (int r = tid; r < nv; r += blockDim.x) {
@@ -691,7 +760,7 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     if (!cfg || !b) return FNP_EINVAL;
     if (b->n_frames < 0 || b->n_cands < 0 || b->n_tiles < 0) return FNP_EINVAL;
     if (cfg->num_mags < 1 || cfg->num_yaw_size < 1) return FNP_EINVAL;
-    if (b->score_splits < 1 || b->split_points < 1) return FNP_EINVAL;
+    if (b->max_items < 0 || b->max_count_rows < 0 || b->split_points < 1) return FNP_EINVAL;
     return FNP_OK;
 }
 
@@ -755,15 +824,13 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     if (b->n_cands == 0) return FNP_OK;
     const int H = cfg->num_mags * cfg->num_yaw_size;
     cudaStream_t st = (cudaStream_t)stream;
-    if (H <= 128) {
-        dim3 g(b->n_cands, divup(H, kScoreThreads), b->score_splits);
-        score_kernel<1><<<g, kScoreThreads, 0, st>>>(*b, H);
-    } else if (H <= 512) {
-        dim3 g(b->n_cands, divup(H, kScoreThreads * 2), b->score_splits);
-        score_kernel<2><<<g, kScoreThreads, 0, st>>>(*b, H);
-    } else {
-        dim3 g(b->n_cands, divup(H, kScoreThreads * 4), b->score_splits);
-        score_kernel<4><<<g, kScoreThreads, 0, st>>>(*b, H);
+    if (!b->items || !b->cand_item_start || !b->cand_split_row || !b->counts) return FNP_EINVAL;
+    plan_items_kernel<<<1, 1024, 0, st>>>(*b, H);
+    write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H);
+    if (b->max_items > 0) {
+        if (H <= 128) score_kernel<1><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
+        else if (H <= 512) score_kernel<2><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
+        else score_kernel<4><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
     }
     FNP_LAUNCH_CHECK();
     return FNP_OK;

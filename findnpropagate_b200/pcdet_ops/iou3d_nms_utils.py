@@ -76,7 +76,7 @@ def _nms(native, boxes, scores, thresh, pre_maxsize=None):
     # defined; "earlier index wins" is this build's documented rule.  `scores` may live on
     # the CPU (as in frustum_proposals_v1.py:994-1030) -- torch >= 1.12 rejects the
     # reference's order[keep.cuda()] in that case, so indices follow `order`'s device.
-    order = scores.sort(0, descending=True, stable=True)[1]
+    order = scores.sort(stable=True, dim=0, descending=True)[1]
     if pre_maxsize is not None:
         order = order[:pre_maxsize]
     boxes = boxes[order.to(boxes.device)].contiguous()

@@ -137,7 +137,7 @@ def _align(x, a=256):
 class SeekerEngine:
     """Batched Box Seeker on one GPU."""
 
-    def __init__(self, params=None, device=None, debug=False, score_splits=None, split_points=2048):
+    def __init__(self, params=None, device=None, debug=False, split_points=None):
         if not torch.cuda.is_available():
             raise RuntimeError("findnpropagate_b200.SeekerEngine needs a CUDA device (no CPU fallback)")
         self.p = resolve_params(params)
@@ -158,8 +158,7 @@ class SeekerEngine:
             cq=float(self.p["cq"]), frustum_min=FRUSTUM_MIN, max_dist=float(self.p["max_dist"]),
             min_cam_iou=float(self.p["min_cam_iou"]), dns_w=float(self.p["dns_w"]), iou_w=float(self.p["iou_w"]))
         self.arena = _Arena(self.device)
-        self.fixed_splits = score_splits
-        self.split_points = int(split_points)
+        self.fixed_split_points = split_points
         self.pts_factor = 2.0
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.launches = 0          # kernels of ours launched (bench bookkeeping)
@@ -240,17 +239,21 @@ class SeekerEngine:
             stream = _lib.current_stream(dev)
             meta = self._upload_meta(plan, stream, slot)
             chunks = -(-H // (128 * (1 if H <= 128 else 2 if H <= 512 else 4)))
-            if self.fixed_splits is not None:
-                S = int(self.fixed_splits)
-            else:
-                want = 8 * self.n_sms
-                S = int(min(16, max(1, -(-want // max(F * chunks, 1)))))
             cap = int(max(plan["total_rows"] * self.pts_factor, 4096))
+            if self.fixed_split_points is not None:
+                sp = int(self.fixed_split_points)
+            else:
+                # ~32 work items per SM: items small enough to balance, large enough to amortise
+                sp = plan["total_rows"] // (self.n_sms * 32)
+                sp = int(min(2048, max(256, 1 << max(sp, 1).bit_length() - 1)))
+            max_rows = cap // sp + F + 1
+            max_items = max_rows * chunks
             Cmax = max(plan["max_cands"], 1)
             sizes = dict(
                 tile_counts=4 * plan["n_tiles"] * Cmax, frustum_pts=16 * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
-                hyp_iou=4 * H * F, counts=4 * H * F * S,
+                hyp_iou=4 * H * F, counts=4 * H * max_rows, items=16 * max_items,
+                cand_item_start=4 * (F + 1), cand_split_row=4 * (F + 1),
                 # outputs, one D2H: boxes(7) score best count npts nvalid per candidate + status
                 )
             sizes["out"] = 4 * (12 * F + 8)
@@ -277,12 +280,14 @@ class SeekerEngine:
                 hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
                 hyp_boxes_dbg=ptr.get("hyp_boxes_dbg"), hyp_iou_dbg=ptr.get("hyp_iou_dbg"),
                 hyp_valid_dbg=ptr.get("hyp_valid_dbg"),
-                score_splits=S, split_points=self.split_points, counts=ptr["counts"],
+                split_points=sp, max_items=max_items, max_count_rows=max_rows,
+                cand_item_start=ptr["cand_item_start"], cand_split_row=ptr["cand_split_row"], items=ptr["items"],
+                counts=ptr["counts"],
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
-            self.launches += 8 if F and plan["n_tiles"] else 0
-            handle = dict(plan=plan, batch=b, S=S, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta)
+            self.launches += 10 if F and plan["n_tiles"] else 0
+            handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta)
             if nms_thresh is not None and F:
                 handle["nms_keep"] = self._stage4_nms(plan, meta, o_boxes, o_best, float(nms_thresh), stream)
             if gt is not None and F:
@@ -336,8 +341,10 @@ class SeekerEngine:
         npts = i32[10 * F:11 * F]
         nvalid = i32[11 * F:12 * F]
         status = i32[12 * F:12 * F + 4]
-        if status[0] != 0:
+        if status[0] & 1:
             raise OverflowError(int(status[1]))
+        if status[0] & 2:
+            raise RuntimeError("scoring work-item tables overflowed (items %d, rows %d)" % (status[2], status[3]))
         ok = best >= 0
         fcs = plan["frame_cand_start"]
         keep = handle["nms_keep"].cpu().numpy().astype(bool) if "nms_keep" in handle else None
@@ -411,7 +418,6 @@ class SeekerEngine:
         assert self.debug
         torch.cuda.synchronize(self.device)
         plan, F, H, M = handle["plan"], handle["plan"]["F"], self.H, self.M
-        S = handle["S"]
 
         def view(name, dtype, shape):
             n = int(np.prod(shape)) * torch.tensor([], dtype=dtype).element_size()
@@ -429,5 +435,6 @@ class SeekerEngine:
             hyp_valid=view("hyp_valid_dbg", torch.uint8, (F, H)).astype(bool),
             hyp_index=view("hyp_index", torch.int32, (F, H)),
             hyp_prep=view("hyp_prep", torch.float32, (F, H, 8)),
-            counts=view("counts", torch.int32, (F, S, H))[:, 0, :],
+            counts=view("counts", torch.int32, (handle["batch"].max_count_rows, H))[
+                np.minimum(view("cand_split_row", torch.int32, (F + 1,))[:F], handle["batch"].max_count_rows - 1)],
         )

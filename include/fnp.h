@@ -142,15 +142,21 @@ typedef struct fnp_seeker_batch {
     float *hyp_boxes_dbg;            /* (F,H,7) all hypothesis boxes by original index, or NULL */
     float *hyp_iou_dbg;              /* (F,H) or NULL                                      */
     uint8_t *hyp_valid_dbg;          /* (F,H) or NULL                                      */
-    int32_t score_splits;            /* S_max >= 1: max point splits per frustum           */
-    int32_t split_points;            /* target points per split                            */
-    int32_t *counts;                 /* (F,S_max,H) per-split partial counts               */
+    int32_t split_points;            /* points per scoring work item (point split)         */
+    int32_t max_items;               /* capacity of `items` = grid of the scoring kernel   */
+    int32_t max_count_rows;          /* capacity (rows) of `counts`                        */
+    int32_t *cand_item_start;        /* (F+1) first work item of each frustum              */
+    int32_t *cand_split_row;         /* (F+1) first partial-count row of each frustum      */
+    int32_t *items;                  /* (max_items,4) work items: frustum, chunk, split, 0 */
+    int32_t *counts;                 /* (max_count_rows,H) per-split partial counts; after
+                                        stage 3 the first row of a frustum holds the totals */
     /* ---- outputs ---- */
     float *out_boxes;                /* (F,7) selected box per candidate                   */
     float *out_score;                /* (F)   its second-stage score                       */
     int32_t *out_best;               /* (F)   compacted index of the winner, -1 if none    */
     int32_t *out_count;              /* (F)   point count of the winner                    */
-    int32_t *status;                 /* (4)   [0] != 0: frustum_pts overflow (needed pts in [1]) */
+    int32_t *status;                 /* (4)   [0] bit0: frustum_pts overflow (needed points in [1]),
+                                        bit1: items/counts overflow ([2] items, [3] rows needed) */
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 256
@@ -191,6 +197,10 @@ int fnp_seg_nms_rotated(const float *boxes, const int32_t *label, const int32_t 
 int fnp_recall_counters(const float *pred, const int32_t *pred_valid, const int32_t *pred_start, const float *gt,
                         const int32_t *gt_start, int n_frames, const float *thresh_host,
                         int n_thresh, long long *counters, void *stream);
+
+/* Test hook: out (4,n) = sinf(x), cosf(x), atan2f(y,x), fnp_exp(x) as evaluated on the
+ * device by this library's build (checked against the oracle's restatements). */
+int fnp_dbg_math(const float *x, const float *y, float *out, int n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,8 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from findnpropagate_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
-    declared = set(re.findall(r"\b(fnp_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"fnp_seeker_cfg", "fnp_seeker_batch"}
+    declared = set(re.findall(r"^(?:int|size_t|const char \*)\s*(fnp_[a-z0-9_]+)\s*\(", hdr, re.M))
     assert declared, "no declarations parsed"
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), "libfnp_sm100.so does not export %s" % name
@@ -31,6 +30,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.SeekerCfg) == 56
     hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
     body = hdr[hdr.index("typedef struct fnp_seeker_batch"):hdr.index("} fnp_seeker_batch;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"[\*\s]([a-z_0-9]+)(?:,\s*([a-z_0-9]+))?;", body)
     flat = [n for pair in names for n in pair if n]
     assert flat == [f[0] for f in _lib.SeekerBatch._fields_]

@@ -21,23 +21,29 @@ def _boxes(rng, n, centre=(14.0, 0.0, -0.5), spread=8.0, yaw="rand"):
     return b
 
 
-def test_device_trig_matches_oracle_restatement():
-    # torch's CUDA sin/cos/atan2 call the same libdevice routines the reference kernels use
+def test_device_math_matches_oracle_restatement():
+    """sinf/cosf/atan2f (libdevice, as compiled into this library by the same nvcc that builds
+    the reference kernels) and fnp_exp, bit for bit against the oracle's C restatements."""
+    from findnpropagate_b200 import _lib
     rng = np.random.default_rng(0)
-    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 50000),
-                        rng.uniform(-1e9, 1e9, 20000), np.linspace(0, np.pi, 97)]).astype(np.float32)
-    xs = torch.from_numpy(x).to(DEV)
-    s, c = torch.sin(xs).cpu().numpy(), torch.cos(xs).cpu().numpy()
-    idx = rng.choice(x.shape[0], 20000, replace=False)
-    idx = np.concatenate([idx, np.arange(x.shape[0] - 97, x.shape[0])])
-    for i in idx:
-        assert O.sinf(x[i]).tobytes() == s[i].tobytes(), (x[i], O.sinf(x[i]), s[i])
-        assert O.cosf(x[i]).tobytes() == c[i].tobytes(), (x[i], O.cosf(x[i]), c[i])
-    y = rng.normal(size=20000).astype(np.float32)
-    z = rng.normal(size=20000).astype(np.float32)
-    a = torch.atan2(torch.from_numpy(y).to(DEV), torch.from_numpy(z).to(DEV)).cpu().numpy()
-    for i in range(0, 20000, 4):
-        assert O.atan2f(y[i], z[i]).tobytes() == a[i].tobytes()
+    x = np.concatenate([rng.uniform(-10, 10, 20000), rng.uniform(-1e5, 1e5, 5000), rng.uniform(-2e5, 2e5, 2000),
+                        rng.uniform(-1e9, 1e9, 4000), rng.uniform(-3e38, 3e38, 500), rng.uniform(-90, 0, 5000),
+                        np.linspace(0, np.pi, 97), [0.0, -0.0, np.inf, -np.inf, np.nan, 105615.0, -105615.0]]).astype(np.float32)
+    y = rng.normal(size=x.shape[0]).astype(np.float32)
+    y[-7:] = [0.0, 0.0, np.inf, 1.0, 1.0, -0.0, np.inf]
+    n = x.shape[0]
+    tx, ty = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+    out = torch.zeros(4, n, device=DEV)
+    assert _lib.lib.fnp_dbg_math(tx.data_ptr(), ty.data_ptr(), out.data_ptr(), n, _lib.current_stream()) == 0
+    out = out.cpu().numpy()
+    bad = {"sin": 0, "cos": 0, "atan2": 0, "exp": 0}
+    for i in range(n):
+        for k, (name, v) in enumerate((("sin", O.sinf(x[i])), ("cos", O.cosf(x[i])), ("atan2", O.atan2f(y[i], x[i])),
+                                       ("exp", O.exp(x[i])))):
+            same = v.tobytes() == out[k, i].tobytes() or (np.isnan(v) and np.isnan(out[k, i]))
+            if not same and not (name == "exp" and x[i] > 0):
+                bad[name] += 1
+    assert bad == {"sin": 0, "cos": 0, "atan2": 0, "exp": 0}, bad
 
 
 def test_points_in_boxes_vs_reference_kernel_and_oracle(ref_ops):
@@ -88,7 +94,7 @@ def test_points_in_boxes_boundary_stress(ref_ops):
     assert n == 256 * 4096
 
 
-def test_points_in_boxes_edge_cases():
+def test_points_in_boxes_edge_cases(ref_ops):
     from findnpropagate_b200.pcdet_ops import roiaware_pool3d_utils as RP
     out = RP.points_in_boxes_gpu(torch.zeros(2, 0, 3, device=DEV), torch.zeros(2, 3, 7, device=DEV))
     assert out.shape == (2, 0)
@@ -96,7 +102,10 @@ def test_points_in_boxes_edge_cases():
     assert torch.equal(out, torch.full((1, 5), -1, dtype=torch.int32, device=DEV))
     nanp = torch.tensor([[[float("nan"), 0, 0], [0, 0, float("nan")], [0, 0, 0]]], device=DEV)
     box = torch.tensor([[[0, 0, 0, 2, 2, 2, 0.1]]], device=DEV)
-    assert RP.points_in_boxes_gpu(nanp, box).cpu().tolist() == [[-1, -1, 0]]
+    # NaN x/y can never be inside; a NaN z passes the reference's `fabsf(z-cz) > dz/2` test
+    ref = torch.full((1, 3), -1, dtype=torch.int32, device=DEV)
+    ref_ops[0].points_in_boxes_gpu(box, nanp, ref)
+    assert RP.points_in_boxes_gpu(nanp, box).cpu().tolist() == ref.cpu().tolist() == [[-1, 0, 0]]
     with pytest.raises(ValueError):
         RP.points_in_boxes_gpu(torch.zeros(1, 5, 3, device=DEV, dtype=torch.float64), box)
     cpu_like = RP.points_in_boxes_cpu(np.zeros((5, 3), np.float32), np.array([[0, 0, 0, 1, 1, 1, 0]], np.float32))
@@ -193,7 +202,7 @@ def test_nms_keep_indices_vs_reference(ref_ops, rotated):
         fn = IU.nms_gpu if rotated else IU.nms_normal_gpu
         keep, _ = fn(tb, ts, thr)
         assert keep.dtype == torch.int64 and keep.is_cuda
-        order = ts.sort(0, descending=True, stable=True)[1]
+        order = ts.sort(stable=True, dim=0, descending=True)[1]
         sb = tb[order].contiguous()
         k_ref = torch.zeros(n, dtype=torch.int64)
         n_ref = (ref_iou.nms_gpu if rotated else ref_iou.nms_normal_gpu)(sb, k_ref, thr)

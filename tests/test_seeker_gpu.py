@@ -35,7 +35,7 @@ def _oracle(fi, params, eng):
                          tables=(eng.base_boxes_host.numpy(), eng.base_corners_host.numpy()), keep_intermediates=True)
 
 
-def _check_against_oracle(eng, frames, params, S_expected=None):
+def _check_against_oracle(eng, frames, params):
     plan = eng.plan(frames)
     pts = eng.upload_points(frames)
     h = eng.execute(plan, pts)
@@ -124,8 +124,8 @@ def test_batch_of_frames_equals_frame_by_frame_and_splits_are_invariant():
     eng = SeekerEngine(params, device="cuda:0", debug=True)
     res, n = _check_against_oracle(eng, frames, params)
     assert res["frames"][1]["pred_boxes"].shape == (0, 7)
-    for S in (1, 5, 16):
-        e2 = SeekerEngine(params, device="cuda:0", score_splits=S, split_points=64)
+    for sp in (1 << 20, 333, 64):
+        e2 = SeekerEngine(params, device="cuda:0", split_points=sp)
         r2 = e2.run(frames)
         assert np.array_equal(r2["cand_count"], res["cand_count"])
         assert np.array_equal(r2["cand_best"], res["cand_best"])

@@ -39,6 +39,19 @@ for perm in itertools.permutations(range(3)):
     acc = fma(Cd[:, :, perm[1]], Pd[:, perm[1], None], acc)
     acc = fma(Cd[:, :, perm[2]], Pd[:, perm[2], None], acc)
     res["bmm_Lx3x3@Lx3x1 order %s" % (perm,)] = int((acc.float() != Z).sum())
+# wider family for the bmm: exact products (fp64), rounded products, partial fusing
+a = [Cd[:, :, k] for k in range(3)]
+bb = [Pd[:, k, None] for k in range(3)]
+ex = [a[k] * bb[k] for k in range(3)]                 # exact in fp64
+rp = [e.float().double() for e in ex]                # rounded products
+r32 = lambda t: t.float().double()
+for i, j, k in itertools.permutations(range(3)):
+    res["bmm nofma ((p%d+p%d)+p%d)" % (i, j, k)] = int((r32(r32(rp[i] + rp[j]) + rp[k]).float() != Z).sum())
+    res["bmm fma(%d, rn(p%d+p%d))" % (i, j, k)] = int((r32(ex[i] + r32(rp[j] + rp[k])).float() != Z).sum())
+    res["bmm rn(fma(%d,p%d))+p%d" % (i, j, k)] = int((r32(r32(ex[i] + rp[j]) + rp[k]).float() != Z).sum())
+res["bmm exact-sum (fp64 accumulate)"] = int(((ex[0] + ex[1] + ex[2]).float() != Z).sum())
+# does a plain elementwise formulation agree with itself?  (sanity of the emulation)
+Zs = (C[:, :, 0] * P[:, 0] ).float()
 res["n_matmul"] = 3 * N
 res["n_bmm"] = 3 * L
 # quantile lerp on CUDA vs CPU

@@ -265,8 +265,8 @@ def run_ours(a):
             cnt[b] = k
         tp = torch.from_numpy(pack).to(dev)
         tc = torch.from_numpy(cnt).to(dev)
-        allp = torch.empty((world,) + tuple(tp.shape), dtype=tp.dtype, device=dev)
-        allc = torch.empty((world, B), dtype=tc.dtype, device=dev)
+        allp = torch.empty((world * B, Kmax, 9), dtype=tp.dtype, device=dev)
+        allc = torch.empty((world * B,), dtype=tc.dtype, device=dev)
         dist.all_gather_into_tensor(allp, tp)
         dist.all_gather_into_tensor(allc, tc)
         rc = torch.tensor([res["recall"][k] for k in sorted(res["recall"])], dtype=torch.int64, device=dev)

@@ -1,0 +1,231 @@
+"""Drop-in for the reference's ``FrustumProposerOG`` dense head and its 2D-box feeder.
+
+Reference: pcdet/models/dense_heads/frustum_proposals_v1.py:142-318 (constructor),
+:523-1067 (get_proposals), :1547-1573 (forward / get_bboxes) and
+pcdet/models/preprocessed_detector.py:7-106 (PreprocessedGLIP).
+
+Same class names, constructor arguments, ``model_cfg.PARAMS`` keys, method names, return
+types and devices; the work is done by :class:`findnpropagate_b200.seeker.SeekerEngine`.
+"""
+import json
+import sys
+import types
+
+import numpy as np
+import torch
+from torch import nn
+
+from .seeker import DEFAULTS, SeekerEngine
+
+
+def _cfg_get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default) if not hasattr(cfg, "get") else cfg.get(key, default)
+
+
+# ----------------------------------------------------------------------------- feeders
+class BoxList:
+    """Unpickling shim for maskrcnn_benchmark.structures.bounding_box.BoxList (GLIP's
+    prediction container; un-vendored dependency of the reference): only the attributes
+    PreprocessedGLIP reads -- ``bbox`` (D,4) xyxy and ``extra_fields['scores'|'labels']``."""
+
+    def __init__(self, bbox=None, image_size=None, mode="xyxy"):
+        self.bbox = bbox
+        self.size = image_size
+        self.mode = mode
+        self.extra_fields = {}
+
+
+def install_boxlist_shim():
+    """Make ``torch.load`` of a GLIP prediction file work without maskrcnn_benchmark."""
+    if "maskrcnn_benchmark.structures.bounding_box" in sys.modules:
+        return
+    pkg = types.ModuleType("maskrcnn_benchmark")
+    sub = types.ModuleType("maskrcnn_benchmark.structures")
+    mod = types.ModuleType("maskrcnn_benchmark.structures.bounding_box")
+    mod.BoxList = BoxList
+    BoxList.__module__ = mod.__name__
+    pkg.structures, sub.bounding_box = sub, mod
+    sys.modules.update({pkg.__name__: pkg, sub.__name__: sub, mod.__name__: mod})
+
+
+class PreprocessedGLIP:
+    """Loads the pickled GLIP predictions + COCO-style meta json and returns, per batch, the
+    5 CPU tensors (boxes xyxy, labels 1..10, scores, batch_idx, cam_idx) --
+    preprocessed_detector.py:7-106."""
+
+    def __init__(self, pred_pth='../data/training_pred/nuscenes_glip_train_pred.pth',
+                 meta_coco='../data/training_pred/nuscenes_infos_train_mono3d.coco.json', class_names=None):
+        self.all_class_names = ['car', 'truck', 'construction_vehicle', 'bus', 'trailer',
+                                'barrier', 'motorcycle', 'bicycle', 'pedestrian', 'traffic_cone']
+        self.class_names = self.all_class_names if class_names is None else class_names
+        install_boxlist_shim()
+        self.glip_bboxes = torch.load(pred_pth, weights_only=False)
+        with open(meta_coco, 'r') as f:
+            self.meta_info = json.load(f)
+        self.map_catid = {(i + 1): (i + 1) for i in range(len(self.all_class_names))}
+        self.token_to_id, self.path_to_id = {}, {}
+        for img_id, image in enumerate(self.meta_info['images']):
+            self.token_to_id[image['token']] = img_id
+            self.path_to_id[image['file_name']] = img_id
+
+    def infer_nusc(self, batch_dict):
+        labels, boxes, scores, idx, cam_idx = [], [], [], [], []
+        for b in range(batch_dict['batch_size']):
+            cur_paths = batch_dict['image_paths'][b]
+            for c in range(6):
+                img_id = self.path_to_id[str(cur_paths[c])]
+                assert batch_dict['metadata'][b]['token'] == self.meta_info['images'][img_id]['token']
+                assert str(cur_paths[c]) == self.meta_info['images'][img_id]['file_name']
+                bl = self.glip_bboxes[img_id]
+                c_boxes = bl.bbox.reshape(-1, 4)
+                c_scores = bl.extra_fields['scores'].reshape(-1)
+                c_labels = bl.extra_fields['labels'].reshape(-1).clone()
+                for i, lbl in enumerate(c_labels):
+                    c_labels[i] = self.map_catid[lbl.item()]
+                boxes.append(c_boxes); labels.append(c_labels); scores.append(c_scores)
+                idx.extend([b] * len(c_boxes)); cam_idx.extend([c] * len(c_boxes))
+        return (torch.cat(boxes, dim=0), torch.cat(labels, dim=0), torch.cat(scores, dim=0),
+                torch.tensor(idx), torch.tensor(cam_idx))
+
+    def __call__(self, batch_dict):
+        if 'image_paths' in batch_dict:
+            return self.infer_nusc(batch_dict)
+        raise TypeError('need kitti / nusc batch dict!')
+
+
+class SyntheticGLIP:
+    """Feeder with the PreprocessedGLIP return contract over synthetic frames
+    (findnpropagate_b200.synth.Frame), keyed by the first image path of each frame."""
+
+    def __init__(self, frames=(), class_names=None):
+        self.by_path = {str(f.image_paths[0]): f for f in frames}
+
+    def add(self, frame):
+        self.by_path[str(frame.image_paths[0])] = frame
+
+    def __call__(self, batch_dict):
+        if 'image_paths' not in batch_dict:
+            raise TypeError('need kitti / nusc batch dict!')
+        boxes, labels, scores, idx, cam = [], [], [], [], []
+        for b in range(batch_dict['batch_size']):
+            f = self.by_path[str(batch_dict['image_paths'][b][0])]
+            boxes.append(torch.from_numpy(np.asarray(f.det_boxes, np.float32)).reshape(-1, 4))
+            labels.append(torch.from_numpy(np.asarray(f.det_labels, np.int64)))
+            scores.append(torch.from_numpy(np.asarray(f.det_scores, np.float32)))
+            cam.append(torch.from_numpy(np.asarray(f.det_cam_idx, np.int64)))
+            idx.extend([b] * len(f.det_scores))
+        return (torch.cat(boxes), torch.cat(labels), torch.cat(scores), torch.tensor(idx, dtype=torch.long),
+                torch.cat(cam))
+
+
+# ----------------------------------------------------------------------------- the head
+class FrustumProposerOG(nn.Module):
+    """Greedy Box Seeker head with the reference's constructor signature
+    (frustum_proposals_v1.py:143-149).  ``image_detector`` may be passed explicitly; otherwise
+    ``PREDS_PATH == 'PreprocessedGLIP'`` builds the GLIP feeder as the reference does."""
+
+    def __init__(self, model_cfg=None, input_channels=None, num_class=None, class_names=None, grid_size=None,
+                 point_cloud_range=None, voxel_size=None, predict_boxes_when_training=True,
+                 lq=0.336, uq=0.356, iou_w=0.95, dst_w=0.226, dns_w=0.05, min_cam_iou=0.3, size_min=0.957,
+                 size_max=1.2, ry_min=0.0, ry_max=torch.pi, cq=0.46, num_mags=6, max_dist=50, num_sizes=4,
+                 num_rotations=10, topk=1, nms_2d=0.7, nms_3d=1.0, score_thr=0.1, nms_normal=0.7, clamp_bottom=0,
+                 image_detector=None, device=None):
+        super().__init__()
+        p = dict(lq=lq, uq=uq, iou_w=iou_w, dst_w=dst_w, dns_w=dns_w, min_cam_iou=min_cam_iou, size_min=size_min,
+                 size_max=size_max, ry_min=ry_min, ry_max=float(ry_max), cq=cq, num_mags=num_mags, max_dist=max_dist,
+                 num_sizes=num_sizes, num_rotations=num_rotations, topk=topk, nms_2d=nms_2d, nms_3d=nms_3d,
+                 score_thr=score_thr, nms_normal=nms_normal, clamp_bottom=clamp_bottom)
+        params = _cfg_get(model_cfg, 'PARAMS')
+        if params is not None:                       # PARAMS override the defaults (:167-196)
+            for k in list(DEFAULTS) + ['aln_w', 'ego_w', 'occl_w', 'rand_center', 'search_depth']:
+                if k in params:
+                    p[k] = params[k]
+        for flag in ('SAVE_BLEND', 'MULTICAM_IOU', 'OCCL_MULT', 'MULT'):
+            if _cfg_get(model_cfg, flag, False):
+                raise NotImplementedError("%s is outside the shipped Box Seeker config" % flag)
+        assert p['nms_3d'] == 0, 'DO NOT USE!'          # the reference's own assertion (:209)
+        self.params = p
+        self.box_fmt = _cfg_get(model_cfg, 'BOX_FORMAT', 'xyxy')
+        if self.box_fmt != 'xyxy':
+            raise NotImplementedError("BOX_FORMAT %r (only 'xyxy' is on the shipped path)" % self.box_fmt)
+        self.image_order = [2, 0, 1, 5, 3, 4]
+        self.image_size = [900, 1600]
+        self.topk, self.score_thr, self.max_dist = p['topk'], p['score_thr'], p['max_dist']
+        self.num_mags, self.num_sizes, self.num_rotations = p['num_mags'], p['num_sizes'], p['num_rotations']
+        if image_detector is not None:
+            self.image_detector = image_detector
+        else:
+            preds_path = _cfg_get(model_cfg, 'PREDS_PATH', 'PreprocessedGLIP')
+            if 'PreprocessedGLIP' not in preds_path:
+                raise NotImplementedError("only the PreprocessedGLIP feeder is on the shipped path")
+            self.image_detector = PreprocessedGLIP(class_names=class_names)
+        self.engine = SeekerEngine(p, device=device)
+        self.anchors = torch.tensor(__import__('findnpropagate_b200.seeker', fromlist=['ANCHORS']).ANCHORS,
+                                    dtype=torch.float32, device=self.engine.device)
+        self.base_boxes = self.engine.base_boxes
+        self.base_corners = self.engine.base_corners
+
+    # -- helpers ---------------------------------------------------------------
+    @staticmethod
+    def _np(x):
+        return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+    def get_proposals(self, batch_dict):
+        """-> (proposal_boxes (K,7) f32 on the GPU, frust_labels (K) int64 CPU, frust_scores (K)
+        f32 CPU, frust_batch_idx (K) int64 CPU), exactly as frustum_proposals_v1.py:1055-1067."""
+        if 'img_aug_matrix' in batch_dict:
+            raise NotImplementedError("img_aug_matrix (image_calibrate) is disabled in the shipped config")
+        B = int(batch_dict['batch_size'])
+        aug = self._np(batch_dict['lidar_aug_matrix']).reshape(B, 4, 4)
+        if not np.array_equal(aug, np.broadcast_to(np.eye(4, dtype=aug.dtype), aug.shape)):
+            raise NotImplementedError("lidar_aug_matrix must be the identity (augmentation is disabled on this path)")
+        det_boxes, det_labels, det_scores, det_batch_idx, det_cam_idx = self.image_detector(batch_dict)
+        pts = batch_dict['points']
+        dev = self.engine.device
+        if isinstance(pts, np.ndarray):
+            pts = torch.from_numpy(np.ascontiguousarray(pts, np.float32))
+        pts = pts.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        bidx = pts[:, 0].contiguous()
+        bounds = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32)).cpu().numpy()
+        if not bool((bidx[1:] >= bidx[:-1]).all()) if bidx.numel() > 1 else False:
+            raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+        from .seeker import camera_matrices
+        cam_mats = camera_matrices(self._np(batch_dict['lidar2image']), self._np(batch_dict['camera2lidar']),
+                                   self._np(batch_dict['camera_intrinsics']))
+        plan = self.engine.plan_arrays(
+            bounds.astype(np.int64), pts.shape[1], 1, cam_mats, self._np(det_boxes).astype(np.float32).reshape(-1, 4),
+            self._np(det_labels).astype(np.int64), self._np(det_scores).astype(np.float32),
+            self._np(det_batch_idx).astype(np.int64), self._np(det_cam_idx).astype(np.int64))
+        while True:
+            h = self.engine.execute(plan, pts)
+            try:
+                res = self.engine.finish(h)
+                break
+            except OverflowError as e:
+                self.engine.pts_factor = max(self.engine.pts_factor * 1.5,
+                                             1.25 * int(e.args[0]) / max(plan["total_rows"], 1))
+        boxes, labels, scores, bi = [], [], [], []
+        for b, fr in enumerate(res["frames"]):
+            boxes.append(fr["pred_boxes"]); labels.append(fr["pred_labels"]); scores.append(fr["pred_scores"])
+            bi.append(np.full(fr["pred_labels"].shape[0], b, np.int64))
+        proposal_boxes = torch.from_numpy(np.concatenate(boxes).reshape(-1, 7)).to(dev)
+        return (proposal_boxes, torch.from_numpy(np.concatenate(labels).astype(np.int64)),
+                torch.from_numpy(np.concatenate(scores).astype(np.float32)), torch.from_numpy(np.concatenate(bi)))
+
+    def get_bboxes(self, batch_dict):
+        boxes, labels, scores, bidx = self.get_proposals(batch_dict)
+        ret = []
+        for k in range(batch_dict['batch_size']):
+            mask = (bidx == k)
+            ret.append(dict(pred_boxes=boxes[mask.to(boxes.device)], pred_scores=scores[mask],
+                            pred_labels=labels[mask].int()))
+        return ret
+
+    def forward(self, batch_dict):
+        batch_dict['final_box_dicts'] = self.get_bboxes(batch_dict)
+        assert not self.training, "not trainable!"
+        return batch_dict

@@ -127,7 +127,8 @@ def test_batch_of_frames_equals_frame_by_frame_and_splits_are_invariant():
     for sp in (1 << 20, 333, 64):
         e2 = SeekerEngine(params, device="cuda:0", split_points=sp)
         r2 = e2.run(frames)
-        assert np.array_equal(r2["cand_count"], res["cand_count"])
+        v = res["cand_valid"]
+        assert np.array_equal(r2["cand_count"][v], res["cand_count"][v])
         assert np.array_equal(r2["cand_best"], res["cand_best"])
         for a, b in zip(r2["frames"], res["frames"]):
             assert np.array_equal(a["pred_boxes"], b["pred_boxes"])
@@ -192,10 +193,55 @@ def test_full_size_properties_cfg2():
     assert res["recall"] == exp
     # idempotence
     res2 = eng.finish(eng.execute(plan, pts))
-    assert np.array_equal(res2["cand_count"], res["cand_count"]) and np.array_equal(res2["cand_boxes"], res["cand_boxes"])
+    v = res["cand_valid"]
+    assert np.array_equal(res2["cand_valid"], v) and np.array_equal(res2["cand_count"][v], res["cand_count"][v])
+    assert np.array_equal(res2["cand_boxes"][v], res["cand_boxes"][v])
     # frustum-point buffer overflow is detected and recovered from
     e3 = SeekerEngine(params, device="cuda:0")
     e3.pts_factor = 0.05
     r3 = e3.run(frames)
     assert e3.pts_factor > 0.05
-    assert np.array_equal(r3["cand_count"], res["cand_count"])
+    assert np.array_equal(r3["cand_count"][v], res["cand_count"][v])
+
+
+def test_reference_compatible_head_and_extraction(tmp_path):
+    """FrustumProposerOG drop-in: same call contract / return types as the reference head
+    (frustum_proposals_v1.py:1055-1067,1554-1573) and the extraction output format."""
+    from findnpropagate_b200 import extract, proposer
+    cfg = synth.CONFIGS["cfg1"]
+    params = synth.seeker_params(cfg)
+    sf = [synth.make_frame(i, cfg) for i in range(3)]
+    feeder = proposer.SyntheticGLIP(sf)
+    head = proposer.FrustumProposerOG(model_cfg=dict(PARAMS=params, PREDS_PATH="PreprocessedGLIP", BOX_FORMAT="xyxy"),
+                                      class_names=synth.CLASS_NAMES, image_detector=feeder).eval()
+    bd = synth.collate(sf)
+    for k, v in list(bd.items()):
+        if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+            bd[k] = torch.from_numpy(v).cuda()              # load_data_to_gpu (models/__init__.py:23-36)
+    boxes, labels, scores, bidx = head.get_proposals(bd)
+    assert boxes.is_cuda and boxes.dtype == torch.float32 and boxes.shape[1] == 7
+    assert labels.dtype == torch.int64 and not labels.is_cuda and scores.dtype == torch.float32
+    assert bidx.dtype == torch.int64 and boxes.shape[0] == labels.shape[0] == scores.shape[0] == bidx.shape[0]
+    out = head(bd)["final_box_dicts"]
+    assert len(out) == 3 and out[0]["pred_labels"].dtype == torch.int32
+    eng = SeekerEngine(params, device="cuda:0")
+    for b, f in enumerate(sf):
+        ora = _oracle(_frame_from_synth(f), params, eng)
+        assert np.array_equal(out[b]["pred_boxes"].cpu().numpy().view(np.uint32), ora["pred_boxes"].view(np.uint32))
+        assert np.array_equal(out[b]["pred_labels"].numpy(), ora["pred_labels"])
+    # numpy batch_dict works too, and options outside the shipped config fail loudly
+    boxes2, _, _, _ = head.get_proposals(synth.collate(sf))
+    assert torch.equal(boxes2, boxes)
+    with pytest.raises(NotImplementedError):
+        proposer.FrustumProposerOG(model_cfg=dict(PARAMS=dict(params, topk=3)), image_detector=feeder)
+    # extraction driver: one .pth per frame, reference format, recall counters
+    frames = [_frame_from_synth(f) for f in sf]
+    merged, total, ar = extract.extract(frames, lambda fs: eng.run(fs, with_recall=True), folder=str(tmp_path),
+                                        batch_frames=2, frame_ids=[f.frame_id for f in sf])
+    exp = None
+    for b, f in enumerate(sf):
+        rd = SO.recall_record(merged[b]["pred_boxes"], f.gt_boxes)
+        exp = rd if exp is None else {k: exp[k] + rd[k] for k in rd}
+        saved = torch.load(str(tmp_path / (f.frame_id.replace(".", "_") + ".pth")), map_location="cpu")
+        assert np.array_equal(saved[0]["pred_boxes"].numpy(), merged[b]["pred_boxes"])
+    assert {k: total[k] for k in exp} == exp and 0.0 <= ar["rcnn_0.3"] <= 1.0

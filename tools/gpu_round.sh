@@ -7,7 +7,7 @@ tail -3 gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${NCU:-1}" = "1" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fnp -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 8 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cull_|hypotheses_|plan_items|recall_|scan_|score_|seg_nms|select_|stats_|write_items' -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 8 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 2 -c 2 -o gpurun_out/prof_score -f python bench.py --steps 1 --warmup 1 --frames 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
 ls -la gpurun_out

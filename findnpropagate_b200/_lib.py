@@ -78,6 +78,9 @@ lib.fnp_seg_nms_rotated.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _v
 lib.fnp_recall_counters.restype = _i
 lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _vp, _vp]
 
+lib.fnp_host_select_candidates.restype = _i
+lib.fnp_host_select_candidates.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
+
 lib.fnp_dbg_math.restype = _i
 lib.fnp_dbg_math.argtypes = [_vp, _vp, _vp, _i, _vp]
 
@@ -87,7 +90,7 @@ EXPORTED = [
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
     "fnp_seeker_score", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated",
-    "fnp_recall_counters",
+    "fnp_recall_counters", "fnp_host_select_candidates",
 ]
 
 

@@ -1,0 +1,131 @@
+// Host-side planning of a seeker batch (C ABI, no CUDA calls): which GLIP 2D boxes become
+// candidate frustums, and in which order.
+//
+// Reference: pcdet/models/dense_heads/frustum_proposals_v1.py:582-595 -- per frame, cameras are
+// visited in image_order [2,0,1,5,3,4]; each camera's boxes go through
+// torchvision.ops.batched_nms(boxes, scores, labels, nms_2d) on the CPU (indices come back in
+// descending score order) and boxes with score < score_thr are skipped.  torchvision's CPU
+// arithmetic is restated here (ops/boxes.py batched_nms + csrc/ops/cpu/nms_kernel.cpp):
+//   * <= 1000 boxes in the group: coordinate trick -- every box is shifted by
+//     label * (max coordinate of the group + 1) in fp32, then one class-agnostic greedy NMS;
+//   * more: one greedy NMS per label on the unshifted boxes;
+//   * greedy NMS: stable descending score order, areas and IoU in fp32,
+//     suppressed when (double)iou > iou_threshold.
+// The reference makes 6 Python-level calls per frame; this does a whole batch in one call.
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+#include "../../include/fnp.h"
+
+namespace {
+
+const int kCamRank[6] = {1, 2, 0, 4, 5, 3};  // rank of camera c in image_order [2,0,1,5,3,4]
+
+struct GreedyNms {
+    std::vector<float> x1, y1, x2, y2, area;
+    std::vector<uint8_t> dead;
+    // boxes given in priority order; keep[i] = survives
+    void run(int n, double thr, std::vector<uint8_t> &keep)
+    {
+        area.resize(n);
+        dead.assign(n, 0);
+        keep.assign(n, 0);
+        for (int i = 0; i < n; i++) area[i] = (x2[i] - x1[i]) * (y2[i] - y1[i]);
+        for (int i = 0; i < n; i++) {
+            if (dead[i]) continue;
+            keep[i] = 1;
+            const float ix1 = x1[i], iy1 = y1[i], ix2 = x2[i], iy2 = y2[i], ia = area[i];
+            for (int j = i + 1; j < n; j++) {
+                if (dead[j]) continue;
+                const float xx1 = std::max(ix1, x1[j]), yy1 = std::max(iy1, y1[j]);
+                const float xx2 = std::min(ix2, x2[j]), yy2 = std::min(iy2, y2[j]);
+                const float w = std::max(0.0f, xx2 - xx1), h = std::max(0.0f, yy2 - yy1);
+                const float inter = w * h;
+                const float ovr = inter / (ia + area[j] - inter);
+                if ((double)ovr > thr) dead[j] = 1;
+            }
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels,
+                                          const float *det_scores, const int64_t *det_frame,
+                                          const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
+                                          float score_thr, int32_t *cand_det, int32_t *frame_cand_start)
+{
+    if (n_dets < 0 || n_frames < 0 || !frame_cand_start) return FNP_EINVAL;
+    if (n_dets > 0 && (!det_boxes || !det_labels || !det_scores || !det_frame || !det_cam || !cand_det))
+        return FNP_EINVAL;
+    for (int b = 0; b <= n_frames; b++) frame_cand_start[b] = 0;
+    if (n_dets == 0) return 0;
+    std::vector<int64_t> group(n_dets);
+    for (int i = 0; i < n_dets; i++) {
+        if (det_cam[i] < 0 || det_cam[i] > 5 || det_frame[i] < 0 || det_frame[i] >= n_frames) return FNP_EINVAL;
+        group[i] = det_frame[i] * 6 + kCamRank[det_cam[i]];
+    }
+    std::vector<int32_t> order(n_dets);
+    std::iota(order.begin(), order.end(), 0);
+    // group ascending, score descending, original index ascending (stable)
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        if (group[a] != group[b]) return group[a] < group[b];
+        return det_scores[a] > det_scores[b];
+    });
+    GreedyNms nms;
+    std::vector<uint8_t> keep, keep_l;
+    std::vector<int> idx_l;
+    const double thr = (double)nms_2d;
+    int n_out = 0;
+    for (int s = 0; s < n_dets;) {
+        int e = s;
+        while (e < n_dets && group[order[e]] == group[order[s]]) e++;
+        const int n = e - s;
+        keep.assign(n, 0);
+        if (n * 4 <= 4000) {
+            float mx = det_boxes[(size_t)order[s] * 4];
+            for (int i = 0; i < n; i++)
+                for (int k = 0; k < 4; k++) mx = std::max(mx, det_boxes[(size_t)order[s + i] * 4 + k]);
+            const float step = mx + 1.0f;
+            nms.x1.resize(n); nms.y1.resize(n); nms.x2.resize(n); nms.y2.resize(n);
+            for (int i = 0; i < n; i++) {
+                const float *bx = det_boxes + (size_t)order[s + i] * 4;
+                const float off = (float)det_labels[order[s + i]] * step;
+                nms.x1[i] = bx[0] + off; nms.y1[i] = bx[1] + off; nms.x2[i] = bx[2] + off; nms.y2[i] = bx[3] + off;
+            }
+            nms.run(n, thr, keep);
+        } else {
+            // per-label NMS on the raw boxes (torchvision's "vanilla" path for large groups)
+            std::vector<int64_t> labels;
+            for (int i = 0; i < n; i++) labels.push_back(det_labels[order[s + i]]);
+            std::sort(labels.begin(), labels.end());
+            labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+            for (int64_t lab : labels) {
+                idx_l.clear();
+                for (int i = 0; i < n; i++)
+                    if (det_labels[order[s + i]] == lab) idx_l.push_back(i);
+                const int m = (int)idx_l.size();
+                nms.x1.resize(m); nms.y1.resize(m); nms.x2.resize(m); nms.y2.resize(m);
+                for (int i = 0; i < m; i++) {
+                    const float *bx = det_boxes + (size_t)order[s + idx_l[i]] * 4;
+                    nms.x1[i] = bx[0]; nms.y1[i] = bx[1]; nms.x2[i] = bx[2]; nms.y2[i] = bx[3];
+                }
+                nms.run(m, thr, keep_l);
+                for (int i = 0; i < m; i++) keep[idx_l[i]] = keep_l[i];
+            }
+        }
+        const int frame = (int)det_frame[order[s]];
+        for (int i = 0; i < n; i++) {
+            const int d = order[s + i];
+            if (keep[i] && !(det_scores[d] < score_thr)) {
+                cand_det[n_out++] = d;
+                frame_cand_start[frame + 1]++;
+            }
+        }
+        s = e;
+    }
+    for (int b = 0; b < n_frames; b++) frame_cand_start[b + 1] += frame_cand_start[b];
+    return n_out;
+}

@@ -198,6 +198,20 @@ int fnp_recall_counters(const float *pred, const int32_t *pred_valid, const int3
                         const int32_t *gt_start, int n_frames, const float *thresh_host,
                         int n_thresh, long long *counters, void *stream);
 
+/* ------------------------------------------------------------- host-side planning
+ * (runs on the CPU, touches no device memory: every pointer here is a HOST pointer)
+ *
+ * Candidate frustums of a batch in reference order: frame, then cameras [2,0,1,5,3,4], then
+ * torchvision.ops.batched_nms order (descending score), dropping score < score_thr
+ * (frustum_proposals_v1.py:582-595).  det_* describe all n_dets GLIP boxes of the batch
+ * (boxes (n_dets,4) xyxy fp32, labels/frame/cam int64).  Writes cand_det (capacity n_dets):
+ * indices into det_* of the candidates, and frame_cand_start (n_frames+1).
+ * Returns the number of candidates (>= 0) or FNP_EINVAL. */
+int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels,
+                               const float *det_scores, const int64_t *det_frame,
+                               const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
+                               float score_thr, int32_t *cand_det, int32_t *frame_cand_start);
+
 /* Test hook: out (4,n) = sinf(x), cosf(x), atan2f(y,x), fnp_exp(x) as evaluated on the
  * device by this library's build (checked against the oracle's restatements). */
 int fnp_dbg_math(const float *x, const float *y, float *out, int n, void *stream);

@@ -12,56 +12,34 @@
 
 namespace fnp {
 
-constexpr int kCullThreads = FNP_CULL_TILE;  // one point per thread
+constexpr int kCullThreads = 256;                       // one point per thread per sub-tile
+constexpr int kCullSub = FNP_CULL_TILE / kCullThreads;  // sub-tiles of one CTA tile
 constexpr int kCullWarps = kCullThreads / 32;
+constexpr int kCullVW = kCullSub * kCullWarps;          // "virtual warps" of a tile, in row order
 constexpr int kStatsFloats = 40;
+static_assert(FNP_CULL_TILE % kCullThreads == 0, "tile must be a whole number of sub-tiles");
 
 // ======================================================================================
-// Stage 1: projection + frustum cull (+ ordered compaction when WRITE)
+// Stage 1: projection + frustum cull + ordered compaction, two passes over the points
+//   pass A (cull_mask_kernel):  per point a bitmask of the frame's candidates whose frustum
+//       contains it (W 32-bit words), per tile the population of every candidate;
+//   scans (scan_tiles_kernel, scan_cands_kernel): exclusive prefixes -> where every tile
+//       writes inside every frustum;
+//   pass B (cull_write_kernel): reads the masks, re-projects only member points into their
+//       camera and scatters (x,y,z,depth) of the *unprojected* point in input order.
+// Tiles without members cost pass B one mask read and nothing else.
 // ======================================================================================
+__device__ __constant__ int kImageOrder[6] = {2, 0, 1, 5, 3, 4};   // frustum_proposals_v1.py:201
+
 struct CullSmem {
-    float cam[6][24];
-    int cam_lo[6], cam_hi[6];  // candidate range (local index) per camera
+    float cam[6][24];       // by camera index
+    int cs[8];              // candidate range per camera RANK, local to the frame: [cs[r], cs[r+1])
+    float4 uni[6];          // per rank: union of the rank's 2D boxes (x1,y1,x2,y2)
 };
 
-template <bool WRITE>
-__global__ void __launch_bounds__(kCullThreads) cull_kernel(const fnp_seeker_batch b, const float img_w,
-                                                            const float img_h)
+// rows [first, first+n) of the point table -> shared memory (generic row stride)
+__device__ __forceinline__ void stage_rows(const float *__restrict__ gsrc, int n_floats, float *s_pts, int tid)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
-    float4 *s_box = reinterpret_cast<float4 *>(smem_raw + sizeof(CullSmem));       // [Cmax]
-    int *s_cnt = reinterpret_cast<int *>(s_box + b.max_cands_per_frame);            // [Cmax][warps]
-    float *s_pts = reinterpret_cast<float *>(s_cnt + b.max_cands_per_frame * kCullWarps);  // tile rows
-
-    const int tile = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = b.tile_frame[tile];
-    const int row0 = b.tile_row0[tile];
-    const int64_t frow = b.frame_row_start[frame];
-    const int n_rows = (int)min((int64_t)kCullThreads, b.frame_row_start[frame + 1] - frow - row0);
-    const int c0 = b.frame_cand_start[frame];
-    const int nc = b.frame_cand_start[frame + 1] - c0;
-    if (nc == 0) return;
-
-    // ---- per-block setup: camera matrices, candidate boxes, per-camera candidate ranges
-    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
-    for (int j = tid; j < nc; j += kCullThreads)
-        s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
-    for (int i = tid; i < nc * kCullWarps; i += kCullThreads) s_cnt[i] = 0;
-    if (tid < 6) {
-        // candidates of one frame are grouped by camera (reference order), find my group
-        int lo = nc, hi = 0;
-        for (int j = 0; j < nc; j++)
-            if (b.cand_cam[c0 + j] == tid) { lo = min(lo, j); hi = max(hi, j + 1); }
-        S.cam_lo[tid] = lo;
-        S.cam_hi[tid] = (hi > lo) ? hi : lo;
-    }
-
-    // ---- stage the tile's rows in shared memory with coalesced 128-bit loads
-    const int stride = b.point_stride;
-    const float *gsrc = b.points + (size_t)(frow + row0) * stride;
-    const int n_floats = n_rows * stride;
     if ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) {
         const int n4 = n_floats >> 2;
         const float4 *g4 = reinterpret_cast<const float4 *>(gsrc);
@@ -71,69 +49,244 @@ __global__ void __launch_bounds__(kCullThreads) cull_kernel(const fnp_seeker_bat
     } else {
         for (int i = tid; i < n_floats; i += kCullThreads) s_pts[i] = __ldg(gsrc + i);
     }
+}
+
+// bits [lo, hi) of word w (bit j of word w = candidate 32 w + j)
+__device__ __forceinline__ unsigned range_bits(int lo, int hi, int w)
+{
+    const int a = min(max(lo - 32 * w, 0), 32), b = min(max(hi - 32 * w, 0), 32);
+    const unsigned below_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+    const unsigned below_a = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
+    return below_b & ~below_a;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCullThreads) cull_mask_kernel(const fnp_seeker_batch b, const float img_w,
+                                                                 const float img_h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
+    const int Cmax = b.max_cands_per_frame;
+    float4 *s_box = reinterpret_cast<float4 *>(smem_raw + sizeof(CullSmem));            // [Cmax]
+    int *s_cnt = reinterpret_cast<int *>(s_box + Cmax);                                  // [kCullVW][Cmax]
+    float *s_pts = reinterpret_cast<float *>(s_cnt + kCullVW * Cmax);                    // staged rows
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = b.tile_frame[tile];
+    const int row0 = b.tile_row0[tile];
+    const int64_t frow = b.frame_row_start[frame];
+    const int frame_rows = (int)(b.frame_row_start[frame + 1] - frow);
+    const int c0 = b.frame_cand_start[frame];
+    const int nc = b.frame_cand_start[frame + 1] - c0;
+    if (nc == 0) return;
+
+    // ---- per-CTA setup
+    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
+    for (int j = tid; j < nc; j += kCullThreads) s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
+    for (int i = tid; i < kCullVW * Cmax; i += kCullThreads) s_cnt[i] = 0;
+    if (tid < 7) S.cs[tid] = b.cam_cand_start[frame * 6 + tid] - c0;
     __syncthreads();
-
-    const bool live = tid < n_rows;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (live) {
-        const float *p = s_pts + tid * stride + b.xyz_offset;
-        x = p[0]; y = p[1]; z = p[2];
-    }
-
-    // ---- project into every camera that has candidates
-    float u[6], v[6], d[6];
-    unsigned on_mask = 0;
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        u[c] = v[c] = d[c] = 0.f;
-        if (S.cam_hi[c] > S.cam_lo[c] && live) {
-            if (project(S.cam[c], x, y, z, img_w, img_h, u[c], v[c], d[c])) on_mask |= 1u << c;
-        }
-    }
-
-    // ---- phase A: per-warp population of every candidate
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        const bool on = (on_mask >> c) & 1u;
-        if (!__any_sync(0xffffffffu, on)) continue;
-        for (int j = S.cam_lo[c]; j < S.cam_hi[c]; j++) {
+    if (tid < 6) {
+        const float INF = __int_as_float(0x7f800000);
+        float4 u = make_float4(INF, INF, -INF, -INF);
+        for (int j = S.cs[tid]; j < S.cs[tid + 1]; j++) {
             const float4 bx = s_box[j];
-            const bool in = on && (v[c] < bx.w) && (v[c] >= bx.y) && (u[c] < bx.z) && (u[c] >= bx.x);
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (lane == 0 && m) s_cnt[j * kCullWarps + warp] = __popc(m);
+            u.x = fminf(u.x, bx.x); u.y = fminf(u.y, bx.y); u.z = fmaxf(u.z, bx.z); u.w = fmaxf(u.w, bx.w);
+        }
+        S.uni[tid] = u;
+    }
+    __syncthreads();
+
+    const int stride = b.point_stride;
+    // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
+    const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
+
+#pragma unroll 1
+    for (int sub = 0; sub < kCullSub; sub++) {
+        const int r0 = row0 + sub * kCullThreads;
+        const int n_rows = min(kCullThreads, frame_rows - r0);
+        if (n_rows <= 0) break;
+        __syncthreads();   // previous sub-tile's readers are done with s_pts
+        stage_rows(b.points + (size_t)(frow + r0) * stride, n_rows * stride, s_pts, tid);
+        __syncthreads();
+        const bool live = tid < n_rows;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (live) {
+            const float *p = s_pts + tid * stride + b.xyz_offset;
+            x = p[0]; y = p[1]; z = p[2];
+        }
+        unsigned mask[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) mask[w] = 0u;
+
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const int lo = S.cs[r], hi = S.cs[r + 1];
+            if (lo == hi) continue;                                  // camera without candidates
+            const float *L = S.cam[kImageOrder[r]];
+            // cheap, division-free "certainly off this image" test
+            const float wx = __fadd_rn(dot3(L + 0, x, y, z), L[3]);
+            const float wy = __fadd_rn(dot3(L + 4, x, y, z), L[7]);
+            const float wz = __fadd_rn(dot3(L + 8, x, y, z), L[11]);
+            const float d = fminf(fmaxf(wz, 1e-5f), 1e5f);
+            const bool off = (wx < -1e-30f) | (wy < -1e-30f) | (wx > __fmul_rn(w_hi, d)) | (wy > __fmul_rn(h_hi, d));
+            const bool maybe = live & !off;
+            if (!__any_sync(0xffffffffu, maybe)) continue;
+            // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
+            const float u = __fdiv_rn(wx, d), v = __fdiv_rn(wy, d);
+            const bool on = maybe & (v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f);
+            const float4 un = S.uni[r];
+            const bool near_box = on & (v < un.w) & (v >= un.y) & (u < un.z) & (u >= un.x);
+            if (!__any_sync(0xffffffffu, near_box)) continue;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                const int j0 = max(lo, 32 * w), j1 = min(hi, 32 * w + 32);
+                for (int j = j0; j < j1; j++) {
+                    const float4 bx = s_box[j];
+                    const bool in = near_box & (v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x);
+                    mask[w] |= (in ? 1u : 0u) << (j - 32 * w);
+                }
+            }
+        }
+
+        // ---- masks out (coalesced per word), per-virtual-warp populations
+        unsigned *mrow = b.pt_mask + ((size_t)tile * W) * FNP_CULL_TILE + sub * kCullThreads + tid;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            if (live) mrow[(size_t)w * FNP_CULL_TILE] = mask[w];
+            unsigned any = __reduce_or_sync(0xffffffffu, mask[w]);
+            while (any) {
+                const int j = __ffs(any) - 1;
+                any &= any - 1;
+                const unsigned m = __ballot_sync(0xffffffffu, (mask[w] >> j) & 1u);
+                if (lane == 0) s_cnt[(sub * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < nc; j += kCullThreads) {
+        int sum = 0;
+#pragma unroll
+        for (int vw = 0; vw < kCullVW; vw++) sum += s_cnt[vw * Cmax + j];
+        b.tile_counts[(size_t)tile * Cmax + j] = sum;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCullThreads) cull_write_kernel(const fnp_seeker_batch b, const float img_w,
+                                                                  const float img_h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
+    const int Cmax = b.max_cands_per_frame;
+    int *s_base = reinterpret_cast<int *>(smem_raw + sizeof(CullSmem));     // [Cmax] first slot of this tile
+    int *s_cnt = s_base + Cmax;                                              // [kCullVW][Cmax]
+    unsigned *s_rm = reinterpret_cast<unsigned *>(s_cnt + kCullVW * Cmax);   // [6][W] rank bit ranges
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = b.tile_frame[tile];
+    const int row0 = b.tile_row0[tile];
+    const int64_t frow = b.frame_row_start[frame];
+    const int frame_rows = (int)(b.frame_row_start[frame + 1] - frow);
+    const int c0 = b.frame_cand_start[frame];
+    const int nc = b.frame_cand_start[frame + 1] - c0;
+    if (nc == 0) return;
+
+    // ---- masks of my kCullSub points; tiles without any member stop here
+    unsigned mask[kCullSub][W];
+    unsigned mine = 0u;
+#pragma unroll
+    for (int sub = 0; sub < kCullSub; sub++) {
+        const bool live = row0 + sub * kCullThreads + tid < frame_rows;
+        const unsigned *mrow = b.pt_mask + ((size_t)tile * W) * FNP_CULL_TILE + sub * kCullThreads + tid;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            mask[sub][w] = live ? mrow[(size_t)w * FNP_CULL_TILE] : 0u;
+            mine |= mask[sub][w];
+        }
+    }
+    if (!__syncthreads_or(mine != 0u)) return;
+
+    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
+    for (int j = tid; j < nc; j += kCullThreads)
+        s_base[j] = b.cand_pt_start[c0 + j] + b.tile_counts[(size_t)tile * Cmax + j];
+    for (int i = tid; i < kCullVW * Cmax; i += kCullThreads) s_cnt[i] = 0;
+    if (tid < 7) S.cs[tid] = b.cam_cand_start[frame * 6 + tid] - c0;
+    __syncthreads();
+    if (tid < 6 * W) s_rm[tid] = range_bits(S.cs[tid / W], S.cs[tid / W + 1], tid % W);
+
+    // ---- phase 1: population of every candidate in every virtual warp, then prefix over them
+#pragma unroll
+    for (int sub = 0; sub < kCullSub; sub++) {
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            unsigned any = __reduce_or_sync(0xffffffffu, mask[sub][w]);
+            while (any) {
+                const int j = __ffs(any) - 1;
+                any &= any - 1;
+                const unsigned m = __ballot_sync(0xffffffffu, (mask[sub][w] >> j) & 1u);
+                if (lane == 0) s_cnt[(sub * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < nc; j += kCullThreads) {
+        int run = 0;
+#pragma unroll
+        for (int vw = 0; vw < kCullVW; vw++) {
+            const int c = s_cnt[vw * Cmax + j];
+            s_cnt[vw * Cmax + j] = run;
+            run += c;
         }
     }
     __syncthreads();
 
-    if (!WRITE) {
-        for (int j = tid; j < nc; j += kCullThreads) {
-            int s = 0;
-#pragma unroll
-            for (int w = 0; w < kCullWarps; w++) s += s_cnt[j * kCullWarps + w];
-            b.tile_counts[(size_t)tile * b.max_cands_per_frame + j] = s;
-        }
-        return;
-    }
-
-    // ---- phase B (WRITE): ordered scatter of (x,y,z,depth) of the unprojected points
+    // ---- phase 2: re-project members into their camera, unproject, ordered scatter
     const unsigned lt = (1u << lane) - 1u;
+    const int stride = b.point_stride;
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
-        const bool on = (on_mask >> c) & 1u;
-        if (!__any_sync(0xffffffffu, on)) continue;
-        float X = 0.f, Y = 0.f, Z = 0.f;
-        if (on) unproject(S.cam[c] + 12, S.cam[c] + 21, u[c], v[c], d[c], X, Y, Z);
-        for (int j = S.cam_lo[c]; j < S.cam_hi[c]; j++) {
-            const float4 bx = s_box[j];
-            const bool in = on && (v[c] < bx.w) && (v[c] >= bx.y) && (u[c] < bx.z) && (u[c] >= bx.x);
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (!in) continue;
-            int base = b.cand_pt_start[c0 + j] + b.tile_counts[(size_t)tile * b.max_cands_per_frame + j];
-            for (int w = 0; w < warp; w++) base += s_cnt[j * kCullWarps + w];
-            const int64_t pos = (int64_t)base + __popc(m & lt);
-            if (pos < b.pts_capacity) {
-                reinterpret_cast<float4 *>(b.frustum_pts)[pos] = make_float4(X, Y, Z, d[c]);
-                if (b.frustum_idx) b.frustum_idx[pos] = row0 + tid;
+    for (int sub = 0; sub < kCullSub; sub++) {
+        unsigned sub_any = 0u;
+#pragma unroll
+        for (int w = 0; w < W; w++) sub_any |= mask[sub][w];
+        if (!__any_sync(0xffffffffu, sub_any != 0u)) continue;
+        const int row = row0 + sub * kCullThreads + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (sub_any) {
+            const float *p = b.points + (size_t)(frow + row) * stride + b.xyz_offset;
+            x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+        }
+        const int *cnt_vw = s_cnt + (sub * kCullWarps + warp) * Cmax;
+#pragma unroll 1
+        for (int r = 0; r < 6; r++) {
+            unsigned rm[W];
+            unsigned has = 0u;
+#pragma unroll
+            for (int w = 0; w < W; w++) { rm[w] = mask[sub][w] & s_rm[r * W + w]; has |= rm[w]; }
+            if (!__any_sync(0xffffffffu, has != 0u)) continue;
+            const float *cm = S.cam[kImageOrder[r]];
+            float u, v, d, X = 0.f, Y = 0.f, Z = 0.f;
+            project(cm, x, y, z, img_w, img_h, u, v, d);
+            unproject(cm + 12, cm + 21, u, v, d, X, Y, Z);
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                unsigned any = __reduce_or_sync(0xffffffffu, rm[w]);
+                while (any) {
+                    const int jb = __ffs(any) - 1;
+                    any &= any - 1;
+                    const bool in = (rm[w] >> jb) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int j = 32 * w + jb;
+                        const int64_t pos = (int64_t)s_base[j] + cnt_vw[j] + __popc(m & lt);
+                        if (pos < b.pts_capacity) {
+                            reinterpret_cast<float4 *>(b.frustum_pts)[pos] = make_float4(X, Y, Z, d);
+                            if (b.frustum_idx) b.frustum_idx[pos] = row;
+                        }
+                    }
+                }
             }
         }
     }
@@ -764,10 +917,34 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     return FNP_OK;
 }
 
-static size_t cull_smem_bytes(const fnp_seeker_batch *b)
+static size_t cull_mask_smem(const fnp_seeker_batch *b)
 {
-    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullWarps) +
+    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullVW) +
            (size_t)kCullThreads * b->point_stride * 4 + 16;
+}
+static size_t cull_write_smem(const fnp_seeker_batch *b, int W)
+{
+    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (4 + 4 * kCullVW) + (size_t)6 * W * 4 + 16;
+}
+
+template <int W>
+static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
+{
+    const size_t sa = cull_mask_smem(b), sb = cull_write_smem(b, W);
+    if (sa > 200 * 1024 || sb > 200 * 1024) return FNP_EINVAL;
+    cudaFuncSetAttribute(cull_mask_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cull_write_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+    cull_mask_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h);
+    scan_tiles_kernel<<<divup(b->n_cands, 4), 128, 0, st>>>(*b);
+    scan_cands_kernel<<<1, 1024, 0, st>>>(*b);
+    cull_write_kernel<W><<<b->n_tiles, kCullThreads, sb, st>>>(*b, cfg->img_w, cfg->img_h);
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_mask_words(int max_cands_per_frame)
+{
+    const int w = divup(max_cands_per_frame > 0 ? max_cands_per_frame : 1, 32);
+    return w <= 1 ? 1 : w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : -1;
 }
 
 extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
@@ -782,17 +959,18 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
         FNP_LAUNCH_CHECK();
         return FNP_OK;
     }
-    if (!b->points || !b->tile_counts || !b->frustum_pts || b->point_stride < 3 ||
-        b->xyz_offset < 0 || b->xyz_offset + 3 > b->point_stride)
+    if (!b->points || !b->tile_counts || !b->frustum_pts || !b->pt_mask || !b->cam_cand_start ||
+        b->point_stride < 3 || b->xyz_offset < 0 || b->xyz_offset + 3 > b->point_stride)
         return FNP_EINVAL;
-    const size_t smem = cull_smem_bytes(b);
-    if (smem > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(cull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cull_kernel<false><<<b->n_tiles, kCullThreads, smem, st>>>(*b, cfg->img_w, cfg->img_h);
-    scan_tiles_kernel<<<divup(b->n_cands, 4), 128, 0, st>>>(*b);
-    scan_cands_kernel<<<1, 1024, 0, st>>>(*b);
-    cull_kernel<true><<<b->n_tiles, kCullThreads, smem, st>>>(*b, cfg->img_w, cfg->img_h);
+    const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
+    if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 256 candidates in one frame
+    switch (W) {
+        case 1: rc = launch_cull<1>(cfg, b, st); break;
+        case 2: rc = launch_cull<2>(cfg, b, st); break;
+        case 4: rc = launch_cull<4>(cfg, b, st); break;
+        default: rc = launch_cull<8>(cfg, b, st); break;
+    }
+    if (rc) return rc;
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }

@@ -16,6 +16,9 @@ import numpy as np
 from . import _lib
 
 IMAGE_ORDER = (2, 0, 1, 5, 3, 4)       # frustum_proposals_v1.py:201
+CAM_RANK = np.zeros(6, dtype=np.int64)  # position of camera c in IMAGE_ORDER
+for _r, _c in enumerate(IMAGE_ORDER):
+    CAM_RANK[_c] = _r
 
 
 def _p(a):

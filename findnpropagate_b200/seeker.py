@@ -239,21 +239,31 @@ class SeekerEngine:
                                                          self.p["nms_2d"], self.p["score_thr"], n_frames=B,
                                                          return_starts=True)
         F = int(sel.shape[0])
+        cand_frame = det_frame[sel].astype(np.int32)
+        cand_cam = det_cam[sel].astype(np.int32)
+        # first candidate of every (frame, camera rank): candidates are already in that order
+        cam_cand_start = np.zeros(B * 6 + 1, np.int32)
+        if F:
+            np.cumsum(np.bincount(cand_frame.astype(np.int64) * 6 + nms2d.CAM_RANK[cand_cam], minlength=B * 6),
+                      out=cam_cand_start[1:])
         n_tiles, tile_frame, tile_row0, frame_tile_start = self._tiles(np.ascontiguousarray(frame_row_start, np.int64))
+        cand_score = np.ascontiguousarray(det_scores[sel], np.float32)
+        # stage-4 priority order inside each frame: descending 2D score, stable
+        nms_order = np.lexsort((np.arange(F), -cand_score.astype(np.float64), cand_frame)).astype(np.int32)
         return dict(
             B=B, F=F, n_tiles=n_tiles, stride=int(stride), xyz_offset=int(xyz_offset),
             total_rows=int(frame_row_start[-1]),
             max_cands=int(np.diff(frame_cand_start).max()) if B else 0,
             frame_row_start=frame_row_start.astype(np.int64), tile_frame=tile_frame, tile_row0=tile_row0,
             frame_tile_start=frame_tile_start, cam_mats=np.ascontiguousarray(cam_mats, np.float32),
-            frame_cand_start=frame_cand_start, cand_frame=det_frame[sel].astype(np.int32),
-            cand_cam=det_cam[sel].astype(np.int32), cand_label=det_labels[sel].astype(np.int32),
+            frame_cand_start=frame_cand_start, cam_cand_start=cam_cand_start, cand_frame=cand_frame,
+            cand_cam=cand_cam, cand_label=det_labels[sel].astype(np.int32),
             cand_box2d=np.ascontiguousarray(det_boxes[sel], np.float32),
-            cand_score=np.ascontiguousarray(det_scores[sel], np.float32), cand_det=sel)
+            cand_score=cand_score, cand_det=sel, nms_order=nms_order)
 
     # ------------------------------------------------------------------ device execution
     _META = ["frame_row_start", "tile_frame", "tile_row0", "frame_tile_start", "cam_mats", "frame_cand_start",
-             "cand_frame", "cand_cam", "cand_label", "cand_box2d"]
+             "cam_cand_start", "cand_frame", "cand_cam", "cand_label", "cand_box2d", "nms_order"]
 
     def _upload_meta(self, plan, stream, slot=0):
         offs, total = {}, 0
@@ -291,14 +301,21 @@ class SeekerEngine:
             max_rows = cap // sp + F + 1
             max_items = max_rows * chunks
             Cmax = max(plan["max_cands"], 1)
+            W = _lib.lib.fnp_seeker_mask_words(Cmax)
+            if W < 0:
+                raise ValueError("more than 256 candidate frustums in one frame (%d) are not supported" % Cmax)
             sizes = dict(
-                tile_counts=4 * plan["n_tiles"] * Cmax, frustum_pts=16 * cap,
+                tile_counts=4 * plan["n_tiles"] * Cmax, pt_mask=4 * plan["n_tiles"] * W * _lib.CULL_TILE,
+                frustum_pts=16 * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
                 hyp_iou=4 * H * F, counts=4 * H * max_rows, items=16 * max_items,
                 cand_item_start=4 * (F + 1), cand_split_row=4 * (F + 1),
-                # outputs, one D2H: boxes(7) score best count npts nvalid per candidate + status
                 )
-            sizes["out"] = 4 * (12 * F + 8)
+            # outputs, one D2H: boxes(7) score best count npts nvalid per candidate, status(4) + pad(4),
+            # recall counters (20 x int64), stage-4 keep flags (F bytes)
+            off_recall = 4 * (12 * F + 8)
+            off_keep = off_recall + 8 * self.N_COUNTERS
+            sizes["out"] = off_keep + _align(F, 8)
             if self.debug:
                 sizes.update(frustum_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
             ptr = {k: self.arena.get(k, v).data_ptr() for k, v in sizes.items() if k != "out"}
@@ -312,11 +329,12 @@ class SeekerEngine:
                 points=points_dev.data_ptr(), point_stride=plan["stride"], xyz_offset=plan["xyz_offset"],
                 frame_row_start=meta["frame_row_start"], tile_frame=meta["tile_frame"], tile_row0=meta["tile_row0"],
                 frame_tile_start=meta["frame_tile_start"], cam_mats=meta["cam_mats"],
-                frame_cand_start=meta["frame_cand_start"], cand_frame=meta["cand_frame"], cand_cam=meta["cand_cam"],
+                frame_cand_start=meta["frame_cand_start"], cam_cand_start=meta["cam_cand_start"],
+                cand_frame=meta["cand_frame"], cand_cam=meta["cand_cam"],
                 cand_label=meta["cand_label"], cand_box2d=meta["cand_box2d"],
                 base_boxes=self.base_boxes.data_ptr(), base_corners=self.base_corners.data_ptr(),
                 mags=self.mags.data_ptr(),
-                tile_counts=ptr["tile_counts"], cand_npts=o_npts, cand_pt_start=o_ptstart,
+                tile_counts=ptr["tile_counts"], pt_mask=ptr["pt_mask"], mask_words=W, cand_npts=o_npts, cand_pt_start=o_ptstart,
                 frustum_pts=ptr["frustum_pts"], frustum_idx=ptr.get("frustum_idx"), pts_capacity=cap,
                 cand_stats=ptr["cand_stats"], centres=ptr["centres"], hyp_prep=ptr["hyp_prep"],
                 hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
@@ -329,11 +347,15 @@ class SeekerEngine:
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
             self.launches += 10 if F and plan["n_tiles"] else 0
-            handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta)
+            handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta,
+                          off_recall=off_recall, off_keep=off_keep, has_nms=False, has_recall=False,
+                          recall_thresh=tuple(recall_thresh))
             if nms_thresh is not None and F:
-                handle["nms_keep"] = self._stage4_nms(plan, meta, o_boxes, o_best, float(nms_thresh), stream)
+                self._stage4_nms(plan, meta, o_boxes, o_best, float(nms_thresh), stream, ob + off_keep)
+                handle["has_nms"] = True
             if gt is not None and F:
-                handle["recall"] = self._recall(plan, meta, o_boxes, o_best, gt, recall_thresh, stream)
+                self._recall(plan, meta, o_boxes, o_best, gt, recall_thresh, stream, out_dev, off_recall)
+                handle["has_recall"] = True
             host = self.arena.get("out_host%d" % slot, sizes["out"], pinned=True)
             host[:sizes["out"]].copy_(out_dev[:sizes["out"]], non_blocking=True)
             handle["out_host"] = host
@@ -341,32 +363,27 @@ class SeekerEngine:
             handle["event"].record()
         return handle
 
-    def _stage4_nms(self, plan, meta, o_boxes, o_best, thresh, stream):
+    N_COUNTERS = 5 + 5 * 3          # generate_recall_record counters for 3 IoU thresholds
+
+    def _stage4_nms(self, plan, meta, o_boxes, o_best, thresh, stream, keep_ptr):
         """Rotated-BEV NMS of each frame's proposals in 2D-score order (the dedup
         PseudoLoader applies later on the CPU, pseudo_loader.py:29-55,755)."""
-        F, B = plan["F"], plan["B"]
-        fcs = plan["frame_cand_start"]
-        # priority order inside each frame: descending 2D score, stable
-        order = np.lexsort((np.arange(F), -plan["cand_score"].astype(np.float64), plan["cand_frame"])).astype(np.int32)
-        order_dev = torch.from_numpy(order).to(self.device, non_blocking=True)
-        keep = torch.empty(F, dtype=torch.uint8, device=self.device)
-        rc = _lib.lib.fnp_seg_nms_rotated(o_boxes, None, order_dev.data_ptr(), o_best, meta["frame_cand_start"], B,
+        rc = _lib.lib.fnp_seg_nms_rotated(o_boxes, None, meta["nms_order"], o_best, meta["frame_cand_start"], plan["B"],
                                           int(min(max(plan["max_cands"], 1), _lib.SEG_NMS_MAX)), thresh,
-                                          keep.data_ptr(), stream)
+                                          keep_ptr, stream)
         _lib.check(rc, "fnp_seg_nms_rotated")
         self.launches += 1
-        self._keepalive = order_dev
-        return keep
 
-    def _recall(self, plan, meta, o_boxes, o_best, gt, thresh, stream):
+    def _recall(self, plan, meta, o_boxes, o_best, gt, thresh, stream, out_dev, off):
         gt_boxes, gt_start = gt
-        counters = torch.zeros(5 + 5 * len(thresh), dtype=torch.int64, device=self.device)
+        assert len(thresh) == 3
+        out_dev[off:off + 8 * self.N_COUNTERS].zero_()
         th = (C.c_float * len(thresh))(*[float(t) for t in thresh])
         rc = _lib.lib.fnp_recall_counters(o_boxes, o_best, meta["frame_cand_start"], gt_boxes.data_ptr(),
-                                          gt_start.data_ptr(), plan["B"], th, len(thresh), counters.data_ptr(), stream)
+                                          gt_start.data_ptr(), plan["B"], th, len(thresh),
+                                          out_dev.data_ptr() + off, stream)
         _lib.check(rc, "fnp_recall_counters")
         self.launches += 1
-        return counters
 
     def finish(self, handle):
         """Wait for the batch and assemble per-frame results (reference output format)."""
@@ -389,7 +406,7 @@ class SeekerEngine:
             raise RuntimeError("scoring work-item tables overflowed (items %d, rows %d)" % (status[2], status[3]))
         ok = best >= 0
         fcs = plan["frame_cand_start"]
-        keep = handle["nms_keep"].cpu().numpy().astype(bool) if "nms_keep" in handle else None
+        keep = raw[handle["off_keep"]:handle["off_keep"] + F].astype(bool) if handle["has_nms"] else None
         frames = []
         for b in range(B):
             s = slice(fcs[b], fcs[b + 1])
@@ -402,8 +419,9 @@ class SeekerEngine:
         res = dict(frames=frames, cand_valid=ok.copy(), cand_best=best.copy(), cand_score2=score.copy(),
                    cand_count=count.copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),
                    cand_boxes=boxes.copy())
-        if "recall" in handle:
-            res["recall"] = self.recall_dict(handle["recall"].cpu().numpy())
+        if handle["has_recall"]:
+            o = handle["off_recall"]
+            res["recall"] = self.recall_dict(raw[o:o + 8 * self.N_COUNTERS].view(np.int64), handle["recall_thresh"])
         return res
 
     @staticmethod

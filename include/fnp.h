@@ -117,6 +117,9 @@ typedef struct fnp_seeker_batch {
     const float *cam_mats;           /* (n_frames,6,24): lidar2image rows 0..2 (12),
                                         combine = cam2lidar_R inv(K) (9), cam2lidar_t (3)  */
     const int32_t *frame_cand_start; /* (n_frames+1) first candidate of each frame         */
+    const int32_t *cam_cand_start;   /* (n_frames*6+1) first candidate of (frame, camera rank r):
+                                        within a frame candidates are grouped by camera in the
+                                        order [2,0,1,5,3,4]; rank r is position r of that list  */
     const int32_t *cand_frame;       /* (F) */
     const int32_t *cand_cam;         /* (F) 0..5 */
     const int32_t *cand_label;       /* (F) 1..A */
@@ -126,6 +129,10 @@ typedef struct fnp_seeker_batch {
     const float *mags;               /* (M) linspace(0,1,M)                                */
     /* ---- workspaces / intermediates (caller allocated) ---- */
     int32_t *tile_counts;            /* (n_tiles, max_cands_per_frame)                     */
+    uint32_t *pt_mask;               /* (n_tiles, mask_words, FNP_CULL_TILE): bit j of word w of a
+                                        point = it lies in the frustum of its frame's candidate
+                                        32 w + j                                            */
+    int32_t mask_words;              /* = fnp_seeker_mask_words(max_cands_per_frame)        */
     int32_t *cand_npts;              /* (F)   P_f                                          */
     int32_t *cand_pt_start;          /* (F+1) start of each frustum in frustum_pts         */
     float *frustum_pts;              /* (pts_capacity,4) x,y,z,depth of the frustum points */
@@ -159,10 +166,14 @@ typedef struct fnp_seeker_batch {
                                         bit1: items/counts overflow ([2] items, [3] rows needed) */
 } fnp_seeker_batch;
 
-#define FNP_CULL_TILE 256
+#define FNP_CULL_TILE 1024
+/* Words of the per-point candidate mask for a batch whose busiest frame has that many
+ * candidates: 1, 2, 4 or 8 (-1: more than 256 candidates per frame are not supported). */
+int fnp_seeker_mask_words(int max_cands_per_frame);
 
 /* Stage 1: fused LiDAR->camera projection + per-2D-box frustum cull + ordered compaction.
- * count pass, scan, write pass (three launches, no host sync). */
+ * Pass A (membership bitmask per point + per-tile populations), two scans, pass B (ordered
+ * scatter of the unprojected member points): four launches, no host sync. */
 int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 /* Stage 1b: per-frustum depth quantiles, point AABB, frustum corners, centre line. */
 int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);

@@ -137,6 +137,20 @@ def test_batch_of_frames_equals_frame_by_frame_and_splits_are_invariant():
     assert r0["frames"][0]["pred_boxes"].shape == (0, 7)
 
 
+@pytest.mark.parametrize("n_boxes", [40, 100, 150])
+def test_many_candidates_per_frame_mask_words(n_boxes):
+    """Frames with more than 32 / 64 / 128 candidate frustums: the per-point membership mask
+    of stage 1 takes 2 / 4 / 8 words; results stay bit-exact against the oracle."""
+    cfg = synth.SynthConfig("many%d" % n_boxes, 16, 720, 1, n_boxes, 4, 6, 1)
+    params = synth.seeker_params(cfg)
+    frames = [_frame_from_synth(synth.make_frame(i, cfg)) for i in range(2)]
+    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    plan = eng.plan(frames)
+    assert plan["max_cands"] > (32 if n_boxes == 40 else 64 if n_boxes == 100 else 128)
+    res, n = _check_against_oracle(eng, frames, params)
+    assert n > n_boxes // 2
+
+
 def test_full_size_properties_cfg2():
     """cfg2 (300k points, 60 boxes, H = 768): properties that do not need the slow oracle on
     every hypothesis -- run twice = identical; membership ordered/unique; counts equal the

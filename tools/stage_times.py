@@ -70,8 +70,9 @@ def main():
     meta = h["meta"]
     ob = h["out_dev"].data_ptr()
     F = plan["F"]
-    for name, fn in (("seg_nms", lambda: eng._stage4_nms(plan, meta, ob, ob + 32 * F, 0.1, stream)),
-                     ("recall", lambda: eng._recall(plan, meta, ob, ob + 32 * F, gt, (0.3, 0.5, 0.7), stream))):
+    for name, fn in (("seg_nms", lambda: eng._stage4_nms(plan, meta, ob, ob + 32 * F, 0.1, stream, ob + h["off_keep"])),
+                     ("recall", lambda: eng._recall(plan, meta, ob, ob + 32 * F, gt, (0.3, 0.5, 0.7), stream,
+                                                    h["out_dev"], h["off_recall"]))):
         fn(); torch.cuda.synchronize()
         e0.record()
         for _ in range(a.iters):

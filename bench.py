@@ -243,9 +243,8 @@ def run_ours(a):
                 pts.copy_(pinned[k % 2], non_blocking=True)
                 ready[k % 2].record(copy_stream)
         plan = eng.plan(batch)
-        if not resident:
-            torch.cuda.current_stream(dev).wait_event(ready[k % 2])
-        h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2)
+        h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2,
+                        points_ready=None if resident else ready[k % 2])
         consumed[k % 2].record()
         res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
         if res is not None and world > 1:

@@ -29,6 +29,12 @@ static_assert(FNP_CULL_TILE % kCullThreads == 0, "tile must be a whole number of
 //       camera and scatters (x,y,z,depth) of the *unprojected* point in input order.
 // Tiles without members cost pass B one mask read and nothing else.
 // ======================================================================================
+// Frustum points are stored pair-interleaved: points 2p and 2p+1 of the buffer share one 32-byte
+// record {x0,x1, y0,y1, z0,z1, d0,d1}, so that the scoring kernel reads (x0,x1) / (y0,y1) /
+// (z0,z1) as the 64-bit operands of Blackwell's packed fp32x2 instructions.  Every frustum
+// starts at an even point index.  pair_slot(i) = float offset of x of point i.
+__device__ __forceinline__ size_t pair_slot(int64_t i) { return (size_t)(i >> 1) * 8 + (size_t)(i & 1); }
+
 __device__ __constant__ int kImageOrder[6] = {2, 0, 1, 5, 3, 4};   // frustum_proposals_v1.py:201
 
 struct CullSmem {
@@ -282,7 +288,8 @@ __global__ void __launch_bounds__(kCullThreads) cull_write_kernel(const fnp_seek
                         const int j = 32 * w + jb;
                         const int64_t pos = (int64_t)s_base[j] + cnt_vw[j] + __popc(m & lt);
                         if (pos < b.pts_capacity) {
-                            reinterpret_cast<float4 *>(b.frustum_pts)[pos] = make_float4(X, Y, Z, d);
+                            float *dst = b.frustum_pts + pair_slot(pos);
+                            dst[0] = X; dst[2] = Y; dst[4] = Z; dst[6] = d;
                             if (b.frustum_idx) b.frustum_idx[pos] = row;
                         }
                     }
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(1024) scan_cands_kernel(const fnp_seeker_batch
     __syncthreads();
     for (int base = 0; base < b.n_cands; base += 1024) {
         const int i = base + tid;
-        const int val = (i < b.n_cands) ? b.cand_npts[i] : 0;
+        const int val = (i < b.n_cands) ? ((b.cand_npts[i] + 1) & ~1) : 0;   // frustums start on a pair boundary
         int inc = val;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -381,7 +388,12 @@ __device__ __forceinline__ float warp_max(float v)
 // k-th smallest (0-based) and (k+1)-th smallest depth of a frustum: MSD radix select on the
 // float bit patterns (depths are >= 1e-5 > 0, so the patterns order like the values).
 // All threads of the block call this; results are block-uniform.
-__device__ void select_pair(const float4 *__restrict__ pts, int n, int k, unsigned *s_hist, unsigned *s_misc,
+__device__ __forceinline__ float pt_depth(const float *__restrict__ pts, int i)
+{
+    return pts[(size_t)(i >> 1) * 8 + 6 + (i & 1)];
+}
+
+__device__ void select_pair(const float *__restrict__ pts, int n, int k, unsigned *s_hist, unsigned *s_misc,
                             float &v_lo, float &v_hi)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -391,7 +403,7 @@ __device__ void select_pair(const float4 *__restrict__ pts, int n, int k, unsign
         for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
         __syncthreads();
         for (int i = tid; i < n; i += nt) {
-            const unsigned key = __float_as_uint(pts[i].w);
+            const unsigned key = __float_as_uint(pt_depth(pts, i));
             if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -418,7 +430,7 @@ __device__ void select_pair(const float4 *__restrict__ pts, int n, int k, unsign
     __syncthreads();
     unsigned c_le = 0, nxt = 0xffffffffu;
     for (int i = tid; i < n; i += nt) {
-        const unsigned key = __float_as_uint(pts[i].w);
+        const unsigned key = __float_as_uint(pt_depth(pts, i));
         if (key <= prefix) c_le++;
         else nxt = min(nxt, key);
     }
@@ -430,7 +442,7 @@ __device__ void select_pair(const float4 *__restrict__ pts, int n, int k, unsign
 }
 
 // torch.quantile(depth, q), linear interpolation (ATen Sorting.cpp quantile_compute + lerp)
-__device__ float block_quantile(const float4 *__restrict__ pts, int n, float q, float dmin, float dmax,
+__device__ float block_quantile(const float *__restrict__ pts, int n, float q, float dmin, float dmax,
                                 unsigned *s_hist, unsigned *s_misc)
 {
     const float pos = __fmul_rn(q, (float)(n - 1));
@@ -462,17 +474,24 @@ __global__ void __launch_bounds__(256) stats_kernel(const fnp_seeker_batch b, co
         if (tid == 0) { st[9] = 0.f; }
         return;
     }
-    const float4 *pts = reinterpret_cast<const float4 *>(b.frustum_pts) + b.cand_pt_start[f];
+    const float *pts = b.frustum_pts + (size_t)(b.cand_pt_start[f] >> 1) * 8;   // starts are even
 
-    // ---- min / max of depth and of x, y, z
+    // ---- min / max of depth and of x, y, z: one 32-byte pair record per thread and iteration
     const float INF = __int_as_float(0x7f800000);
     float mn[4] = {INF, INF, INF, INF}, mx[4] = {-INF, -INF, -INF, -INF};
-    for (int i = tid; i < n; i += blockDim.x) {
-        const float4 p = pts[i];
-        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-        mn[3] = fminf(mn[3], p.w); mx[3] = fmaxf(mx[3], p.w);
+    const float4 *rec = reinterpret_cast<const float4 *>(pts);
+    for (int p = tid; 2 * p < n; p += blockDim.x) {
+        const float4 a = rec[2 * p], c = rec[2 * p + 1];          // x0 x1 y0 y1 | z0 z1 d0 d1
+        mn[0] = fminf(mn[0], a.x); mx[0] = fmaxf(mx[0], a.x);
+        mn[1] = fminf(mn[1], a.z); mx[1] = fmaxf(mx[1], a.z);
+        mn[2] = fminf(mn[2], c.x); mx[2] = fmaxf(mx[2], c.x);
+        mn[3] = fminf(mn[3], c.z); mx[3] = fmaxf(mx[3], c.z);
+        if (2 * p + 1 < n) {
+            mn[0] = fminf(mn[0], a.y); mx[0] = fmaxf(mx[0], a.y);
+            mn[1] = fminf(mn[1], a.w); mx[1] = fmaxf(mx[1], a.w);
+            mn[2] = fminf(mn[2], c.y); mx[2] = fmaxf(mx[2], c.y);
+            mn[3] = fminf(mn[3], c.w); mx[3] = fmaxf(mx[3], c.w);
+        }
     }
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -725,6 +744,7 @@ __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch
         b.cand_split_row[b.n_cands] = s_carry_r;
         b.status[2] = s_carry_i;
         b.status[3] = s_carry_r;
+        b.status[4] = 0;            // work-item counter of the persistent scoring CTAs
         if (s_carry_i > b.max_items || s_carry_r > b.max_count_rows) b.status[0] |= 2;
     }
 }
@@ -740,93 +760,169 @@ __global__ void __launch_bounds__(128) write_items_kernel(const fnp_seeker_batch
         reinterpret_cast<int4 *>(b.items)[i0 + i] = make_int4(f, i % nchunks, i / nchunks, 0);
 }
 
+// Packed-fp32x2 form of the in-box predicate for TWO points against one hypothesis.  Same
+// arithmetic per lane as in_box() (sub.rn, mul.rn, fma.rn are IEEE per lane):
+//   sx = x - cx, sy = y - cy, sz = z - cz, lx = fma(sx, cosa, rn(sy * -sina)),
+//   ly = fma(sy, cosa, rn(sx * sina)), inside = !(|sz| > hz) & |lx| <= tx & |ly| <= ty.
+// 7 packed FP instructions (FADD2 x3, FMUL2 x2, FFMA2 x2) + 6 FSETP + 2 predicated IADD per
+// two tests, instead of 14 + 6 + 2.
+struct HypPacked {
+    unsigned long long cx2, cy2, cz2, cosa2, nsina2, sina2;   // each value duplicated in both halves
+    float hz, tx, ty;
+};
+
+__device__ __forceinline__ unsigned long long dup2(float v)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ float lo_half(unsigned long long v) { return __uint_as_float((unsigned)v); }
+
+__device__ __forceinline__ void count_pair(int &cnt, unsigned long long xx, unsigned long long yy,
+                                           unsigned long long zz, const HypPacked &h)
+{
+    asm("{\n"
+        " .reg .b64 sx, sy, sz, m1, m2, lx, ly;\n"
+        " .reg .f32 a0, a1, b0, b1, c0, c1;\n"
+        " .reg .pred p, q;\n"
+        " sub.rn.f32x2 sx, %1, %4;\n"
+        " sub.rn.f32x2 sy, %2, %5;\n"
+        " sub.rn.f32x2 sz, %3, %6;\n"
+        " mul.rn.f32x2 m1, sy, %8;\n"
+        " mul.rn.f32x2 m2, sx, %9;\n"
+        " fma.rn.f32x2 lx, sx, %7, m1;\n"
+        " fma.rn.f32x2 ly, sy, %7, m2;\n"
+        " mov.b64 {a0, a1}, lx;\n"
+        " mov.b64 {b0, b1}, ly;\n"
+        " mov.b64 {c0, c1}, sz;\n"
+        " abs.f32 a0, a0;\n abs.f32 a1, a1;\n abs.f32 b0, b0;\n abs.f32 b1, b1;\n abs.f32 c0, c0;\n abs.f32 c1, c1;\n"
+        " setp.leu.f32 p, c0, %10;\n"
+        " setp.le.and.f32 p, a0, %11, p;\n"
+        " setp.le.and.f32 p, b0, %12, p;\n"
+        " setp.leu.f32 q, c1, %10;\n"
+        " setp.le.and.f32 q, a1, %11, q;\n"
+        " setp.le.and.f32 q, b1, %12, q;\n"
+        " @p add.s32 %0, %0, 1;\n"
+        " @q add.s32 %0, %0, 1;\n"
+        "}\n"
+        : "+r"(cnt)
+        : "l"(xx), "l"(yy), "l"(zz), "l"(h.cx2), "l"(h.cy2), "l"(h.cz2), "l"(h.cosa2), "l"(h.nsina2), "l"(h.sina2),
+          "f"(h.hz), "f"(h.tx), "f"(h.ty));
+}
+
+// Persistent CTAs pull (frustum, hypothesis chunk, point split) work items off a device
+// counter.  A CTA keeps K hypotheses per thread in registers for the whole item and streams
+// the item's points through a two-stage shared-memory ring filled by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx); every thread reads every staged pair record with
+// broadcast LDS.128 + LDS.64.
 template <int K>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_batch b, const int H)
 {
-    __shared__ __align__(128) float4 s_tile[2][kScoreTile];
+    __shared__ __align__(128) float4 s_tile[2][kScoreTile / 2][2];   // [stage][pair][x0x1y0y1 | z0z1d0d1]
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_item;
 
-    if ((int)blockIdx.x >= b.status[2] || (b.status[0] & 2)) return;
-    const int4 item = reinterpret_cast<const int4 *>(b.items)[blockIdx.x];
-    const int f = item.x;
-    const int chunk = item.y;
-    const int split = item.z;
     const int tid = threadIdx.x;
-    const int nv = b.hyp_nvalid[f];
-    const int h_base = chunk * (kScoreThreads * K);
-    const int npts = b.cand_npts[f];
-    const int p0 = split * b.split_points;
-    const int p1 = min(npts, p0 + b.split_points);
-    const float4 *gpts = reinterpret_cast<const float4 *>(b.frustum_pts) + b.cand_pt_start[f] + p0;
-    const int n = p1 - p0;
-    const int n_tiles = (n + kScoreTile - 1) / kScoreTile;
-
+    if (b.status[0] & 2) return;
+    const int n_items = b.status[2];
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < 2 && t < n_tiles; t++) {
-            const uint32_t bytes = (uint32_t)min(kScoreTile, n - t * kScoreTile) * 16u;
-            mbar_expect_tx(&s_bar[t], bytes);
-            tma_load_1d(s_tile[t], gpts + (size_t)t * kScoreTile, bytes, &s_bar[t]);
-        }
-    }
+    unsigned it = 0;   // tiles consumed so far by this CTA: stage = it & 1, parity = (it >> 1) & 1
 
-    // hypotheses of this thread live in registers for the whole CTA lifetime
-    BoxPrep hp[K];
-    int cnt[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int r = h_base + k * kScoreThreads + tid;
-        cnt[k] = 0;
-        if (r < nv) {
-            const float4 *src = reinterpret_cast<const float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
-            const float4 a = __ldg(src), c = __ldg(src + 1);
-            hp[k].cx = a.x; hp[k].cy = a.y; hp[k].cz = a.z; hp[k].hz = a.w;
-            hp[k].cosa = c.x; hp[k].sina = c.y; hp[k].tx = c.z; hp[k].ty = c.w;
-        } else {
-            hp[k].cx = hp[k].cy = hp[k].cz = 0.f; hp[k].hz = -1.f;   // never inside
-            hp[k].cosa = 1.f; hp[k].sina = 0.f; hp[k].tx = hp[k].ty = -1.f;
-        }
-    }
+    for (;;) {
+        __syncthreads();                       // everyone is done with the previous item (and s_item)
+        if (tid == 0) s_item = atomicAdd(&b.status[4], 1);
+        __syncthreads();
+        const int item_id = s_item;
+        if (item_id >= n_items) break;
+        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];
+        const int f = item.x, chunk = item.y, split = item.z;
+        const int nv = b.hyp_nvalid[f];
+        const int h_base = chunk * (kScoreThreads * K);
+        const int npts = b.cand_npts[f];
+        const int p0 = split * b.split_points;                    // even: split_points is even
+        const int n = min(npts, p0 + b.split_points) - p0;
+        const int n_rec = (n + 1) >> 1;                           // pair records of this item
+        const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
+        constexpr int kRecTile = kScoreTile / 2;
+        const int n_tiles = (n_rec + kRecTile - 1) / kRecTile;
 
-    for (int t = 0; t < n_tiles; t++) {
-        const int s = t & 1;
-        mbar_wait(&s_bar[s], (uint32_t)((t >> 1) & 1));
-        const int m = min(kScoreTile, n - t * kScoreTile);
-        const float4 *tp = s_tile[s];
-        int i = 0;
-        for (; i + 4 <= m; i += 4) {
-            const float4 q0 = tp[i], q1 = tp[i + 1], q2 = tp[i + 2], q3 = tp[i + 3];
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                count_if(cnt[k], in_box(q0.x, q0.y, q0.z, hp[k]));
-                count_if(cnt[k], in_box(q1.x, q1.y, q1.z, hp[k]));
-                count_if(cnt[k], in_box(q2.x, q2.y, q2.z, hp[k]));
-                count_if(cnt[k], in_box(q3.x, q3.y, q3.z, hp[k]));
+        if (tid == 0) {
+            for (int t = 0; t < 2 && t < n_tiles; t++) {
+                const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - t * kRecTile) * 32u;
+                const unsigned st = (it + t) & 1u;
+                mbar_expect_tx(&s_bar[st], bytes);
+                tma_load_1d(s_tile[st], grec + (size_t)t * kRecTile * 2, bytes, &s_bar[st]);
             }
         }
-        for (; i < m; i++) {
-            const float4 q = tp[i];
-#pragma unroll
-            for (int k = 0; k < K; k++) count_if(cnt[k], in_box(q.x, q.y, q.z, hp[k]));
-        }
-        __syncthreads();  // everyone is done with stage s
-        if (tid == 0 && t + 2 < n_tiles) {
-            const uint32_t bytes = (uint32_t)min(kScoreTile, n - (t + 2) * kScoreTile) * 16u;
-            mbar_expect_tx(&s_bar[s], bytes);
-            tma_load_1d(s_tile[s], gpts + (size_t)(t + 2) * kScoreTile, bytes, &s_bar[s]);
-        }
-    }
 
-    int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
+        HypPacked hp[K];
+        int cnt[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int r = h_base + k * kScoreThreads + tid;
-        if (r < nv) out[r] = cnt[k];
+        for (int k = 0; k < K; k++) {
+            const int r = h_base + k * kScoreThreads + tid;
+            cnt[k] = 0;
+            float4 a = make_float4(0.f, 0.f, 0.f, -1.f), c = make_float4(1.f, 0.f, -1.f, -1.f);   // never inside
+            if (r < nv) {
+                const float4 *src = reinterpret_cast<const float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
+                a = __ldg(src); c = __ldg(src + 1);
+            }
+            hp[k].cx2 = dup2(a.x); hp[k].cy2 = dup2(a.y); hp[k].cz2 = dup2(a.z); hp[k].hz = a.w;
+            hp[k].cosa2 = dup2(c.x); hp[k].nsina2 = dup2(-c.y); hp[k].sina2 = dup2(c.y);
+            hp[k].tx = c.z; hp[k].ty = c.w;
+        }
+
+        for (int t = 0; t < n_tiles; t++, it++) {
+            const unsigned st = it & 1u;
+            mbar_wait(&s_bar[st], (it >> 1) & 1u);
+            const int m_pts = min(kScoreTile, n - t * kScoreTile);   // points in this tile
+            const int m_full = m_pts >> 1;                            // complete pairs
+            const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(s_tile[st]);
+            int i = 0;
+            for (; i + 2 <= m_full; i += 2) {
+                const ulonglong2 xy0 = tp[2 * i], zd0 = tp[2 * i + 1];
+                const ulonglong2 xy1 = tp[2 * i + 2], zd1 = tp[2 * i + 3];
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    count_pair(cnt[k], xy0.x, xy0.y, zd0.x, hp[k]);
+                    count_pair(cnt[k], xy1.x, xy1.y, zd1.x, hp[k]);
+                }
+            }
+            for (; i < m_full; i++) {
+                const ulonglong2 xy = tp[2 * i], zd = tp[2 * i + 1];
+#pragma unroll
+                for (int k = 0; k < K; k++) count_pair(cnt[k], xy.x, xy.y, zd.x, hp[k]);
+            }
+            if (m_pts & 1) {   // last point of the frustum: lane 0 of a half-filled record
+                const float4 xy = s_tile[st][m_full][0], zd = s_tile[st][m_full][1];
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    BoxPrep bp;
+                    bp.cx = lo_half(hp[k].cx2); bp.cy = lo_half(hp[k].cy2); bp.cz = lo_half(hp[k].cz2);
+                    bp.cosa = lo_half(hp[k].cosa2); bp.sina = lo_half(hp[k].sina2);
+                    bp.hz = hp[k].hz; bp.tx = hp[k].tx; bp.ty = hp[k].ty;
+                    count_if(cnt[k], in_box(xy.x, xy.z, zd.x, bp));
+                }
+            }
+            __syncthreads();  // everyone is done with stage st
+            if (tid == 0 && t + 2 < n_tiles) {
+                const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - (t + 2) * kRecTile) * 32u;
+                mbar_expect_tx(&s_bar[st], bytes);
+                tma_load_1d(s_tile[st], grec + (size_t)(t + 2) * kRecTile * 2, bytes, &s_bar[st]);
+            }
+        }
+
+        int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int r = h_base + k * kScoreThreads + tid;
+            if (r < nv) out[r] = cnt[k];
+        }
     }
 }
 
@@ -913,7 +1009,7 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     if (!cfg || !b) return FNP_EINVAL;
     if (b->n_frames < 0 || b->n_cands < 0 || b->n_tiles < 0) return FNP_EINVAL;
     if (cfg->num_mags < 1 || cfg->num_yaw_size < 1) return FNP_EINVAL;
-    if (b->max_items < 0 || b->max_count_rows < 0 || b->split_points < 1) return FNP_EINVAL;
+    if (b->max_items < 0 || b->max_count_rows < 0 || b->split_points < 2 || (b->split_points & 1)) return FNP_EINVAL;
     return FNP_OK;
 }
 
@@ -1006,9 +1102,18 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     plan_items_kernel<<<1, 1024, 0, st>>>(*b, H);
     write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H);
     if (b->max_items > 0) {
-        if (H <= 128) score_kernel<1><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
-        else if (H <= 512) score_kernel<2><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
-        else score_kernel<4><<<b->max_items, kScoreThreads, 0, st>>>(*b, H);
+        static int n_sms = 0;
+        if (n_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        // persistent CTAs: a whole number of CTAs per SM (148 SMs on B200), capped by the item capacity
+        const int per_sm = (H <= 128) ? 12 : (H <= 512) ? 8 : 5;
+        const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
+        if (H <= 128) score_kernel<1><<<grid, kScoreThreads, 0, st>>>(*b, H);
+        else if (H <= 512) score_kernel<2><<<grid, kScoreThreads, 0, st>>>(*b, H);
+        else score_kernel<4><<<grid, kScoreThreads, 0, st>>>(*b, H);
     }
     FNP_LAUNCH_CHECK();
     return FNP_OK;

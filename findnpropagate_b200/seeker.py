@@ -280,9 +280,13 @@ class SeekerEngine:
         base = dev.data_ptr()
         return {k: base + o for k, o in offs.items()}
 
-    def execute(self, plan, points_dev, nms_thresh=None, gt=None, recall_thresh=(0.3, 0.5, 0.7), slot=0):
+    def execute(self, plan, points_dev, nms_thresh=None, gt=None, recall_thresh=(0.3, 0.5, 0.7), slot=0,
+                points_ready=None):
         """Enqueue the whole batch on the current stream.  points_dev: CUDA float32 tensor
-        holding the rows of all frames back to back.  Returns a handle for `finish`."""
+        holding the rows of all frames back to back.  points_ready: optional CUDA event the
+        kernels must wait for (the H2D copy of the points on another stream); the small
+        metadata upload is issued *before* that wait so that it does not queue behind the
+        next step's point copy in the H2D engine.  Returns a handle for `finish`."""
         _lib.require_cuda(points_dev)
         assert points_dev.dtype == torch.float32 and points_dev.is_contiguous()
         F, B, H, M = plan["F"], plan["B"], self.H, self.M
@@ -290,10 +294,12 @@ class SeekerEngine:
         with torch.cuda.device(dev):
             stream = _lib.current_stream(dev)
             meta = self._upload_meta(plan, stream, slot)
+            if points_ready is not None:
+                torch.cuda.current_stream(dev).wait_event(points_ready)
             chunks = -(-H // (128 * (1 if H <= 128 else 2 if H <= 512 else 4)))
-            cap = int(max(plan["total_rows"] * self.pts_factor, 4096))
+            cap = int(max(plan["total_rows"] * self.pts_factor, 4096) + 2 * F + 2) & ~1
             if self.fixed_split_points is not None:
-                sp = int(self.fixed_split_points)
+                sp = max(2, (int(self.fixed_split_points) + 1) & ~1)      # splits start on a pair boundary
             else:
                 # ~32 work items per SM: items small enough to balance, large enough to amortise
                 sp = plan["total_rows"] // (self.n_sms * 32)
@@ -482,12 +488,20 @@ class SeekerEngine:
         def view(name, dtype, shape):
             n = int(np.prod(shape)) * torch.tensor([], dtype=dtype).element_size()
             return self.arena.bufs[name][:n].view(dtype).view(*shape).cpu().numpy()
-        pt_start = view("cand_pt_start", torch.int32, (F + 1,))
-        total = int(pt_start[-1])
+        padded_start = view("cand_pt_start", torch.int32, (F + 1,))
+        total = int(padded_start[-1])
+        # pair-interleaved records {x0,x1,y0,y1,z0,z1,d0,d1} -> one (x,y,z,d) row per point, padding removed
+        rec = view("frustum_pts", torch.float32, (total // 2, 4, 2))
+        rows = rec.transpose(0, 2, 1).reshape(total, 4)
+        idx = view("frustum_idx", torch.int32, (total,))
+        npts = handle["out_host"].numpy()[:handle["out_bytes"]].view(np.int32)[10 * F:11 * F]
+        sel = np.concatenate([np.arange(padded_start[f], padded_start[f] + npts[f]) for f in range(F)]
+                             + [np.zeros(0, np.int64)]).astype(np.int64)
+        pt_start = np.concatenate([[0], np.cumsum(npts)]).astype(np.int32)
         return dict(
             pt_start=pt_start,
-            frustum_pts=view("frustum_pts", torch.float32, (total, 4)),
-            frustum_idx=view("frustum_idx", torch.int32, (total,)),
+            frustum_pts=np.ascontiguousarray(rows[sel]),
+            frustum_idx=np.ascontiguousarray(idx[sel]),
             stats=view("cand_stats", torch.float32, (F, _lib.STATS_FLOATS)),
             centres=view("centres", torch.float32, (F, M, 3)),
             hyp_boxes=view("hyp_boxes_dbg", torch.float32, (F, H, 7)),

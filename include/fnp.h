@@ -135,9 +135,13 @@ typedef struct fnp_seeker_batch {
     int32_t mask_words;              /* = fnp_seeker_mask_words(max_cands_per_frame)        */
     int32_t *cand_npts;              /* (F)   P_f                                          */
     int32_t *cand_pt_start;          /* (F+1) start of each frustum in frustum_pts         */
-    float *frustum_pts;              /* (pts_capacity,4) x,y,z,depth of the frustum points */
+    float *frustum_pts;              /* (pts_capacity/2, 8) frustum points, pair-interleaved: points 2p
+                                        and 2p+1 of the buffer share the record {x0,x1,y0,y1,z0,z1,
+                                        d0,d1} (xyz of the unprojected point, camera depth); every
+                                        frustum starts at an even point index, so cand_pt_start[f+1]
+                                        - cand_pt_start[f] = cand_npts[f] rounded up to even  */
     int32_t *frustum_idx;            /* (pts_capacity) source row within the frame, or NULL */
-    int64_t pts_capacity;
+    int64_t pts_capacity;            /* points; even */
     float *cand_stats;               /* (F,40): [0]dmin [1]dmax [2]dcentre [3..5]pmin [6..8]pmax
                                         [9]n_points [16..39] clamped frustum corners (8,3)  */
     float *centres;                  /* (F,M,3) */
@@ -149,7 +153,7 @@ typedef struct fnp_seeker_batch {
     float *hyp_boxes_dbg;            /* (F,H,7) all hypothesis boxes by original index, or NULL */
     float *hyp_iou_dbg;              /* (F,H) or NULL                                      */
     uint8_t *hyp_valid_dbg;          /* (F,H) or NULL                                      */
-    int32_t split_points;            /* points per scoring work item (point split)         */
+    int32_t split_points;            /* points per scoring work item (point split); even   */
     int32_t max_items;               /* capacity of `items` = grid of the scoring kernel   */
     int32_t max_count_rows;          /* capacity (rows) of `counts`                        */
     int32_t *cand_item_start;        /* (F+1) first work item of each frustum              */
@@ -162,8 +166,9 @@ typedef struct fnp_seeker_batch {
     float *out_score;                /* (F)   its second-stage score                       */
     int32_t *out_best;               /* (F)   compacted index of the winner, -1 if none    */
     int32_t *out_count;              /* (F)   point count of the winner                    */
-    int32_t *status;                 /* (4)   [0] bit0: frustum_pts overflow (needed points in [1]),
-                                        bit1: items/counts overflow ([2] items, [3] rows needed) */
+    int32_t *status;                 /* (8)   [0] bit0: frustum_pts overflow (needed points in [1]),
+                                        bit1: items/counts overflow ([2] items, [3] rows needed);
+                                        [4] work-item counter of the scoring kernel; [5..7] spare */
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024

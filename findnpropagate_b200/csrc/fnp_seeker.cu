@@ -684,10 +684,16 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
 constexpr int kScoreThreads = 128;
 constexpr int kScoreTile = 512;  // points per TMA stage (8 KB)
 
-__host__ __device__ inline int hyps_per_cta(int H) { return kScoreThreads * (H <= 128 ? 1 : (H <= 512 ? 2 : 4)); }
+constexpr int kScoreKMax = 4;                                   // hypotheses per thread in a full chunk
+constexpr int kScoreChunk = kScoreThreads * kScoreKMax;         // hypotheses of a full chunk
+
+// The nv valid hypotheses of a frustum are cut into nv / 512 full chunks (4 per thread) and one
+// remainder chunk of ceil(rem / 128) per thread, so that the padding stays below 128 hypotheses
+// per frustum (with 512-wide chunks only, the padded work was 1.42x the useful work on cfg2).
+__host__ __device__ inline int score_chunks(int nv) { return (nv + kScoreChunk - 1) / kScoreChunk; }
 
 // Work items of the scoring stage.  Frustum f with P_f points and nv_f valid hypotheses is cut
-// into S_f = ceil(P_f / split_points) point splits x ceil(nv_f / hyps_per_cta) hypothesis
+// into S_f = ceil(P_f / split_points) point splits x score_chunks(nv_f) hypothesis
 // chunks; every (split, chunk) pair is one CTA-sized item, so the largest frustums no longer
 // set the kernel's duration.  Split s of frustum f writes its partial counts to row
 // split_row[f] + s of `counts`; select_kernel adds the S_f rows (a fixed-order integer
@@ -697,7 +703,6 @@ __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch
     __shared__ int s_warp_i[32], s_warp_r[32];
     __shared__ int s_carry_i, s_carry_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hpc = hyps_per_cta(H);
     if (tid == 0) { s_carry_i = 0; s_carry_r = 0; }
     __syncthreads();
     for (int base = 0; base < b.n_cands; base += 1024) {
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch
             const int np = b.cand_npts[f], nv = b.hyp_nvalid[f];
             if (np > 0 && nv > 0) {
                 rows = (np + b.split_points - 1) / b.split_points;
-                items = rows * ((nv + hpc - 1) / hpc);
+                items = rows * score_chunks(nv);
             }
         }
         int inc_i = items, inc_r = rows;
@@ -754,10 +759,14 @@ __global__ void __launch_bounds__(128) write_items_kernel(const fnp_seeker_batch
     const int f = blockIdx.x;
     const int i0 = b.cand_item_start[f], n = b.cand_item_start[f + 1] - i0;
     if (n <= 0 || (b.status[0] & 2)) return;
-    const int hpc = hyps_per_cta(H);
-    const int nchunks = (b.hyp_nvalid[f] + hpc - 1) / hpc;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)   // split-major: neighbours share a point tile
-        reinterpret_cast<int4 *>(b.items)[i0 + i] = make_int4(f, i % nchunks, i / nchunks, 0);
+    const int nv = b.hyp_nvalid[f];
+    const int nchunks = score_chunks(nv);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // split-major: neighbours share a point tile
+        const int c = i % nchunks;
+        const int left = nv - c * kScoreChunk;             // hypotheses from this chunk's base on
+        const int K = left >= kScoreChunk ? kScoreKMax : (left + kScoreThreads - 1) / kScoreThreads;
+        reinterpret_cast<int4 *>(b.items)[i0 + i] = make_int4(f, c * kScoreChunk, i / nchunks, K);
+    }
 }
 
 // Packed-fp32x2 form of the in-box predicate for TWO points against one hypothesis.  Same
@@ -816,112 +825,126 @@ __device__ __forceinline__ void count_pair(int &cnt, unsigned long long xx, unsi
 // counter.  A CTA keeps K hypotheses per thread in registers for the whole item and streams
 // the item's points through a two-stage shared-memory ring filled by TMA bulk copies
 // (cp.async.bulk + mbarrier complete_tx); every thread reads every staged pair record with
-// broadcast LDS.128 + LDS.64.
+// broadcast LDS.128.
+struct ScoreSmem {
+    float4 tile[2][kScoreTile / 2][2];   // [stage][pair][x0x1y0y1 | z0z1d0d1]
+    uint64_t bar[2];
+    int item;
+};
+
 template <int K>
+__device__ __forceinline__ void score_item(const fnp_seeker_batch &b, const int H, ScoreSmem &S, unsigned &it,
+                                           const int f, const int h_base, const int split)
+{
+    const int tid = threadIdx.x;
+    const int nv = b.hyp_nvalid[f];
+    const int npts = b.cand_npts[f];
+    const int p0 = split * b.split_points;                    // even: split_points is even
+    const int n = min(npts, p0 + b.split_points) - p0;
+    const int n_rec = (n + 1) >> 1;                           // pair records of this item
+    const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
+    constexpr int kRecTile = kScoreTile / 2;
+    const int n_tiles = (n_rec + kRecTile - 1) / kRecTile;
+
+    if (tid == 0) {
+        for (int t = 0; t < 2 && t < n_tiles; t++) {
+            const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - t * kRecTile) * 32u;
+            const unsigned st = (it + t) & 1u;
+            mbar_expect_tx(&S.bar[st], bytes);
+            tma_load_1d(S.tile[st], grec + (size_t)t * kRecTile * 2, bytes, &S.bar[st]);
+        }
+    }
+
+    HypPacked hp[K];
+    int cnt[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = h_base + k * kScoreThreads + tid;
+        cnt[k] = 0;
+        float4 a = make_float4(0.f, 0.f, 0.f, -1.f), c = make_float4(1.f, 0.f, -1.f, -1.f);   // never inside
+        if (r < nv) {
+            const float4 *src = reinterpret_cast<const float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
+            a = __ldg(src); c = __ldg(src + 1);
+        }
+        hp[k].cx2 = dup2(a.x); hp[k].cy2 = dup2(a.y); hp[k].cz2 = dup2(a.z); hp[k].hz = a.w;
+        hp[k].cosa2 = dup2(c.x); hp[k].nsina2 = dup2(-c.y); hp[k].sina2 = dup2(c.y);
+        hp[k].tx = c.z; hp[k].ty = c.w;
+    }
+
+    for (int t = 0; t < n_tiles; t++, it++) {
+        const unsigned st = it & 1u;
+        mbar_wait(&S.bar[st], (it >> 1) & 1u);
+        const int m_pts = min(kScoreTile, n - t * kScoreTile);   // points in this tile
+        const int m_full = m_pts >> 1;                            // complete pairs
+        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(S.tile[st]);
+        int i = 0;
+        for (; i + 2 <= m_full; i += 2) {
+            const ulonglong2 xy0 = tp[2 * i], zd0 = tp[2 * i + 1];
+            const ulonglong2 xy1 = tp[2 * i + 2], zd1 = tp[2 * i + 3];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                count_pair(cnt[k], xy0.x, xy0.y, zd0.x, hp[k]);
+                count_pair(cnt[k], xy1.x, xy1.y, zd1.x, hp[k]);
+            }
+        }
+        for (; i < m_full; i++) {
+            const ulonglong2 xy = tp[2 * i], zd = tp[2 * i + 1];
+#pragma unroll
+            for (int k = 0; k < K; k++) count_pair(cnt[k], xy.x, xy.y, zd.x, hp[k]);
+        }
+        if (m_pts & 1) {   // last point of the frustum: lane 0 of a half-filled record
+            const float4 xy = S.tile[st][m_full][0], zd = S.tile[st][m_full][1];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                BoxPrep bp;
+                bp.cx = lo_half(hp[k].cx2); bp.cy = lo_half(hp[k].cy2); bp.cz = lo_half(hp[k].cz2);
+                bp.cosa = lo_half(hp[k].cosa2); bp.sina = lo_half(hp[k].sina2);
+                bp.hz = hp[k].hz; bp.tx = hp[k].tx; bp.ty = hp[k].ty;
+                count_if(cnt[k], in_box(xy.x, xy.z, zd.x, bp));
+            }
+        }
+        __syncthreads();  // everyone is done with stage st
+        if (tid == 0 && t + 2 < n_tiles) {
+            const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - (t + 2) * kRecTile) * 32u;
+            mbar_expect_tx(&S.bar[st], bytes);
+            tma_load_1d(S.tile[st], grec + (size_t)(t + 2) * kRecTile * 2, bytes, &S.bar[st]);
+        }
+    }
+
+    int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int r = h_base + k * kScoreThreads + tid;
+        if (r < nv) out[r] = cnt[k];
+    }
+}
+
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_batch b, const int H)
 {
-    __shared__ __align__(128) float4 s_tile[2][kScoreTile / 2][2];   // [stage][pair][x0x1y0y1 | z0z1d0d1]
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_item;
+    __shared__ __align__(128) ScoreSmem S;
 
     const int tid = threadIdx.x;
     if (b.status[0] & 2) return;
     const int n_items = b.status[2];
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
         mbar_fence_init();
     }
     unsigned it = 0;   // tiles consumed so far by this CTA: stage = it & 1, parity = (it >> 1) & 1
 
     for (;;) {
-        __syncthreads();                       // everyone is done with the previous item (and s_item)
-        if (tid == 0) s_item = atomicAdd(&b.status[4], 1);
+        __syncthreads();                       // everyone is done with the previous item (and S.item)
+        if (tid == 0) S.item = atomicAdd(&b.status[4], 1);
         __syncthreads();
-        const int item_id = s_item;
+        const int item_id = S.item;
         if (item_id >= n_items) break;
-        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];
-        const int f = item.x, chunk = item.y, split = item.z;
-        const int nv = b.hyp_nvalid[f];
-        const int h_base = chunk * (kScoreThreads * K);
-        const int npts = b.cand_npts[f];
-        const int p0 = split * b.split_points;                    // even: split_points is even
-        const int n = min(npts, p0 + b.split_points) - p0;
-        const int n_rec = (n + 1) >> 1;                           // pair records of this item
-        const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
-        constexpr int kRecTile = kScoreTile / 2;
-        const int n_tiles = (n_rec + kRecTile - 1) / kRecTile;
-
-        if (tid == 0) {
-            for (int t = 0; t < 2 && t < n_tiles; t++) {
-                const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - t * kRecTile) * 32u;
-                const unsigned st = (it + t) & 1u;
-                mbar_expect_tx(&s_bar[st], bytes);
-                tma_load_1d(s_tile[st], grec + (size_t)t * kRecTile * 2, bytes, &s_bar[st]);
-            }
-        }
-
-        HypPacked hp[K];
-        int cnt[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const int r = h_base + k * kScoreThreads + tid;
-            cnt[k] = 0;
-            float4 a = make_float4(0.f, 0.f, 0.f, -1.f), c = make_float4(1.f, 0.f, -1.f, -1.f);   // never inside
-            if (r < nv) {
-                const float4 *src = reinterpret_cast<const float4 *>(b.hyp_prep + ((size_t)f * H + r) * 8);
-                a = __ldg(src); c = __ldg(src + 1);
-            }
-            hp[k].cx2 = dup2(a.x); hp[k].cy2 = dup2(a.y); hp[k].cz2 = dup2(a.z); hp[k].hz = a.w;
-            hp[k].cosa2 = dup2(c.x); hp[k].nsina2 = dup2(-c.y); hp[k].sina2 = dup2(c.y);
-            hp[k].tx = c.z; hp[k].ty = c.w;
-        }
-
-        for (int t = 0; t < n_tiles; t++, it++) {
-            const unsigned st = it & 1u;
-            mbar_wait(&s_bar[st], (it >> 1) & 1u);
-            const int m_pts = min(kScoreTile, n - t * kScoreTile);   // points in this tile
-            const int m_full = m_pts >> 1;                            // complete pairs
-            const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(s_tile[st]);
-            int i = 0;
-            for (; i + 2 <= m_full; i += 2) {
-                const ulonglong2 xy0 = tp[2 * i], zd0 = tp[2 * i + 1];
-                const ulonglong2 xy1 = tp[2 * i + 2], zd1 = tp[2 * i + 3];
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    count_pair(cnt[k], xy0.x, xy0.y, zd0.x, hp[k]);
-                    count_pair(cnt[k], xy1.x, xy1.y, zd1.x, hp[k]);
-                }
-            }
-            for (; i < m_full; i++) {
-                const ulonglong2 xy = tp[2 * i], zd = tp[2 * i + 1];
-#pragma unroll
-                for (int k = 0; k < K; k++) count_pair(cnt[k], xy.x, xy.y, zd.x, hp[k]);
-            }
-            if (m_pts & 1) {   // last point of the frustum: lane 0 of a half-filled record
-                const float4 xy = s_tile[st][m_full][0], zd = s_tile[st][m_full][1];
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    BoxPrep bp;
-                    bp.cx = lo_half(hp[k].cx2); bp.cy = lo_half(hp[k].cy2); bp.cz = lo_half(hp[k].cz2);
-                    bp.cosa = lo_half(hp[k].cosa2); bp.sina = lo_half(hp[k].sina2);
-                    bp.hz = hp[k].hz; bp.tx = hp[k].tx; bp.ty = hp[k].ty;
-                    count_if(cnt[k], in_box(xy.x, xy.z, zd.x, bp));
-                }
-            }
-            __syncthreads();  // everyone is done with stage st
-            if (tid == 0 && t + 2 < n_tiles) {
-                const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - (t + 2) * kRecTile) * 32u;
-                mbar_expect_tx(&s_bar[st], bytes);
-                tma_load_1d(s_tile[st], grec + (size_t)(t + 2) * kRecTile * 2, bytes, &s_bar[st]);
-            }
-        }
-
-        int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const int r = h_base + k * kScoreThreads + tid;
-            if (r < nv) out[r] = cnt[k];
+        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, first hypothesis, split, K
+        switch (item.w) {
+            case 1: score_item<1>(b, H, S, it, item.x, item.y, item.z); break;
+            case 2: score_item<2>(b, H, S, it, item.x, item.y, item.z); break;
+            case 3: score_item<3>(b, H, S, it, item.x, item.y, item.z); break;
+            default: score_item<4>(b, H, S, it, item.x, item.y, item.z); break;
         }
     }
 }
@@ -1109,11 +1132,9 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
             cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
         }
         // persistent CTAs: a whole number of CTAs per SM (148 SMs on B200), capped by the item capacity
-        const int per_sm = (H <= 128) ? 12 : (H <= 512) ? 8 : 5;
+        const int per_sm = 6;
         const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
-        if (H <= 128) score_kernel<1><<<grid, kScoreThreads, 0, st>>>(*b, H);
-        else if (H <= 512) score_kernel<2><<<grid, kScoreThreads, 0, st>>>(*b, H);
-        else score_kernel<4><<<grid, kScoreThreads, 0, st>>>(*b, H);
+        score_kernel<<<grid, kScoreThreads, 0, st>>>(*b, H);
     }
     FNP_LAUNCH_CHECK();
     return FNP_OK;

@@ -296,7 +296,7 @@ class SeekerEngine:
             meta = self._upload_meta(plan, stream, slot)
             if points_ready is not None:
                 torch.cuda.current_stream(dev).wait_event(points_ready)
-            chunks = -(-H // (128 * (1 if H <= 128 else 2 if H <= 512 else 4)))
+            chunks = -(-H // 512)      # hypothesis chunks per frustum (csrc: score_chunks)
             cap = int(max(plan["total_rows"] * self.pts_factor, 4096) + 2 * F + 2) & ~1
             if self.fixed_split_points is not None:
                 sp = max(2, (int(self.fixed_split_points) + 1) & ~1)      # splits start on a pair boundary

@@ -158,7 +158,8 @@ typedef struct fnp_seeker_batch {
     int32_t max_count_rows;          /* capacity (rows) of `counts`                        */
     int32_t *cand_item_start;        /* (F+1) first work item of each frustum              */
     int32_t *cand_split_row;         /* (F+1) first partial-count row of each frustum      */
-    int32_t *items;                  /* (max_items,4) work items: frustum, chunk, split, 0 */
+    int32_t *items;                  /* (max_items,4) work items: frustum, first hypothesis, split,
+                                        hypotheses per thread (1..4)                         */
     int32_t *counts;                 /* (max_count_rows,H) per-split partial counts; after
                                         stage 3 the first row of a frustum holds the totals */
     /* ---- outputs ---- */

@@ -38,7 +38,8 @@ class SeekerBatch(C.Structure):
         ("cam_mats", _vp), ("frame_cand_start", _vp), ("cam_cand_start", _vp), ("cand_frame", _vp), ("cand_cam", _vp),
         ("cand_label", _vp), ("cand_box2d", _vp), ("base_boxes", _vp), ("base_corners", _vp),
         ("mags", _vp),
-        ("tile_counts", _vp), ("pt_mask", _vp), ("mask_words", C.c_int32), ("cand_npts", _vp), ("cand_pt_start", _vp), ("frustum_pts", _vp),
+        ("tile_counts", _vp), ("tile_dst", _vp), ("tile_base", _vp), ("cell_masks", _vp), ("mask_words", C.c_int32),
+        ("stage_pts", _vp), ("stage_idx", _vp), ("cand_npts", _vp), ("cand_pt_start", _vp), ("frustum_pts", _vp),
         ("frustum_idx", _vp), ("pts_capacity", C.c_int64), ("cand_stats", _vp), ("centres", _vp),
         ("hyp_prep", _vp), ("hyp_index", _vp), ("hyp_iou", _vp), ("hyp_nvalid", _vp),
         ("hyp_boxes_dbg", _vp), ("hyp_iou_dbg", _vp), ("hyp_valid_dbg", _vp),
@@ -75,10 +76,12 @@ for _n in ("fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses
     getattr(lib, _n).argtypes = [C.POINTER(SeekerCfg), C.POINTER(SeekerBatch), _vp]
 lib.fnp_seeker_mask_words.restype = _i
 lib.fnp_seeker_mask_words.argtypes = [_i]
+lib.fnp_seeker_cell_mask_bytes.restype = C.c_size_t
+lib.fnp_seeker_cell_mask_bytes.argtypes = [C.POINTER(SeekerCfg), _i, _i]
 lib.fnp_seg_nms_rotated.restype = _i
 lib.fnp_seg_nms_rotated.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]
 lib.fnp_recall_counters.restype = _i
-lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _vp, _vp]
+lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(_f), _i, _vp, _vp]
 
 lib.fnp_host_select_candidates.restype = _i
 lib.fnp_host_select_candidates.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
@@ -91,7 +94,7 @@ EXPORTED = [
     "fnp_version", "fnp_points_in_boxes", "fnp_count_in_boxes", "fnp_boxes_overlap_bev",
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
-    "fnp_seeker_score", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words",
+    "fnp_seeker_score", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates",
 ]
 

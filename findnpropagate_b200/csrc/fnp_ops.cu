@@ -217,6 +217,17 @@ __device__ float box_overlap(const RBox &A, const RBox &B)
     return __fmul_rn(fabsf(area), 0.5f);
 }
 
+// True only when box_overlap(A, B) is exactly 0: the centres are further apart than both half
+// diagonals plus a slack that covers the 1e-2 corner margin of in_box2d and all rounding, so the
+// polygon clipper would find no edge intersection and no contained corner (cnt == 0 -> area 0).
+__device__ __forceinline__ bool surely_disjoint(const RBox &A, const RBox &B)
+{
+    const float ddx = A.cx - B.cx, ddy = A.cy - B.cy;
+    const float ra = A.tx + A.ty, rb = B.tx + B.ty;        // >= half diagonal + margin (L1 >= L2)
+    const float r = ra + rb + 0.1f;
+    return ddx * ddx + ddy * ddy > 1.0001f * r * r;
+}
+
 __device__ __forceinline__ float iou_bev(const RBox &A, const RBox &B)
 {
     const float ov = box_overlap(A, B);
@@ -374,14 +385,16 @@ __global__ void __launch_bounds__(256) seg_nms_kernel(const float *__restrict__ 
     }
     for (int i = threadIdx.x; i < cb; i += blockDim.x) s_remv[i] = 0ULL;
     __syncthreads();
-    // bitmask: one (row, 64-column word) per thread iteration
-    for (int w = threadIdx.x; w < n * cb; w += blockDim.x) {
-        const int i = w / cb, cblk = w - i * cb;
-        unsigned long long bits = 0ULL;
-        const int j0 = cblk * 64, j1 = min(n, j0 + 64);
-        for (int j = max(j0, i + 1); j < j1; j++)
-            if (s_lab[i] >= 0 && s_lab[i] == s_lab[j] && iou_bev(s_rb[i], s_rb[j]) > thresh) bits |= 1ULL << (j - j0);
-        s_mask[w] = bits;
+    for (int w = threadIdx.x; w < n * cb; w += blockDim.x) s_mask[w] = 0ULL;
+    __syncthreads();
+    // bitmask, one (i, j) pair per thread iteration (the upper triangle of an n x n grid);
+    // far-apart pairs are dismissed without running the polygon clipper
+    const bool prefilter = thresh >= 0.f;
+    for (int p = threadIdx.x; p < n * n; p += blockDim.x) {
+        const int i = p / n, j = p - i * n;
+        if (j <= i || s_lab[i] < 0 || s_lab[i] != s_lab[j]) continue;
+        if (prefilter && surely_disjoint(s_rb[i], s_rb[j])) continue;
+        if (iou_bev(s_rb[i], s_rb[j]) > thresh) atomicOr(&s_mask[(size_t)i * cb + (j >> 6)], 1ULL << (j & 63));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -399,12 +412,13 @@ __global__ void __launch_bounds__(256) seg_nms_kernel(const float *__restrict__ 
 // ======================================================================================
 // Recall counters
 // ======================================================================================
-__global__ void __launch_bounds__(128) recall_kernel(const float *__restrict__ pred, const int32_t *__restrict__ pred_valid,
+__global__ void __launch_bounds__(256) recall_kernel(const float *__restrict__ pred, const int32_t *__restrict__ pred_valid,
                                                      const int32_t *__restrict__ pred_start,
                                                      const float *__restrict__ gt, const int32_t *__restrict__ gt_start,
                                                      int n_thresh, float t0, float t1, float t2, float t3, float t4,
                                                      float t5, float t6, float t7, long long *__restrict__ counters)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
     const float thr[8] = {t0, t1, t2, t3, t4, t5, t6, t7};
     const int fr = blockIdx.x;
     const int p0 = pred_start[fr], K = pred_start[fr + 1] - p0;
@@ -419,40 +433,54 @@ __global__ void __launch_bounds__(128) recall_kernel(const float *__restrict__ p
         G--;
     }
     if (G == 0) return;
+    RBox *s_g = reinterpret_cast<RBox *>(smem);          // [G]
+    RBox *s_p = s_g + G;                                  // [K]
+    int *s_best = reinterpret_cast<int *>(s_p + K);       // [G] float bits; IoU >= 0 orders like int
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        s_g[i] = prep_rbox(gt + (size_t)(g0 + i) * 8);
+        s_best[i] = __float_as_int(-1.f);
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        s_p[i] = prep_rbox(pred + (size_t)(p0 + i) * 7);
+        if (pred_valid && pred_valid[p0 + i] < 0) s_p[i].pad = -1.f;   // not a proposal
+    }
+    __syncthreads();
+    // one (gt, proposal) pair per thread iteration: boxes_iou3d_gpu (iou3d_nms_utils.py:48-81),
+    // elementwise fp32 like torch; pairs whose BEV overlap is provably 0 have IoU 0
+    for (int q = threadIdx.x; q < G * K; q += blockDim.x) {
+        const int gi = q / K, k = q - gi * K;
+        if (s_p[k].pad < 0.f) continue;
+        float iou = 0.f;
+        if (!surely_disjoint(s_p[k], s_g[gi])) {
+            const float *g = gt + (size_t)(g0 + gi) * 8;
+            const float *p = pred + (size_t)(p0 + k) * 7;
+            const float ov_bev = box_overlap(s_p[k], s_g[gi]);
+            const float g_hi = __fadd_rn(g[2], __fmul_rn(g[5], 0.5f)), g_lo = __fsub_rn(g[2], __fmul_rn(g[5], 0.5f));
+            const float p_hi = __fadd_rn(p[2], __fmul_rn(p[5], 0.5f)), p_lo = __fsub_rn(p[2], __fmul_rn(p[5], 0.5f));
+            const float ov_h = fmaxf(__fsub_rn(fminf(p_hi, g_hi), fmaxf(p_lo, g_lo)), 0.f);
+            const float ov3 = __fmul_rn(ov_bev, ov_h);
+            const float vg = __fmul_rn(__fmul_rn(g[3], g[4]), g[5]);
+            const float vp = __fmul_rn(__fmul_rn(p[3], p[4]), p[5]);
+            iou = __fdiv_rn(ov3, fmaxf(__fsub_rn(__fadd_rn(vp, vg), ov3), 1e-6f));
+        }
+        if (iou >= 0.f) atomicMax(&s_best[gi], __float_as_int(iou));
+    }
+    __syncthreads();
     long long local[5 + 5 * 8];
     for (int i = 0; i < 5 + 5 * 8; i++) local[i] = 0;
     for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
-        const float *g = gt + (size_t)(g0 + gi) * 8;
-        const int lab = (int)g[7];
+        const int lab = (int)gt[(size_t)(g0 + gi) * 8 + 7];
         const bool k3 = (lab == 1 || lab == 8 || lab == 9);
         const bool k6 = k3 || lab == 3 || lab == 5 || lab == 6;
         local[0]++;
         local[1] += k3; local[2] += k6; local[3] += !k6; local[4] += !k3;
-        if (K > 0) {
-            const RBox gb = prep_rbox(g);
-            const float g_hi = __fadd_rn(g[2], __fmul_rn(g[5], 0.5f)), g_lo = __fsub_rn(g[2], __fmul_rn(g[5], 0.5f));
-            const float vg = __fmul_rn(__fmul_rn(g[3], g[4]), g[5]);
-            float best = -1.f;
-            for (int k = 0; k < K; k++) {
-                if (pred_valid && pred_valid[p0 + k] < 0) continue;
-                const float *p = pred + (size_t)(p0 + k) * 7;
-                const RBox pb = prep_rbox(p);
-                // boxes_iou3d_gpu (iou3d_nms_utils.py:48-81), elementwise fp32 like torch
-                const float ov_bev = box_overlap(pb, gb);
-                const float p_hi = __fadd_rn(p[2], __fmul_rn(p[5], 0.5f)), p_lo = __fsub_rn(p[2], __fmul_rn(p[5], 0.5f));
-                const float ov_h = fmaxf(__fsub_rn(fminf(p_hi, g_hi), fmaxf(p_lo, g_lo)), 0.f);
-                const float ov3 = __fmul_rn(ov_bev, ov_h);
-                const float vp = __fmul_rn(__fmul_rn(p[3], p[4]), p[5]);
-                const float iou = __fdiv_rn(ov3, fmaxf(__fsub_rn(__fadd_rn(vp, vg), ov3), 1e-6f));
-                best = fmaxf(best, iou);
+        const float best = __int_as_float(s_best[gi]);
+        for (int t = 0; t < n_thresh; t++)
+            if (best > thr[t]) {
+                local[5 + 5 * t]++;
+                local[5 + 5 * t + 1] += k3; local[5 + 5 * t + 2] += k6;
+                local[5 + 5 * t + 3] += !k6; local[5 + 5 * t + 4] += !k3;
             }
-            for (int t = 0; t < n_thresh; t++)
-                if (best > thr[t]) {
-                    local[5 + 5 * t]++;
-                    local[5 + 5 * t + 1] += k3; local[5 + 5 * t + 2] += k6;
-                    local[5 + 5 * t + 3] += !k6; local[5 + 5 * t + 4] += !k3;
-                }
-        }
     }
     for (int i = 0; i < 5 + 5 * n_thresh; i++) {
         long long v = local[i];
@@ -609,16 +637,19 @@ extern "C" int fnp_seg_nms_rotated(const float *boxes, const int32_t *label, con
 }
 
 extern "C" int fnp_recall_counters(const float *pred, const int32_t *pred_valid, const int32_t *pred_start, const float *gt,
-                                   const int32_t *gt_start, int n_frames, const float *thresh_host, int n_thresh,
-                                   long long *counters, void *stream)
+                                   const int32_t *gt_start, int n_frames, int max_pred_per_frame, int max_gt_per_frame,
+                                   const float *thresh_host, int n_thresh, long long *counters, void *stream)
 {
-    if (n_frames < 0 || n_thresh < 0 || n_thresh > 8) return FNP_EINVAL;
-    if (n_frames == 0) return FNP_OK;
+    if (n_frames < 0 || n_thresh < 0 || n_thresh > 8 || max_pred_per_frame < 0 || max_gt_per_frame < 0) return FNP_EINVAL;
+    if (n_frames == 0 || max_gt_per_frame == 0) return FNP_OK;
     if (!pred_start || !gt_start || !counters || (n_thresh && !thresh_host)) return FNP_EINVAL;
     float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n_thresh; i++) t[i] = thresh_host[i];
-    recall_kernel<<<n_frames, 128, 0, (cudaStream_t)stream>>>(pred, pred_valid, pred_start, gt, gt_start, n_thresh, t[0], t[1], t[2],
-                                                              t[3], t[4], t[5], t[6], t[7], counters);
+    const size_t smem = (size_t)(max_pred_per_frame + max_gt_per_frame) * sizeof(RBox) + (size_t)max_gt_per_frame * 4 + 16;
+    if (smem > 200 * 1024) return FNP_EINVAL;
+    cudaFuncSetAttribute(recall_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    recall_kernel<<<n_frames, 256, smem, (cudaStream_t)stream>>>(pred, pred_valid, pred_start, gt, gt_start, n_thresh, t[0], t[1],
+                                                                 t[2], t[3], t[4], t[5], t[6], t[7], counters);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }

@@ -20,14 +20,19 @@ constexpr int kStatsFloats = 40;
 static_assert(FNP_CULL_TILE % kCullThreads == 0, "tile must be a whole number of sub-tiles");
 
 // ======================================================================================
-// Stage 1: projection + frustum cull + ordered compaction, two passes over the points
-//   pass A (cull_mask_kernel):  per point a bitmask of the frame's candidates whose frustum
-//       contains it (W 32-bit words), per tile the population of every candidate;
-//   scans (scan_tiles_kernel, scan_cands_kernel): exclusive prefixes -> where every tile
-//       writes inside every frustum;
-//   pass B (cull_write_kernel): reads the masks, re-projects only member points into their
-//       camera and scatters (x,y,z,depth) of the *unprojected* point in input order.
-// Tiles without members cost pass B one mask read and nothing else.
+// Stage 1: projection + frustum cull + ordered compaction
+//   cell_table_kernel:  per (frame, camera rank) a grid of 64-px image cells, each holding the
+//       bitmask of the rank's candidates whose 2D box touches the cell (conservative);
+//   cull_stage_kernel:  reads every point ONCE.  Per camera a division-free "certainly off
+//       this image" test on packed point pairs, the reference's exact IEEE u, v only for the
+//       survivors, one cell lookup, exact box tests for the few bits set there.  Membership
+//       stays in registers; ballot/popc give per-(warp, candidate) populations, one atomicAdd
+//       per tile reserves the tile's slice of a staging buffer, and member points are written
+//       there as (x, y, z, depth) of the *unprojected* point, candidate-major, in input order;
+//   scans (scan_tiles_kernel, scan_cands_kernel): exclusive prefixes of the per-tile
+//       populations -> where every tile's slice lands inside every frustum;
+//   cull_gather_kernel: copies the slices to their final, input-ordered position in the
+//       pair-interleaved frustum buffer (deterministic, whatever order the tiles ran in).
 // ======================================================================================
 // Frustum points are stored pair-interleaved: points 2p and 2p+1 of the buffer share one 32-byte
 // record {x0,x1, y0,y1, z0,z1, d0,d1}, so that the scoring kernel reads (x0,x1) / (y0,y1) /
@@ -37,25 +42,19 @@ __device__ __forceinline__ size_t pair_slot(int64_t i) { return (size_t)(i >> 1)
 
 __device__ __constant__ int kImageOrder[6] = {2, 0, 1, 5, 3, 4};   // frustum_proposals_v1.py:201
 
-struct CullSmem {
+constexpr int kCellPx = 64;          // cell edge of the candidate lookup grid, pixels
+constexpr float kCellInv = 1.0f / kCellPx;
+
+__host__ __device__ inline int cell_cols(float img_w) { return (int)((img_w + kCellPx - 1) / kCellPx); }
+__host__ __device__ inline int cell_rows(float img_h) { return (int)((img_h + kCellPx - 1) / kCellPx); }
+
+struct alignas(16) CullSmem {
     float cam[6][24];       // by camera index
     int cs[8];              // candidate range per camera RANK, local to the frame: [cs[r], cs[r+1])
-    float4 uni[6];          // per rank: union of the rank's 2D boxes (x1,y1,x2,y2)
+    int tile_base;          // first staging slot of this tile
+    int tile_total;
 };
-
-// rows [first, first+n) of the point table -> shared memory (generic row stride)
-__device__ __forceinline__ void stage_rows(const float *__restrict__ gsrc, int n_floats, float *s_pts, int tid)
-{
-    if ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) {
-        const int n4 = n_floats >> 2;
-        const float4 *g4 = reinterpret_cast<const float4 *>(gsrc);
-        float4 *s4 = reinterpret_cast<float4 *>(s_pts);
-        for (int i = tid; i < n4; i += kCullThreads) s4[i] = __ldg(g4 + i);
-        for (int i = (n4 << 2) + tid; i < n_floats; i += kCullThreads) s_pts[i] = __ldg(gsrc + i);
-    } else {
-        for (int i = tid; i < n_floats; i += kCullThreads) s_pts[i] = __ldg(gsrc + i);
-    }
-}
+static_assert(sizeof(CullSmem) % 16 == 0, "the float4 box table follows this struct in shared memory");
 
 // bits [lo, hi) of word w (bit j of word w = candidate 32 w + j)
 __device__ __forceinline__ unsigned range_bits(int lo, int hi, int w)
@@ -66,16 +65,71 @@ __device__ __forceinline__ unsigned range_bits(int lo, int hi, int w)
     return below_b & ~below_a;
 }
 
+// One CTA per (frame, camera rank): cell -> candidates of that rank whose box may contain a
+// pixel of the cell.  Conservative (a superset); the exact test follows in cull_stage_kernel.
 template <int W>
-__global__ void __launch_bounds__(kCullThreads) cull_mask_kernel(const fnp_seeker_batch b, const float img_w,
-                                                                 const float img_h)
+__global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch b, const int n_cu, const int n_cv)
+{
+    extern __shared__ unsigned s_cells[];                 // [n_cu * n_cv][W]
+    const int frame = blockIdx.x / 6, r = blockIdx.x % 6;
+    const int n_cells = n_cu * n_cv;
+    const int c0 = b.frame_cand_start[frame];
+    const int lo = b.cam_cand_start[frame * 6 + r] - c0, hi = b.cam_cand_start[frame * 6 + r + 1] - c0;
+    unsigned *out = b.cell_masks + ((size_t)frame * 6 + r) * n_cells * W;
+    for (int i = threadIdx.x; i < n_cells * W; i += blockDim.x) s_cells[i] = 0u;
+    __syncthreads();
+    for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+        const float4 bx = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
+        if (!(bx.z > bx.x) || !(bx.w > bx.y)) continue;   // empty (or NaN) box: no point can match
+        // cell cu covers u in [64 cu, 64 cu + 64); a member has x1 <= u < x2
+        const int cu0 = max(0, (int)floorf(fmaxf(bx.x, 0.f) * kCellInv));
+        const int cu1 = min(n_cu - 1, (int)floorf(fminf(bx.z, 65536.f) * kCellInv));
+        const int cv0 = max(0, (int)floorf(fmaxf(bx.y, 0.f) * kCellInv));
+        const int cv1 = min(n_cv - 1, (int)floorf(fminf(bx.w, 65536.f) * kCellInv));
+        for (int cv = cv0; cv <= cv1; cv++)
+            for (int cu = cu0; cu <= cu1; cu++) atomicOr(&s_cells[(cv * n_cu + cu) * W + (j >> 5)], 1u << (j & 31));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cells * W; i += blockDim.x) out[i] = s_cells[i];
+}
+
+// wx, wy, wz of two points against one camera: the three rows of lidar2image, each
+// fma(a2, z, fma(a1, y, a0 * x)) + a3 as in project(), evaluated on packed pairs (per-lane IEEE).
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long row2(const float *__restrict__ a, unsigned long long x2,
+                                                   unsigned long long y2, unsigned long long z2)
+{
+    unsigned long long t;
+    const unsigned long long a0 = pack2(a[0], a[0]), a1 = pack2(a[1], a[1]), a2 = pack2(a[2], a[2]), a3 = pack2(a[3], a[3]);
+    asm("{\n .reg .b64 t;\n mul.rn.f32x2 t, %1, %4;\n fma.rn.f32x2 t, %2, %5, t;\n fma.rn.f32x2 t, %3, %6, t;\n"
+        " add.rn.f32x2 %0, t, %7;\n}\n"
+        : "=l"(t)
+        : "l"(a0), "l"(a1), "l"(a2), "l"(x2), "l"(y2), "l"(z2), "l"(a3));
+    return t;
+}
+
+constexpr int kPtsPerThread = kCullSub;   // a thread owns row (sub * kCullThreads + tid) of every sub-tile
+
+template <int W>
+__global__ void __launch_bounds__(kCullThreads) cull_stage_kernel(const fnp_seeker_batch b, const float img_w,
+                                                                  const float img_h, const int n_cu, const int n_cv)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
     const int Cmax = b.max_cands_per_frame;
     float4 *s_box = reinterpret_cast<float4 *>(smem_raw + sizeof(CullSmem));            // [Cmax]
     int *s_cnt = reinterpret_cast<int *>(s_box + Cmax);                                  // [kCullVW][Cmax]
-    float *s_pts = reinterpret_cast<float *>(s_cnt + kCullVW * Cmax);                    // staged rows
+    int *s_off = s_cnt + kCullVW * Cmax;                                                 // [Cmax] slice offset of a candidate
+    unsigned *s_rm = reinterpret_cast<unsigned *>(s_off + Cmax);                         // [6][W] rank bit ranges
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,6 +140,21 @@ __global__ void __launch_bounds__(kCullThreads) cull_mask_kernel(const fnp_seeke
     const int c0 = b.frame_cand_start[frame];
     const int nc = b.frame_cand_start[frame + 1] - c0;
     if (nc == 0) return;
+
+    // ---- my points (issued first: the loads overlap the per-CTA setup)
+    const int stride = b.point_stride;
+    float x[kPtsPerThread], y[kPtsPerThread], z[kPtsPerThread];
+    bool live[kPtsPerThread];
+#pragma unroll
+    for (int s = 0; s < kPtsPerThread; s++) {
+        const int row = row0 + s * kCullThreads + tid;
+        live[s] = row < frame_rows;
+        x[s] = y[s] = z[s] = 0.f;
+        if (live[s]) {
+            const float *p = b.points + (size_t)(frow + row) * stride + b.xyz_offset;
+            x[s] = __ldg(p); y[s] = __ldg(p + 1); z[s] = __ldg(p + 2);
+        }
+    }
 
     // ---- per-CTA setup
     for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
@@ -93,151 +162,84 @@ __global__ void __launch_bounds__(kCullThreads) cull_mask_kernel(const fnp_seeke
     for (int i = tid; i < kCullVW * Cmax; i += kCullThreads) s_cnt[i] = 0;
     if (tid < 7) S.cs[tid] = b.cam_cand_start[frame * 6 + tid] - c0;
     __syncthreads();
-    if (tid < 6) {
-        const float INF = __int_as_float(0x7f800000);
-        float4 u = make_float4(INF, INF, -INF, -INF);
-        for (int j = S.cs[tid]; j < S.cs[tid + 1]; j++) {
-            const float4 bx = s_box[j];
-            u.x = fminf(u.x, bx.x); u.y = fminf(u.y, bx.y); u.z = fmaxf(u.z, bx.z); u.w = fmaxf(u.w, bx.w);
-        }
-        S.uni[tid] = u;
-    }
-    __syncthreads();
+    if (tid < 6 * W) s_rm[tid] = range_bits(S.cs[tid / W], S.cs[tid / W + 1], tid % W);
 
-    const int stride = b.point_stride;
+    unsigned mask[kPtsPerThread][W];
+#pragma unroll
+    for (int s = 0; s < kPtsPerThread; s++)
+#pragma unroll
+        for (int w = 0; w < W; w++) mask[s][w] = 0u;
+
     // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
     const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
+    const int n_cells = n_cu * n_cv;
 
+    // ---- membership
 #pragma unroll 1
-    for (int sub = 0; sub < kCullSub; sub++) {
-        const int r0 = row0 + sub * kCullThreads;
-        const int n_rows = min(kCullThreads, frame_rows - r0);
-        if (n_rows <= 0) break;
-        __syncthreads();   // previous sub-tile's readers are done with s_pts
-        stage_rows(b.points + (size_t)(frow + r0) * stride, n_rows * stride, s_pts, tid);
-        __syncthreads();
-        const bool live = tid < n_rows;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (live) {
-            const float *p = s_pts + tid * stride + b.xyz_offset;
-            x = p[0]; y = p[1]; z = p[2];
+    for (int r = 0; r < 6; r++) {
+        if (S.cs[r] == S.cs[r + 1]) continue;                       // camera without candidates
+        const float *L = S.cam[kImageOrder[r]];
+        float wx[kPtsPerThread], wy[kPtsPerThread], d[kPtsPerThread];
+        bool maybe[kPtsPerThread];
+        bool any_maybe = false;
+#pragma unroll
+        for (int s = 0; s < kPtsPerThread; s += 2) {
+            const unsigned long long x2 = pack2(x[s], x[s + 1]), y2 = pack2(y[s], y[s + 1]), z2 = pack2(z[s], z[s + 1]);
+            float wz0, wz1;
+            unpack2(row2(L + 0, x2, y2, z2), wx[s], wx[s + 1]);
+            unpack2(row2(L + 4, x2, y2, z2), wy[s], wy[s + 1]);
+            unpack2(row2(L + 8, x2, y2, z2), wz0, wz1);
+            d[s] = fminf(fmaxf(wz0, 1e-5f), 1e5f);
+            d[s + 1] = fminf(fmaxf(wz1, 1e-5f), 1e5f);
         }
-        unsigned mask[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) mask[w] = 0u;
-
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            const int lo = S.cs[r], hi = S.cs[r + 1];
-            if (lo == hi) continue;                                  // camera without candidates
-            const float *L = S.cam[kImageOrder[r]];
+        for (int s = 0; s < kPtsPerThread; s++) {
             // cheap, division-free "certainly off this image" test
-            const float wx = __fadd_rn(dot3(L + 0, x, y, z), L[3]);
-            const float wy = __fadd_rn(dot3(L + 4, x, y, z), L[7]);
-            const float wz = __fadd_rn(dot3(L + 8, x, y, z), L[11]);
-            const float d = fminf(fmaxf(wz, 1e-5f), 1e5f);
-            const bool off = (wx < -1e-30f) | (wy < -1e-30f) | (wx > __fmul_rn(w_hi, d)) | (wy > __fmul_rn(h_hi, d));
-            const bool maybe = live & !off;
-            if (!__any_sync(0xffffffffu, maybe)) continue;
+            const bool off = (wx[s] < -1e-30f) | (wy[s] < -1e-30f) | (wx[s] > __fmul_rn(w_hi, d[s])) |
+                             (wy[s] > __fmul_rn(h_hi, d[s]));
+            maybe[s] = live[s] & !off;
+            any_maybe |= maybe[s];
+        }
+        if (!__any_sync(0xffffffffu, any_maybe)) continue;
+        const unsigned *cells = b.cell_masks + ((size_t)frame * 6 + r) * n_cells * W;
+#pragma unroll
+        for (int s = 0; s < kPtsPerThread; s++) {
+            if (!maybe[s]) continue;
             // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
-            const float u = __fdiv_rn(wx, d), v = __fdiv_rn(wy, d);
-            const bool on = maybe & (v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f);
-            const float4 un = S.uni[r];
-            const bool near_box = on & (v < un.w) & (v >= un.y) & (u < un.z) & (u >= un.x);
-            if (!__any_sync(0xffffffffu, near_box)) continue;
+            const float u = __fdiv_rn(wx[s], d[s]), v = __fdiv_rn(wy[s], d[s]);
+            if (!((v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f))) continue;
+            const int cell = min((int)(v * kCellInv), n_cv - 1) * n_cu + min((int)(u * kCellInv), n_cu - 1);
+            const unsigned *cm = cells + (size_t)cell * W;
 #pragma unroll
             for (int w = 0; w < W; w++) {
-                const int j0 = max(lo, 32 * w), j1 = min(hi, 32 * w + 32);
-                for (int j = j0; j < j1; j++) {
-                    const float4 bx = s_box[j];
-                    const bool in = near_box & (v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x);
-                    mask[w] |= (in ? 1u : 0u) << (j - 32 * w);
+                unsigned m = __ldg(cm + w);
+                while (m) {
+                    const int jb = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 bx = s_box[32 * w + jb];
+                    const bool in = (v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x);
+                    mask[s][w] |= (in ? 1u : 0u) << jb;
                 }
             }
         }
+    }
 
-        // ---- masks out (coalesced per word), per-virtual-warp populations
-        unsigned *mrow = b.pt_mask + ((size_t)tile * W) * FNP_CULL_TILE + sub * kCullThreads + tid;
+    // ---- populations per (virtual warp, candidate)
+#pragma unroll
+    for (int s = 0; s < kPtsPerThread; s++) {
 #pragma unroll
         for (int w = 0; w < W; w++) {
-            if (live) mrow[(size_t)w * FNP_CULL_TILE] = mask[w];
-            unsigned any = __reduce_or_sync(0xffffffffu, mask[w]);
+            unsigned any = __reduce_or_sync(0xffffffffu, mask[s][w]);
             while (any) {
                 const int j = __ffs(any) - 1;
                 any &= any - 1;
-                const unsigned m = __ballot_sync(0xffffffffu, (mask[w] >> j) & 1u);
-                if (lane == 0) s_cnt[(sub * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
+                const unsigned m = __ballot_sync(0xffffffffu, (mask[s][w] >> j) & 1u);
+                if (lane == 0) s_cnt[(s * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
             }
         }
     }
     __syncthreads();
-    for (int j = tid; j < nc; j += kCullThreads) {
-        int sum = 0;
-#pragma unroll
-        for (int vw = 0; vw < kCullVW; vw++) sum += s_cnt[vw * Cmax + j];
-        b.tile_counts[(size_t)tile * Cmax + j] = sum;
-    }
-}
-
-template <int W>
-__global__ void __launch_bounds__(kCullThreads) cull_write_kernel(const fnp_seeker_batch b, const float img_w,
-                                                                  const float img_h)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
-    const int Cmax = b.max_cands_per_frame;
-    int *s_base = reinterpret_cast<int *>(smem_raw + sizeof(CullSmem));     // [Cmax] first slot of this tile
-    int *s_cnt = s_base + Cmax;                                              // [kCullVW][Cmax]
-    unsigned *s_rm = reinterpret_cast<unsigned *>(s_cnt + kCullVW * Cmax);   // [6][W] rank bit ranges
-
-    const int tile = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = b.tile_frame[tile];
-    const int row0 = b.tile_row0[tile];
-    const int64_t frow = b.frame_row_start[frame];
-    const int frame_rows = (int)(b.frame_row_start[frame + 1] - frow);
-    const int c0 = b.frame_cand_start[frame];
-    const int nc = b.frame_cand_start[frame + 1] - c0;
-    if (nc == 0) return;
-
-    // ---- masks of my kCullSub points; tiles without any member stop here
-    unsigned mask[kCullSub][W];
-    unsigned mine = 0u;
-#pragma unroll
-    for (int sub = 0; sub < kCullSub; sub++) {
-        const bool live = row0 + sub * kCullThreads + tid < frame_rows;
-        const unsigned *mrow = b.pt_mask + ((size_t)tile * W) * FNP_CULL_TILE + sub * kCullThreads + tid;
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            mask[sub][w] = live ? mrow[(size_t)w * FNP_CULL_TILE] : 0u;
-            mine |= mask[sub][w];
-        }
-    }
-    if (!__syncthreads_or(mine != 0u)) return;
-
-    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
-    for (int j = tid; j < nc; j += kCullThreads)
-        s_base[j] = b.cand_pt_start[c0 + j] + b.tile_counts[(size_t)tile * Cmax + j];
-    for (int i = tid; i < kCullVW * Cmax; i += kCullThreads) s_cnt[i] = 0;
-    if (tid < 7) S.cs[tid] = b.cam_cand_start[frame * 6 + tid] - c0;
-    __syncthreads();
-    if (tid < 6 * W) s_rm[tid] = range_bits(S.cs[tid / W], S.cs[tid / W + 1], tid % W);
-
-    // ---- phase 1: population of every candidate in every virtual warp, then prefix over them
-#pragma unroll
-    for (int sub = 0; sub < kCullSub; sub++) {
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            unsigned any = __reduce_or_sync(0xffffffffu, mask[sub][w]);
-            while (any) {
-                const int j = __ffs(any) - 1;
-                any &= any - 1;
-                const unsigned m = __ballot_sync(0xffffffffu, (mask[sub][w] >> j) & 1u);
-                if (lane == 0) s_cnt[(sub * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
-            }
-        }
-    }
-    __syncthreads();
+    // exclusive prefix over the virtual warps of every candidate; the tile's population of it
     for (int j = tid; j < nc; j += kCullThreads) {
         int run = 0;
 #pragma unroll
@@ -246,36 +248,58 @@ __global__ void __launch_bounds__(kCullThreads) cull_write_kernel(const fnp_seek
             s_cnt[vw * Cmax + j] = run;
             run += c;
         }
+        b.tile_counts[(size_t)tile * Cmax + j] = run;
+        s_off[j] = run;
     }
     __syncthreads();
-
-    // ---- phase 2: re-project members into their camera, unproject, ordered scatter
-    const unsigned lt = (1u << lane) - 1u;
-    const int stride = b.point_stride;
+    // exclusive prefix over candidates (one warp), then reserve the tile's staging slice
+    if (warp == 0) {
+        int carry = 0;
+        for (int j0 = 0; j0 < nc; j0 += 32) {
+            const int j = j0 + lane;
+            const int val = (j < nc) ? s_off[j] : 0;
+            int inc = val;
 #pragma unroll
-    for (int sub = 0; sub < kCullSub; sub++) {
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (j < nc) s_off[j] = carry + inc - val;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            S.tile_total = carry;
+            S.tile_base = carry ? atomicAdd(&b.status[5], carry) : 0;
+            b.tile_base[tile] = S.tile_base;
+        }
+    }
+    __syncthreads();
+    const int total = S.tile_total;
+    if (total == 0) return;
+    const int64_t base = S.tile_base;
+    if (base + total > b.pts_capacity) return;      // overflow: scan_cands_kernel raises the flag
+
+    // ---- re-project members into their camera, unproject, ordered write into the slice
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int s = 0; s < kPtsPerThread; s++) {
         unsigned sub_any = 0u;
 #pragma unroll
-        for (int w = 0; w < W; w++) sub_any |= mask[sub][w];
+        for (int w = 0; w < W; w++) sub_any |= mask[s][w];
         if (!__any_sync(0xffffffffu, sub_any != 0u)) continue;
-        const int row = row0 + sub * kCullThreads + tid;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (sub_any) {
-            const float *p = b.points + (size_t)(frow + row) * stride + b.xyz_offset;
-            x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
-        }
-        const int *cnt_vw = s_cnt + (sub * kCullWarps + warp) * Cmax;
+        const int row = row0 + s * kCullThreads + tid;
+        const int *cnt_vw = s_cnt + (s * kCullWarps + warp) * Cmax;
 #pragma unroll 1
         for (int r = 0; r < 6; r++) {
             unsigned rm[W];
             unsigned has = 0u;
 #pragma unroll
-            for (int w = 0; w < W; w++) { rm[w] = mask[sub][w] & s_rm[r * W + w]; has |= rm[w]; }
+            for (int w = 0; w < W; w++) { rm[w] = mask[s][w] & s_rm[r * W + w]; has |= rm[w]; }
             if (!__any_sync(0xffffffffu, has != 0u)) continue;
             const float *cm = S.cam[kImageOrder[r]];
-            float u, v, d, X = 0.f, Y = 0.f, Z = 0.f;
-            project(cm, x, y, z, img_w, img_h, u, v, d);
-            unproject(cm + 12, cm + 21, u, v, d, X, Y, Z);
+            float u, v, dd, X = 0.f, Y = 0.f, Z = 0.f;
+            project(cm, x[s], y[s], z[s], img_w, img_h, u, v, dd);
+            unproject(cm + 12, cm + 21, u, v, dd, X, Y, Z);
 #pragma unroll
             for (int w = 0; w < W; w++) {
                 unsigned any = __reduce_or_sync(0xffffffffu, rm[w]);
@@ -286,16 +310,63 @@ __global__ void __launch_bounds__(kCullThreads) cull_write_kernel(const fnp_seek
                     const unsigned m = __ballot_sync(0xffffffffu, in);
                     if (in) {
                         const int j = 32 * w + jb;
-                        const int64_t pos = (int64_t)s_base[j] + cnt_vw[j] + __popc(m & lt);
-                        if (pos < b.pts_capacity) {
-                            float *dst = b.frustum_pts + pair_slot(pos);
-                            dst[0] = X; dst[2] = Y; dst[4] = Z; dst[6] = d;
-                            if (b.frustum_idx) b.frustum_idx[pos] = row;
-                        }
+                        const int64_t pos = base + s_off[j] + cnt_vw[j] + __popc(m & lt);
+                        reinterpret_cast<float4 *>(b.stage_pts)[pos] = make_float4(X, Y, Z, dd);
+                        if (b.stage_idx) b.stage_idx[pos] = row;
                     }
                 }
             }
         }
+    }
+}
+
+// One CTA per tile: move the tile's staging slice to its final place in every frustum.
+__global__ void __launch_bounds__(256) cull_gather_kernel(const fnp_seeker_batch b)
+{
+    extern __shared__ int s_o[];                           // [Cmax + 1] slice offsets, then [Cmax] destinations
+    const int Cmax = b.max_cands_per_frame;
+    int *s_dst = s_o + Cmax + 1;
+    __shared__ int s_total;
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int frame = b.tile_frame[tile];
+    const int c0 = b.frame_cand_start[frame];
+    const int nc = b.frame_cand_start[frame + 1] - c0;
+    if (nc == 0 || b.status[0] != 0) return;
+    if (tid < 32) {
+        int carry = 0;
+        for (int j0 = 0; j0 < nc; j0 += 32) {
+            const int j = j0 + lane;
+            const int val = (j < nc) ? b.tile_counts[(size_t)tile * Cmax + j] : 0;
+            int inc = val;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (j < nc) {
+                s_o[j] = carry + inc - val;
+                s_dst[j] = b.cand_pt_start[c0 + j] + b.tile_dst[(size_t)tile * Cmax + j];
+            }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) { s_o[nc] = carry; s_total = carry; }
+    }
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0) return;
+    const int64_t base = b.tile_base[tile];
+    for (int k = tid; k < total; k += blockDim.x) {
+        // candidate of slot k: the last j with s_o[j] <= k
+        int lo = 0, hi = nc;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_o[mid] <= k) lo = mid; else hi = mid;
+        }
+        const int64_t pos = (int64_t)s_dst[lo] + (k - s_o[lo]);
+        const float4 rec = reinterpret_cast<const float4 *>(b.stage_pts)[base + k];
+        float *dst = b.frustum_pts + pair_slot(pos);
+        dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
+        if (b.frustum_idx) b.frustum_idx[pos] = b.stage_idx[base + k];
     }
 }
 
@@ -311,15 +382,15 @@ __global__ void __launch_bounds__(128) scan_tiles_kernel(const fnp_seeker_batch 
     int carry = 0;
     for (int t = t0; t < t1; t += 32) {
         const int i = t + lane;
-        int *cell = b.tile_counts + (size_t)i * b.max_cands_per_frame + j;
-        const int val = (i < t1) ? *cell : 0;
+        const size_t cell = (size_t)i * b.max_cands_per_frame + j;
+        const int val = (i < t1) ? b.tile_counts[cell] : 0;
         int inc = val;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int n = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += n;
         }
-        if (i < t1) *cell = carry + inc - val;
+        if (i < t1) b.tile_dst[cell] = carry + inc - val;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) b.cand_npts[f] = carry;
@@ -1036,28 +1107,33 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     return FNP_OK;
 }
 
-static size_t cull_mask_smem(const fnp_seeker_batch *b)
+static size_t cull_stage_smem(const fnp_seeker_batch *b, int W)
 {
-    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullVW) +
-           (size_t)kCullThreads * b->point_stride * 4 + 16;
-}
-static size_t cull_write_smem(const fnp_seeker_batch *b, int W)
-{
-    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (4 + 4 * kCullVW) + (size_t)6 * W * 4 + 16;
+    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullVW + 4) + (size_t)6 * W * 4 + 16;
 }
 
 template <int W>
 static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
 {
-    const size_t sa = cull_mask_smem(b), sb = cull_write_smem(b, W);
-    if (sa > 200 * 1024 || sb > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_mask_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
-    cudaFuncSetAttribute(cull_write_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
-    cull_mask_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h);
+    const int n_cu = cell_cols(cfg->img_w), n_cv = cell_rows(cfg->img_h);
+    const size_t sa = cull_stage_smem(b, W), sc = (size_t)n_cu * n_cv * W * 4;
+    const size_t sg = ((size_t)2 * b->max_cands_per_frame + 1) * 4;
+    if (sa > 200 * 1024 || sc > 200 * 1024) return FNP_EINVAL;
+    cudaFuncSetAttribute(cull_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cell_table_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
+    cell_table_kernel<W><<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv);
+    cull_stage_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv);
     scan_tiles_kernel<<<divup(b->n_cands, 4), 128, 0, st>>>(*b);
     scan_cands_kernel<<<1, 1024, 0, st>>>(*b);
-    cull_write_kernel<W><<<b->n_tiles, kCullThreads, sb, st>>>(*b, cfg->img_w, cfg->img_h);
+    cull_gather_kernel<<<b->n_tiles, 256, sg, st>>>(*b);
     return FNP_OK;
+}
+
+extern "C" size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_frames, int max_cands_per_frame)
+{
+    const int W = fnp_seeker_mask_words(max_cands_per_frame);
+    if (!cfg || n_frames < 0 || W < 0) return 0;
+    return (size_t)n_frames * 6 * cell_cols(cfg->img_w) * cell_rows(cfg->img_h) * W * 4;
 }
 
 extern "C" int fnp_seeker_mask_words(int max_cands_per_frame)
@@ -1072,15 +1148,17 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (b->n_cands == 0 || b->n_tiles == 0) {
-        cudaMemsetAsync(b->status, 0, 4 * sizeof(int32_t), st);
+        cudaMemsetAsync(b->status, 0, 8 * sizeof(int32_t), st);
         cudaMemsetAsync(b->cand_pt_start, 0, sizeof(int32_t) * (size_t)(b->n_cands + 1), st);
         if (b->n_cands) cudaMemsetAsync(b->cand_npts, 0, sizeof(int32_t) * (size_t)b->n_cands, st);
         FNP_LAUNCH_CHECK();
         return FNP_OK;
     }
-    if (!b->points || !b->tile_counts || !b->frustum_pts || !b->pt_mask || !b->cam_cand_start ||
-        b->point_stride < 3 || b->xyz_offset < 0 || b->xyz_offset + 3 > b->point_stride)
+    if (!b->points || !b->tile_counts || !b->tile_dst || !b->tile_base || !b->frustum_pts || !b->stage_pts ||
+        !b->cell_masks || !b->cam_cand_start || b->point_stride < 3 || b->xyz_offset < 0 ||
+        b->xyz_offset + 3 > b->point_stride || (b->frustum_idx && !b->stage_idx))
         return FNP_EINVAL;
+    cudaMemsetAsync(b->status, 0, 8 * sizeof(int32_t), st);      // [5] = staging cursor
     const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
     if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 256 candidates in one frame
     switch (W) {

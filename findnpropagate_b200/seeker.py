@@ -312,8 +312,9 @@ class SeekerEngine:
             if W < 0:
                 raise ValueError("more than 256 candidate frustums in one frame (%d) are not supported" % Cmax)
             sizes = dict(
-                tile_counts=4 * plan["n_tiles"] * Cmax, pt_mask=4 * plan["n_tiles"] * W * _lib.CULL_TILE,
-                frustum_pts=16 * cap,
+                tile_counts=4 * plan["n_tiles"] * Cmax, tile_dst=4 * plan["n_tiles"] * Cmax,
+                tile_base=4 * plan["n_tiles"], cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
+                frustum_pts=16 * cap, stage_pts=16 * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
                 hyp_iou=4 * H * F, counts=4 * H * max_rows, items=16 * max_items,
                 cand_item_start=4 * (F + 1), cand_split_row=4 * (F + 1),
@@ -324,7 +325,7 @@ class SeekerEngine:
             off_keep = off_recall + 8 * self.N_COUNTERS
             sizes["out"] = off_keep + _align(F, 8)
             if self.debug:
-                sizes.update(frustum_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
+                sizes.update(frustum_idx=4 * cap, stage_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
             ptr = {k: self.arena.get(k, v).data_ptr() for k, v in sizes.items() if k != "out"}
             out_dev = self.arena.get("out%d" % slot, sizes["out"])
             ob = out_dev.data_ptr()
@@ -341,7 +342,8 @@ class SeekerEngine:
                 cand_label=meta["cand_label"], cand_box2d=meta["cand_box2d"],
                 base_boxes=self.base_boxes.data_ptr(), base_corners=self.base_corners.data_ptr(),
                 mags=self.mags.data_ptr(),
-                tile_counts=ptr["tile_counts"], pt_mask=ptr["pt_mask"], mask_words=W, cand_npts=o_npts, cand_pt_start=o_ptstart,
+                tile_counts=ptr["tile_counts"], tile_dst=ptr["tile_dst"], tile_base=ptr["tile_base"],
+                cell_masks=ptr["cell_masks"], mask_words=W, stage_pts=ptr["stage_pts"], stage_idx=ptr.get("stage_idx"), cand_npts=o_npts, cand_pt_start=o_ptstart,
                 frustum_pts=ptr["frustum_pts"], frustum_idx=ptr.get("frustum_idx"), pts_capacity=cap,
                 cand_stats=ptr["cand_stats"], centres=ptr["centres"], hyp_prep=ptr["hyp_prep"],
                 hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
@@ -353,7 +355,7 @@ class SeekerEngine:
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
-            self.launches += 10 if F and plan["n_tiles"] else 0
+            self.launches += 11 if F and plan["n_tiles"] else 0
             handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta,
                           off_recall=off_recall, off_keep=off_keep, has_nms=False, has_recall=False,
                           recall_thresh=tuple(recall_thresh))
@@ -382,12 +384,12 @@ class SeekerEngine:
         self.launches += 1
 
     def _recall(self, plan, meta, o_boxes, o_best, gt, thresh, stream, out_dev, off):
-        gt_boxes, gt_start = gt
+        gt_boxes, gt_start, max_gt = gt
         assert len(thresh) == 3
         out_dev[off:off + 8 * self.N_COUNTERS].zero_()
         th = (C.c_float * len(thresh))(*[float(t) for t in thresh])
         rc = _lib.lib.fnp_recall_counters(o_boxes, o_best, meta["frame_cand_start"], gt_boxes.data_ptr(),
-                                          gt_start.data_ptr(), plan["B"], th, len(thresh),
+                                          gt_start.data_ptr(), plan["B"], max(plan["max_cands"], 1), int(max_gt), th, len(thresh),
                                           out_dev.data_ptr() + off, stream)
         _lib.check(rc, "fnp_recall_counters")
         self.launches += 1
@@ -476,7 +478,8 @@ class SeekerEngine:
             g.append(gb.reshape(-1, 8))
             start.append(start[-1] + gb.shape[0])
         gt = torch.from_numpy(np.ascontiguousarray(np.concatenate(g) if g else np.zeros((0, 8), np.float32)))
-        return gt.to(self.device), torch.tensor(start, dtype=torch.int32).to(self.device)
+        max_gt = int(np.diff(start).max()) if len(start) > 1 else 0
+        return gt.to(self.device), torch.tensor(start, dtype=torch.int32).to(self.device), max_gt
 
     # ------------------------------------------------------------------ debug views
     def debug_views(self, handle):

@@ -128,11 +128,18 @@ typedef struct fnp_seeker_batch {
     const float *base_corners;       /* (A,J,8,3)                                          */
     const float *mags;               /* (M) linspace(0,1,M)                                */
     /* ---- workspaces / intermediates (caller allocated) ---- */
-    int32_t *tile_counts;            /* (n_tiles, max_cands_per_frame)                     */
-    uint32_t *pt_mask;               /* (n_tiles, mask_words, FNP_CULL_TILE): bit j of word w of a
-                                        point = it lies in the frustum of its frame's candidate
-                                        32 w + j                                            */
+    int32_t *tile_counts;            /* (n_tiles, max_cands_per_frame) members of every candidate in
+                                        every tile                                          */
+    int32_t *tile_dst;               /* (n_tiles, max_cands_per_frame) their exclusive prefix over
+                                        the tiles of the frame                              */
+    int32_t *tile_base;              /* (n_tiles) first staging slot of the tile            */
+    uint32_t *cell_masks;            /* fnp_seeker_cell_mask_bytes(): per (frame, camera rank, 64-px
+                                        image cell) the bitmask (mask_words words) of the rank's
+                                        candidates whose 2D box touches the cell            */
     int32_t mask_words;              /* = fnp_seeker_mask_words(max_cands_per_frame)        */
+    float *stage_pts;                /* (pts_capacity, 4) staging: the members of a tile, candidate-
+                                        major, as x,y,z,depth                               */
+    int32_t *stage_idx;              /* (pts_capacity) their source rows; required iff frustum_idx */
     int32_t *cand_npts;              /* (F)   P_f                                          */
     int32_t *cand_pt_start;          /* (F+1) start of each frustum in frustum_pts         */
     float *frustum_pts;              /* (pts_capacity/2, 8) frustum points, pair-interleaved: points 2p
@@ -169,17 +176,20 @@ typedef struct fnp_seeker_batch {
     int32_t *out_count;              /* (F)   point count of the winner                    */
     int32_t *status;                 /* (8)   [0] bit0: frustum_pts overflow (needed points in [1]),
                                         bit1: items/counts overflow ([2] items, [3] rows needed);
-                                        [4] work-item counter of the scoring kernel; [5..7] spare */
+                                        [4] work-item counter of the scoring kernel; [5] staging
+                                        cursor of stage 1; [6..7] spare                     */
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024
 /* Words of the per-point candidate mask for a batch whose busiest frame has that many
  * candidates: 1, 2, 4 or 8 (-1: more than 256 candidates per frame are not supported). */
 int fnp_seeker_mask_words(int max_cands_per_frame);
+/* Bytes of fnp_seeker_batch.cell_masks for a batch (0 on bad arguments). */
+size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_frames, int max_cands_per_frame);
 
 /* Stage 1: fused LiDAR->camera projection + per-2D-box frustum cull + ordered compaction.
- * Pass A (membership bitmask per point + per-tile populations), two scans, pass B (ordered
- * scatter of the unprojected member points): four launches, no host sync. */
+ * Cell table, one pass over the points (membership, per-tile populations, member points into a
+ * per-tile staging slice), two scans, an ordered gather: five launches, no host sync. */
 int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 /* Stage 1b: per-frustum depth quantiles, point AABB, frustum corners, centre line. */
 int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
@@ -210,10 +220,12 @@ int fnp_seg_nms_rotated(const float *boxes, const int32_t *label, const int32_t 
  * gt (sum G,8) = box7 + class label with gt_start (n_frames+1); thresh (n_thresh<=8).
  * counters (int64): [0]=gt, [1]=num_3known, [2]=num_6known, [3]=num_4unknown,
  * [4]=num_7unknown, then per threshold t: [5+5t+0]=rcnn, +1 = 3known, +2 = 6known,
- * +3 = 4unknown, +4 = 7unknown.  Counters are ACCUMULATED (caller zeroes them). */
+ * +3 = 4unknown, +4 = 7unknown.  Counters are ACCUMULATED (caller zeroes them).
+ * max_pred_per_frame / max_gt_per_frame: upper bounds of the per-frame row counts (they size
+ * the shared memory of the kernel; 64 (max_pred + max_gt) + 4 max_gt bytes must fit in 200 KB). */
 int fnp_recall_counters(const float *pred, const int32_t *pred_valid, const int32_t *pred_start, const float *gt,
-                        const int32_t *gt_start, int n_frames, const float *thresh_host,
-                        int n_thresh, long long *counters, void *stream);
+                        const int32_t *gt_start, int n_frames, int max_pred_per_frame, int max_gt_per_frame,
+                        const float *thresh_host, int n_thresh, long long *counters, void *stream);
 
 /* ------------------------------------------------------------- host-side planning
  * (runs on the CPU, touches no device memory: every pointer here is a HOST pointer)

@@ -263,7 +263,7 @@ def test_seg_nms_and_recall_counters():
     counters = torch.zeros(20, dtype=torch.int64, device=DEV)
     th = (C.c_float * 3)(0.3, 0.5, 0.7)
     rc = _lib.lib.fnp_recall_counters(tb.data_ptr(), tv.data_ptr(), ts.data_ptr(), tg.data_ptr(), tgs.data_ptr(), 4,
-                                      th, 3, counters.data_ptr(), _lib.current_stream())
+                                      int(np.diff(start).max()), 12, th, 3, counters.data_ptr(), _lib.current_stream())
     assert rc == 0
     from findnpropagate_b200.seeker import SeekerEngine
     got = SeekerEngine.recall_dict(counters.cpu().numpy())

@@ -42,49 +42,71 @@ def parse():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed regions.  NVML in a thread (a few
+    ms per sample, so that even a 20 ms timed region is covered); nvidia-smi -lms as fallback."""
+    BAD = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period_s=0.004):
+        self.index, self.period, self.rows = index, period_s, []
+        self.stop_flag, self.thread, self.proc, self.nvml = False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _poll_nvml(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.rows.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), float(mx),
+                                  int(get_reasons(self.h)), n.nvmlDeviceGetUtilizationRates(self.h).gpu))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((float(r[0]), float(r[1]), int(r[2], 16), 100))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        top = sorted(sm)[len(sm) // 2:]          # samples under load = upper half
-        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        top = sm[len(sm) // 2:]                  # samples under load = upper half
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        reasons = sorted(name for name, bit in self.BAD if bits & bit)
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(r[1] for r in self.rows)), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------- data
@@ -340,7 +362,17 @@ def run_ours(a):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    issue_peak_tests = eng.n_sms * 4 * 32 * sm_clock * 1e6 / 11.0   # 11 issue slots per point-box test
+    # measured ceiling of the scoring loop's instruction mix with register operands and nothing but
+    # the SM pipes in the way (tools/ubench/score_mix.cu, V0, 6 CTAs/SM; profiles/r01d_score_mix_ceiling.txt)
+    PIPE_TESTS_PER_CLK_SM = 10.85
+    pipe_peak_tests = eng.n_sms * PIPE_TESTS_PER_CLK_SM * sm_clock * 1e6
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")))
+        if tj.get("config") == a.config and tj.get("frames") == B:
+            traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
 
     if rank == 0:
         n_frames = B * world
@@ -368,12 +400,14 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "fnp::score_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "the scoring kernel is FP32-issue-bound, not HBM-bound (DESIGN.md): "
-                                 "issue_frac = tests/s over n_SM*4*32*clk/11",
-                         "issue_frac": tests / (score_ms * 1e-3) / issue_peak_tests},
+                         "note": "the scoring kernel is bound by the SM's ALU/FMA pipes, not by HBM (DESIGN.md section 4): "
+                                 "pipe_frac = point-box tests/s over the measured ceiling of its instruction mix "
+                                 "(10.85 tests/clk/SM x SMs x clock)",
+                         "pipe_frac": tests / (score_ms * 1e-3) / pipe_peak_tests,
+                         "point_box_tests_per_launch": tests},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

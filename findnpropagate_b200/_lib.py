@@ -86,11 +86,14 @@ lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINT
 lib.fnp_host_select_candidates.restype = _i
 lib.fnp_host_select_candidates.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
 
+lib.fnp_upload_from_pinned.restype = _i
+lib.fnp_upload_from_pinned.argtypes = [_vp, _vp, C.c_size_t, _vp]
+
 lib.fnp_dbg_math.restype = _i
 lib.fnp_dbg_math.argtypes = [_vp, _vp, _vp, _i, _vp]
 
 EXPORTED = [
-    "fnp_dbg_math",
+    "fnp_dbg_math", "fnp_upload_from_pinned",
     "fnp_version", "fnp_points_in_boxes", "fnp_count_in_boxes", "fnp_boxes_overlap_bev",
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",

@@ -489,6 +489,15 @@ __global__ void __launch_bounds__(256) recall_kernel(const float *__restrict__ p
     }
 }
 
+// Small host->device upload executed by SMs: `src` is pinned (page-locked, UVA-mapped) host
+// memory.  Used for the per-batch metadata so that it does not queue behind a large point
+// copy in the H2D copy engine (copies of different streams are not served in issue order).
+__global__ void __launch_bounds__(256) upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 // test hook: the device math routines exactly as this library's kernels see them
 __global__ void dbg_math_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ out, int n)
 {
@@ -508,6 +517,20 @@ extern "C" int fnp_dbg_math(const float *x, const float *y, float *out, int n, v
 {
     if (n <= 0) return FNP_OK;
     dbg_math_kernel<<<divup(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, out, n);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_upload_from_pinned(void *dst, const void *src_pinned_host, size_t bytes, void *stream)
+{
+    if (bytes == 0) return FNP_OK;
+    if (!dst || !src_pinned_host || (bytes & 15) || (reinterpret_cast<uintptr_t>(dst) & 15) ||
+        (reinterpret_cast<uintptr_t>(src_pinned_host) & 15))
+        return FNP_EINVAL;
+    const size_t n16 = bytes >> 4;
+    const int grid = (int)((n16 + 255) / 256 < 296 ? (n16 + 255) / 256 : 296);
+    upload_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst),
+                                                          reinterpret_cast<const uint4 *>(src_pinned_host), n16);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }

@@ -276,7 +276,11 @@ class SeekerEngine:
             a = plan[k]
             hv[offs[k]:offs[k] + a.nbytes] = a.reshape(-1).view(np.uint8)
         dev = self.arena.get("meta_dev%d" % slot, total)
-        dev[:total].copy_(host[:total], non_blocking=True)
+        # by a kernel reading the pinned block, not by the copy engine: an H2D memcpy here can be
+        # served after the NEXT step's 200 MB point copy and stall this step's kernels behind it
+        _lib.check(_lib.lib.fnp_upload_from_pinned(dev.data_ptr(), host.data_ptr(), total, stream),
+                   "fnp_upload_from_pinned")
+        self.launches += 1
         base = dev.data_ptr()
         return {k: base + o for k, o in offs.items()}
 

@@ -241,6 +241,12 @@ int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels
                                const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
                                float score_thr, int32_t *cand_det, int32_t *frame_cand_start);
 
+/* Host->device upload of a small block by a kernel instead of the copy engine: src is pinned,
+ * UVA-mapped host memory (cudaHostAlloc / torch pin_memory), dst device memory, both 16-byte
+ * aligned, bytes a multiple of 16.  The per-batch metadata goes this way so that it cannot queue
+ * behind a large point copy of another stream in the H2D engine. */
+int fnp_upload_from_pinned(void *dst, const void *src_pinned_host, size_t bytes, void *stream);
+
 /* Test hook: out (4,n) = sinf(x), cosf(x), atan2f(y,x), fnp_exp(x) as evaluated on the
  * device by this library's build (checked against the oracle's restatements). */
 int fnp_dbg_math(const float *x, const float *y, float *out, int n, void *stream);

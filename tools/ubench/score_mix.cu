@@ -54,7 +54,7 @@ __device__ __forceinline__ void pair_v1(unsigned long long &acc, unsigned long l
 constexpr int K = 4, TILE_PAIRS = 256;
 
 template <int V>
-__global__ void __launch_bounds__(128) kern(float *out, int iters, float seed)
+__global__ void __launch_bounds__(128) kern(float *out, int iters, float seed, const float *__restrict__ prm)
 {
     __shared__ __align__(16) float4 tile[TILE_PAIRS][2];
     for (int i = threadIdx.x; i < TILE_PAIRS; i += 128) {
@@ -66,10 +66,11 @@ __global__ void __launch_bounds__(128) kern(float *out, int iters, float seed)
     int cnt[K];
     unsigned long long acc[K];
     for (int k = 0; k < K; k++) {
-        const float c = seed + threadIdx.x + 128 * k;
-        hp[k].cx2 = dup2(c); hp[k].cy2 = dup2(c * 0.5f); hp[k].cz2 = dup2(0.f);
-        hp[k].cosa2 = dup2(0.8f); hp[k].nsina2 = dup2(-0.6f); hp[k].sina2 = dup2(0.6f);
-        hp[k].hz = 2.f; hp[k].tx = 40.f; hp[k].ty = 20.f;
+        // every hypothesis parameter is a run-time value in its own register, as in the product kernel
+        const float *q = prm + ((threadIdx.x + 128 * k) & 1023) * 8;
+        hp[k].cx2 = dup2(q[0]); hp[k].cy2 = dup2(q[1]); hp[k].cz2 = dup2(q[2]);
+        hp[k].cosa2 = dup2(q[4]); hp[k].nsina2 = dup2(-q[5]); hp[k].sina2 = dup2(q[5]);
+        hp[k].hz = q[3]; hp[k].tx = q[6]; hp[k].ty = q[7];
         cnt[k] = 0; acc[k] = 0ull;
     }
     const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tile);
@@ -100,14 +101,23 @@ void run(const char *name, int ctas_per_sm)
     int sms = 0, khz = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
-    float *out;
+    float *out, *prm;
     const int blocks = sms * ctas_per_sm, iters = 400;
     cudaMalloc(&out, blocks * 128 * sizeof(float));
-    kern<V><<<blocks, 128>>>(out, 4, 0.37f);
+    cudaMalloc(&prm, 1024 * 8 * sizeof(float));
+    {
+        float h[1024 * 8];
+        for (int i = 0; i < 1024; i++) {
+            h[i * 8 + 0] = 0.37f * i; h[i * 8 + 1] = 0.11f * i; h[i * 8 + 2] = 0.01f * i; h[i * 8 + 3] = 2.f + 0.001f * i;
+            h[i * 8 + 4] = 0.8f; h[i * 8 + 5] = 0.6f; h[i * 8 + 6] = 40.f + 0.01f * i; h[i * 8 + 7] = 20.f + 0.01f * i;
+        }
+        cudaMemcpy(prm, h, sizeof(h), cudaMemcpyHostToDevice);
+    }
+    kern<V><<<blocks, 128>>>(out, 4, 0.37f, prm);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    kern<V><<<blocks, 128>>>(out, iters, 0.37f);
+    kern<V><<<blocks, 128>>>(out, iters, 0.37f, prm);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -117,6 +127,7 @@ void run(const char *name, int ctas_per_sm)
     printf("%-34s ctas/SM %d  %8.3f ms  %7.2f tests/clk/SM  %.3e tests/s (clock %d MHz assumed)\n", name, ctas_per_sm, ms,
            tests / clk / sms, tests / (ms * 1e-3), khz / 1000);
     cudaFree(out);
+    cudaFree(prm);
 }
 
 int main()

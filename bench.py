@@ -173,25 +173,46 @@ def cpu_baseline(frames, params, n_frames):
                       "%d frame(s), single thread, oracle port" % n_frames}
 
 
+_REF = {}
+
+
+def _ref_init(frames, params, kind):
+    """Pool initializer (spawned process): single-threaded torch, frames of the workload."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch
+    torch.set_num_threads(1)
+    _REF.update(frames=frames, params=params, kind=kind)
+    import oracle as O
+    O.lib()
+    if kind == "reference":
+        import build_ref
+        build_ref.load("roiaware_pool3d_cuda")
+
+
+def _ref_job(i):
+    return _cpu_frame((_REF["frames"][i % len(_REF["frames"])], _REF["params"], _REF["kind"]))
+
+
 def run_reference_arm(a):
     """bench.py --impl reference: the reference's CPU implementation of the path on all host
-    cores (frame-parallel, one frame per process)."""
+    cores (frame-parallel, one frame per process).  Processes are SPAWNED, not forked: forking
+    after torch has started its thread pools deadlocks the children."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     kind = cpu_kind()
-    frames, params = make_frames(a.config, 0, min(a.distinct, max(2, cores)), "cpu")
-    per_step = max(1, min(cores, 8))
-    jobs = [(frames[i % len(frames)], params, kind) for i in range(per_step)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes=min(cores, per_step)) as pool:
-        for _ in range(max(a.warmup, 1) if a.warmup else 0):
-            pool.map(_cpu_frame, jobs[:min(len(jobs), 2)])
+    procs = max(1, min(cores, 16))
+    frames, params = make_frames(a.config, 0, min(a.distinct, procs), "cpu")
+    per_step = procs                              # bounded sample: one frame per process and step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(processes=procs, initializer=_ref_init, initargs=(frames, params, kind)) as pool:
+        for _ in range(a.warmup):
+            pool.map(_ref_job, range(per_step), chunksize=1)
         t = time.perf_counter()
         for _ in range(a.steps):
-            pool.map(_cpu_frame, jobs)
+            pool.map(_ref_job, range(per_step), chunksize=1)
         dt = time.perf_counter() - t
     fps = per_step * a.steps / dt
     H = params["num_mags"] * params["num_rotations"] * params["num_sizes"]
@@ -201,8 +222,9 @@ def run_reference_arm(a):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s frames (BASELINE.json configs[1] shape), %d hypotheses/frustum; bounded sample: "
                                "%d frames per step" % (a.config, H, per_step)},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": min(cores, per_step), "kind": kind,
-                         "sample": "%d frames per step, frame-parallel over %d processes" % (per_step, min(cores, per_step))},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": kind,
+                         "sample": "%d frames per step, frame-parallel over %d processes (host has %d cores)"
+                                   % (per_step, procs, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,7 +268,9 @@ def run_ours(a):
     gt = eng.upload_gt(batch)
     in_bytes = pinned[0].numel() * 4
 
-    Kmax = 0
+    # two compute streams, one per slot: consecutive batches overlap on the device, so the small
+    # latency-bound kernels at the end of batch k run under the big kernels of batch k+1
+    comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     copy_stream = torch.cuda.Stream(device=dev)
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -255,7 +279,6 @@ def run_ours(a):
 
     def step(k, resident, prev):
         """One pass of the hot path over one batch; returns the new handle."""
-        nonlocal Kmax
         pts = dev_pts[k % 2]
         if not resident:
             # H2D of this step's points from pinned host memory, inside the timed region, on a
@@ -265,33 +288,40 @@ def run_ours(a):
                 pts.copy_(pinned[k % 2], non_blocking=True)
                 ready[k % 2].record(copy_stream)
         plan = eng.plan(batch)
-        h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2,
-                        points_ready=None if resident else ready[k % 2])
-        consumed[k % 2].record()
+        with torch.cuda.stream(comp[k % 2]):
+            h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2,
+                            points_ready=None if resident else ready[k % 2])
+            consumed[k % 2].record()
         res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
         if res is not None and world > 1:
-            gather_results(res, plan)
+            pending.append(res)
         return h, res
 
-    def gather_results(res, plan):
-        # frame-sharded run: one all_gather of fixed-stride packed proposals + one
-        # all_reduce of the recall counters per step (NCCL over NVLink)
-        nonlocal Kmax
-        Kmax = max(Kmax, plan["max_cands"], 1)
-        pack = np.zeros((B, Kmax, 9), np.float32)
-        cnt = np.zeros((B,), np.int32)
-        for b, fr in enumerate(res["frames"]):
+    pending = []            # results of this rank's shard, exchanged once per run (not per step)
+
+    def gather_results():
+        # frame-sharded run: ONE all_gather of fixed-stride packed proposals (+ its count vector) and
+        # ONE all_reduce of the recall counters for the whole shard (NCCL over NVLink), as in
+        # findnpropagate_b200.extract.gather_shards; kcap is fixed, so no size negotiation is needed
+        frames_l = [fr for res in pending for fr in res["frames"]]
+        kcap = 256
+        pack = torch.zeros((len(frames_l), kcap, 9), dtype=torch.float32, pin_memory=True)
+        cnt = torch.zeros((len(frames_l),), dtype=torch.int32, pin_memory=True)
+        pk, ck = pack.numpy(), cnt.numpy()
+        for i, fr in enumerate(frames_l):
             k = fr["pred_boxes"].shape[0]
-            pack[b, :k, :7] = fr["pred_boxes"]; pack[b, :k, 7] = fr["pred_scores"]; pack[b, :k, 8] = fr["pred_labels"]
-            cnt[b] = k
-        tp = torch.from_numpy(pack).to(dev)
-        tc = torch.from_numpy(cnt).to(dev)
-        allp = torch.empty((world * B, Kmax, 9), dtype=tp.dtype, device=dev)
-        allc = torch.empty((world * B,), dtype=tc.dtype, device=dev)
+            pk[i, :k, :7] = fr["pred_boxes"]; pk[i, :k, 7] = fr["pred_scores"]; pk[i, :k, 8] = fr["pred_labels"]
+            ck[i] = k
+        tp, tc = pack.to(dev, non_blocking=True), cnt.to(dev, non_blocking=True)
+        allp = torch.empty((world * len(frames_l), kcap, 9), dtype=tp.dtype, device=dev)
+        allc = torch.empty((world * len(frames_l),), dtype=tc.dtype, device=dev)
         dist.all_gather_into_tensor(allp, tp)
         dist.all_gather_into_tensor(allc, tc)
-        rc = torch.tensor([res["recall"][k] for k in sorted(res["recall"])], dtype=torch.int64, device=dev)
+        keys = sorted(pending[0]["recall"]) if pending else []
+        rc = torch.tensor([sum(res["recall"][k] for res in pending) for k in keys], dtype=torch.int64, device=dev)
         dist.all_reduce(rc)
+        pending.clear()
+        return allp, allc, rc
 
     def timed(resident, steps, warmup):
         prev = None
@@ -299,20 +329,27 @@ def run_ours(a):
             prev, _ = step(k, resident, prev)
         if prev is not None:
             eng.finish(prev)
+        pending.clear()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launches
+        cur = torch.cuda.current_stream(dev)
         e0.record()
+        for st in comp + [copy_stream]:
+            st.wait_event(e0)                  # nothing of the timed region starts before e0
         prev, last = None, None
         for k in range(steps):
             prev, r = step(k, resident, prev)
             last = r or last
         last = eng.finish(prev)
         if world > 1:
-            gather_results(last, prev["plan"])
+            pending.append(last)
+            gather_results()
+        for st in comp + [copy_stream]:
+            cur.wait_stream(st)                # e1 after everything the timed region enqueued
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -389,8 +426,8 @@ def run_ours(a):
                                params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B),
                 "frames_per_step_per_gpu": B, "distinct_frames": a.distinct,
                 "l2_policy": "inputs larger than L2: %.0f MB of points per step, two alternating input sets" % (in_bytes / 1e6),
-                "sharding": "frame-wise, no data-path collective; per step one all_gather of packed proposals + one "
-                            "all_reduce of recall counters" if world > 1 else "single GPU"},
+                "sharding": "frame-wise, no data-path collective; one all_gather of packed proposals + one "
+                            "all_reduce of recall counters per run, inside the timed region" if world > 1 else "single GPU"},
             "hypotheses_per_s": F_step * H * world * a.steps / (ms_res * 1e-3),
             "point_box_tests_per_s_scoring_kernel": tests / (score_ms * 1e-3),
             "e2e": {"value": n_frames * a.steps / (ms_e2e * 1e-3), "unit": "frames/s",

@@ -456,65 +456,186 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-// k-th smallest (0-based) and (k+1)-th smallest depth of a frustum: MSD radix select on the
-// float bit patterns (depths are >= 1e-5 > 0, so the patterns order like the values).
+// k-th (0-based) and (k+1)-th smallest depth of a frustum, exactly.  Depths are >= 1e-5 > 0, so
+// their bit patterns order like the values and everything below is integer arithmetic on
+// rel = key - kmin.  Range-normalised MSD radix select: the first 11-bit digit already spreads the
+// keys over [kmin, kmax] (2048 bins), a bin with few enough keys is finished by rank counting in
+// shared memory, a crowded one is refined by the next 11 bits.  Typical frustum: one histogram
+// pass + one collect pass, both from the shared-memory key cache when the frustum fits.
 // All threads of the block call this; results are block-uniform.
+constexpr int kSelBits = 11, kSelBins = 1 << kSelBits;
+constexpr int kSelList = 512;      // keys finished by rank counting
+constexpr int kStatsCache = 4096;  // depth keys cached in shared memory
+constexpr int kStatsThreads = 256;
+
 __device__ __forceinline__ float pt_depth(const float *__restrict__ pts, int i)
 {
     return pts[(size_t)(i >> 1) * 8 + 6 + (i & 1)];
 }
 
-__device__ void select_pair(const float *__restrict__ pts, int n, int k, unsigned *s_hist, unsigned *s_misc,
-                            float &v_lo, float &v_hi)
+struct SelSmem {
+    unsigned hist[kSelBins];
+    unsigned list[kSelList];
+    unsigned key[kStatsCache];
+    unsigned warp_sum[kStatsThreads / 32];
+    unsigned misc[8];   // 0 bin, 1 keys below it, 2 keys in it, 3 next non-empty bin, 4 list fill, 5 min key above, 6/7 results
+};
+
+// Calls f(key) for every depth key of the frustum, block-strided.  Uncached frustums (the few
+// large ones, which set the duration of the whole kernel) are read as pair records with four
+// independent 16-byte loads in flight per thread.
+template <typename F>
+__device__ __forceinline__ void for_each_key(const float *__restrict__ pts, const SelSmem &S, bool cached, int n, F f)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
-    unsigned prefix = 0, mask = 0;
-    int rank = k;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < n; i += nt) {
-            const unsigned key = __float_as_uint(pt_depth(pts, i));
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    if (cached) {
+        for (int i = tid; i < n; i += nt) f(S.key[i]);
+        return;
+    }
+    const float4 *rec = reinterpret_cast<const float4 *>(pts);
+    const int np = (n + 1) >> 1;                         // pair records
+    for (int p0 = tid; p0 < np; p0 += 4 * nt) {
+        float4 c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * nt;
+            if (p < np) c[u] = __ldg(rec + 2 * p + 1);   // z0 z1 d0 d1
         }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned acc = 0;
-            int bin = 0;
-            for (; bin < 256; bin++) {
-                const unsigned c = s_hist[bin];
-                if (acc + c > (unsigned)rank) break;
-                acc += c;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * nt;
+            if (p < np) {
+                f(__float_as_uint(c[u].z));
+                if (2 * p + 1 < n) f(__float_as_uint(c[u].w));
             }
-            s_misc[0] = (unsigned)bin;
-            s_misc[1] = acc;
+        }
+    }
+}
+
+__device__ void select_pair(const float *__restrict__ pts, SelSmem &S, bool cached, int n, int k, unsigned kmin,
+                            unsigned kmax, float &v_lo, float &v_hi)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    if (kmin == kmax) { v_lo = v_hi = __uint_as_float(kmin); return; }
+    int shift = max(0, (32 - __clz(kmax - kmin)) - kSelBits);   // digit = (rel >> shift) & 2047; level 1: rel >> shift < 2048
+    int pshift = 32;          // current set: (rel >> pshift) == (lo_rel >> pshift); 32 = every key
+    unsigned lo_rel = 0;
+    int rank = k;             // rank of the wanted key inside the current set
+    // keys above the current set: the nearest non-empty bin seen so far (nb_*), whose minimum is only
+    // needed if the (k+1)-th key is not in the final bin; it is evaluated lazily in a later pass
+    bool nb_valid = false;
+    unsigned nb_lo = 0;
+    int nb_shift = 0;
+    unsigned above = 0xffffffffu;
+    for (;;) {
+        for (int i = tid; i < kSelBins; i += nt) S.hist[i] = 0;
+        if (tid == 0) { S.misc[3] = kSelBins; S.misc[4] = 0; S.misc[5] = 0xffffffffu; }
+        __syncthreads();
+        unsigned my_above = 0xffffffffu;
+        for_each_key(pts, S, cached, n, [&](unsigned key) {
+            const unsigned rel = key - kmin;
+            if (nb_valid && (rel >> nb_shift) == (nb_lo >> nb_shift)) my_above = min(my_above, key);
+            if (pshift < 32 && (rel >> pshift) != (lo_rel >> pshift)) return;
+            atomicAdd(&S.hist[(rel >> shift) & (kSelBins - 1)], 1u);
+        });
+        if (nb_valid) {
+            my_above = __reduce_min_sync(0xffffffffu, my_above);
+            if (lane == 0 && my_above != 0xffffffffu) atomicMin(&S.misc[5], my_above);
         }
         __syncthreads();
-        prefix |= s_misc[0] << shift;
-        mask |= 255u << shift;
-        rank -= (int)s_misc[1];
+        if (nb_valid) { above = min(above, S.misc[5]); nb_valid = false; }
+        // ---- locate the bin holding `rank`: 8 bins per thread, block scan of the 256 partial sums
+        unsigned c[kSelBins / kStatsThreads], local = 0;
+#pragma unroll
+        for (int j = 0; j < kSelBins / kStatsThreads; j++) { c[j] = S.hist[tid * (kSelBins / kStatsThreads) + j]; local += c[j]; }
+        unsigned inc = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) S.warp_sum[warp] = inc;
+        __syncthreads();
+        unsigned excl = inc - local;
+        for (int w = 0; w < warp; w++) excl += S.warp_sum[w];
+        if ((unsigned)rank >= excl && (unsigned)rank < excl + local) {
+            unsigned acc = excl;
+#pragma unroll
+            for (int j = 0; j < kSelBins / kStatsThreads; j++) {
+                if ((unsigned)rank >= acc && (unsigned)rank < acc + c[j]) {
+                    S.misc[0] = tid * (kSelBins / kStatsThreads) + j;
+                    S.misc[1] = acc;
+                    S.misc[2] = c[j];
+                }
+                acc += c[j];
+            }
+        }
+        __syncthreads();
+        const unsigned B = S.misc[0], below = S.misc[1], cB = S.misc[2];
+#pragma unroll
+        for (int j = 0; j < kSelBins / kStatsThreads; j++) {
+            const unsigned bin = tid * (kSelBins / kStatsThreads) + j;
+            if (bin > B && c[j]) atomicMin(&S.misc[3], bin);
+        }
+        __syncthreads();
+        const unsigned Bn = S.misc[3];
+        rank -= (int)below;
+        const unsigned hi_part = (pshift < 32) ? ((lo_rel >> pshift) << pshift) : 0u;
+        const unsigned bin_lo = hi_part | (B << shift);
+        const bool has_next = Bn < (unsigned)kSelBins;
+        const unsigned next_lo = hi_part | (Bn << shift);
+        const bool second_in_bin = (unsigned)(rank + 1) < cB;
+
+        if (shift == 0) {                         // a bin is one exact key
+            v_lo = __uint_as_float(kmin + bin_lo);
+            if (second_in_bin) v_hi = v_lo;
+            else if (has_next) v_hi = __uint_as_float(kmin + next_lo);
+            else v_hi = (above != 0xffffffffu) ? __uint_as_float(above) : v_lo;
+            __syncthreads();
+            return;
+        }
+        if (cB <= (unsigned)kSelList) {           // finish: collect the bin, rank by counting
+            unsigned nmin = 0xffffffffu;
+            for_each_key(pts, S, cached, n, [&](unsigned key) {
+                const unsigned rel = key - kmin;
+                if (pshift < 32 && (rel >> pshift) != (lo_rel >> pshift)) return;
+                const unsigned digit = (rel >> shift) & (kSelBins - 1);
+                if (digit == B) S.list[atomicAdd(&S.misc[4], 1u)] = key;
+                else if (!second_in_bin && has_next && digit == Bn) nmin = min(nmin, key);
+            });
+            if (!second_in_bin && has_next) {
+                nmin = __reduce_min_sync(0xffffffffu, nmin);
+                if (lane == 0 && nmin != 0xffffffffu) atomicMin(&S.misc[5], nmin);
+            }
+            __syncthreads();
+            const int m = (int)cB;
+            for (int e = tid; e < m; e += nt) {
+                const unsigned key = S.list[e];
+                int lt = 0, le = 0;
+                for (int j = 0; j < m; j++) { const unsigned o = S.list[j]; lt += o < key; le += o <= key; }
+                if (lt <= rank && rank < le) S.misc[6] = key;               // same value from every writer
+                if (second_in_bin && lt <= rank + 1 && rank + 1 < le) S.misc[7] = key;
+            }
+            __syncthreads();
+            v_lo = __uint_as_float(S.misc[6]);
+            if (second_in_bin) v_hi = __uint_as_float(S.misc[7]);
+            else if (has_next) v_hi = __uint_as_float(S.misc[5]);
+            else v_hi = (above != 0xffffffffu) ? __uint_as_float(above) : v_lo;
+            __syncthreads();
+            return;
+        }
+        // ---- refine the crowded bin with the next digit
+        if (has_next) { nb_valid = true; nb_lo = next_lo; nb_shift = shift; }
+        lo_rel = bin_lo;
+        pshift = shift;
+        shift = max(0, shift - kSelBits);
         __syncthreads();
     }
-    v_lo = __uint_as_float(prefix);
-    // neighbour: count of keys <= v_lo and the smallest key above it
-    if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0xffffffffu; }
-    __syncthreads();
-    unsigned c_le = 0, nxt = 0xffffffffu;
-    for (int i = tid; i < n; i += nt) {
-        const unsigned key = __float_as_uint(pt_depth(pts, i));
-        if (key <= prefix) c_le++;
-        else nxt = min(nxt, key);
-    }
-    atomicAdd(&s_misc[2], c_le);
-    atomicMin(&s_misc[3], nxt);
-    __syncthreads();
-    v_hi = ((int)s_misc[2] >= k + 2 || s_misc[3] == 0xffffffffu) ? v_lo : __uint_as_float(s_misc[3]);
-    __syncthreads();
 }
 
 // torch.quantile(depth, q), linear interpolation (ATen Sorting.cpp quantile_compute + lerp)
-__device__ float block_quantile(const float *__restrict__ pts, int n, float q, float dmin, float dmax,
-                                unsigned *s_hist, unsigned *s_misc)
+__device__ float block_quantile(const float *__restrict__ pts, SelSmem &S, bool cached, int n, float q, float dmin,
+                                float dmax)
 {
     const float pos = __fmul_rn(q, (float)(n - 1));
     const float lo = floorf(pos), hi = ceilf(pos);
@@ -524,17 +645,16 @@ __device__ float block_quantile(const float *__restrict__ pts, int n, float q, f
     if (khi == 0) { a = dmin; bv = dmin; }
     else if (klo == n - 1) { a = dmax; bv = dmax; }
     else {
-        select_pair(pts, n, klo, s_hist, s_misc, a, bv);
+        select_pair(pts, S, cached, n, klo, __float_as_uint(dmin), __float_as_uint(dmax), a, bv);
         if (khi == klo) bv = a;
     }
     const float diff = __fsub_rn(bv, a);
     return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), bv);
 }
 
-__global__ void __launch_bounds__(256) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+__global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
-    __shared__ unsigned s_hist[256];
-    __shared__ unsigned s_misc[4];
+    __shared__ SelSmem S;
     __shared__ float s_red[8][8];
     __shared__ float s_geo[16];  // close[3], vec[3]
     const int f = blockIdx.x;
@@ -551,17 +671,34 @@ __global__ void __launch_bounds__(256) stats_kernel(const fnp_seeker_batch b, co
     const float INF = __int_as_float(0x7f800000);
     float mn[4] = {INF, INF, INF, INF}, mx[4] = {-INF, -INF, -INF, -INF};
     const float4 *rec = reinterpret_cast<const float4 *>(pts);
-    for (int p = tid; 2 * p < n; p += blockDim.x) {
-        const float4 a = rec[2 * p], c = rec[2 * p + 1];          // x0 x1 y0 y1 | z0 z1 d0 d1
-        mn[0] = fminf(mn[0], a.x); mx[0] = fmaxf(mx[0], a.x);
-        mn[1] = fminf(mn[1], a.z); mx[1] = fmaxf(mx[1], a.z);
-        mn[2] = fminf(mn[2], c.x); mx[2] = fmaxf(mx[2], c.x);
-        mn[3] = fminf(mn[3], c.z); mx[3] = fmaxf(mx[3], c.z);
-        if (2 * p + 1 < n) {
-            mn[0] = fminf(mn[0], a.y); mx[0] = fmaxf(mx[0], a.y);
-            mn[1] = fminf(mn[1], a.w); mx[1] = fmaxf(mx[1], a.w);
-            mn[2] = fminf(mn[2], c.y); mx[2] = fmaxf(mx[2], c.y);
-            mn[3] = fminf(mn[3], c.w); mx[3] = fmaxf(mx[3], c.w);
+    const bool cached = n <= kStatsCache;                         // depth keys stay in shared memory
+    const int np = (n + 1) >> 1;
+    for (int p0 = tid; p0 < np; p0 += 4 * kStatsThreads) {        // four records (8 loads) in flight per thread
+        float4 ra[4], rc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * kStatsThreads;
+            if (p < np) { ra[u] = rec[2 * p]; rc[u] = rec[2 * p + 1]; }   // x0 x1 y0 y1 | z0 z1 d0 d1
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * kStatsThreads;
+            if (p >= np) continue;
+            const float4 a = ra[u], c = rc[u];
+            if (cached) {
+                S.key[2 * p] = __float_as_uint(c.z);
+                if (2 * p + 1 < n) S.key[2 * p + 1] = __float_as_uint(c.w);
+            }
+            mn[0] = fminf(mn[0], a.x); mx[0] = fmaxf(mx[0], a.x);
+            mn[1] = fminf(mn[1], a.z); mx[1] = fmaxf(mx[1], a.z);
+            mn[2] = fminf(mn[2], c.x); mx[2] = fmaxf(mx[2], c.x);
+            mn[3] = fminf(mn[3], c.z); mx[3] = fmaxf(mx[3], c.z);
+            if (2 * p + 1 < n) {
+                mn[0] = fminf(mn[0], a.y); mx[0] = fmaxf(mx[0], a.y);
+                mn[1] = fminf(mn[1], a.w); mx[1] = fmaxf(mx[1], a.w);
+                mn[2] = fminf(mn[2], c.y); mx[2] = fmaxf(mx[2], c.y);
+                mn[3] = fminf(mn[3], c.w); mx[3] = fmaxf(mx[3], c.w);
+            }
         }
     }
 #pragma unroll
@@ -580,9 +717,9 @@ __global__ void __launch_bounds__(256) stats_kernel(const fnp_seeker_batch b, co
     __syncthreads();
 
     // ---- depth quantiles (frustum_proposals_v1.py:616-648)
-    const float qmin = block_quantile(pts, n, cfg.lq, mn[3], mx[3], s_hist, s_misc);
-    const float qmax = block_quantile(pts, n, cfg.uq, mn[3], mx[3], s_hist, s_misc);
-    const float qc = block_quantile(pts, n, cfg.cq, mn[3], mx[3], s_hist, s_misc);
+    const float qmin = block_quantile(pts, S, cached, n, cfg.lq, mn[3], mx[3]);
+    const float qmax = block_quantile(pts, S, cached, n, cfg.uq, mn[3], mx[3]);
+    const float qc = block_quantile(pts, S, cached, n, cfg.cq, mn[3], mx[3]);
     const float dmax = fminf(qmax, cfg.max_dist);
     const float dmin = fmaxf(qmin, cfg.frustum_min);
 

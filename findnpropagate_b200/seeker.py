@@ -330,12 +330,15 @@ class SeekerEngine:
             sizes["out"] = off_keep + _align(F, 8)
             if self.debug:
                 sizes.update(frustum_idx=4 * cap, stage_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
-            ptr = {k: self.arena.get(k, v).data_ptr() for k, v in sizes.items() if k != "out"}
+            # every slot owns its intermediates, so that batches of different slots may be in flight on
+            # different streams at the same time (slot 0 keeps the plain names: debug_views reads them)
+            sfx = "" if slot == 0 else "@%d" % slot
+            ptr = {k: self.arena.get(k + sfx, v).data_ptr() for k, v in sizes.items() if k != "out"}
             out_dev = self.arena.get("out%d" % slot, sizes["out"])
             ob = out_dev.data_ptr()
             o_boxes, o_score, o_best, o_count = ob, ob + 28 * F, ob + 32 * F, ob + 36 * F
             o_npts, o_nvalid, o_status = ob + 40 * F, ob + 44 * F, ob + 48 * F
-            o_ptstart = self.arena.get("cand_pt_start", 4 * (F + 1)).data_ptr()
+            o_ptstart = self.arena.get("cand_pt_start" + sfx, 4 * (F + 1)).data_ptr()
             b = _lib.SeekerBatch(
                 n_frames=B, n_cands=F, n_tiles=plan["n_tiles"], max_cands_per_frame=Cmax,
                 points=points_dev.data_ptr(), point_stride=plan["stride"], xyz_offset=plan["xyz_offset"],

@@ -294,27 +294,32 @@ def run_ours(a):
             consumed[k % 2].record()
         res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
         if res is not None and world > 1:
+            res["plan_score"], res["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
             pending.append(res)
         return h, res
 
     pending = []            # results of this rank's shard, exchanged once per run (not per step)
 
     def gather_results():
-        # frame-sharded run: ONE all_gather of fixed-stride packed proposals (+ its count vector) and
+        # frame-sharded run: ONE all_gather of fixed-stride packed proposals (+ per-frame counts) and
         # ONE all_reduce of the recall counters for the whole shard (NCCL over NVLink), as in
-        # findnpropagate_b200.extract.gather_shards; kcap is fixed, so no size negotiation is needed
-        frames_l = [fr for res in pending for fr in res["frames"]]
-        kcap = 256
-        pack = torch.zeros((len(frames_l), kcap, 9), dtype=torch.float32, pin_memory=True)
-        cnt = torch.zeros((len(frames_l),), dtype=torch.int32, pin_memory=True)
+        # findnpropagate_b200.extract.gather_shards.  Per step the proposals of all frames are packed
+        # back to back ([box7, score, label] rows) into a fixed-capacity slab, so no sizes are negotiated.
+        n_steps, cap = len(pending), B * 64
+        pack = torch.zeros((n_steps, cap, 9), dtype=torch.float32, pin_memory=True)
+        cnt = torch.zeros((n_steps, B), dtype=torch.int32, pin_memory=True)
         pk, ck = pack.numpy(), cnt.numpy()
-        for i, fr in enumerate(frames_l):
-            k = fr["pred_boxes"].shape[0]
-            pk[i, :k, :7] = fr["pred_boxes"]; pk[i, :k, 7] = fr["pred_scores"]; pk[i, :k, 8] = fr["pred_labels"]
-            ck[i] = k
+        for i, res in enumerate(pending):
+            m = res["cand_valid"]
+            n = int(m.sum())
+            assert n <= cap
+            pk[i, :n, :7] = res["cand_boxes"][m]
+            pk[i, :n, 7] = res["plan_score"][m]
+            pk[i, :n, 8] = res["plan_label"][m]
+            ck[i] = [fr["pred_boxes"].shape[0] for fr in res["frames"]]
         tp, tc = pack.to(dev, non_blocking=True), cnt.to(dev, non_blocking=True)
-        allp = torch.empty((world * len(frames_l), kcap, 9), dtype=tp.dtype, device=dev)
-        allc = torch.empty((world * len(frames_l),), dtype=tc.dtype, device=dev)
+        allp = torch.empty((world,) + tuple(tp.shape), dtype=tp.dtype, device=dev)
+        allc = torch.empty((world,) + tuple(tc.shape), dtype=tc.dtype, device=dev)
         dist.all_gather_into_tensor(allp, tp)
         dist.all_gather_into_tensor(allc, tc)
         keys = sorted(pending[0]["recall"]) if pending else []
@@ -328,7 +333,12 @@ def run_ours(a):
         for k in range(warmup):
             prev, _ = step(k, resident, prev)
         if prev is not None:
-            eng.finish(prev)
+            r = eng.finish(prev)
+            if world > 1:
+                r["plan_score"], r["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
+                pending.append(r)
+        if world > 1 and pending:
+            gather_results()               # warm-up of the exchange too (NCCL connects lazily per collective)
         pending.clear()
         torch.cuda.synchronize()
         if world > 1:
@@ -346,6 +356,7 @@ def run_ours(a):
             last = r or last
         last = eng.finish(prev)
         if world > 1:
+            last["plan_score"], last["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
             pending.append(last)
             gather_results()
         for st in comp + [copy_stream]:

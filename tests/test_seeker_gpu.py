@@ -218,6 +218,49 @@ def test_full_size_properties_cfg2():
     assert np.array_equal(r3["cand_count"][v], res["cand_count"][v])
 
 
+def test_stress_cfg5_whole_frame_vs_oracle(monkeypatch):
+    """BASELINE.json configs[4]: 1M-point frame, 200 2D boxes, 128 x 24 = 3072 hypotheses per
+    frustum.  The whole-frame oracle runs on it stage by stage; to keep it to seconds, oracle
+    count calls above 2e7 point-box tests are answered by the op-level count kernel
+    (fnp_count_in_boxes, itself pinned bit-exact against the oracle and the reference kernel in
+    test_ops_gpu.py), smaller ones by the C oracle.  Also checks stage-4 NMS and recall."""
+    from findnpropagate_b200 import _lib
+    cfg = synth.CONFIGS["cfg5"]
+    params = synth.seeker_params(cfg)
+    frames = [_frame_from_synth(synth.make_frame(0, cfg, device="cuda:0"))]
+    assert frames[0].points.shape[0] > 900_000
+    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    assert eng.H == 3072
+    c_oracle = O.count_in_boxes
+    calls = {"oracle": 0, "gpu": 0}
+
+    def count(points, boxes):
+        if points.shape[0] * boxes.shape[0] <= 2e7:
+            calls["oracle"] += 1
+            return c_oracle(points, boxes)
+        calls["gpu"] += 1
+        p4 = np.zeros((points.shape[0], 4), np.float32)
+        p4[:, :3] = points[:, :3]
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+        tp, tb = d(p4), d(np.ascontiguousarray(boxes, np.float32))
+        ps, bs = d(np.array([0, points.shape[0]], np.int32)), d(np.array([0, boxes.shape[0]], np.int32))
+        cnt = torch.zeros(boxes.shape[0], dtype=torch.int32, device="cuda:0")
+        assert _lib.lib.fnp_count_in_boxes(tp.data_ptr(), ps.data_ptr(), tb.data_ptr(), bs.data_ptr(), 1, cnt.data_ptr(),
+                                           _lib.current_stream()) == 0
+        return cnt.cpu().numpy()
+
+    monkeypatch.setattr(O, "count_in_boxes", count)
+    res, n = _check_against_oracle(eng, frames, params)
+    assert n > 100 and calls["oracle"] > 0 and calls["gpu"] > 0
+    r2 = eng.run(frames, nms_thresh=0.1, with_recall=True)
+    fr = r2["frames"][0]
+    kept = O.nms_rotated(fr["pred_boxes"], fr["pred_scores"], 0.1)
+    m = np.zeros(fr["pred_boxes"].shape[0], bool)
+    m[kept] = True
+    assert np.array_equal(fr["nms_keep"], m)
+    assert r2["recall"] == SO.recall_record(fr["pred_boxes"], frames[0].gt_boxes)
+
+
 def test_reference_compatible_head_and_extraction(tmp_path):
     """FrustumProposerOG drop-in: same call contract / return types as the reference head
     (frustum_proposals_v1.py:1055-1067,1554-1573) and the extraction output format."""

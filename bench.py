@@ -431,9 +431,12 @@ def run_ours(a):
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_res / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s frames (BASELINE.json configs[1] shape: 10 sweeps ~%dk points, 6 cameras, ~%d 2D boxes, "
+                "workload": "%s frames (%s: ~%dk points, 6 cameras, ~%d 2D boxes, "
                             "%d depths x %d yaws = %d hypotheses/frustum), batch of %d frames per step per GPU"
-                            % (a.config, int(np.mean([f.points.shape[0] for f in batch]) / 1000), F_step // B,
+                            % (a.config, {"cfg1": "BASELINE.json configs[0] shape, 1 sweep",
+                                          "cfg2": "BASELINE.json configs[1] shape, 10 sweeps",
+                                          "cfg5": "BASELINE.json configs[4] shape, 128 beams"}.get(a.config, "custom"),
+                               int(np.mean([f.points.shape[0] for f in batch]) / 1000), F_step // B,
                                params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B),
                 "frames_per_step_per_gpu": B, "distinct_frames": a.distinct,
                 "l2_policy": "inputs larger than L2: %.0f MB of points per step, two alternating input sets" % (in_bytes / 1e6),

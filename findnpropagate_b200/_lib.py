@@ -43,8 +43,8 @@ class SeekerBatch(C.Structure):
         ("frustum_idx", _vp), ("pts_capacity", C.c_int64), ("cand_stats", _vp), ("centres", _vp),
         ("hyp_prep", _vp), ("hyp_index", _vp), ("hyp_iou", _vp), ("hyp_nvalid", _vp),
         ("hyp_boxes_dbg", _vp), ("hyp_iou_dbg", _vp), ("hyp_valid_dbg", _vp),
-        ("split_points", C.c_int32), ("max_items", C.c_int32), ("max_count_rows", C.c_int32),
-        ("cand_item_start", _vp), ("cand_split_row", _vp), ("items", _vp), ("counts", _vp),
+        ("split_points", C.c_int32), ("max_items", C.c_int32),
+        ("cand_item_start", _vp), ("items", _vp), ("counts", _vp),
         ("out_boxes", _vp), ("out_score", _vp), ("out_best", _vp), ("out_count", _vp),
         ("status", _vp),
     ]

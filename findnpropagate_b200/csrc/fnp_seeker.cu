@@ -903,62 +903,53 @@ __host__ __device__ inline int score_chunks(int nv) { return (nv + kScoreChunk -
 // Work items of the scoring stage.  Frustum f with P_f points and nv_f valid hypotheses is cut
 // into S_f = ceil(P_f / split_points) point splits x score_chunks(nv_f) hypothesis
 // chunks; every (split, chunk) pair is one CTA-sized item, so the largest frustums no longer
-// set the kernel's duration.  Split s of frustum f writes its partial counts to row
-// split_row[f] + s of `counts`; select_kernel adds the S_f rows (a fixed-order integer
-// reduction, no atomics).
+// set the kernel's duration.  A thread keeps its counts in registers for the whole item and adds
+// them to row f of `counts` with one integer RED per hypothesis at the end (integer addition is
+// associative: the totals do not depend on the order in which the splits finish).
 __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch b, const int H)
 {
-    __shared__ int s_warp_i[32], s_warp_r[32];
-    __shared__ int s_carry_i, s_carry_r;
+    __shared__ int s_warp_i[32];
+    __shared__ int s_carry_i;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry_i = 0; s_carry_r = 0; }
+    if (tid == 0) s_carry_i = 0;
     __syncthreads();
     for (int base = 0; base < b.n_cands; base += 1024) {
         const int f = base + tid;
-        int rows = 0, items = 0;
+        int items = 0;
         if (f < b.n_cands) {
             const int np = b.cand_npts[f], nv = b.hyp_nvalid[f];
-            if (np > 0 && nv > 0) {
-                rows = (np + b.split_points - 1) / b.split_points;
-                items = rows * score_chunks(nv);
-            }
+            if (np > 0 && nv > 0) items = ((np + b.split_points - 1) / b.split_points) * score_chunks(nv);
         }
-        int inc_i = items, inc_r = rows;
+        int inc_i = items;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int a = __shfl_up_sync(0xffffffffu, inc_i, o);
-            const int c = __shfl_up_sync(0xffffffffu, inc_r, o);
-            if (lane >= o) { inc_i += a; inc_r += c; }
+            if (lane >= o) inc_i += a;
         }
-        if (lane == 31) { s_warp_i[warp] = inc_i; s_warp_r[warp] = inc_r; }
+        if (lane == 31) s_warp_i[warp] = inc_i;
         __syncthreads();
         if (warp == 0) {
-            int wi = s_warp_i[lane], wr = s_warp_r[lane];
+            int wi = s_warp_i[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int a = __shfl_up_sync(0xffffffffu, wi, o);
-                const int c = __shfl_up_sync(0xffffffffu, wr, o);
-                if (lane >= o) { wi += a; wr += c; }
+                if (lane >= o) wi += a;
             }
-            s_warp_i[lane] = wi; s_warp_r[lane] = wr;
+            s_warp_i[lane] = wi;
         }
         __syncthreads();
-        const int ci = s_carry_i, cr = s_carry_r;
-        if (f < b.n_cands) {
-            b.cand_item_start[f] = ci + (warp ? s_warp_i[warp - 1] : 0) + inc_i - items;
-            b.cand_split_row[f] = cr + (warp ? s_warp_r[warp - 1] : 0) + inc_r - rows;
-        }
+        const int ci = s_carry_i;
+        if (f < b.n_cands) b.cand_item_start[f] = ci + (warp ? s_warp_i[warp - 1] : 0) + inc_i - items;
         __syncthreads();
-        if (tid == 1023) { s_carry_i = ci + s_warp_i[31]; s_carry_r = cr + s_warp_r[31]; }
+        if (tid == 1023) s_carry_i = ci + s_warp_i[31];
         __syncthreads();
     }
     if (tid == 0) {
         b.cand_item_start[b.n_cands] = s_carry_i;
-        b.cand_split_row[b.n_cands] = s_carry_r;
         b.status[2] = s_carry_i;
-        b.status[3] = s_carry_r;
+        b.status[3] = 0;
         b.status[4] = 0;            // work-item counter of the persistent scoring CTAs
-        if (s_carry_i > b.max_items || s_carry_r > b.max_count_rows) b.status[0] |= 2;
+        if (s_carry_i > b.max_items) b.status[0] |= 2;
     }
 }
 
@@ -1119,11 +1110,11 @@ __device__ __forceinline__ void score_item(const fnp_seeker_batch &b, const int 
         }
     }
 
-    int *out = b.counts + (size_t)(b.cand_split_row[f] + split) * H;
+    int *out = b.counts + (size_t)f * H;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int r = h_base + k * kScoreThreads + tid;
-        if (r < nv) out[r] = cnt[k];
+        if (r < nv && cnt[k]) atomicAdd(out + r, cnt[k]);      // RED.ADD, result unused
     }
 }
 
@@ -1172,20 +1163,13 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
         if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
         return;
     }
-    const int S = b.cand_split_row[f + 1] - b.cand_split_row[f];
-    if (S <= 0 || (b.status[0] & 2)) {
+    if (b.status[0] & 2) {
         if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
         return;
     }
-    int *cbase = b.counts + (size_t)b.cand_split_row[f] * H;
-    // total counts (plane 0 receives the sum), block max
+    const int *cbase = b.counts + (size_t)f * H;
     int mx = 0;
-    for (int r = tid; r < nv; r += blockDim.x) {
-        int c = cbase[r];
-        for (int s = 1; s < S; s++) c += cbase[(size_t)s * H + r];
-        cbase[r] = c;
-        mx = max(mx, c);
-    }
+    for (int r = tid; r < nv; r += blockDim.x) mx = max(mx, cbase[r]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) s_i[warp] = mx;
@@ -1240,7 +1224,7 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     if (!cfg || !b) return FNP_EINVAL;
     if (b->n_frames < 0 || b->n_cands < 0 || b->n_tiles < 0) return FNP_EINVAL;
     if (cfg->num_mags < 1 || cfg->num_yaw_size < 1) return FNP_EINVAL;
-    if (b->max_items < 0 || b->max_count_rows < 0 || b->split_points < 2 || (b->split_points & 1)) return FNP_EINVAL;
+    if (b->max_items < 0 || b->split_points < 2 || (b->split_points & 1)) return FNP_EINVAL;
     return FNP_OK;
 }
 
@@ -1336,7 +1320,8 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     if (b->n_cands == 0) return FNP_OK;
     const int H = cfg->num_mags * cfg->num_yaw_size;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!b->items || !b->cand_item_start || !b->cand_split_row || !b->counts) return FNP_EINVAL;
+    if (!b->items || !b->cand_item_start || !b->counts) return FNP_EINVAL;
+    cudaMemsetAsync(b->counts, 0, sizeof(int32_t) * (size_t)b->n_cands * H, st);
     plan_items_kernel<<<1, 1024, 0, st>>>(*b, H);
     write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H);
     if (b->max_items > 0) {

@@ -309,8 +309,7 @@ class SeekerEngine:
                 # 2048 -> 0.737 ms, 512 -> 0.666 ms, 256 -> 0.663 ms), large enough to amortise an item
                 sp = plan["total_rows"] // (self.n_sms * 128)
                 sp = int(min(2048, max(256, 1 << max(sp, 1).bit_length() - 1)))
-            max_rows = cap // sp + F + 1
-            max_items = max_rows * chunks
+            max_items = (cap // sp + F + 1) * chunks
             Cmax = max(plan["max_cands"], 1)
             W = _lib.lib.fnp_seeker_mask_words(Cmax)
             if W < 0:
@@ -320,8 +319,8 @@ class SeekerEngine:
                 tile_base=4 * plan["n_tiles"], cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
                 frustum_pts=16 * cap, stage_pts=16 * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
-                hyp_iou=4 * H * F, counts=4 * H * max_rows, items=16 * max_items,
-                cand_item_start=4 * (F + 1), cand_split_row=4 * (F + 1),
+                hyp_iou=4 * H * F, counts=4 * H * F, items=16 * max_items,
+                cand_item_start=4 * (F + 1),
                 )
             # outputs, one D2H: boxes(7) score best count npts nvalid per candidate, status(4) + pad(4),
             # recall counters (20 x int64), stage-4 keep flags (F bytes)
@@ -356,8 +355,8 @@ class SeekerEngine:
                 hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
                 hyp_boxes_dbg=ptr.get("hyp_boxes_dbg"), hyp_iou_dbg=ptr.get("hyp_iou_dbg"),
                 hyp_valid_dbg=ptr.get("hyp_valid_dbg"),
-                split_points=sp, max_items=max_items, max_count_rows=max_rows,
-                cand_item_start=ptr["cand_item_start"], cand_split_row=ptr["cand_split_row"], items=ptr["items"],
+                split_points=sp, max_items=max_items,
+                cand_item_start=ptr["cand_item_start"], items=ptr["items"],
                 counts=ptr["counts"],
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
@@ -419,7 +418,7 @@ class SeekerEngine:
         if status[0] & 1:
             raise OverflowError(int(status[1]))
         if status[0] & 2:
-            raise RuntimeError("scoring work-item tables overflowed (items %d, rows %d)" % (status[2], status[3]))
+            raise RuntimeError("scoring work-item table overflowed (%d items)" % status[2])
         ok = best >= 0
         fcs = plan["frame_cand_start"]
         keep = raw[handle["off_keep"]:handle["off_keep"] + F].astype(bool) if handle["has_nms"] else None
@@ -520,6 +519,5 @@ class SeekerEngine:
             hyp_valid=view("hyp_valid_dbg", torch.uint8, (F, H)).astype(bool),
             hyp_index=view("hyp_index", torch.int32, (F, H)),
             hyp_prep=view("hyp_prep", torch.float32, (F, H, 8)),
-            counts=view("counts", torch.int32, (handle["batch"].max_count_rows, H))[
-                np.minimum(view("cand_split_row", torch.int32, (F + 1,))[:F], handle["batch"].max_count_rows - 1)],
+            counts=view("counts", torch.int32, (F, H)),
         )

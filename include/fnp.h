@@ -161,21 +161,19 @@ typedef struct fnp_seeker_batch {
     float *hyp_iou_dbg;              /* (F,H) or NULL                                      */
     uint8_t *hyp_valid_dbg;          /* (F,H) or NULL                                      */
     int32_t split_points;            /* points per scoring work item (point split); even   */
-    int32_t max_items;               /* capacity of `items` = grid of the scoring kernel   */
-    int32_t max_count_rows;          /* capacity (rows) of `counts`                        */
+    int32_t max_items;               /* capacity of `items`                                */
     int32_t *cand_item_start;        /* (F+1) first work item of each frustum              */
-    int32_t *cand_split_row;         /* (F+1) first partial-count row of each frustum      */
     int32_t *items;                  /* (max_items,4) work items: frustum, first hypothesis, split,
                                         hypotheses per thread (1..4)                         */
-    int32_t *counts;                 /* (max_count_rows,H) per-split partial counts; after
-                                        stage 3 the first row of a frustum holds the totals */
+    int32_t *counts;                 /* (F,H) point count of every compacted hypothesis (zeroed by
+                                        fnp_seeker_score, accumulated per point split)      */
     /* ---- outputs ---- */
     float *out_boxes;                /* (F,7) selected box per candidate                   */
     float *out_score;                /* (F)   its second-stage score                       */
     int32_t *out_best;               /* (F)   compacted index of the winner, -1 if none    */
     int32_t *out_count;              /* (F)   point count of the winner                    */
     int32_t *status;                 /* (8)   [0] bit0: frustum_pts overflow (needed points in [1]),
-                                        bit1: items/counts overflow ([2] items, [3] rows needed);
+                                        bit1: items overflow ([2] items needed);
                                         [4] work-item counter of the scoring kernel; [5] staging
                                         cursor of stage 1; [6..7] spare                     */
 } fnp_seeker_batch;

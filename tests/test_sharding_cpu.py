@@ -95,3 +95,22 @@ def test_glip_feeder_roundtrip(tmp_path):
     boxes, labels, scores, bidx, cam = feeder(bd)
     assert boxes.shape == (36, 4) and labels.shape == (36,) and cam.tolist()[:6] == [0, 0, 0, 1, 1, 1]
     assert bidx.tolist() == [0] * 18 + [1] * 18
+
+
+def test_pseudo_file_reader_roundtrip(tmp_path):
+    """extract.save_frame -> pseudo_loader.load_pseudos: the reference's file format and the (K,8)
+    layout of PseudoLoader.load_pseudos (pseudo_loader.py:561-679); missing file -> empty."""
+    from findnpropagate_b200 import extract, pseudo_loader
+    rng = np.random.default_rng(0)
+    pred = dict(pred_boxes=rng.normal(size=(5, 7)).astype(np.float32), pred_scores=rng.random(5).astype(np.float32),
+                pred_labels=np.array([1, 9, 3, 9, 10], np.int32))
+    path = extract.save_frame(str(tmp_path), "n015-2018.pcd.bin", pred)
+    assert path.endswith("n015-2018_pcd_bin.pth")
+    boxes, scores = pseudo_loader.load_pseudos(tmp_path, "n015-2018.pcd.bin")
+    assert boxes.shape == (5, 8) and boxes.dtype == np.float32
+    assert np.array_equal(boxes[:, :7], pred["pred_boxes"]) and np.array_equal(boxes[:, 7], pred["pred_labels"])
+    assert np.array_equal(scores, pred["pred_scores"])
+    b9, s9 = pseudo_loader.load_pseudos(tmp_path, "n015-2018.pcd.bin", labels={9})
+    assert b9.shape == (2, 8) and np.all(b9[:, 7] == 9)
+    e, es = pseudo_loader.load_pseudos(tmp_path, "missing")
+    assert e.shape == (0, 8) and es.shape == (0,)

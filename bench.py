@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--frames", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated per rank")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

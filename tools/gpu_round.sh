@@ -1,13 +1,14 @@
 #!/bin/bash
-# One GPU session: parity tests, smoke, bench, ncu launch list + full capture of the scoring kernel.
+# One full GPU session: parity tests, smoke, bench, ncu launch list + full capture of every kernel.
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --timeout=900 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -q --timeout=900 2>&1 | tail -5 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+python tools/stage_times.py --frames 128 > gpurun_out/stage_times_128.json 2> gpurun_out/stage_times.err; tail -3 gpurun_out/stage_times.err
 if [ "${NCU:-1}" = "1" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cull_|hypotheses_|plan_items|recall_|scan_|score_|seg_nms|select_|stats_|write_items' -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 8 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 2 -c 2 -o gpurun_out/prof_score -f python bench.py --steps 1 --warmup 1 --frames 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cull_|cell_table|hypotheses_|plan_items|recall_|scan_|score_|seg_nms|select_|stats_|write_items|upload_' -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+python tools/ncu_summary.py gpurun_out/launches.csv
+ncu --set full --clock-control none --import-source on -k 'regex:cull_|cell_table|hypotheses_|recall_|scan_|score_|seg_nms|select_|stats_' -s 15 -c 12 -o gpurun_out/prof_all -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+python tools/ncu_kernels.py gpurun_out/prof_all.ncu-rep
 fi
-ls -la gpurun_out

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libfnp_sm100.so")
+SO_PATH = os.environ.get("FNP_LIB_PATH") or os.path.join(HERE, "libfnp_sm100.so")   # override: A/B builds
 
 if not os.path.exists(SO_PATH):
     raise ImportError(

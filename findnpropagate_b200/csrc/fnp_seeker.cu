@@ -120,7 +120,7 @@ __device__ __forceinline__ unsigned long long row2(const float *__restrict__ a, 
 constexpr int kPtsPerThread = kCullSub;   // a thread owns row (sub * kCullThreads + tid) of every sub-tile
 
 template <int W>
-__global__ void __launch_bounds__(kCullThreads) cull_stage_kernel(const fnp_seeker_batch b, const float img_w,
+__global__ void __launch_bounds__(kCullThreads, 5) cull_stage_kernel(const fnp_seeker_batch b, const float img_w,
                                                                   const float img_h, const int n_cu, const int n_cv)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

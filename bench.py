@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated per rank")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--score-mode", default="auto", choices=["auto", "direct", "sweep"],
+                    help="stage-2b kernel (include/fnp.h FNP_SCORE_*); both give the same counts")
+    ap.add_argument("--split-points", type=int, default=None)
     return ap.parse_args()
 
 
@@ -251,7 +254,7 @@ def run_ours(a):
     frames_d, params = make_frames(a.config, rank * a.distinct, a.distinct, str(dev))
     B = a.frames
     batch = [frames_d[i % a.distinct] for i in range(B)]
-    eng = SeekerEngine(params, device=dev)
+    eng = SeekerEngine(params, device=dev, score_mode=a.score_mode, split_points=a.split_points)
     H = eng.H
     # two input sets (A/B) so that consecutive steps never touch the same HBM lines; each is
     # B x ~7.7 MB of points, well above the 126 MB L2 for the default B

@@ -45,12 +45,16 @@ class SeekerBatch(C.Structure):
         ("hyp_boxes_dbg", _vp), ("hyp_iou_dbg", _vp), ("hyp_valid_dbg", _vp),
         ("split_points", C.c_int32), ("max_items", C.c_int32),
         ("cand_item_start", _vp), ("items", _vp), ("counts", _vp),
+        ("score_mode", C.c_int32), ("sweep_cols", _vp),
         ("out_boxes", _vp), ("out_score", _vp), ("out_best", _vp), ("out_count", _vp),
         ("status", _vp),
     ]
 
 
 CULL_TILE = 1024
+SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
+SWEEP_MIN_MAGS = 16
+SWEEP_COL_FLOATS = 20
 SEG_NMS_MAX = 1024
 STATS_FLOATS = 40
 
@@ -74,6 +78,8 @@ for _n in ("fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses
            "fnp_seeker_select", "fnp_seeker_run"):
     getattr(lib, _n).restype = _i
     getattr(lib, _n).argtypes = [C.POINTER(SeekerCfg), C.POINTER(SeekerBatch), _vp]
+lib.fnp_seeker_score_mode.restype = _i
+lib.fnp_seeker_score_mode.argtypes = [C.POINTER(SeekerCfg), C.POINTER(SeekerBatch)]
 lib.fnp_seeker_mask_words.restype = _i
 lib.fnp_seeker_mask_words.argtypes = [_i]
 lib.fnp_seeker_cell_mask_bytes.restype = C.c_size_t
@@ -97,7 +103,7 @@ EXPORTED = [
     "fnp_version", "fnp_points_in_boxes", "fnp_count_in_boxes", "fnp_boxes_overlap_bev",
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
-    "fnp_seeker_score", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
+    "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates",
 ]
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/fnp.h"
+#include "fnp_sweep.cuh"   // BoxPrep, in_box (shared with the host model of the sweep)
 
 #define FNP_LAUNCH_CHECK()                         \
     do {                                           \
@@ -15,20 +16,6 @@
 namespace fnp {
 
 __host__ __device__ inline int divup(int a, int b) { return (a + b - 1) / b; }
-
-// ---------------------------------------------------------------------------------------
-// In-box predicate.  Reference arithmetic (roiaware_pool3d_kernel.cu:16-36 as compiled for
-// sm_100a): z test and x/y tests are evaluated in fp64,
-//     in_z  = !((double)|z-cz| > (double)dz * 0.5)
-//     in_xy = (double)|lx| < (double)dx*0.5 + (double)1e-5f   (same for y)
-// with lx = fma(sx, cosa, rn(sy * -sina)), ly = fma(sy, cosa, rn(sx * sina)),
-// cosa = cosf(-rz), sina = sinf(-rz).  The fp64 compares are hoisted exactly into fp32
-// thresholds per box: |l| < t  <=>  |l| <= pred(t), pred(t) = largest float strictly below t.
-// ---------------------------------------------------------------------------------------
-struct BoxPrep {
-    float cx, cy, cz, hz;      // centre, half height threshold
-    float cosa, sina, tx, ty;  // rotation by -heading, strict-less thresholds as <=
-};
 
 __device__ __forceinline__ float strict_lt_threshold(float dim)
 {
@@ -52,16 +39,6 @@ __device__ __forceinline__ BoxPrep prep_box(const float *__restrict__ b)
     p.tx = strict_lt_threshold(b[3]);
     p.ty = strict_lt_threshold(b[4]);
     return p;
-}
-
-__device__ __forceinline__ bool in_box(float x, float y, float z, const BoxPrep &p)
-{
-    const float sz = __fsub_rn(z, p.cz);
-    const float sx = __fsub_rn(x, p.cx);
-    const float sy = __fsub_rn(y, p.cy);
-    const float lx = __fmaf_rn(sx, p.cosa, __fmul_rn(sy, -p.sina));
-    const float ly = __fmaf_rn(sy, p.cosa, __fmul_rn(sx, p.sina));
-    return !(fabsf(sz) > p.hz) && (fabsf(lx) <= p.tx) && (fabsf(ly) <= p.ty);
 }
 
 // cnt += p as ONE predicated IADD (the C form compiles to add + predicated move)

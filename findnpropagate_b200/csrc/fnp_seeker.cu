@@ -906,7 +906,7 @@ __host__ __device__ inline int score_chunks(int nv) { return (nv + kScoreChunk -
 // set the kernel's duration.  A thread keeps its counts in registers for the whole item and adds
 // them to row f of `counts` with one integer RED per hypothesis at the end (integer addition is
 // associative: the totals do not depend on the order in which the splits finish).
-__global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch b, const int H)
+__global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch b, const int H, const int sweep)
 {
     __shared__ int s_warp_i[32];
     __shared__ int s_carry_i;
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch
         int items = 0;
         if (f < b.n_cands) {
             const int np = b.cand_npts[f], nv = b.hyp_nvalid[f];
-            if (np > 0 && nv > 0) items = ((np + b.split_points - 1) / b.split_points) * score_chunks(nv);
+            if (np > 0 && nv > 0) items = ((np + b.split_points - 1) / b.split_points) * (sweep ? 1 : score_chunks(nv));
         }
         int inc_i = items;
 #pragma unroll
@@ -953,13 +953,13 @@ __global__ void __launch_bounds__(1024) plan_items_kernel(const fnp_seeker_batch
     }
 }
 
-__global__ void __launch_bounds__(128) write_items_kernel(const fnp_seeker_batch b, const int H)
+__global__ void __launch_bounds__(128) write_items_kernel(const fnp_seeker_batch b, const int H, const int sweep)
 {
     const int f = blockIdx.x;
     const int i0 = b.cand_item_start[f], n = b.cand_item_start[f + 1] - i0;
     if (n <= 0 || (b.status[0] & 2)) return;
     const int nv = b.hyp_nvalid[f];
-    const int nchunks = score_chunks(nv);
+    const int nchunks = sweep ? 1 : score_chunks(nv);   // the sweep kernel takes all hypotheses of a split at once
     for (int i = threadIdx.x; i < n; i += blockDim.x) {   // split-major: neighbours share a point tile
         const int c = i % nchunks;
         const int left = nv - c * kScoreChunk;             // hypotheses from this chunk's base on
@@ -1149,6 +1149,201 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_b
 }
 
 // ======================================================================================
+// Stage 2b, sweep mode: per-hypothesis point counts without testing every pair
+// ======================================================================================
+// Arithmetic and derivation: fnp_sweep.cuh (shared with the host model tools/sweep_model.cu).
+// One CTA per frustum: line fit + deviation of every column.  Dynamic shared memory: 12 J words.
+__global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch b, const int J, const int M)
+{
+    extern __shared__ int s_raw[];
+    int *s_first = s_raw;                                  // [J]
+    int *s_last = s_raw + J;                               // [J]
+    int *s_r0 = s_raw + 2 * J;                             // [J] compacted slot of the column's first valid step
+    float *s_c0 = reinterpret_cast<float *>(s_raw + 3 * J);   // [J][3]
+    float *s_c1 = s_c0 + 3 * J;                            // [J][3], later the slopes
+    unsigned *s_dev = reinterpret_cast<unsigned *>(s_c1 + 3 * J);   // [J][3] max deviation (float bits, >= 0)
+    __shared__ unsigned s_maxabs;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int H = J * M;
+    const int nv = b.hyp_nvalid[f];
+    SweepCol *out = reinterpret_cast<SweepCol *>(b.sweep_cols) + (size_t)f * J;
+    for (int j = tid; j < J; j += blockDim.x) {
+        s_first[j] = 0x7fffffff;
+        s_last[j] = -1;
+        s_dev[3 * j] = s_dev[3 * j + 1] = s_dev[3 * j + 2] = 0u;
+    }
+    if (tid == 0) s_maxabs = 0u;
+    __syncthreads();
+    const int *hidx = b.hyp_index + (size_t)f * H;
+    float mabs = 0.f;
+    for (int r = tid; r < nv; r += blockDim.x) {
+        const int h = hidx[r], m = h / J, j = h - m * J;
+        atomicMin(&s_first[j], m);
+        atomicMax(&s_last[j], m);
+        const float *pp = b.hyp_prep + ((size_t)f * H + r) * 8;
+        mabs = fmaxf(mabs, fmaxf(fabsf(pp[0]), fmaxf(fabsf(pp[1]), fabsf(pp[2]))));
+    }
+    if (tid < 6 && nv > 0) mabs = fmaxf(mabs, fabsf(b.cand_stats[(size_t)f * kStatsFloats + 3 + tid]));   // point AABB
+    atomicMax(&s_maxabs, __float_as_uint(mabs));
+    __syncthreads();
+    for (int r = tid; r < nv; r += blockDim.x) {
+        const int h = hidx[r], m = h / J, j = h - m * J;
+        const bool first = (m == s_first[j]), last = (m == s_last[j]);
+        if (first || last) {
+            float Cv[3];
+            sweep_axes(load_prep(b.hyp_prep, (size_t)f * H + r), Cv);
+            for (int k = 0; k < 3; k++) {
+                if (first) s_c0[3 * j + k] = Cv[k];
+                if (last) s_c1[3 * j + k] = Cv[k];
+            }
+            if (first) s_r0[j] = r;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 3 * J; i += blockDim.x) {
+        const int j = i / 3;
+        const int span = s_last[j] - s_first[j];
+        s_c1[i] = span > 0 ? __fdiv_rn(__fsub_rn(s_c1[i], s_c0[i]), (float)span) : 0.f;   // slope per depth step
+    }
+    __syncthreads();
+    for (int r = tid; r < nv; r += blockDim.x) {
+        const int h = hidx[r], m = h / J, j = h - m * J;
+        float Cv[3];
+        sweep_axes(load_prep(b.hyp_prep, (size_t)f * H + r), Cv);
+        const float dm = (float)(m - s_first[j]);
+        for (int k = 0; k < 3; k++) {
+            const float line = __fmaf_rn(s_c1[3 * j + k], dm, s_c0[3 * j + k]);
+            atomicMax(&s_dev[3 * j + k], __float_as_uint(fabsf(__fsub_rn(Cv[k], line))));
+        }
+    }
+    __syncthreads();
+    const float eps = sweep_eps(__uint_as_float(s_maxabs));
+    for (int j = tid; j < J; j += blockDim.x) {
+        const int m0 = s_first[j], m1 = s_last[j];
+        SweepCol c;
+        if (m1 >= m0) {
+            // every hypothesis of the column carries the same cosa, sina, tx, ty, hz: read the first one
+            const float dev[3] = {__uint_as_float(s_dev[3 * j]), __uint_as_float(s_dev[3 * j + 1]),
+                                  __uint_as_float(s_dev[3 * j + 2])};
+            c = sweep_col_build(m0, m1, s_c0 + 3 * j, s_c1 + 3 * j, dev,
+                                load_prep(b.hyp_prep, (size_t)f * H + s_r0[j]), eps);
+        } else {
+            c = SweepCol{};
+            c.m0 = 0; c.m1 = -1;
+        }
+        out[j] = c;
+    }
+}
+
+constexpr int kSweepThreads = 256;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kSweepChunk = 256;   // points per (column, chunk) warp item
+
+// Dynamic shared memory of sweep_score_kernel for split_points SP, H = M*J hypotheses, J columns.
+__host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
+{
+    return (size_t)SP * 12 + (size_t)H * 4 + (size_t)((H + 1) & ~1) * 2 + (size_t)J * sizeof(SweepCol) + 16;
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 4) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int H = J * M, SP = b.split_points;
+    SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
+    float *s_x = reinterpret_cast<float *>(s_col + J);                          // [SP]
+    float *s_y = s_x + SP;
+    float *s_z = s_y + SP;
+    int *s_diff = reinterpret_cast<int *>(s_z + SP);                            // [J][M] difference array, then counts
+    short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
+    int *s_item = reinterpret_cast<int *>(s_slot + ((H + 1) & ~1));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b.status[0] & 2) return;
+    const int n_items = b.status[2];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) *s_item = atomicAdd(&b.status[4], 1);
+        __syncthreads();
+        const int item_id = *s_item;
+        if (item_id >= n_items) break;
+        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, -, split, -
+        const int f = item.x, split = item.z;
+        const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
+        const int p0 = split * SP;
+        const int n = min(npts, p0 + SP) - p0;
+
+        // ---- stage: column parameters, point split as SoA, cleared arrays
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
+            float4 *dst = reinterpret_cast<float4 *>(s_col);
+            for (int i = tid; i < J * (FNP_SWEEP_COL_FLOATS / 4); i += kSweepThreads) dst[i] = __ldg(src + i);
+            const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
+            const int n_rec = (n + 1) >> 1;
+            for (int r = tid; r < n_rec; r += kSweepThreads) {
+                const float4 xy = __ldg(grec + 2 * r), zd = __ldg(grec + 2 * r + 1);
+                reinterpret_cast<float2 *>(s_x)[r] = make_float2(xy.x, xy.y);
+                reinterpret_cast<float2 *>(s_y)[r] = make_float2(xy.z, xy.w);
+                reinterpret_cast<float2 *>(s_z)[r] = make_float2(zd.x, zd.y);
+            }
+            for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
+        }
+        __syncthreads();
+        {
+            const int *hidx = b.hyp_index + (size_t)f * H;
+            for (int r = tid; r < nv; r += kSweepThreads) s_slot[hidx[r]] = (short)r;
+        }
+        __syncthreads();
+
+        // ---- sweep: warp items = (column, chunk of kSweepChunk points)
+        const int n_chunks = (n + kSweepChunk - 1) / kSweepChunk;
+        const int n_witems = J * n_chunks;
+        for (int wi = warp; wi < n_witems; wi += kSweepWarps) {
+            const int j = wi % J, ch = wi / J;
+            const SweepCol c = s_col[j];            // warp-uniform: lives in registers for the whole item
+            if (c.m1 < c.m0) continue;
+            int *diff = s_diff + j * M + c.m0;       // indexed by dm = m - m0
+            const short *slot = s_slot + c.m0 * J + j;
+            const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
+            int base_cnt = 0;
+            const int i_end = min(n, (ch + 1) * kSweepChunk);
+            for (int i = ch * kSweepChunk + lane; i < i_end; i += 32)
+                base_cnt += sweep_point(c, s_x[i], s_y[i], s_z[i], diff, slot, J, prep_f,
+                                        [](int *p, int v) { atomicAdd(p, v); });
+            base_cnt = __reduce_add_sync(0xffffffffu, base_cnt);
+            if (lane == 0 && base_cnt) atomicAdd(diff, base_cnt);   // ranges that start at the column's first step
+        }
+        __syncthreads();
+
+        // ---- prefix sum over the depth steps of every column (warp per column, in place)
+        for (int j = warp; j < J; j += kSweepWarps) {
+            int carry = 0;
+            for (int mb = 0; mb < M; mb += 32) {
+                const int m = mb + lane;
+                int v = m < M ? s_diff[j * M + m] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += t;
+                }
+                v += carry;
+                if (m < M) s_diff[j * M + m] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        int *out = b.counts + (size_t)f * H;
+        for (int h = tid; h < H; h += kSweepThreads) {
+            const int r = s_slot[h];
+            if (r >= 0) {
+                const int m = h / J, j = h - m * J;
+                const int cnt = s_diff[j * M + m];
+                if (cnt) atomicAdd(out + r, cnt);      // RED.ADD: the splits of a frustum add up in any order
+            }
+        }
+    }
+}
+
+// ======================================================================================
 // Stage 3: score + greedy argmax
 // ======================================================================================
 __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
@@ -1313,31 +1508,73 @@ extern "C" int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker
     return FNP_OK;
 }
 
+// Scoring mode of a batch (see FNP_SCORE_* in fnp.h); < 0: invalid request.
+static int resolve_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
+{
+    const int J = cfg->num_yaw_size, M = cfg->num_mags;
+    const long long H = (long long)J * M;
+    const bool fits = b->sweep_cols && H <= 32767 && sweep_smem_bytes(b->split_points, (int)H, J) <= 200 * 1024 &&
+                      (size_t)12 * J * 4 <= 48 * 1024;
+    switch (b->score_mode) {
+        case FNP_SCORE_DIRECT: return FNP_SCORE_DIRECT;
+        case FNP_SCORE_SWEEP: return fits ? FNP_SCORE_SWEEP : -1;
+        case FNP_SCORE_AUTO: return (fits && M >= FNP_SWEEP_MIN_MAGS) ? FNP_SCORE_SWEEP : FNP_SCORE_DIRECT;
+        default: return -1;
+    }
+}
+
 extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
 {
     int rc = check_batch(cfg, b);
     if (rc) return rc;
     if (b->n_cands == 0) return FNP_OK;
-    const int H = cfg->num_mags * cfg->num_yaw_size;
+    const int J = cfg->num_yaw_size, M = cfg->num_mags, H = M * J;
     cudaStream_t st = (cudaStream_t)stream;
     if (!b->items || !b->cand_item_start || !b->counts) return FNP_EINVAL;
+    const int mode = resolve_score_mode(cfg, b);
+    if (mode < 0) return FNP_EINVAL;
+    const int sweep = mode == FNP_SCORE_SWEEP;
+    static int n_sms = 0;
+    if (n_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     cudaMemsetAsync(b->counts, 0, sizeof(int32_t) * (size_t)b->n_cands * H, st);
-    plan_items_kernel<<<1, 1024, 0, st>>>(*b, H);
-    write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H);
+    if (sweep) sweep_prep_kernel<<<b->n_cands, 128, (size_t)12 * J * 4, st>>>(*b, J, M);
+    plan_items_kernel<<<1, 1024, 0, st>>>(*b, H, sweep);
+    write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H, sweep);
     if (b->max_items > 0) {
-        static int n_sms = 0;
-        if (n_sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        }
         // persistent CTAs: a whole number of CTAs per SM (148 SMs on B200), capped by the item capacity
-        const int per_sm = 6;
-        const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
-        score_kernel<<<grid, kScoreThreads, 0, st>>>(*b, H);
+        if (sweep) {
+            const size_t smem = sweep_smem_bytes(b->split_points, H, J);
+            static size_t smem_set = 0;
+            if (smem > smem_set) {
+                cudaFuncSetAttribute(sweep_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                smem_set = smem;
+            }
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_score_kernel, kSweepThreads, smem);
+            if (per_sm < 1) return FNP_EINVAL;
+            const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
+            sweep_score_kernel<<<grid, kSweepThreads, smem, st>>>(*b, J, M);
+        } else {
+            const int per_sm = 6;
+            const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
+            score_kernel<<<grid, kScoreThreads, 0, st>>>(*b, H);
+        }
     }
     FNP_LAUNCH_CHECK();
     return FNP_OK;
+}
+
+/* Which scoring kernel fnp_seeker_score would run for this batch: FNP_SCORE_DIRECT or FNP_SCORE_SWEEP
+ * (FNP_EINVAL: the requested mode cannot run, e.g. SWEEP without sweep_cols). */
+extern "C" int fnp_seeker_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
+{
+    if (!cfg || !b) return FNP_EINVAL;
+    const int m = resolve_score_mode(cfg, b);
+    return m < 0 ? FNP_EINVAL : m;
 }
 
 extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)

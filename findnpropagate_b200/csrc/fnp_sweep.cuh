@@ -1,0 +1,224 @@
+// Depth-sweep scoring (stage 2b, FNP_SCORE_SWEEP): the arithmetic shared by the device kernels
+// in fnp_seeker.cu and by the host model tools/sweep_model.cu, which runs the same functions on
+// the CPU to check the range logic without a GPU.  Every operation is a single IEEE fp32
+// operation on both sides (the library is built with -fmad=false; the host model with
+// -ffp-contract=off), so the two agree bit for bit.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/fnp.h"
+
+#if defined(__CUDACC__)
+#define FNP_HD __host__ __device__ __forceinline__
+#else
+#define FNP_HD inline
+#endif
+
+namespace fnp {
+
+#if defined(__CUDA_ARCH__)
+FNP_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+FNP_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+FNP_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+FNP_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+FNP_HD float f_div(float a, float b) { return __fdiv_rn(a, b); }
+FNP_HD int f2i_up(float a) { return __float2int_ru(a); }
+FNP_HD int f2i_down(float a) { return __float2int_rd(a); }
+FNP_HD float4 ld4(const float4 *p) { return __ldg(p); }
+#else
+FNP_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
+FNP_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
+FNP_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
+FNP_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+FNP_HD float f_div(float a, float b) { volatile float r = a / b; return r; }
+FNP_HD int f2i_up(float a) { return (int)ceilf(a); }
+FNP_HD int f2i_down(float a) { return (int)floorf(a); }
+FNP_HD float4 ld4(const float4 *p) { return *p; }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// In-box predicate.  Reference arithmetic (roiaware_pool3d_kernel.cu:16-36 as compiled for
+// sm_100a): z test and x/y tests are evaluated in fp64,
+//     in_z  = !((double)|z-cz| > (double)dz * 0.5)
+//     in_xy = (double)|lx| < (double)dx*0.5 + (double)1e-5f   (same for y)
+// with lx = fma(sx, cosa, rn(sy * -sina)), ly = fma(sy, cosa, rn(sx * sina)),
+// cosa = cosf(-rz), sina = sinf(-rz).  The fp64 compares are hoisted exactly into fp32
+// thresholds per box: |l| < t  <=>  |l| <= pred(t), pred(t) = largest float strictly below t.
+// ---------------------------------------------------------------------------------------
+struct BoxPrep {
+    float cx, cy, cz, hz;      // centre, half height threshold
+    float cosa, sina, tx, ty;  // rotation by -heading, strict-less thresholds as <=
+};
+
+FNP_HD bool in_box(float x, float y, float z, const BoxPrep &p)
+{
+    const float sz = f_sub(z, p.cz);
+    const float sx = f_sub(x, p.cx);
+    const float sy = f_sub(y, p.cy);
+    const float lx = f_fma(sx, p.cosa, f_mul(sy, -p.sina));
+    const float ly = f_fma(sy, p.cosa, f_mul(sx, p.sina));
+    return !(fabsf(sz) > p.hz) && (fabsf(lx) <= p.tx) && (fabsf(ly) <= p.ty);
+}
+
+FNP_HD BoxPrep load_prep(const float *hyp_prep, size_t idx)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(hyp_prep + idx * 8);
+    const float4 a = ld4(src), c = ld4(src + 1);
+    BoxPrep p;
+    p.cx = a.x; p.cy = a.y; p.cz = a.z; p.hz = a.w;
+    p.cosa = c.x; p.sina = c.y; p.tx = c.z; p.ty = c.w;
+    return p;
+}
+
+// The H = M*J hypotheses of a frustum form J columns (one per yaw x size entry of the prior
+// table); the M hypotheses of a column share cosa, sina, tx, ty, hz and differ only in their
+// centre, which advances along the centre line (plus the slowly varying front shift).  In the
+// column's rotated frame,  lx = U - Cu(m),  ly = V - Cv(m),  sz = z - Cz(m)  with
+//     U = x cosa - y sina,  V = y cosa + x sina,   Cu(m) = cx_m cosa - cy_m sina, ...
+// so a point is inside hypothesis m iff Cu(m), Cv(m), Cz(m) fall into three intervals around
+// (U, V, z).  Each C.(m) is a straight line in m up to a measured deviation:
+//     |C(m) - (C0 + s (m - m0))| <= delta      for every VALID m of the column,
+// with (C0, s) through the first and last valid depth step m0, m1 and delta taken over the actual
+// centres (sweep_prep_kernel).  With eps bounding the fp32 rounding of both the exact predicate
+// and this solve, and dl = delta + eps,
+//     |P - C0 - s dm| <= t - dl   =>  inside   on that axis (definitely),
+//     |P - C0 - s dm| >  t + dl   =>  outside  on that axis (definitely),
+// which are two nested ranges of dm = m - m0 per axis; intersected over the three axes they give
+// a DEFINITE range [a, e] and a POSSIBLE range [A, B] containing it.  The definite range goes into
+// the column's difference array (+1 at a, -1 at e+1), the at most few depth steps of
+// [A, B] \ [a, e] take the exact predicate in_box() against the hypothesis itself, and a prefix
+// sum over m yields the counts.  The counts are the same integers the direct kernel produces: the
+// only approximate quantity, the range ends, is used with a margin that covers its error, and
+// everything inside the margin is decided by the exact predicate.
+//
+// An axis whose total travel |s|(m1 - m0) is below 4 eps is treated as constant (the travel is
+// added to its dl); a column in which t - dl < 0 has no definite range and degrades to exact
+// tests of the possible range, so the result is correct for any geometry and fast for the
+// seeker's.
+struct SweepCol {
+    float cosa, sina;
+    int m0, m1;          // first / last valid depth step of the column (m0 > m1: none)
+    float c0[3];         // Cu, Cv, Cz at m0
+    float inv_s[3];      // 1 / slope per depth step (0 on a constant axis)
+    float w_in[3];       // (t - dl) |inv_s|  (depth steps; -inf when t < dl) | constant axis: t - dl (metres)
+    float w_p[3];        // (t + dl) |inv_s|                                  | constant axis: t + dl
+    int const_mask;      // bit k: axis k is constant over the column
+    float eps, pad0, pad1;
+};
+static_assert(sizeof(SweepCol) == FNP_SWEEP_COL_FLOATS * 4, "SweepCol layout is part of the ABI workspace size");
+
+FNP_HD void sweep_axes(const BoxPrep &p, float C[3])
+{
+    C[0] = f_fma(p.cx, p.cosa, f_mul(p.cy, -p.sina));
+    C[1] = f_fma(p.cy, p.cosa, f_mul(p.cx, p.sina));
+    C[2] = p.cz;
+}
+
+// eps: bound of the accumulated fp32 rounding of the exact predicate and of the range solve.
+// Operands reach 2 maxabs (x - cx); both sides together stay below 12 ulp of that magnitude
+// (DESIGN.md section 4); eps = 2 maxabs 2^-18 = 32 ulp leaves a factor > 2.5.
+FNP_HD float sweep_eps(float maxabs)
+{
+    const float scale = fmaxf(f_mul(2.f, maxabs), 64.f);
+    return f_mul(scale, 3.814697265625e-06f);
+}
+
+// Column parameters from the line fit: c0 = C at the first valid step, slope per step, dev =
+// max |C(m) - line(m)| over the valid steps, p = any hypothesis of the column (rotation, size).
+FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float slope[3], const float dev[3],
+                                const BoxPrep &p, float eps)
+{
+    const float INF = INFINITY;
+    SweepCol c;
+    c.m0 = m0; c.m1 = m1;
+    c.const_mask = 0;
+    c.eps = eps; c.pad0 = 0.f; c.pad1 = 0.f;
+    c.cosa = p.cosa; c.sina = p.sina;
+    const float t[3] = {p.tx, p.ty, p.hz};
+    const float span = (float)(m1 - m0);
+    for (int k = 0; k < 3; k++) {
+        const float s = slope[k];
+        float dl = f_add(dev[k], eps);
+        c.c0[k] = c0[k];
+        const float travel = f_mul(fabsf(s), span);
+        if (!(travel > f_mul(4.f, eps))) {
+            c.const_mask |= 1 << k;
+            dl = f_add(dl, travel);
+            c.inv_s[k] = 0.f;
+            c.w_in[k] = f_sub(t[k], dl);
+            c.w_p[k] = f_add(t[k], dl);
+        } else {
+            const float inv = f_div(1.f, s);
+            c.inv_s[k] = inv;
+            const float win = f_sub(t[k], dl);
+            c.w_in[k] = win >= 0.f ? f_mul(win, fabsf(inv)) : -INF;
+            c.w_p[k] = f_mul(f_add(t[k], dl), fabsf(inv));
+        }
+    }
+    return c;
+}
+
+// One point against one column.  `diff` is the column's difference array indexed by dm = m - m0
+// (dm in [0, D]); `slot` the compacted hypothesis slot of (m0 + dm, column) at slot[dm * J], or
+// -1; `prep_f` the frustum's compacted hypotheses.  add(ptr, v) adds v to *ptr (a shared-memory
+// RED on the device).  Returns 1 if the definite range starts at dm = 0 (the caller sums these
+// per warp and adds them to diff[0] once), else 0.
+template <class Add>
+FNP_HD int sweep_point(const SweepCol &c, const float x, const float y, const float z, int *diff, const short *slot,
+                       const int J, const float *prep_f, Add add)
+{
+    const float INF = INFINITY;
+    const int D = c.m1 - c.m0;
+    const float Df = (float)D;
+    const float P[3] = {f_fma(x, c.cosa, f_mul(y, -c.sina)), f_fma(y, c.cosa, f_mul(x, c.sina)), z};
+    float lo = -INF, hi = INF, plo = -INF, phi = INF;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float num = f_sub(P[k], c.c0[k]);
+        if (c.const_mask & (1 << k)) {
+            const float d = fabsf(num);
+            if (!(d <= c.w_in[k])) lo = INF;
+            if (!(d <= c.w_p[k])) plo = INF;
+        } else {
+            const float q = f_mul(num, c.inv_s[k]);
+            lo = fmaxf(lo, f_sub(q, c.w_in[k])); hi = fminf(hi, f_add(q, c.w_in[k]));
+            plo = fmaxf(plo, f_sub(q, c.w_p[k])); phi = fminf(phi, f_add(q, c.w_p[k]));
+        }
+    }
+    // clamp to the column's depth steps before the conversion: dm in [0, D]
+    const int a = f2i_up(fminf(fmaxf(lo, 0.f), Df + 1.f));      // first definite step
+    const int e = f2i_down(fmaxf(fminf(hi, Df), -1.f));         // last definite step
+    const int A = f2i_up(fminf(fmaxf(plo, 0.f), Df + 1.f));     // first possible step
+    const int B = f2i_down(fmaxf(fminf(phi, Df), -1.f));        // last possible step
+    const bool has_def = a <= e;
+    int base = 0;
+    if (has_def) {
+        if (a == 0) base = 1; else add(diff + a, 1);
+        if (e < D) add(diff + e + 1, -1);
+    }
+    if (A <= B) {
+        // exact predicate for the steps that are possible but not definite: [A, a-1] and [e+1, B],
+        // or all of [A, B] when there is no definite range
+        const int e1 = has_def ? a - 1 : B;
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && !has_def) break;
+            const int d_lo = pass == 0 ? A : e + 1;
+            const int d_hi = pass == 0 ? e1 : B;
+            for (int dm = d_lo; dm <= d_hi; dm++) {
+                const int r = slot[dm * J];
+                if (r < 0) continue;
+#ifdef FNP_SWEEP_MODEL
+                g_exact_tests++;   // host model only: how many exact predicates the sweep takes
+#endif
+                if (in_box(x, y, z, load_prep(prep_f, (size_t)r))) {
+                    add(diff + dm, 1);
+                    if (dm < D) add(diff + dm + 1, -1);
+                }
+            }
+        }
+    }
+    return base;
+}
+
+}  // namespace fnp

@@ -137,7 +137,7 @@ def _align(x, a=256):
 class SeekerEngine:
     """Batched Box Seeker on one GPU."""
 
-    def __init__(self, params=None, device=None, debug=False, split_points=None):
+    def __init__(self, params=None, device=None, debug=False, split_points=None, score_mode="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("findnpropagate_b200.SeekerEngine needs a CUDA device (no CPU fallback)")
         self.p = resolve_params(params)
@@ -159,6 +159,9 @@ class SeekerEngine:
             min_cam_iou=float(self.p["min_cam_iou"]), dns_w=float(self.p["dns_w"]), iou_w=float(self.p["iou_w"]))
         self.arena = _Arena(self.device)
         self.fixed_split_points = split_points
+        # "auto" | "direct" | "sweep": which stage-2b kernel counts the points (same counts either way)
+        self.score_mode = {"auto": _lib.SCORE_AUTO, "direct": _lib.SCORE_DIRECT, "sweep": _lib.SCORE_SWEEP}[score_mode]
+        self.last_score_mode = None
         self.pts_factor = 2.0
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.launches = 0          # kernels of ours launched (bench bookkeeping)
@@ -320,7 +323,7 @@ class SeekerEngine:
                 frustum_pts=16 * cap, stage_pts=16 * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
                 hyp_iou=4 * H * F, counts=4 * H * F, items=16 * max_items,
-                cand_item_start=4 * (F + 1),
+                cand_item_start=4 * (F + 1), sweep_cols=4 * _lib.SWEEP_COL_FLOATS * self.J * F,
                 )
             # outputs, one D2H: boxes(7) score best count npts nvalid per candidate, status(4) + pad(4),
             # recall counters (20 x int64), stage-4 keep flags (F bytes)
@@ -357,11 +360,13 @@ class SeekerEngine:
                 hyp_valid_dbg=ptr.get("hyp_valid_dbg"),
                 split_points=sp, max_items=max_items,
                 cand_item_start=ptr["cand_item_start"], items=ptr["items"],
-                counts=ptr["counts"],
+                counts=ptr["counts"], score_mode=self.score_mode, sweep_cols=ptr["sweep_cols"],
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
-            self.launches += 11 if F and plan["n_tiles"] else 0
+            mode = _lib.lib.fnp_seeker_score_mode(C.byref(self.cfg), C.byref(b))
+            self.last_score_mode = {_lib.SCORE_DIRECT: "direct", _lib.SCORE_SWEEP: "sweep"}.get(mode)
+            self.launches += (11 + (mode == _lib.SCORE_SWEEP)) if F and plan["n_tiles"] else 0
             handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta,
                           off_recall=off_recall, off_keep=off_keep, has_nms=False, has_recall=False,
                           recall_thresh=tuple(recall_thresh))

@@ -167,6 +167,9 @@ typedef struct fnp_seeker_batch {
                                         hypotheses per thread (1..4)                         */
     int32_t *counts;                 /* (F,H) point count of every compacted hypothesis (zeroed by
                                         fnp_seeker_score, accumulated per point split)      */
+    int32_t score_mode;              /* FNP_SCORE_AUTO / FNP_SCORE_DIRECT / FNP_SCORE_SWEEP */
+    float *sweep_cols;               /* (F,J,FNP_SWEEP_COL_FLOATS) per (frustum, yaw-size column) depth-
+                                        sweep parameters; required for the sweep mode       */
     /* ---- outputs ---- */
     float *out_boxes;                /* (F,7) selected box per candidate                   */
     float *out_score;                /* (F)   its second-stage score                       */
@@ -179,6 +182,21 @@ typedef struct fnp_seeker_batch {
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024
+/* Scoring modes (fnp_seeker_batch.score_mode).  Both produce the same counts, bit for bit.
+ *   DIRECT: every valid hypothesis tests every frustum point (P_f * nv_f in-box predicates).
+ *   SWEEP : the M hypotheses of one (yaw, size) column share rotation and size and their centres
+ *           advance along the centre line, so a point is inside for one contiguous range of depth
+ *           steps; the range is solved per (point, column) with a conservative error bound, added
+ *           to a per-column difference array, and only the depth steps within the error bound
+ *           of a range end take the exact predicate.  Work: P_f * J range solves instead of
+ *           P_f * M * J predicates.
+ *   AUTO  : SWEEP when num_mags >= FNP_SWEEP_MIN_MAGS, sweep_cols != NULL and its shared
+ *           memory fits; DIRECT otherwise. */
+#define FNP_SCORE_AUTO 0
+#define FNP_SCORE_DIRECT 1
+#define FNP_SCORE_SWEEP 2
+#define FNP_SWEEP_MIN_MAGS 16
+#define FNP_SWEEP_COL_FLOATS 20
 /* Words of the per-point candidate mask for a batch whose busiest frame has that many
  * candidates: 1, 2, 4 or 8 (-1: more than 256 candidates per frame are not supported). */
 int fnp_seeker_mask_words(int max_cands_per_frame);
@@ -193,8 +211,12 @@ int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *
 int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 /* Stage 2a: hypothesis grid, softmin front shift, distance + 2D-IoU filters, compaction. */
 int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
-/* Stage 2b: points-in-boxes scoring (TMA-staged point tiles, register-resident hypotheses). */
+/* Stage 2b: points-in-boxes scoring.  DIRECT: TMA-staged point tiles against register-resident
+ * hypotheses; SWEEP: per-(point, column) depth-range solve + difference arrays in shared memory. */
 int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* The scoring kernel fnp_seeker_score runs for this batch: FNP_SCORE_DIRECT or FNP_SCORE_SWEEP
+ * (FNP_EINVAL if the requested mode cannot run).  Host-only query, enqueues nothing. */
+int fnp_seeker_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b);
 /* Stage 3: density + IoU score and greedy argmax per frustum. */
 int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 /* All five stages back to back on `stream`. */

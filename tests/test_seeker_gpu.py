@@ -302,3 +302,57 @@ def test_reference_compatible_head_and_extraction(tmp_path):
         saved = torch.load(str(tmp_path / (f.frame_id.replace(".", "_") + ".pth")), map_location="cpu")
         assert np.array_equal(saved[0]["pred_boxes"].numpy(), merged[b]["pred_boxes"])
     assert {k: total[k] for k in exp} == exp and 0.0 <= ar["rcnn_0.3"] <= 1.0
+
+
+@pytest.mark.parametrize("cfg_name,override,n_frames,split", [
+    ("tiny", None, 3, None), ("cfg1", None, 3, 64), ("cfg1", dict(num_mags=40, num_sizes=2), 2, 333),
+    ("cfg2", None, 2, None), ("cfg2", dict(num_mags=17, num_rotations=5), 1, 2048),
+])
+def test_sweep_and_direct_scoring_give_identical_counts(cfg_name, override, n_frames, split):
+    """Stage 2b has two kernels (include/fnp.h FNP_SCORE_*): DIRECT tests every (point, valid
+    hypothesis) pair, SWEEP solves one depth range per (point, yaw-size column) and takes the
+    exact predicate only next to the range ends.  Their (F, H) count tables must be the same
+    integers, for every hypothesis, whatever the point split, and match the oracle."""
+    cfg = synth.CONFIGS[cfg_name]
+    params = synth.seeker_params(cfg)
+    if override:
+        params.update(override)
+    frames = [_frame_from_synth(synth.make_frame(i, cfg, device="cuda:0" if cfg_name == "cfg2" else "cpu"))
+              for i in range(n_frames)]
+    out = {}
+    for mode in ("direct", "sweep"):
+        eng = SeekerEngine(params, device="cuda:0", debug=True, score_mode=mode, split_points=split)
+        plan = eng.plan(frames)
+        h = eng.execute(plan, eng.upload_points(frames))
+        res = eng.finish(h)
+        assert eng.last_score_mode == mode
+        dbg = eng.debug_views(h)
+        nv = res["cand_nvalid"]
+        out[mode] = (res, [dbg["counts"][f, :nv[f]].copy() for f in range(plan["F"])], dbg)
+    (rd, cd, dbg), (rs, cs, _) = out["direct"], out["sweep"]
+    assert sum(int(c.sum()) for c in cd) > 0
+    for f, (a, b) in enumerate(zip(cd, cs)):
+        assert np.array_equal(a, b), "frustum %d: sweep counts differ from direct counts" % f
+    assert np.array_equal(rd["cand_best"], rs["cand_best"])
+    v = rd["cand_valid"]
+    assert np.array_equal(rd["cand_boxes"][v].view(np.uint32), rs["cand_boxes"][v].view(np.uint32))
+    # and the oracle on a few frustums (all valid hypotheses of each)
+    nv = rd["cand_nvalid"]
+    checked = 0
+    for f in range(0, len(cd), max(1, len(cd) // 6)):
+        p = dbg["frustum_pts"][dbg["pt_start"][f]:dbg["pt_start"][f + 1], :3]
+        if nv[f] and p.shape[0] and p.shape[0] * nv[f] < 3e7:
+            hb = dbg["hyp_boxes"][f][dbg["hyp_index"][f, :nv[f]]]
+            assert np.array_equal(O.count_in_boxes(p, hb), cs[f])
+            checked += 1
+    assert checked > 0
+
+
+def test_score_mode_auto_picks_sweep_for_deep_grids_only():
+    from findnpropagate_b200 import _lib
+    for name, want in (("cfg1", "direct"), ("cfg2", "sweep")):
+        cfg = synth.CONFIGS[name]
+        eng = SeekerEngine(synth.seeker_params(cfg), device="cuda:0")
+        eng.run([_frame_from_synth(synth.make_frame(0, cfg, device="cuda:0" if name == "cfg2" else "cpu"))])
+        assert eng.last_score_mode == want
+        assert (eng.M >= _lib.SWEEP_MIN_MAGS) == (want == "sweep")

@@ -30,11 +30,12 @@ def main():
     ap.add_argument("--distinct", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--split-points", type=int, default=None)
+    ap.add_argument("--score-mode", default="auto", choices=["auto", "direct", "sweep"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     frames, params = make_frames(a.config, 0, a.distinct, str(dev))
     batch = [frames[i % a.distinct] for i in range(a.frames)]
-    eng = SeekerEngine(params, device=dev, split_points=a.split_points)
+    eng = SeekerEngine(params, device=dev, split_points=a.split_points, score_mode=a.score_mode)
     t0 = time.perf_counter()
     for _ in range(5):
         plan = eng.plan(batch)
@@ -51,7 +52,7 @@ def main():
     stages = [("cull", L.fnp_seeker_cull), ("frustum_stats", L.fnp_seeker_frustum_stats),
               ("hypotheses", L.fnp_seeker_hypotheses), ("score", L.fnp_seeker_score), ("select", L.fnp_seeker_select),
               ("run(all five)", L.fnp_seeker_run)]
-    out = {"config": a.config, "frames": a.frames, "split_points": h["sp"], "F": plan["F"], "H": eng.H, "host_plan_ms": host_plan_ms,
+    out = {"config": a.config, "frames": a.frames, "score_mode": eng.last_score_mode, "split_points": h["sp"], "F": plan["F"], "H": eng.H, "host_plan_ms": host_plan_ms,
            "host_finish_ms": host_finish_ms, "sum_P_f": int(res["cand_npts"].sum()),
            "valid_hyps": int(res["cand_nvalid"].sum()),
            "tests": int((res["cand_npts"].astype(np.int64) * res["cand_nvalid"]).sum()), "stages_ms": {}}

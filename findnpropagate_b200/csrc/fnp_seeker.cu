@@ -1239,40 +1239,69 @@ constexpr int kSweepThreads = 256;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kSweepChunk = 256;   // points per (column, chunk) warp item
 
+// Entries of the uncertain-step queue of a CTA: (point | column << 16, packed steps).
+__host__ __device__ inline int sweep_queue_cap(int SP, int J)
+{
+    // a quarter of the (point, column) pairs (~13 % have an entry on cfg2).  Measured on 128 cfg2 frames,
+    // SP = 1024: a queue twice this size costs one resident CTA per SM and 19 % of the kernel's time,
+    // more than the exact predicates taken in place when the queue is full.
+    const int want = (SP * J / 4 + 31) & ~31;
+    return want < 512 ? 512 : want > 4096 ? 4096 : want;
+}
+
 // Dynamic shared memory of sweep_score_kernel for split_points SP, H = M*J hypotheses, J columns.
 __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
 {
-    return (size_t)SP * 12 + (size_t)H * 4 + (size_t)((H + 1) & ~1) * 2 + (size_t)J * sizeof(SweepCol) + 16;
+    return (size_t)J * sizeof(SweepCol) + (size_t)SP * 12 + (size_t)H * 4 + (size_t)sweep_queue_cap(SP, J) * 8 +
+           (size_t)((H + 3) & ~3) * 2 + 16;
 }
 
+// Persistent CTAs pull (frustum, point split) items.  Per item:
+//   stage   column parameters, the split's points as SoA, cleared difference arrays, slot table;
+//   sweep   warps pull (column, 256-point chunk) pieces off a shared counter; per point one range
+//           solve (sweep_solve), the definite range into the column's difference array
+//           (shared-memory RED), the uncertain steps -- if any -- as one entry into the CTA's queue;
+//   drain   the queue is expanded to single depth steps and spread evenly over the lanes: every
+//           lane takes one exact predicate at a time, whichever point and column it belongs to;
+//   scan    prefix sum over the depth steps of every column, one integer RED per valid hypothesis
+//           into row f of `counts`.
 __global__ void __launch_bounds__(kSweepThreads, 4) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int H = J * M, SP = b.split_points;
+    const int QCAP = sweep_queue_cap(SP, J);
     SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
-    float *s_x = reinterpret_cast<float *>(s_col + J);                          // [SP]
+    uint2 *s_q = reinterpret_cast<uint2 *>(s_col + J);                          // [QCAP] uncertain-step queue
+    float *s_x = reinterpret_cast<float *>(s_q + QCAP);                         // [SP]  (SP is even: 8 B aligned rows)
     float *s_y = s_x + SP;
     float *s_z = s_y + SP;
     int *s_diff = reinterpret_cast<int *>(s_z + SP);                            // [J][M] difference array, then counts
     short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
-    int *s_item = reinterpret_cast<int *>(s_slot + ((H + 1) & ~1));
+    int *s_ctl = reinterpret_cast<int *>(s_slot + ((H + 3) & ~3));              // [0] item [1] next piece [2] queue size [3] queue head
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (b.status[0] & 2) return;
     const int n_items = b.status[2];
+    auto red = [](int *p, int v) { atomicAdd(p, v); };
+
     for (;;) {
         __syncthreads();
-        if (tid == 0) *s_item = atomicAdd(&b.status[4], 1);
+        if (tid == 0) {
+            s_ctl[0] = atomicAdd(&b.status[4], 1);
+            s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0;
+        }
         __syncthreads();
-        const int item_id = *s_item;
+        const int item_id = s_ctl[0];
         if (item_id >= n_items) break;
         const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, -, split, -
         const int f = item.x, split = item.z;
         const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
         const int p0 = split * SP;
         const int n = min(npts, p0 + SP) - p0;
+        const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
 
-        // ---- stage: column parameters, point split as SoA, cleared arrays
+        // ---- stage
         {
             const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
             float4 *dst = reinterpret_cast<float4 *>(s_col);
@@ -1294,23 +1323,90 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_score_kernel(const fnp
         }
         __syncthreads();
 
-        // ---- sweep: warp items = (column, chunk of kSweepChunk points)
+        // ---- sweep
         const int n_chunks = (n + kSweepChunk - 1) / kSweepChunk;
-        const int n_witems = J * n_chunks;
-        for (int wi = warp; wi < n_witems; wi += kSweepWarps) {
-            const int j = wi % J, ch = wi / J;
-            const SweepCol c = s_col[j];            // warp-uniform: lives in registers for the whole item
+        const int n_pieces = J * n_chunks;
+        for (;;) {
+            int piece = 0;
+            if (lane == 0) piece = atomicAdd(&s_ctl[1], 1);
+            piece = __shfl_sync(0xffffffffu, piece, 0);
+            if (piece >= n_pieces) break;
+            const int j = piece % J, ch = piece / J;
+            const SweepCol c = s_col[j];            // warp-uniform: lives in registers for the whole piece
             if (c.m1 < c.m0) continue;
+            const int D = c.m1 - c.m0;
             int *diff = s_diff + j * M + c.m0;       // indexed by dm = m - m0
-            const short *slot = s_slot + c.m0 * J + j;
-            const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
+            const short *slot_col = s_slot + c.m0 * J + j;
             int base_cnt = 0;
             const int i_end = min(n, (ch + 1) * kSweepChunk);
-            for (int i = ch * kSweepChunk + lane; i < i_end; i += 32)
-                base_cnt += sweep_point(c, s_x[i], s_y[i], s_z[i], diff, slot, J, prep_f,
-                                        [](int *p, int v) { atomicAdd(p, v); });
+            for (int i0 = ch * kSweepChunk; i0 < i_end; i0 += 32) {
+                const int i = min(i0 + lane, i_end - 1);
+                const bool live = i0 + lane < i_end;
+                const float x = s_x[i], y = s_y[i], z = s_z[i];
+                const SweepRanges r = sweep_solve(c, x, y, z);
+                unsigned w = 0;
+                if (live) {
+                    base_cnt += sweep_add_definite(r, D, diff, red);
+                    w = sweep_pack_uncertain(r);
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, w != 0u);
+                if (mk) {
+                    int qb = 0;
+                    if (lane == 0) qb = atomicAdd(&s_ctl[2], __popc(mk));
+                    qb = __shfl_sync(0xffffffffu, qb, 0) + __popc(mk & lt_mask);
+                    if (w) {
+                        if (qb < QCAP) {
+                            s_q[qb] = make_uint2((unsigned)i | ((unsigned)j << 16), w);
+                        } else {   // queue full: take the exact predicates here
+                            const int cnt = sweep_uncertain_count(w);
+                            for (int k = 0; k < cnt; k++)
+                                sweep_exact_step(x, y, z, sweep_uncertain_step(w, k), D, diff, slot_col, J, prep_f, red);
+                        }
+                    }
+                }
+            }
             base_cnt = __reduce_add_sync(0xffffffffu, base_cnt);
             if (lane == 0 && base_cnt) atomicAdd(diff, base_cnt);   // ranges that start at the column's first step
+        }
+        __syncthreads();
+
+        // ---- drain: 32 queue entries per warp at a time, expanded to steps, one step per lane and pass
+        const int qn = min(s_ctl[2], QCAP);
+        for (;;) {
+            int qb = 0;
+            if (lane == 0) qb = atomicAdd(&s_ctl[3], 32);
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (qb >= qn) break;
+            uint2 ent = make_uint2(0u, 0u);
+            if (qb + lane < qn) ent = s_q[qb + lane];
+            const int cnt = sweep_uncertain_count(ent.y);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                // owner = first lane whose inclusive prefix exceeds t
+                int own = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, own + step - 1);
+                    if (v <= t) own += step;
+                }
+                own = min(own, 31);
+                const unsigned e0 = __shfl_sync(0xffffffffu, ent.x, own);
+                const unsigned e1 = __shfl_sync(0xffffffffu, ent.y, own);
+                const int first = __shfl_sync(0xffffffffu, incl - cnt, own);
+                if (t < total) {
+                    const int i = (int)(e0 & 0xffffu), j = (int)(e0 >> 16);
+                    const int m0 = s_col[j].m0, D = s_col[j].m1 - m0;
+                    sweep_exact_step(s_x[i], s_y[i], s_z[i], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
+                                     s_slot + m0 * J + j, J, prep_f, red);
+                }
+            }
         }
         __syncthreads();
 
@@ -1513,7 +1609,7 @@ static int resolve_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch 
 {
     const int J = cfg->num_yaw_size, M = cfg->num_mags;
     const long long H = (long long)J * M;
-    const bool fits = b->sweep_cols && H <= 32767 && sweep_smem_bytes(b->split_points, (int)H, J) <= 200 * 1024 &&
+    const bool fits = b->sweep_cols && H <= 32767 && M <= 255 && J <= 65535 && b->split_points <= 65536 && sweep_smem_bytes(b->split_points, (int)H, J) <= 200 * 1024 &&
                       (size_t)12 * J * 4 <= 48 * 1024;
     switch (b->score_mode) {
         case FNP_SCORE_DIRECT: return FNP_SCORE_DIRECT;

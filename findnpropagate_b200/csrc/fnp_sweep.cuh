@@ -32,8 +32,9 @@ FNP_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
 FNP_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
 FNP_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
 FNP_HD float f_div(float a, float b) { volatile float r = a / b; return r; }
-FNP_HD int f2i_up(float a) { return (int)ceilf(a); }
-FNP_HD int f2i_down(float a) { return (int)floorf(a); }
+FNP_HD int f2i_sat(float a) { return a >= 2147483648.f ? 0x7fffffff : a <= -2147483648.f ? (int)0x80000000 : (int)a; }
+FNP_HD int f2i_up(float a) { return f2i_sat(ceilf(a)); }      // saturating like cvt.rpi.s32.f32
+FNP_HD int f2i_down(float a) { return f2i_sat(floorf(a)); }
 FNP_HD float4 ld4(const float4 *p) { return *p; }
 #endif
 
@@ -92,18 +93,16 @@ FNP_HD BoxPrep load_prep(const float *hyp_prep, size_t idx)
 // only approximate quantity, the range ends, is used with a margin that covers its error, and
 // everything inside the margin is decided by the exact predicate.
 //
-// An axis whose total travel |s|(m1 - m0) is below 4 eps is treated as constant (the travel is
-// added to its dl); a column in which t - dl < 0 has no definite range and degrades to exact
-// tests of the possible range, so the result is correct for any geometry and fast for the
-// seeker's.
+// A column in which t - dl < 0 has no definite range and degrades to exact tests of the possible
+// range, so the result is correct for any geometry and fast for the seeker's.
 struct SweepCol {
     float cosa, sina;
     int m0, m1;          // first / last valid depth step of the column (m0 > m1: none)
     float c0[3];         // Cu, Cv, Cz at m0
-    float inv_s[3];      // 1 / slope per depth step (0 on a constant axis)
-    float w_in[3];       // (t - dl) |inv_s|  (depth steps; -inf when t < dl) | constant axis: t - dl (metres)
-    float w_p[3];        // (t + dl) |inv_s|                                  | constant axis: t + dl
-    int const_mask;      // bit k: axis k is constant over the column
+    float inv_s[3];      // 1 / slope per depth step
+    float w_in[3];       // (t - dl) |inv_s|  (depth steps; -inf when t < dl)
+    float w_p[3];        // (t + dl) |inv_s|
+    int pseudo_mask;     // bit k: axis k does not travel; it carries a pseudo slope (statistics only)
     float eps, pad0, pad1;
 };
 static_assert(sizeof(SweepCol) == FNP_SWEEP_COL_FLOATS * 4, "SweepCol layout is part of the ABI workspace size");
@@ -126,99 +125,110 @@ FNP_HD float sweep_eps(float maxabs)
 
 // Column parameters from the line fit: c0 = C at the first valid step, slope per step, dev =
 // max |C(m) - line(m)| over the valid steps, p = any hypothesis of the column (rotation, size).
+// An axis whose travel |s| (m1 - m0) is below 4 eps gets the pseudo slope eps / (D + 1) instead
+// (the line then strays from the fitted one by at most travel + eps, which is added to dl), so
+// that the range solve needs no special case for constant axes.
 FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float slope[3], const float dev[3],
                                 const BoxPrep &p, float eps)
 {
     const float INF = INFINITY;
     SweepCol c;
     c.m0 = m0; c.m1 = m1;
-    c.const_mask = 0;
+    c.pseudo_mask = 0;
     c.eps = eps; c.pad0 = 0.f; c.pad1 = 0.f;
     c.cosa = p.cosa; c.sina = p.sina;
     const float t[3] = {p.tx, p.ty, p.hz};
     const float span = (float)(m1 - m0);
     for (int k = 0; k < 3; k++) {
-        const float s = slope[k];
+        float s = slope[k];
         float dl = f_add(dev[k], eps);
         c.c0[k] = c0[k];
         const float travel = f_mul(fabsf(s), span);
         if (!(travel > f_mul(4.f, eps))) {
-            c.const_mask |= 1 << k;
-            dl = f_add(dl, travel);
-            c.inv_s[k] = 0.f;
-            c.w_in[k] = f_sub(t[k], dl);
-            c.w_p[k] = f_add(t[k], dl);
-        } else {
-            const float inv = f_div(1.f, s);
-            c.inv_s[k] = inv;
-            const float win = f_sub(t[k], dl);
-            c.w_in[k] = win >= 0.f ? f_mul(win, fabsf(inv)) : -INF;
-            c.w_p[k] = f_mul(f_add(t[k], dl), fabsf(inv));
+            c.pseudo_mask |= 1 << k;
+            s = f_div(eps, f_add(span, 1.f));
+            dl = f_add(f_add(dl, travel), eps);
         }
+        const float inv = f_div(1.f, s);
+        c.inv_s[k] = inv;
+        const float win = f_sub(t[k], dl);
+        c.w_in[k] = win >= 0.f ? f_mul(win, fabsf(inv)) : -INF;
+        c.w_p[k] = f_mul(f_add(t[k], dl), fabsf(inv));
     }
     return c;
 }
 
-// One point against one column.  `diff` is the column's difference array indexed by dm = m - m0
-// (dm in [0, D]); `slot` the compacted hypothesis slot of (m0 + dm, column) at slot[dm * J], or
-// -1; `prep_f` the frustum's compacted hypotheses.  add(ptr, v) adds v to *ptr (a shared-memory
-// RED on the device).  Returns 1 if the definite range starts at dm = 0 (the caller sums these
-// per warp and adds them to diff[0] once), else 0.
-template <class Add>
-FNP_HD int sweep_point(const SweepCol &c, const float x, const float y, const float z, int *diff, const short *slot,
-                       const int J, const float *prep_f, Add add)
+// Ranges of dm = m - m0 for one point against one column: definite [a, e], possible [A, B]
+// (empty when the first bound exceeds the second); [a, e] lies inside [A, B], both inside [0, D].
+struct SweepRanges {
+    int a, e, A, B;
+};
+
+FNP_HD SweepRanges sweep_solve(const SweepCol &c, const float x, const float y, const float z)
 {
-    const float INF = INFINITY;
-    const int D = c.m1 - c.m0;
-    const float Df = (float)D;
+    const float Df = (float)(c.m1 - c.m0);
     const float P[3] = {f_fma(x, c.cosa, f_mul(y, -c.sina)), f_fma(y, c.cosa, f_mul(x, c.sina)), z};
-    float lo = -INF, hi = INF, plo = -INF, phi = INF;
+    float lo = 0.f, hi = Df, plo = 0.f, phi = Df;      // already clamped to the column's depth steps
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float num = f_sub(P[k], c.c0[k]);
-        if (c.const_mask & (1 << k)) {
-            const float d = fabsf(num);
-            if (!(d <= c.w_in[k])) lo = INF;
-            if (!(d <= c.w_p[k])) plo = INF;
-        } else {
-            const float q = f_mul(num, c.inv_s[k]);
-            lo = fmaxf(lo, f_sub(q, c.w_in[k])); hi = fminf(hi, f_add(q, c.w_in[k]));
-            plo = fmaxf(plo, f_sub(q, c.w_p[k])); phi = fminf(phi, f_add(q, c.w_p[k]));
-        }
+        const float q = f_mul(f_sub(P[k], c.c0[k]), c.inv_s[k]);
+        lo = fmaxf(lo, f_sub(q, c.w_in[k])); hi = fminf(hi, f_add(q, c.w_in[k]));
+        plo = fmaxf(plo, f_sub(q, c.w_p[k])); phi = fminf(phi, f_add(q, c.w_p[k]));
     }
-    // clamp to the column's depth steps before the conversion: dm in [0, D]
-    const int a = f2i_up(fminf(fmaxf(lo, 0.f), Df + 1.f));      // first definite step
-    const int e = f2i_down(fmaxf(fminf(hi, Df), -1.f));         // last definite step
-    const int A = f2i_up(fminf(fmaxf(plo, 0.f), Df + 1.f));     // first possible step
-    const int B = f2i_down(fmaxf(fminf(phi, Df), -1.f));        // last possible step
-    const bool has_def = a <= e;
-    int base = 0;
-    if (has_def) {
-        if (a == 0) base = 1; else add(diff + a, 1);
-        if (e < D) add(diff + e + 1, -1);
-    }
-    if (A <= B) {
-        // exact predicate for the steps that are possible but not definite: [A, a-1] and [e+1, B],
-        // or all of [A, B] when there is no definite range
-        const int e1 = has_def ? a - 1 : B;
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1 && !has_def) break;
-            const int d_lo = pass == 0 ? A : e + 1;
-            const int d_hi = pass == 0 ? e1 : B;
-            for (int dm = d_lo; dm <= d_hi; dm++) {
-                const int r = slot[dm * J];
-                if (r < 0) continue;
+    SweepRanges r;
+    r.a = f2i_up(lo);      // float -> int saturates: an empty range stays empty
+    r.e = f2i_down(hi);
+    r.A = f2i_up(plo);
+    r.B = f2i_down(phi);
+    return r;
+}
+
+// The depth steps that are possible but not definite take the exact predicate.  They are
+// [A, a-1] and [e+1, B], or all of [A, B] when there is no definite range; packed as
+// (first step, count) x 2 in one word (8 bits each: the sweep mode needs M <= 255); 0 = none.
+FNP_HD unsigned sweep_pack_uncertain(const SweepRanges &r)
+{
+    if (r.A > r.B) return 0u;
+    if (r.a > r.e) return (unsigned)r.A | ((unsigned)(r.B - r.A + 1) << 8);
+    if (r.a == r.A && r.e == r.B) return 0u;      // everything possible is definite
+    return (unsigned)r.A | ((unsigned)(r.a - r.A) << 8) | ((unsigned)(r.e + 1) << 16) | ((unsigned)(r.B - r.e) << 24);
+}
+FNP_HD int sweep_uncertain_count(unsigned w) { return (int)((w >> 8) & 0xffu) + (int)(w >> 24); }
+// k-th uncertain step (0 <= k < count) of a packed word
+FNP_HD int sweep_uncertain_step(unsigned w, int k)
+{
+    const int n1 = (int)((w >> 8) & 0xffu);
+    return k < n1 ? (int)(w & 0xffu) + k : (int)((w >> 16) & 0xffu) + (k - n1);
+}
+
+// Exact predicate of point (x, y, z) against the hypothesis at depth step m0 + dm of column j.
+// `slot_col` = slot table of the column (slot_col[dm * J], -1: not a valid hypothesis), diff = the
+// column's difference array indexed by dm, D = m1 - m0.  add(ptr, v): *ptr += v.
+template <class Add>
+FNP_HD void sweep_exact_step(const float x, const float y, const float z, const int dm, const int D, int *diff,
+                             const short *slot_col, const int J, const float *prep_f, Add add)
+{
+    const int r = slot_col[dm * J];
+    if (r < 0) return;
 #ifdef FNP_SWEEP_MODEL
-                g_exact_tests++;   // host model only: how many exact predicates the sweep takes
+    g_exact_tests++;   // host model only: how many exact predicates the sweep takes
 #endif
-                if (in_box(x, y, z, load_prep(prep_f, (size_t)r))) {
-                    add(diff + dm, 1);
-                    if (dm < D) add(diff + dm + 1, -1);
-                }
-            }
-        }
+    if (in_box(x, y, z, load_prep(prep_f, (size_t)r))) {
+        add(diff + dm, 1);
+        if (dm < D) add(diff + dm + 1, -1);
     }
-    return base;
+}
+
+// Definite range into the difference array.  Returns 1 if it starts at dm = 0 (the caller sums
+// these per warp and adds them to diff[0] once), else 0.
+template <class Add>
+FNP_HD int sweep_add_definite(const SweepRanges &r, const int D, int *diff, Add add)
+{
+    if (r.a > r.e) return 0;
+    if (r.e < D) add(diff + r.e + 1, -1);
+    if (r.a == 0) return 1;
+    add(diff + r.a, 1);
+    return 0;
 }
 
 }  // namespace fnp

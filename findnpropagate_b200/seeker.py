@@ -308,10 +308,14 @@ class SeekerEngine:
             if self.fixed_split_points is not None:
                 sp = max(2, (int(self.fixed_split_points) + 1) & ~1)      # splits start on a pair boundary
             else:
-                # point splits small enough to balance the persistent CTAs (measured on cfg2, 32 frames:
-                # 2048 -> 0.737 ms, 512 -> 0.666 ms, 256 -> 0.663 ms), large enough to amortise an item
+                # point splits small enough to balance the persistent CTAs (measured on cfg2, 32 frames,
+                # direct kernel: 2048 -> 0.737 ms, 512 -> 0.666 ms, 256 -> 0.663 ms), large enough to amortise
+                # an item; the sweep kernel stages a whole split in shared memory and has its best time at
+                # 1024 (128 cfg2 frames: 512 -> 1.28 ms, 1024 -> 1.20 ms, 2048 -> 1.37 ms)
                 sp = plan["total_rows"] // (self.n_sms * 128)
                 sp = int(min(2048, max(256, 1 << max(sp, 1).bit_length() - 1)))
+                if self.M >= _lib.SWEEP_MIN_MAGS and self.score_mode != _lib.SCORE_DIRECT:
+                    sp = min(sp, 1024)
             max_items = (cap // sp + F + 1) * chunks
             Cmax = max(plan["max_cands"], 1)
             W = _lib.lib.fnp_seeker_mask_words(Cmax)

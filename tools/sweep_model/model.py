@@ -27,7 +27,7 @@ def build(force=False):
     lib = C.CDLL(SO)
     lib.sweep_model_counts.restype = C.c_int
     lib.sweep_model_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                       C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -57,7 +57,7 @@ def prep_boxes(boxes, cosf, sinf):
     return out
 
 
-def run_frustum(lib, xyz, prep, hidx, J, M, split=2048):
+def run_frustum(lib, xyz, prep, hidx, J, M, split=2048, cols_out=None, dev_out=None):
     """-> counts_sweep, counts_brute (nv), stats dict"""
     xyz = np.ascontiguousarray(xyz[:, :3], np.float32)
     prep = np.ascontiguousarray(prep, np.float32)
@@ -67,10 +67,12 @@ def run_frustum(lib, xyz, prep, hidx, J, M, split=2048):
     st = np.zeros(8, np.int64)
     maxabs = float(np.abs(xyz).max()) if xyz.shape[0] else 0.0
     rc = lib.sweep_model_counts(xyz.ctypes.data, xyz.shape[0], prep.ctypes.data, hidx.ctypes.data, nv, J, M,
-                                C.c_float(maxabs), split, cs.ctypes.data, cb.ctypes.data, st.ctypes.data)
+                                C.c_float(maxabs), split, cs.ctypes.data, cb.ctypes.data, st.ctypes.data,
+                                cols_out.ctypes.data if cols_out is not None else None,
+                                dev_out.ctypes.data if dev_out is not None else None)
     assert rc == 0
-    return cs[:nv], cb[:nv], dict(exact_tests=int(st[0]), adds=int(st[1]), pairs=int(st[2]), const_axes=int(st[3]),
-                                  columns=int(st[4]))
+    return cs[:nv], cb[:nv], dict(exact_tests=int(st[0]), adds=int(st[1]), pairs=int(st[2]), pseudo_axes=int(st[3]),
+                                  columns=int(st[4]), pairs_definite=int(st[5]), pairs_uncertain=int(st[6]))
 
 
 def run_frame(lib, cfg_name, seed=0, split=2048, params_override=None):
@@ -90,7 +92,8 @@ def run_frame(lib, cfg_name, seed=0, split=2048, params_override=None):
                       (f.det_boxes, f.det_labels, f.det_scores, f.det_cam_idx), params, keep_intermediates=True)
     M = max(int(params["num_mags"]), 1)
     J = int(params["num_rotations"]) * int(params["num_sizes"])
-    tot = dict(exact_tests=0, adds=0, pairs=0, const_axes=0, columns=0, brute_tests=0, frustums=0)
+    tot = dict(exact_tests=0, adds=0, pairs=0, pseudo_axes=0, columns=0, pairs_definite=0, pairs_uncertain=0,
+               brute_tests=0, frustums=0)
     res = []
     for r in o["frustums"]:
         if "xyz" not in r or not r["valid"].any():

@@ -1,5 +1,5 @@
 // Host model of the depth-sweep scoring kernel (FNP_SCORE_SWEEP): runs the SAME functions the
-// device kernels call (findnpropagate_b200/csrc/fnp_sweep.cuh: sweep_col_build, sweep_point,
+// device kernels call (findnpropagate_b200/csrc/fnp_sweep.cuh: sweep_col_build, sweep_solve, sweep_pack_uncertain, sweep_exact_step,
 // in_box) serially on the CPU, next to the brute-force count with in_box(), so that the range
 // logic can be checked without a GPU (tests/test_sweep_model_cpu.py).  Test infrastructure; not
 // part of the product library.
@@ -13,7 +13,7 @@
 
 struct float4 { float x, y, z, w; };
 #define FNP_SWEEP_MODEL 1
-static long long g_exact_tests = 0;   // incremented by sweep_point under FNP_SWEEP_MODEL
+static long long g_exact_tests = 0;   // incremented by sweep_exact_step under FNP_SWEEP_MODEL
 #include "../../findnpropagate_b200/csrc/fnp_sweep.cuh"
 
 using namespace fnp;
@@ -24,10 +24,11 @@ using namespace fnp;
 // adds, [2] (point, column) pairs, [3] constant-axis columns*axes, [4] columns, [5] pairs with a
 // definite range.  split: points per split (the splits must add up like on the device).
 extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, const int *hidx, int nv, int J, int M,
-                                  float maxabs_pts, int split, int *counts_sweep, int *counts_brute, long long *stats)
+                                  float maxabs_pts, int split, int *counts_sweep, int *counts_brute, long long *stats,
+                                  float *cols_out /* (J, FNP_SWEEP_COL_FLOATS) or NULL */, float *dev_out /* (J,3) or NULL */)
 {
     const int H = J * M;
-    if (H > 32767) return -1;
+    if (H > 32767 || M > 255) return -1;
     memset(stats, 0, 8 * sizeof(long long));
     // ---- sweep_prep_kernel
     std::vector<int> first(J, 0x7fffffff), last(J, -1), r0(J, 0);
@@ -66,12 +67,14 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
         if (last[j] >= first[j]) {
             cols[j] = sweep_col_build(first[j], last[j], &c0[3 * j], &c1[3 * j], &dev[3 * j], load_prep(prep, r0[j]), eps);
             stats[4]++;
-            for (int k = 0; k < 3; k++) stats[3] += (cols[j].const_mask >> k) & 1;
+            for (int k = 0; k < 3; k++) stats[3] += (cols[j].pseudo_mask >> k) & 1;
         } else {
             memset(&cols[j], 0, sizeof(SweepCol));
             cols[j].m0 = 0; cols[j].m1 = -1;
         }
     }
+    if (cols_out) memcpy(cols_out, cols.data(), sizeof(SweepCol) * J);
+    if (dev_out) memcpy(dev_out, dev.data(), sizeof(float) * 3 * J);
     // ---- sweep_score_kernel, one item per split
     std::vector<short> slot(H, -1);
     for (int r = 0; r < nv; r++) slot[hidx[r]] = (short)r;
@@ -87,9 +90,20 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
             int *d = diff.data() + j * M + c.m0;
             const short *sl = slot.data() + c.m0 * J + j;
             int base = 0;
+            const int D = c.m1 - c.m0;
+            auto add = [&](int *q, int v) { *q += v; n_add++; };
             for (int i = 0; i < np; i++) {
                 const float *p = pts + (size_t)(p0 + i) * 3;
-                base += sweep_point(c, p[0], p[1], p[2], d, sl, J, prep, [&](int *q, int v) { *q += v; n_add++; });
+                const SweepRanges r = sweep_solve(c, p[0], p[1], p[2]);
+                base += sweep_add_definite(r, D, d, add);
+                // the device queues (point, column, packed steps) and drains the queue densely; the
+                // arithmetic per queued step is sweep_uncertain_step + sweep_exact_step, as here
+                const unsigned w = sweep_pack_uncertain(r);
+                const int cnt = sweep_uncertain_count(w);
+                for (int k = 0; k < cnt; k++)
+                    sweep_exact_step(p[0], p[1], p[2], sweep_uncertain_step(w, k), D, d, sl, J, prep, add);
+                stats[5] += (r.a <= r.e);
+                stats[6] += (w != 0);
                 stats[2]++;
             }
             d[0] += base;

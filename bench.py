@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--score-mode", default="auto", choices=["auto", "direct", "sweep"],
                     help="stage-2b kernel (include/fnp.h FNP_SCORE_*); both give the same counts")
     ap.add_argument("--split-points", type=int, default=None)
+    ap.add_argument("--e2e-pack", default="on", choices=["on", "off"],
+                    help="e2e arm: gather x,y,z on the host (threaded) and upload 12 B/point instead of all columns")
+    ap.add_argument("--pack-threads", type=int, default=None)
     return ap.parse_args()
 
 
@@ -239,7 +242,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from findnpropagate_b200 import _lib
-    from findnpropagate_b200.seeker import SeekerEngine
+    from findnpropagate_b200.seeker import HostPointFeeder, SeekerEngine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,27 +277,27 @@ def run_ours(a):
     # two compute streams, one per slot: consecutive batches overlap on the device, so the small
     # latency-bound kernels at the end of batch k run under the big kernels of batch k+1
     comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    for e in consumed:
-        e.record()
+    feeder = HostPointFeeder(eng, pack=(a.e2e_pack == "on"), n_threads=a.pack_threads)
+    copy_stream = feeder.copy_stream
+    f_stride, f_off = feeder.layout
 
-    def step(k, resident, prev):
+    def step(k, resident, prev, more=True):
         """One pass of the hot path over one batch; returns the new handle."""
-        pts = dev_pts[k % 2]
-        if not resident:
-            # H2D of this step's points from pinned host memory, inside the timed region, on a
-            # copy stream so that it overlaps the previous step's kernels
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[k % 2])
-                pts.copy_(pinned[k % 2], non_blocking=True)
-                ready[k % 2].record(copy_stream)
-        plan = eng.plan(batch)
+        if resident:
+            pts, ready = dev_pts[k % 2], None
+            plan = eng.plan(batch)
+        else:
+            # this step's points come from (pinned) host memory inside the timed region: threaded gather
+            # of x,y,z into a pinned staging slot (started one step ahead), H2D on a copy stream so that
+            # it overlaps the previous step's kernels
+            pts, ready = feeder.upload(k % 2)
+            if more:
+                feeder.submit((k + 1) % 2, pinned[(k + 1) % 2])
+            plan = eng.plan(batch, stride=f_stride, xyz_offset=0 if f_stride else 0)
         with torch.cuda.stream(comp[k % 2]):
-            h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2,
-                            points_ready=None if resident else ready[k % 2])
-            consumed[k % 2].record()
+            h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2, points_ready=ready)
+            if not resident:
+                feeder.mark_consumed(k % 2)
         res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
         if res is not None and world > 1:
             res["plan_score"], res["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
@@ -333,8 +336,10 @@ def run_ours(a):
 
     def timed(resident, steps, warmup):
         prev = None
+        if not resident and warmup > 0:
+            feeder.submit(0, pinned[0])
         for k in range(warmup):
-            prev, _ = step(k, resident, prev)
+            prev, _ = step(k, resident, prev, more=k + 1 < warmup)
         if prev is not None:
             r = eng.finish(prev)
             if world > 1:
@@ -353,9 +358,12 @@ def run_ours(a):
         e0.record()
         for st in comp + [copy_stream]:
             st.wait_event(e0)                  # nothing of the timed region starts before e0
+        t_host = time.perf_counter()
+        if not resident:
+            feeder.submit(0, pinned[0])        # the first gather is inside the timed region as well
         prev, last = None, None
         for k in range(steps):
-            prev, r = step(k, resident, prev)
+            prev, r = step(k, resident, prev, more=k + 1 < steps)
             last = r or last
         last = eng.finish(prev)
         if world > 1:
@@ -366,7 +374,7 @@ def run_ours(a):
             cur.wait_stream(st)                # e1 after everything the timed region enqueued
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_host) if not resident else 0.0)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -381,49 +389,81 @@ def run_ours(a):
     ms_e2e, _, _ = timed(False, a.steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- dominant kernel (scoring) in isolation, CUDA events on the launching stream
+    # ---- the two heaviest stages in isolation, CUDA events on the launching stream, L2 flushed
     plan = eng.plan(batch)
     h = eng.execute(plan, dev_pts[0])
     res = eng.finish(h)
+    score_mode = eng.last_score_mode
     stream = _lib.current_stream(dev)
     import ctypes as C
-    for _ in range(3):
-        _lib.lib.fnp_seeker_score(C.byref(eng.cfg), C.byref(h["batch"]), stream)
-    iters = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scr = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    tot = 0.0
-    for _ in range(iters):
-        scr.zero_()                                   # flush L2 (256 MB > 126 MB)
-        e0.record()
-        _lib.lib.fnp_seeker_score(C.byref(eng.cfg), C.byref(h["batch"]), stream)
-        e1.record()
-        torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    score_ms = tot / iters
+
+    def stage_ms(fn, iters=10):
+        for _ in range(3):
+            fn(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(iters):
+            scr.zero_()                                   # flush L2 (256 MB > 126 MB)
+            e0.record()
+            rc = fn(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            assert rc == 0
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    cull_ms = stage_ms(_lib.lib.fnp_seeker_cull)          # later stages read what cull leaves: run it first
+    for fn in (_lib.lib.fnp_seeker_frustum_stats, _lib.lib.fnp_seeker_hypotheses):
+        fn(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+    score_ms = stage_ms(_lib.lib.fnp_seeker_score)
     npts = res["cand_npts"].astype(np.int64)
     nval = res["cand_nvalid"].astype(np.int64)
-    alg_bytes = float(16 * npts[nval > 0].sum() + 36 * nval.sum())
+    n_rows = int(plan["total_rows"])
+    n_dets = sum(len(f.det_scores) for f in batch)
+    # algorithmic bytes per launch, SURVEY.md section 8(d): stage 1 = 16 N + 16 sum P_f + 16 D;
+    # stage 2 = 16 sum P_f + 28 nv + 4 nv (+ 4 nv for the 2D IoU the score needs) over the valid hypotheses
+    alg = {"cull": float(16 * n_rows + 16 * npts.sum() + 16 * n_dets),
+           "score": float(16 * npts[nval > 0].sum() + 36 * nval.sum())}
     tests = float((npts * nval).sum())
+    J = int(params["num_rotations"] * params["num_sizes"])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (score_ms * 1e-3) / 1e9
-    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    # measured ceiling of the scoring loop's instruction mix with register operands and nothing but
-    # the SM pipes in the way (tools/ubench/score_mix.cu, V0, 6 CTAs/SM; profiles/r01d_score_mix_ceiling.txt)
-    PIPE_TESTS_PER_CLK_SM = 10.85
-    pipe_peak_tests = eng.n_sms * PIPE_TESTS_PER_CLK_SM * sm_clock * 1e6
-    traffic = None
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
+    traffic = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
         if tj.get("config") == a.config and tj.get("frames") == B:
-            traffic = float(tj["dram_bytes_per_launch"])
+            traffic = tj.get("dram_bytes_per_launch", {})
     except Exception:
         pass
+    score_kernel = "fnp::sweep_score_kernel" if score_mode == "sweep" else "fnp::score_kernel"
+
+    def roof(name, kernel, ms, note):
+        ach = alg[name] / (ms * 1e-3) / 1e9
+        return {"kernel": kernel, "stage": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic.get(kernel), "peak_source": peak_src, "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": alg[name], "note": note}
+    roofs = {
+        "score": roof("score", score_kernel, score_ms,
+                      "stage 2b (per-hypothesis point counts), timed through fnp_seeker_score (includes its small "
+                      "planning kernels).  Bound by instruction issue, not HBM (DESIGN.md section 4): the sweep kernel "
+                      "solves one depth range per (point, column) pair instead of testing every (point, hypothesis) pair"
+                      if score_mode == "sweep" else
+                      "stage 2b, direct kernel: bound by the SM's ALU/FMA pipes, not by HBM (DESIGN.md section 4)"),
+        "cull": roof("cull", "fnp::cull_stage_kernel", cull_ms,
+                     "stage 1 (projection x 6 cameras + frustum cull + ordered compaction), timed through "
+                     "fnp_seeker_cull (five launches); HBM-bound by design, instruction-issue-bound as measured"),
+    }
+    dominant = "score" if score_ms >= cull_ms else "cull"
+    other = "cull" if dominant == "score" else "score"
+    roofs["score"].update({
+        "score_mode": score_mode, "point_box_tests_equivalent_per_launch": tests,
+        "point_column_range_solves_per_launch": float(npts[nval > 0].sum() * J) if score_mode == "sweep" else None})
 
     if rank == 0:
         n_frames = B * world
@@ -446,22 +486,19 @@ def run_ours(a):
                 "sharding": "frame-wise, no data-path collective; one all_gather of packed proposals + one "
                             "all_reduce of recall counters per run, inside the timed region" if world > 1 else "single GPU"},
             "hypotheses_per_s": F_step * H * world * a.steps / (ms_res * 1e-3),
-            "point_box_tests_per_s_scoring_kernel": tests / (score_ms * 1e-3),
+            "point_box_tests_equivalent_per_s_scoring_stage": tests / (score_ms * 1e-3),
             "e2e": {"value": n_frames * a.steps / (ms_e2e * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(in_bytes + sum(plan[k].nbytes for k in eng._META)),
+                    "h2d_bytes_per_step": int((n_rows * 12 if feeder.pack else in_bytes)
+                                              + sum(plan[k].nbytes for k in eng._META)),
                     "d2h_bytes_per_step": int(4 * (12 * plan["F"] + 8) + plan["F"]),
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "host_input_bytes_per_step": int(in_bytes),
+                    "host_pack": ("x,y,z gathered on the host by %d threads (fnp_host_pack_xyz), 12 B/point uploaded"
+                                  % feeder.n_threads) if feeder.pack else "off: all %d columns uploaded" % batch[0].points.shape[1]},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "fnp::score_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "the scoring kernel is bound by the SM's ALU/FMA pipes, not by HBM (DESIGN.md section 4): "
-                                 "pipe_frac = point-box tests/s over the measured ceiling of its instruction mix "
-                                 "(10.85 tests/clk/SM x SMs x clock)",
-                         "pipe_frac": tests / (score_ms * 1e-3) / pipe_peak_tests,
-                         "point_box_tests_per_launch": tests},
+            "roofline": roofs[dominant],
+            "roofline_second_kernel": roofs[other],
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

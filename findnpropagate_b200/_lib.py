@@ -92,6 +92,12 @@ lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINT
 lib.fnp_host_select_candidates.restype = _i
 lib.fnp_host_select_candidates.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
 
+for _n in ("fnp_host_pack_xyz", "fnp_host_pack_xyz_begin"):
+    getattr(lib, _n).restype = _i
+    getattr(lib, _n).argtypes = [_vp, C.c_int64, _i, _i, _vp, _i]
+lib.fnp_host_pack_wait.restype = _i
+lib.fnp_host_pack_wait.argtypes = [_i]
+
 lib.fnp_upload_from_pinned.restype = _i
 lib.fnp_upload_from_pinned.argtypes = [_vp, _vp, C.c_size_t, _vp]
 
@@ -104,7 +110,8 @@ EXPORTED = [
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
     "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
-    "fnp_recall_counters", "fnp_host_select_candidates",
+    "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
+    "fnp_host_pack_wait",
 ]
 
 

@@ -129,3 +129,100 @@ extern "C" int fnp_host_select_candidates(const float *det_boxes, const int64_t 
     for (int b = 0; b < n_frames; b++) frame_cand_start[b + 1] += frame_cand_start[b];
     return n_out;
 }
+
+// ---------------------------------------------------------------------------------------
+// Host-side column gather of the point table.
+//
+// The reference uploads every column of `points` ([batch_idx,] x, y, z, intensity, time:
+// pcdet/models/__init__.py:23-36 load_data_to_gpu) although the seeker reads xyz only
+// (frustum_proposals_v1.py:571-575).  With host buffers on one side of a PCIe link the point
+// table IS the end-to-end cost (20 B/point at ~55 GB/s against ~2.5 ms of kernels per 128
+// frames), so the host side of the path gathers x, y, z into a pinned staging buffer and only
+// those 12 B/point cross the link.  Worker threads split the rows; stores are non-temporal so
+// that the staging buffer is not read into the cache before it is overwritten.
+// ---------------------------------------------------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+namespace {
+
+void pack_rows(const float *src, int64_t r0, int64_t r1, int stride, int off, float *dst)
+{
+    const float *s = src + r0 * stride + off;
+    float *d = dst + r0 * 3;
+    for (int64_t r = r0; r < r1; r++, s += stride, d += 3) {
+#if defined(__SSE2__)
+        const int *si = reinterpret_cast<const int *>(s);
+        int *di = reinterpret_cast<int *>(d);
+        _mm_stream_si32(di, si[0]);
+        _mm_stream_si32(di + 1, si[1]);
+        _mm_stream_si32(di + 2, si[2]);
+#else
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+#endif
+    }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
+
+struct PackJob {
+    std::vector<std::thread> threads;
+    bool used = false;
+};
+constexpr int kMaxPackJobs = 16;
+PackJob g_jobs[kMaxPackJobs];
+std::mutex g_jobs_mutex;
+
+}  // namespace
+
+extern "C" int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
+                                       int n_threads)
+{
+    if (rows < 0 || stride < 3 || xyz_offset < 0 || xyz_offset + 3 > stride || (rows > 0 && (!src_host || !dst_host)))
+        return FNP_EINVAL;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    int ticket = -1;
+    {
+        std::lock_guard<std::mutex> lk(g_jobs_mutex);
+        for (int i = 0; i < kMaxPackJobs; i++)
+            if (!g_jobs[i].used) { ticket = i; g_jobs[i].used = true; break; }
+    }
+    if (ticket < 0) return FNP_EWORKSPACE;      // too many gathers in flight
+    PackJob &job = g_jobs[ticket];
+    const int64_t per = (rows + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        const int64_t r0 = (int64_t)t * per, r1 = std::min(rows, r0 + per);
+        if (r0 >= r1) break;
+        job.threads.emplace_back(pack_rows, src_host, r0, r1, stride, xyz_offset, dst_host);
+    }
+    return ticket;
+}
+
+extern "C" int fnp_host_pack_wait(int ticket)
+{
+    if (ticket < 0 || ticket >= kMaxPackJobs) return FNP_EINVAL;
+    PackJob &job = g_jobs[ticket];
+    {
+        std::lock_guard<std::mutex> lk(g_jobs_mutex);
+        if (!job.used) return FNP_EINVAL;
+    }
+    for (auto &t : job.threads) t.join();
+    job.threads.clear();
+    std::lock_guard<std::mutex> lk(g_jobs_mutex);
+    job.used = false;
+    return FNP_OK;
+}
+
+extern "C" int fnp_host_pack_xyz(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
+                                 int n_threads)
+{
+    const int t = fnp_host_pack_xyz_begin(src_host, rows, stride, xyz_offset, dst_host, n_threads);
+    if (t < 0) return t;
+    return fnp_host_pack_wait(t);
+}

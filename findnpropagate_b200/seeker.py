@@ -194,13 +194,16 @@ class SeekerEngine:
                 self._cam_cache[keys[b]] = mm[i].copy()
         return out
 
-    def plan(self, frames: List[FrameInput], xyz_offset=0):
-        """Everything the host contributes to a batch, as numpy arrays."""
+    def plan(self, frames: List[FrameInput], xyz_offset=0, stride=None):
+        """Everything the host contributes to a batch, as numpy arrays.  stride / xyz_offset describe
+        the DEVICE point table handed to execute() (default: the frames' own row layout; (3, 0) for
+        a table gathered by HostPointFeeder)."""
         B = len(frames)
         n_rows = np.array([f.points.shape[0] for f in frames], dtype=np.int64)
         frame_row_start = np.zeros(B + 1, np.int64)
         np.cumsum(n_rows, out=frame_row_start[1:])
-        stride = int(frames[0].points.shape[1]) if B else 5
+        if stride is None:
+            stride = int(frames[0].points.shape[1]) if B else 5
         n_det = [len(f.det_scores) for f in frames]
         det_frame = np.repeat(np.arange(B, dtype=np.int64), n_det)
         if B:
@@ -530,3 +533,78 @@ class SeekerEngine:
             hyp_prep=view("hyp_prep", torch.float32, (F, H, 8)),
             counts=view("counts", torch.int32, (F, H)),
         )
+
+
+class HostPointFeeder:
+    """Host buffers -> device point table for SeekerEngine.execute, double buffered.
+
+    The reference uploads every column of the point table (pcdet/models/__init__.py:23-36) although
+    the seeker reads xyz only.  submit() starts a threaded gather of x, y, z into a pinned staging
+    slot on the host (fnp_host_pack_xyz_begin: returns at once, the workers do not hold the GIL);
+    upload() waits for it and enqueues the H2D copy of the 12 B/point table on the copy stream.
+    Slots alternate, so the gather of batch k+1 runs while batch k crosses PCIe and batch k-1 is in
+    the kernels.  With pack=False the rows are uploaded as they are (all columns)."""
+
+    def __init__(self, engine: "SeekerEngine", pack=True, n_threads=None, slots=2):
+        import os
+        self.eng, self.pack, self.slots = engine, bool(pack), int(slots)
+        self.n_threads = int(n_threads) if n_threads else max(1, min(16, len(os.sched_getaffinity(0)) - 1))
+        self.copy_stream = torch.cuda.Stream(device=engine.device)
+        self.ready = [torch.cuda.Event() for _ in range(self.slots)]       # H2D of the slot complete
+        self.consumed = [torch.cuda.Event() for _ in range(self.slots)]    # kernels done with the slot
+        for e in self.consumed:
+            e.record()
+        self.ticket = [None] * self.slots
+        self.host = [None] * self.slots
+        self.dev = [None] * self.slots
+        self.src = [None] * self.slots
+        self.copied = [torch.cuda.Event() for _ in range(self.slots)]      # staging slot read by the DMA
+        self.copied_valid = [False] * self.slots
+
+    @property
+    def layout(self):
+        """(stride, xyz_offset) of the device table, for SeekerEngine.plan."""
+        return (3, 0) if self.pack else (None, None)
+
+    def submit(self, slot, points_host: torch.Tensor, xyz_offset=0):
+        """points_host: (rows, C) float32 CPU tensor (pinned for pack=False).  Starts the gather."""
+        assert points_host.dtype == torch.float32 and points_host.is_contiguous() and not points_host.is_cuda
+        rows, C_ = points_host.shape
+        self.src[slot] = points_host
+        if not self.pack:
+            return
+        nbytes = rows * 12
+        if self.host[slot] is None or self.host[slot].numel() < nbytes:
+            self.host[slot] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, pin_memory=True)
+        if self.copied_valid[slot]:
+            self.copied[slot].synchronize()          # the DMA has read the previous contents of the slot
+        t = _lib.lib.fnp_host_pack_xyz_begin(points_host.data_ptr(), rows, C_, xyz_offset, self.host[slot].data_ptr(),
+                                             self.n_threads)
+        if t < 0:
+            _lib.check(t, "fnp_host_pack_xyz_begin")
+        self.ticket[slot] = t
+
+    def upload(self, slot):
+        """Waits for the slot's gather, enqueues its H2D copy; returns (device table, ready event)."""
+        src = self.src[slot]
+        rows, C_ = src.shape
+        if self.pack:
+            _lib.check(_lib.lib.fnp_host_pack_wait(self.ticket[slot]), "fnp_host_pack_wait")
+            self.ticket[slot] = None
+            width, host = 3, self.host[slot][:rows * 12].view(torch.float32).view(rows, 3)
+        else:
+            width, host = C_, src
+        if self.dev[slot] is None or self.dev[slot].numel() < rows * width:
+            self.dev[slot] = torch.empty(int(rows * width * 1.25) + 64, dtype=torch.float32, device=self.eng.device)
+        dev = self.dev[slot][:rows * width].view(rows, width)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])
+            dev.copy_(host, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+            self.copied[slot].record(self.copy_stream)
+            self.copied_valid[slot] = True
+        return dev, self.ready[slot]
+
+    def mark_consumed(self, slot):
+        """Call on the compute stream after the kernels that read the slot's device table."""
+        self.consumed[slot].record()

@@ -261,6 +261,18 @@ int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels
                                const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
                                float score_thr, int32_t *cand_det, int32_t *frame_cand_start);
 
+/* Column gather of the point table on the host: x, y, z of `rows` rows of `stride` floats (xyz at
+ * column xyz_offset) into dst_host (rows,3), so that only the 12 B/point the path reads cross PCIe
+ * (the reference uploads every column: pcdet/models/__init__.py:23-36).  n_threads worker threads
+ * split the rows.  _begin returns a ticket (>= 0) at once and gathers in the background;
+ * fnp_host_pack_wait(ticket) blocks until that gather is complete (FNP_EWORKSPACE: more than 16
+ * gathers in flight).  dst_host is typically pinned memory the next H2D copy reads. */
+int fnp_host_pack_xyz(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
+                      int n_threads);
+int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
+                            int n_threads);
+int fnp_host_pack_wait(int ticket);
+
 /* Host->device upload of a small block by a kernel instead of the copy engine: src is pinned,
  * UVA-mapped host memory (cudaHostAlloc / torch pin_memory), dst device memory, both 16-byte
  * aligned, bytes a multiple of 16.  The per-batch metadata goes this way so that it cannot queue

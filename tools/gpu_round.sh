@@ -7,8 +7,8 @@ python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/
 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 python tools/stage_times.py --frames 128 > gpurun_out/stage_times_128.json 2> gpurun_out/stage_times.err; tail -3 gpurun_out/stage_times.err
 if [ "${NCU:-1}" = "1" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cull_|cell_table|hypotheses_|plan_items|recall_|scan_|score_|seg_nms|select_|stats_|write_items|upload_' -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cull_|cell_table|hypotheses_|plan_items|recall_|scan_|score_|sweep_|seg_nms|select_|stats_|write_items|upload_' -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 python tools/ncu_summary.py gpurun_out/launches.csv
-ncu --set full --clock-control none --import-source on -k 'regex:cull_|cell_table|hypotheses_|recall_|scan_|score_|seg_nms|select_|stats_' -s 15 -c 12 -o gpurun_out/prof_all -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:cull_|cell_table|hypotheses_|recall_|scan_|score_|sweep_|seg_nms|select_|stats_' -s 16 -c 13 -o gpurun_out/prof_all -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 python tools/ncu_kernels.py gpurun_out/prof_all.ncu-rep
 fi

@@ -40,8 +40,10 @@ def parse():
     ap.add_argument("--score-mode", default="auto", choices=["auto", "direct", "sweep"],
                     help="stage-2b kernel (include/fnp.h FNP_SCORE_*); both give the same counts")
     ap.add_argument("--split-points", type=int, default=None)
-    ap.add_argument("--e2e-pack", default="on", choices=["on", "off"],
-                    help="e2e arm: gather x,y,z on the host (threaded) and upload 12 B/point instead of all columns")
+    ap.add_argument("--e2e-pack", default="auto", choices=["auto", "on", "off"],
+                    help="e2e arm: gather x,y,z on the host (threaded) and upload 12 B/point instead of all columns; "
+                         "auto = on for one rank per host (the gather needs the host's cores and memory bandwidth: "
+                         "with several ranks sharing them the plain upload, 20 B/point of DMA reads, is cheaper)")
     ap.add_argument("--pack-threads", type=int, default=None)
     return ap.parse_args()
 
@@ -277,7 +279,8 @@ def run_ours(a):
     # two compute streams, one per slot: consecutive batches overlap on the device, so the small
     # latency-bound kernels at the end of batch k run under the big kernels of batch k+1
     comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    feeder = HostPointFeeder(eng, pack=(a.e2e_pack == "on"), n_threads=a.pack_threads)
+    feeder = HostPointFeeder(eng, pack=(a.e2e_pack == "on" or (a.e2e_pack == "auto" and world == 1)),
+                             n_threads=a.pack_threads)
     copy_stream = feeder.copy_stream
     f_stride, f_off = feeder.layout
 

@@ -121,3 +121,81 @@ def extract(frames, compute_fn: Callable, folder: Optional[str] = None, batch_fr
     merged, total = gather_shards(local, recall, n, rank, world, device=device)
     ar = {("rcnn_%s" % t): (total.get("rcnn_%s" % t, 0) / max(total.get("gt", 0), 1)) for t in THRESH}
     return merged, total, ar
+
+
+def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch_frames: int = 32, rank: int = 0,
+                     world: int = 1, nms_thresh: Optional[float] = None, workers: int = 4, pack_xyz: bool = True,
+                     device=None):
+    """tools/extract_pseudo_labels.py:113-146 over a nuScenes info list, pipelined end to end:
+
+        worker threads   NuScenesFeed.prefetch: read + transform + filter the next batch of frames
+        host threads     HostPointFeeder: gather x,y,z of the batch into a pinned slot
+        copy stream      H2D of the 12 B/point table
+        compute stream   the five seeker stages (+ stage-4 NMS, recall counters), one D2H per batch
+        this thread      per-frame .pth files (``save_frame``), recall bookkeeping
+
+    Batch k+1 is read, gathered and uploaded while batch k is in the kernels.  Frames are sharded
+    by rank as in ``extract``; returns (all_preds in dataset order, recall dict, AR per threshold)."""
+    import torch
+    from .seeker import HostPointFeeder
+    n = len(feed)
+    mine = shard_indices(n, rank, world)
+    if folder is not None:
+        os.makedirs(folder, exist_ok=True)
+    feeder = HostPointFeeder(engine, pack=pack_xyz)
+    stride, _ = feeder.layout
+    local, recall = [], {}
+
+    def finish(job):
+        h, ids, rerun = job
+        while True:
+            try:
+                res = engine.finish(h)
+                break
+            except OverflowError as e:      # frustum-point buffer too small: grow it, run the batch again
+                engine.pts_factor = max(engine.pts_factor * 1.5, 1.25 * int(e.args[0]) / max(h["plan"]["total_rows"], 1))
+                h = rerun()
+        for j, fid in enumerate(ids):
+            local.append(res["frames"][j])
+            if folder is not None:
+                save_frame(folder, fid, res["frames"][j])
+        for k, v in res.get("recall", {}).items():
+            recall[k] = recall.get(k, 0) + int(v)
+
+    def stage(slot, frames):
+        rows = sum(f.points.shape[0] for f in frames)
+        width = frames[0].points.shape[1]
+        host = torch.empty((rows, width), dtype=torch.float32, pin_memory=not pack_xyz)
+        r = 0
+        for f in frames:
+            host[r:r + f.points.shape[0]] = torch.from_numpy(f.points)
+            r += f.points.shape[0]
+        feeder.submit(slot, host)
+
+    prev, k = None, 0
+    batches = feed.prefetch(mine, detector, batch_frames=batch_frames, workers=workers)
+    cur = next(batches, None)
+    if cur is not None:
+        stage(0, cur[0])
+    while cur is not None:
+        frames, ids, _ = cur
+        slot = k % 2
+        pts, ready = feeder.upload(slot)
+        nxt = next(batches, None)
+        if nxt is not None:
+            stage((k + 1) % 2, nxt[0])                      # gathered while this batch runs
+        plan = engine.plan(frames, stride=stride)
+        gt = engine.upload_gt(frames)
+        def run(plan=plan, pts=pts, gt=gt, slot=slot, ready=ready):
+            h = engine.execute(plan, pts, nms_thresh=nms_thresh, gt=gt, slot=slot, points_ready=ready)
+            feeder.mark_consumed(slot)
+            return h
+        h = run()
+        if prev is not None:
+            finish(prev)                                    # overlaps the kernels of this batch
+        prev, cur, k = (h, ids, run), nxt, k + 1
+    if prev is not None:
+        finish(prev)
+    merged, total = gather_shards(local, recall, n, rank, world, device=device or "cpu")
+    ar = {("rcnn_%s" % t): (total.get("rcnn_%s" % t, 0) / max(total.get("gt", 0), 1)) for t in THRESH}
+    return merged, total, ar

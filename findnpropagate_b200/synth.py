@@ -299,3 +299,27 @@ def seeker_params(cfg: SynthConfig) -> dict:
     return dict(lq=0.0, uq=0.25, cq=1.0, iou_w=1.0, nms_normal=1.0, dst_w=0.0, dns_w=1.0,
                 min_cam_iou=0.3, score_thr=0.45, nms_2d=0.4, nms_3d=0.0, clamp_bottom=1,
                 num_sizes=cfg.num_sizes, num_mags=cfg.num_mags, num_rotations=cfg.num_rotations)
+
+
+def write_nuscenes_tree(root, frames):
+    """Write synthetic frames as a nuScenes-format tree (LiDAR .bin files of 5 floats per point,
+    no sweeps) and return the matching info dicts (the fields NuScenesDataset reads,
+    nuscenes_dataset.py:105-233) -- the on-disk input of findnpropagate_b200.nuscenes_feed."""
+    import os
+    infos = []
+    names = ["CAM_FRONT", "CAM_FRONT_RIGHT", "CAM_FRONT_LEFT", "CAM_BACK", "CAM_BACK_LEFT", "CAM_BACK_RIGHT"]
+    for f in frames:
+        rel = os.path.join("samples", "LIDAR_TOP", f.frame_id + ".bin")
+        os.makedirs(os.path.join(root, os.path.dirname(rel)), exist_ok=True)
+        np.ascontiguousarray(f.points, np.float32).tofile(os.path.join(root, rel))
+        cams = {}
+        for c, name in enumerate(names):
+            cams[name] = dict(data_path=f.image_paths[c], sensor2lidar_rotation=f.camera2lidar[c, :3, :3].astype(np.float64),
+                              sensor2lidar_translation=f.camera2lidar[c, :3, 3].astype(np.float64),
+                              camera_intrinsics=f.camera_intrinsics[c, :3, :3].astype(np.float64),
+                              sensor2ego_rotation=[1.0, 0.0, 0.0, 0.0], sensor2ego_translation=[0.0, 0.0, 0.0])
+        gt = np.asarray(f.gt_boxes, np.float32)
+        infos.append(dict(lidar_path=rel, token=f.token, sweeps=[], cams=cams, gt_boxes=gt[:, :9].copy(),
+                          gt_names=np.array([CLASS_NAMES[int(c) - 1] for c in gt[:, -1]]),
+                          num_lidar_pts=np.full(gt.shape[0], 10)))
+    return infos

@@ -103,3 +103,26 @@ def test_unsupported_options_raise():
         seeker.resolve_params(dict(topk=2, nms_3d=0, dst_w=0))
     with pytest.raises(NotImplementedError):
         seeker.resolve_params(dict(nms_3d=0, dst_w=0.2))
+
+
+def test_host_pack_xyz_gathers_the_columns():
+    """fnp_host_pack_xyz[_begin/_wait]: x,y,z of every row into a contiguous (rows,3) table, any
+    stride / offset / thread count, empty input, and bad arguments rejected."""
+    from findnpropagate_b200 import _lib
+    rng = np.random.default_rng(3)
+    for rows, stride, off, nt in ((0, 5, 0, 4), (1, 3, 0, 1), (1001, 5, 0, 3), (4097, 6, 1, 16), (50000, 5, 0, 7)):
+        src = rng.random((rows, stride), dtype=np.float32)
+        dst = np.full((rows, 3), -1, np.float32)
+        assert _lib.lib.fnp_host_pack_xyz(src.ctypes.data, rows, stride, off, dst.ctypes.data, nt) == 0
+        assert np.array_equal(dst, src[:, off:off + 3])
+    src = rng.random((1000, 5), dtype=np.float32)
+    a, b = np.empty((1000, 3), np.float32), np.empty((1000, 3), np.float32)
+    t1 = _lib.lib.fnp_host_pack_xyz_begin(src.ctypes.data, 1000, 5, 0, a.ctypes.data, 2)
+    t2 = _lib.lib.fnp_host_pack_xyz_begin(src.ctypes.data, 1000, 5, 2, b.ctypes.data, 2)
+    assert t1 >= 0 and t2 >= 0 and t1 != t2
+    assert _lib.lib.fnp_host_pack_wait(t2) == 0 and _lib.lib.fnp_host_pack_wait(t1) == 0
+    assert np.array_equal(a, src[:, :3]) and np.array_equal(b, src[:, 2:5])
+    assert _lib.lib.fnp_host_pack_wait(t1) == -1                       # already collected
+    assert _lib.lib.fnp_host_pack_xyz(src.ctypes.data, 10, 2, 0, a.ctypes.data, 1) == -1      # stride < 3
+    assert _lib.lib.fnp_host_pack_xyz(src.ctypes.data, 10, 5, 3, a.ctypes.data, 1) == -1      # columns past the row
+    assert _lib.lib.fnp_host_pack_xyz(None, 10, 5, 0, a.ctypes.data, 1) == -1

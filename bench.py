@@ -362,6 +362,7 @@ def run_ours(a):
         for st in comp + [copy_stream]:
             st.wait_event(e0)                  # nothing of the timed region starts before e0
         t_host = time.perf_counter()
+        h0 = dict(eng.host_s)
         if not resident:
             feeder.submit(0, pinned[0])        # the first gather is inside the timed region as well
         prev, last = None, None
@@ -383,13 +384,14 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             dist.barrier()
-        return ms, last, eng.launches - l0
+        host_ms = {k: 1e3 * (eng.host_s[k] - h0[k]) / steps for k in h0}
+        return ms, last, eng.launches - l0, host_ms
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_res, last, launches = timed(True, a.steps, a.warmup)
-    ms_e2e, _, _ = timed(False, a.steps, a.warmup)
+    ms_res, last, launches, host_res = timed(True, a.steps, a.warmup)
+    ms_e2e, _, _, host_e2e = timed(False, a.steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the two heaviest stages in isolation, CUDA events on the launching stream, L2 flushed
@@ -499,6 +501,8 @@ def run_ours(a):
                     "host_pack": ("x,y,z gathered on the host by %d threads (fnp_host_pack_xyz), 12 B/point uploaded"
                                   % feeder.n_threads) if feeder.pack else "off: all %d columns uploaded" % batch[0].points.shape[1]},
             "gpu_launches": int(launches),
+            "host_ms_per_step": {"resident": host_res, "e2e": host_e2e,
+                                 "note": "main-thread time in SeekerEngine.plan / execute / finish (after its event wait) per step"},
             "clocks": clocks,
             "roofline": roofs[dominant],
             "roofline_second_kernel": roofs[other],

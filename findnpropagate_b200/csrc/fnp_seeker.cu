@@ -1152,7 +1152,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const fnp_seeker_b
 // Stage 2b, sweep mode: per-hypothesis point counts without testing every pair
 // ======================================================================================
 // Arithmetic and derivation: fnp_sweep.cuh (shared with the host model tools/sweep_model.cu).
-// One CTA per frustum: line fit + deviation of every column.  Dynamic shared memory: 12 J words.
+// One CTA per frustum: line fit + deviation of every column.  Dynamic shared memory: 15 J words.
 __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch b, const int J, const int M)
 {
     extern __shared__ int s_raw[];
@@ -1161,7 +1161,8 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
     int *s_r0 = s_raw + 2 * J;                             // [J] compacted slot of the column's first valid step
     float *s_c0 = reinterpret_cast<float *>(s_raw + 3 * J);   // [J][3]
     float *s_c1 = s_c0 + 3 * J;                            // [J][3], later the slopes
-    unsigned *s_dev = reinterpret_cast<unsigned *>(s_c1 + 3 * J);   // [J][3] max deviation (float bits, >= 0)
+    unsigned *s_dev = reinterpret_cast<unsigned *>(s_c1 + 3 * J);   // [J][3] max of C - line (float bits, >= 0)
+    unsigned *s_den = s_dev + 3 * J;                                // [J][3] max of line - C
     __shared__ unsigned s_maxabs;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int H = J * M;
@@ -1171,6 +1172,7 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
         s_first[j] = 0x7fffffff;
         s_last[j] = -1;
         s_dev[3 * j] = s_dev[3 * j + 1] = s_dev[3 * j + 2] = 0u;
+        s_den[3 * j] = s_den[3 * j + 1] = s_den[3 * j + 2] = 0u;
     }
     if (tid == 0) s_maxabs = 0u;
     __syncthreads();
@@ -1213,7 +1215,9 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
         const float dm = (float)(m - s_first[j]);
         for (int k = 0; k < 3; k++) {
             const float line = __fmaf_rn(s_c1[3 * j + k], dm, s_c0[3 * j + k]);
-            atomicMax(&s_dev[3 * j + k], __float_as_uint(fabsf(__fsub_rn(Cv[k], line))));
+            const float d = __fsub_rn(Cv[k], line);
+            if (d > 0.f) atomicMax(&s_dev[3 * j + k], __float_as_uint(d));
+            if (d < 0.f) atomicMax(&s_den[3 * j + k], __float_as_uint(-d));
         }
     }
     __syncthreads();
@@ -1225,7 +1229,9 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
             // every hypothesis of the column carries the same cosa, sina, tx, ty, hz: read the first one
             const float dev[3] = {__uint_as_float(s_dev[3 * j]), __uint_as_float(s_dev[3 * j + 1]),
                                   __uint_as_float(s_dev[3 * j + 2])};
-            c = sweep_col_build(m0, m1, s_c0 + 3 * j, s_c1 + 3 * j, dev,
+            const float den[3] = {__uint_as_float(s_den[3 * j]), __uint_as_float(s_den[3 * j + 1]),
+                                  __uint_as_float(s_den[3 * j + 2])};
+            c = sweep_col_build(m0, m1, s_c0 + 3 * j, s_c1 + 3 * j, dev, den,
                                 load_prep(b.hyp_prep, (size_t)f * H + s_r0[j]), eps);
         } else {
             c = SweepCol{};
@@ -1265,7 +1271,10 @@ __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
 //           lane takes one exact predicate at a time, whichever point and column it belongs to;
 //   scan    prefix sum over the depth steps of every column, one integer RED per valid hypothesis
 //           into row f of `counts`.
-__global__ void __launch_bounds__(kSweepThreads, 4) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
+#ifndef FNP_SWEEP_MIN_CTAS
+#define FNP_SWEEP_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int H = J * M, SP = b.split_points;
@@ -1339,28 +1348,47 @@ __global__ void __launch_bounds__(kSweepThreads, 4) sweep_score_kernel(const fnp
             const short *slot_col = s_slot + c.m0 * J + j;
             int base_cnt = 0;
             const int i_end = min(n, (ch + 1) * kSweepChunk);
-            for (int i0 = ch * kSweepChunk; i0 < i_end; i0 += 32) {
-                const int i = min(i0 + lane, i_end - 1);
-                const bool live = i0 + lane < i_end;
-                const float x = s_x[i], y = s_y[i], z = s_z[i];
-                const SweepRanges r = sweep_solve(c, x, y, z);
-                unsigned w = 0;
-                if (live) {
-                    base_cnt += sweep_add_definite(r, D, diff, red);
-                    w = sweep_pack_uncertain(r);
+            // two points per lane and pass: the two range solves are independent instruction chains
+            for (int i0 = ch * kSweepChunk; i0 < i_end; i0 += 64) {
+                int ia = i0 + lane, ib = i0 + 32 + lane;
+                const bool live_a = ia < i_end, live_b = ib < i_end;
+                ia = min(ia, i_end - 1); ib = min(ib, i_end - 1);
+                const float xa = s_x[ia], ya = s_y[ia], za = s_z[ia];
+                const float xb = s_x[ib], yb = s_y[ib], zb = s_z[ib];
+                const SweepRanges ra = sweep_solve(c, xa, ya, za);
+                const SweepRanges rb = sweep_solve(c, xb, yb, zb);
+                unsigned wa = 0, wb = 0;
+                if (live_a) {
+                    base_cnt += sweep_add_definite(ra, D, diff, red);
+                    wa = sweep_pack_uncertain(ra);
                 }
-                const unsigned mk = __ballot_sync(0xffffffffu, w != 0u);
-                if (mk) {
+                if (live_b) {
+                    base_cnt += sweep_add_definite(rb, D, diff, red);
+                    wb = sweep_pack_uncertain(rb);
+                }
+                const unsigned mka = __ballot_sync(0xffffffffu, wa != 0u), mkb = __ballot_sync(0xffffffffu, wb != 0u);
+                if (mka | mkb) {
+                    const int na = __popc(mka);
                     int qb = 0;
-                    if (lane == 0) qb = atomicAdd(&s_ctl[2], __popc(mk));
-                    qb = __shfl_sync(0xffffffffu, qb, 0) + __popc(mk & lt_mask);
-                    if (w) {
-                        if (qb < QCAP) {
-                            s_q[qb] = make_uint2((unsigned)i | ((unsigned)j << 16), w);
+                    if (lane == 0) qb = atomicAdd(&s_ctl[2], na + __popc(mkb));
+                    qb = __shfl_sync(0xffffffffu, qb, 0);
+                    const int qa = qb + __popc(mka & lt_mask), qbb = qb + na + __popc(mkb & lt_mask);
+                    if (wa) {
+                        if (qa < QCAP) {
+                            s_q[qa] = make_uint2((unsigned)ia | ((unsigned)j << 16), wa);
                         } else {   // queue full: take the exact predicates here
-                            const int cnt = sweep_uncertain_count(w);
+                            const int cnt = sweep_uncertain_count(wa);
                             for (int k = 0; k < cnt; k++)
-                                sweep_exact_step(x, y, z, sweep_uncertain_step(w, k), D, diff, slot_col, J, prep_f, red);
+                                sweep_exact_step(xa, ya, za, sweep_uncertain_step(wa, k), D, diff, slot_col, J, prep_f, red);
+                        }
+                    }
+                    if (wb) {
+                        if (qbb < QCAP) {
+                            s_q[qbb] = make_uint2((unsigned)ib | ((unsigned)j << 16), wb);
+                        } else {
+                            const int cnt = sweep_uncertain_count(wb);
+                            for (int k = 0; k < cnt; k++)
+                                sweep_exact_step(xb, yb, zb, sweep_uncertain_step(wb, k), D, diff, slot_col, J, prep_f, red);
                         }
                     }
                 }
@@ -1610,7 +1638,7 @@ static int resolve_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch 
     const int J = cfg->num_yaw_size, M = cfg->num_mags;
     const long long H = (long long)J * M;
     const bool fits = b->sweep_cols && H <= 32767 && M <= 255 && J <= 65535 && b->split_points <= 65536 && sweep_smem_bytes(b->split_points, (int)H, J) <= 200 * 1024 &&
-                      (size_t)12 * J * 4 <= 48 * 1024;
+                      (size_t)15 * J * 4 <= 48 * 1024;
     switch (b->score_mode) {
         case FNP_SCORE_DIRECT: return FNP_SCORE_DIRECT;
         case FNP_SCORE_SWEEP: return fits ? FNP_SCORE_SWEEP : -1;
@@ -1637,7 +1665,7 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     cudaMemsetAsync(b->counts, 0, sizeof(int32_t) * (size_t)b->n_cands * H, st);
-    if (sweep) sweep_prep_kernel<<<b->n_cands, 128, (size_t)12 * J * 4, st>>>(*b, J, M);
+    if (sweep) sweep_prep_kernel<<<b->n_cands, 128, (size_t)15 * J * 4, st>>>(*b, J, M);
     plan_items_kernel<<<1, 1024, 0, st>>>(*b, H, sweep);
     write_items_kernel<<<b->n_cands, 128, 0, st>>>(*b, H, sweep);
     if (b->max_items > 0) {

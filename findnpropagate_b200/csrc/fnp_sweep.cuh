@@ -123,13 +123,16 @@ FNP_HD float sweep_eps(float maxabs)
     return f_mul(scale, 3.814697265625e-06f);
 }
 
-// Column parameters from the line fit: c0 = C at the first valid step, slope per step, dev =
-// max |C(m) - line(m)| over the valid steps, p = any hypothesis of the column (rotation, size).
+// Column parameters from the line fit: c0 = C at the first valid step, slope per step, dev_pos /
+// dev_neg = max of C(m) - line(m) and of line(m) - C(m) over the valid steps (both >= 0), p = any
+// hypothesis of the column (rotation, size).  The line is moved to the middle of the band the
+// centres occupy (the front shift bends every column the same way, so the deviations are mostly
+// one-sided and this halves delta).
 // An axis whose travel |s| (m1 - m0) is below 4 eps gets the pseudo slope eps / (D + 1) instead
 // (the line then strays from the fitted one by at most travel + eps, which is added to dl), so
 // that the range solve needs no special case for constant axes.
-FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float slope[3], const float dev[3],
-                                const BoxPrep &p, float eps)
+FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float slope[3], const float dev_pos[3],
+                                const float dev_neg[3], const BoxPrep &p, float eps)
 {
     const float INF = INFINITY;
     SweepCol c;
@@ -141,8 +144,8 @@ FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float s
     const float span = (float)(m1 - m0);
     for (int k = 0; k < 3; k++) {
         float s = slope[k];
-        float dl = f_add(dev[k], eps);
-        c.c0[k] = c0[k];
+        float dl = f_add(f_mul(0.5f, f_add(dev_pos[k], dev_neg[k])), eps);
+        c.c0[k] = f_add(c0[k], f_mul(0.5f, f_sub(dev_pos[k], dev_neg[k])));
         const float travel = f_mul(fabsf(s), span);
         if (!(travel > f_mul(4.f, eps))) {
             c.pseudo_mask |= 1 << k;

@@ -18,6 +18,7 @@ per-frame Python loop replaced by five fused CUDA stages over a *batch* of frame
 There is no CPU compute path: the engine raises if CUDA or the extension is missing.
 """
 import ctypes as C
+import time
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -166,6 +167,7 @@ class SeekerEngine:
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.launches = 0          # kernels of ours launched (bench bookkeeping)
         self._cam_cache, self._tile_cache = {}, {}
+        self.host_s = dict(plan=0.0, execute=0.0, finish=0.0)   # host time spent per call kind (bench bookkeeping)
 
     # ------------------------------------------------------------------ host planning
     def _cam_mats(self, frames):
@@ -198,6 +200,7 @@ class SeekerEngine:
         """Everything the host contributes to a batch, as numpy arrays.  stride / xyz_offset describe
         the DEVICE point table handed to execute() (default: the frames' own row layout; (3, 0) for
         a table gathered by HostPointFeeder)."""
+        t0 = time.perf_counter()
         B = len(frames)
         n_rows = np.array([f.points.shape[0] for f in frames], dtype=np.int64)
         frame_row_start = np.zeros(B + 1, np.int64)
@@ -216,8 +219,10 @@ class SeekerEngine:
             det_boxes, det_labels = np.zeros((0, 4), np.float32), np.zeros(0, np.int64)
             det_scores, det_cam = np.zeros(0, np.float32), np.zeros(0, np.int64)
             cam_mats = np.zeros((0, 6, 24), np.float32)
-        return self.plan_arrays(frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
-                                det_frame, det_cam)
+        out = self.plan_arrays(frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
+                               det_frame, det_cam)
+        self.host_s["plan"] += time.perf_counter() - t0
+        return out
 
     def _tiles(self, frame_row_start):
         key = frame_row_start.tobytes()
@@ -297,6 +302,7 @@ class SeekerEngine:
         kernels must wait for (the H2D copy of the points on another stream); the small
         metadata upload is issued *before* that wait so that it does not queue behind the
         next step's point copy in the H2D engine.  Returns a handle for `finish`."""
+        t0 = time.perf_counter()
         _lib.require_cuda(points_dev)
         assert points_dev.dtype == torch.float32 and points_dev.is_contiguous()
         F, B, H, M = plan["F"], plan["B"], self.H, self.M
@@ -388,6 +394,7 @@ class SeekerEngine:
             handle["out_host"] = host
             handle["event"] = torch.cuda.Event()
             handle["event"].record()
+        self.host_s["execute"] += time.perf_counter() - t0
         return handle
 
     N_COUNTERS = 5 + 5 * 3          # generate_recall_record counters for 3 IoU thresholds
@@ -415,6 +422,7 @@ class SeekerEngine:
     def finish(self, handle):
         """Wait for the batch and assemble per-frame results (reference output format)."""
         handle["event"].synchronize()
+        t0 = time.perf_counter()
         plan = handle["plan"]
         F, B = plan["F"], plan["B"]
         raw = handle["out_host"].numpy()[:handle["out_bytes"]]
@@ -433,15 +441,19 @@ class SeekerEngine:
             raise RuntimeError("scoring work-item table overflowed (%d items)" % status[2])
         ok = best >= 0
         fcs = plan["frame_cand_start"]
-        keep = raw[handle["off_keep"]:handle["off_keep"] + F].astype(bool) if handle["has_nms"] else None
+        # compact once, then hand every frame a slice (views of the compacted arrays: no per-frame
+        # boolean indexing -- 128 frames: 1.4 ms -> 0.4 ms of host time per batch)
+        idx = np.flatnonzero(ok)
+        c_boxes, c_scores = boxes[idx], plan["cand_score"][idx]
+        c_labels = plan["cand_label"][idx].astype(np.int32)
+        c_keep = raw[handle["off_keep"]:handle["off_keep"] + F][idx].astype(bool) if handle["has_nms"] else None
+        st = np.searchsorted(idx, fcs).tolist()
         frames = []
         for b in range(B):
-            s = slice(fcs[b], fcs[b + 1])
-            m = ok[s]
-            d = dict(pred_boxes=boxes[s][m].copy(), pred_scores=plan["cand_score"][s][m].copy(),
-                     pred_labels=plan["cand_label"][s][m].astype(np.int32))
-            if keep is not None:
-                d["nms_keep"] = keep[s][m]
+            d = dict(pred_boxes=c_boxes[st[b]:st[b + 1]], pred_scores=c_scores[st[b]:st[b + 1]],
+                     pred_labels=c_labels[st[b]:st[b + 1]])
+            if c_keep is not None:
+                d["nms_keep"] = c_keep[st[b]:st[b + 1]]
             frames.append(d)
         res = dict(frames=frames, cand_valid=ok.copy(), cand_best=best.copy(), cand_score2=score.copy(),
                    cand_count=count.copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),
@@ -449,6 +461,7 @@ class SeekerEngine:
         if handle["has_recall"]:
             o = handle["off_recall"]
             res["recall"] = self.recall_dict(raw[o:o + 8 * self.N_COUNTERS].view(np.int64), handle["recall_thresh"])
+        self.host_s["finish"] += time.perf_counter() - t0
         return res
 
     @staticmethod

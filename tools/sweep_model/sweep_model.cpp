@@ -32,7 +32,7 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
     memset(stats, 0, 8 * sizeof(long long));
     // ---- sweep_prep_kernel
     std::vector<int> first(J, 0x7fffffff), last(J, -1), r0(J, 0);
-    std::vector<float> c0(3 * J, 0.f), c1(3 * J, 0.f), dev(3 * J, 0.f);
+    std::vector<float> c0(3 * J, 0.f), c1(3 * J, 0.f), dev(3 * J, 0.f), den(3 * J, 0.f);
     float maxabs = maxabs_pts;
     for (int r = 0; r < nv; r++) {
         const int h = hidx[r], m = h / J, j = h - m * J;
@@ -58,14 +58,16 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
         const float dm = (float)(m - first[j]);
         for (int k = 0; k < 3; k++) {
             const float line = f_fma(c1[3 * j + k], dm, c0[3 * j + k]);
-            dev[3 * j + k] = fmaxf(dev[3 * j + k], fabsf(f_sub(C[k], line)));
+            const float d = f_sub(C[k], line);
+            if (d > 0.f) dev[3 * j + k] = fmaxf(dev[3 * j + k], d);
+            if (d < 0.f) den[3 * j + k] = fmaxf(den[3 * j + k], -d);
         }
     }
     const float eps = sweep_eps(maxabs);
     std::vector<SweepCol> cols(J);
     for (int j = 0; j < J; j++) {
         if (last[j] >= first[j]) {
-            cols[j] = sweep_col_build(first[j], last[j], &c0[3 * j], &c1[3 * j], &dev[3 * j], load_prep(prep, r0[j]), eps);
+            cols[j] = sweep_col_build(first[j], last[j], &c0[3 * j], &c1[3 * j], &dev[3 * j], &den[3 * j], load_prep(prep, r0[j]), eps);
             stats[4]++;
             for (int k = 0; k < 3; k++) stats[3] += (cols[j].pseudo_mask >> k) & 1;
         } else {

@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU (BASELINE.json configs[2]: batches of 256 frames)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated per rank")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -303,7 +303,7 @@ def run_ours(a):
                 feeder.mark_consumed(k % 2)
         res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
         if res is not None and world > 1:
-            res["plan_score"], res["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
+            res["plan_score"], res["plan_label"], res["plan_fcs"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"], prev["plan"]["frame_cand_start"]
             pending.append(res)
         return h, res
 
@@ -314,9 +314,12 @@ def run_ours(a):
         # ONE all_reduce of the recall counters for the whole shard (NCCL over NVLink), as in
         # findnpropagate_b200.extract.gather_shards.  Per step the proposals of all frames are packed
         # back to back ([box7, score, label] rows) into a fixed-capacity slab, so no sizes are negotiated.
+        # The pinned slab comes from the engine's grow-only arena (a fresh cudaHostAlloc per exchange
+        # cost milliseconds); only the used rows are written, the counts say which they are.
         n_steps, cap = len(pending), B * 64
-        pack = torch.zeros((n_steps, cap, 9), dtype=torch.float32, pin_memory=True)
-        cnt = torch.zeros((n_steps, B), dtype=torch.int32, pin_memory=True)
+        pack = eng.arena.get("gather_pack", n_steps * cap * 9 * 4, pinned=True)[:n_steps * cap * 9 * 4] \
+            .view(torch.float32).view(n_steps, cap, 9)
+        cnt = eng.arena.get("gather_cnt", n_steps * B * 4, pinned=True)[:n_steps * B * 4].view(torch.int32).view(n_steps, B)
         pk, ck = pack.numpy(), cnt.numpy()
         for i, res in enumerate(pending):
             m = res["cand_valid"]
@@ -325,7 +328,8 @@ def run_ours(a):
             pk[i, :n, :7] = res["cand_boxes"][m]
             pk[i, :n, 7] = res["plan_score"][m]
             pk[i, :n, 8] = res["plan_label"][m]
-            ck[i] = [fr["pred_boxes"].shape[0] for fr in res["frames"]]
+            csum = np.concatenate([[0], np.cumsum(m)])
+            ck[i] = np.diff(csum[res["plan_fcs"]])
         tp, tc = pack.to(dev, non_blocking=True), cnt.to(dev, non_blocking=True)
         allp = torch.empty((world,) + tuple(tp.shape), dtype=tp.dtype, device=dev)
         allc = torch.empty((world,) + tuple(tc.shape), dtype=tc.dtype, device=dev)
@@ -346,11 +350,14 @@ def run_ours(a):
         if prev is not None:
             r = eng.finish(prev)
             if world > 1:
-                r["plan_score"], r["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
+                r["plan_score"], r["plan_label"], r["plan_fcs"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"], prev["plan"]["frame_cand_start"]
                 pending.append(r)
         if world > 1 and pending:
             gather_results()               # warm-up of the exchange too (NCCL connects lazily per collective)
         pending.clear()
+        if world > 1:                          # the exchange's pinned slabs at their final size, outside the timing
+            eng.arena.get("gather_pack", steps * B * 64 * 9 * 4, pinned=True)
+            eng.arena.get("gather_cnt", steps * B * 4, pinned=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -371,7 +378,7 @@ def run_ours(a):
             last = r or last
         last = eng.finish(prev)
         if world > 1:
-            last["plan_score"], last["plan_label"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"]
+            last["plan_score"], last["plan_label"], last["plan_fcs"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"], prev["plan"]["frame_cand_start"]
             pending.append(last)
             gather_results()
         for st in comp + [copy_stream]:

@@ -138,10 +138,10 @@ extern "C" int fnp_host_select_candidates(const float *det_boxes, const int64_t 
 // (frustum_proposals_v1.py:571-575).  With host buffers on one side of a PCIe link the point
 // table IS the end-to-end cost (20 B/point at ~55 GB/s against ~2.5 ms of kernels per 128
 // frames), so the host side of the path gathers x, y, z into a pinned staging buffer and only
-// those 12 B/point cross the link.  Worker threads split the rows; stores are non-temporal so
-// that the staging buffer is not read into the cache before it is overwritten.
+// those 12 B/point cross the link.  Worker threads split the rows.
 // ---------------------------------------------------------------------------------------
 #include <atomic>
+#include <cstdint>
 #include <mutex>
 #include <thread>
 #if defined(__SSE2__)
@@ -150,21 +150,37 @@ extern "C" int fnp_host_select_candidates(const float *det_boxes, const int64_t 
 
 namespace {
 
+// Rows [r0, r1).  Four rows make three 16-byte vectors, written with non-temporal stores: the
+// staging buffer is not read into the cache before it is overwritten (measured on the 16-core
+// GPU box, 41 M rows of 5 floats: 84 GB/s in with plain stores, 100 GB/s with these; 4-byte
+// non-temporal stores were slower than plain ones, tools/probes/pack_probe.cpp).
 void pack_rows(const float *src, int64_t r0, int64_t r1, int stride, int off, float *dst)
 {
     const float *s = src + r0 * stride + off;
     float *d = dst + r0 * 3;
-    for (int64_t r = r0; r < r1; r++, s += stride, d += 3) {
+    int64_t r = r0;
 #if defined(__SSE2__)
-        const int *si = reinterpret_cast<const int *>(s);
-        int *di = reinterpret_cast<int *>(d);
-        _mm_stream_si32(di, si[0]);
-        _mm_stream_si32(di + 1, si[1]);
-        _mm_stream_si32(di + 2, si[2]);
-#else
-        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
-#endif
+    for (; r < r1 && (reinterpret_cast<uintptr_t>(d) & 15); r++, s += stride, d += 3) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+    if (stride == 5) {
+        // 4 rows = 20 floats a[0..3] b[4..7] c[8..11] e[12..15] f[16..19]; wanted: 0 1 2 5 | 6 7 10 11 | 12 15 16 17
+        for (; r + 4 <= r1; r += 4, s += 20, d += 12) {
+            const __m128 a = _mm_loadu_ps(s), b = _mm_loadu_ps(s + 4), c = _mm_loadu_ps(s + 8), e = _mm_loadu_ps(s + 12),
+                         f = (r + 5 <= r1 || off == 0) ? _mm_loadu_ps(s + 16) : _mm_set_ps(0.f, 0.f, s[17], s[16]);
+            const __m128 o0 = _mm_shuffle_ps(a, _mm_shuffle_ps(a, b, _MM_SHUFFLE(1, 1, 2, 2)), _MM_SHUFFLE(2, 0, 1, 0));
+            const __m128 o1 = _mm_shuffle_ps(_mm_shuffle_ps(b, b, _MM_SHUFFLE(3, 3, 3, 2)), c, _MM_SHUFFLE(3, 2, 1, 0));
+            const __m128 o2 = _mm_shuffle_ps(_mm_shuffle_ps(e, e, _MM_SHUFFLE(3, 3, 3, 0)), f, _MM_SHUFFLE(1, 0, 1, 0));
+            _mm_stream_ps(d, o0); _mm_stream_ps(d + 4, o1); _mm_stream_ps(d + 8, o2);
+        }
+    } else {
+        for (; r + 4 <= r1; r += 4, s += 4 * (int64_t)stride, d += 12) {
+            const float *s1 = s + stride, *s2 = s1 + stride, *s3 = s2 + stride;
+            _mm_stream_ps(d, _mm_set_ps(s1[0], s[2], s[1], s[0]));
+            _mm_stream_ps(d + 4, _mm_set_ps(s2[1], s2[0], s1[2], s1[1]));
+            _mm_stream_ps(d + 8, _mm_set_ps(s3[2], s3[1], s3[0], s2[2]));
+        }
     }
+#endif
+    for (; r < r1; r++, s += stride, d += 3) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
 #if defined(__SSE2__)
     _mm_sfence();
 #endif

@@ -308,6 +308,7 @@ def run_ours(a):
         return h, res
 
     pending = []            # results of this rank's shard, exchanged once per run (not per step)
+    exchange_ms = [0.0]     # host + device time of that exchange in the last timed run (it is inside the timing)
 
     def gather_results():
         # frame-sharded run: ONE all_gather of fixed-stride packed proposals (+ per-frame counts) and
@@ -380,7 +381,10 @@ def run_ours(a):
         if world > 1:
             last["plan_score"], last["plan_label"], last["plan_fcs"] = prev["plan"]["cand_score"], prev["plan"]["cand_label"], prev["plan"]["frame_cand_start"]
             pending.append(last)
+            t_x = time.perf_counter()
             gather_results()
+            torch.cuda.synchronize()
+            exchange_ms[0] = 1e3 * (time.perf_counter() - t_x)
         for st in comp + [copy_stream]:
             cur.wait_stream(st)                # e1 after everything the timed region enqueued
         e1.record()
@@ -495,8 +499,9 @@ def run_ours(a):
                                params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B),
                 "frames_per_step_per_gpu": B, "distinct_frames": a.distinct,
                 "l2_policy": "inputs larger than L2: %.0f MB of points per step, two alternating input sets" % (in_bytes / 1e6),
-                "sharding": "frame-wise, no data-path collective; one all_gather of packed proposals + one "
-                            "all_reduce of recall counters per run, inside the timed region" if world > 1 else "single GPU"},
+                "sharding": ("frame-wise, no data-path collective; one all_gather of packed proposals + one "
+                             "all_reduce of recall counters per run, inside the timed region (%.2f ms of the run)"
+                             % exchange_ms[0]) if world > 1 else "single GPU"},
             "hypotheses_per_s": F_step * H * world * a.steps / (ms_res * 1e-3),
             "point_box_tests_equivalent_per_s_scoring_stage": tests / (score_ms * 1e-3),
             "e2e": {"value": n_frames * a.steps / (ms_e2e * 1e-3), "unit": "frames/s",

@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
     float *s_c1 = s_c0 + 3 * J;                            // [J][3], later the slopes
     unsigned *s_dev = reinterpret_cast<unsigned *>(s_c1 + 3 * J);   // [J][3] max of C - line (float bits, >= 0)
     unsigned *s_den = s_dev + 3 * J;                                // [J][3] max of line - C
-    __shared__ unsigned s_maxabs;
+    __shared__ unsigned s_maxabs, s_maxabs_z;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int H = J * M;
     const int nv = b.hyp_nvalid[f];
@@ -1174,19 +1174,25 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
         s_dev[3 * j] = s_dev[3 * j + 1] = s_dev[3 * j + 2] = 0u;
         s_den[3 * j] = s_den[3 * j + 1] = s_den[3 * j + 2] = 0u;
     }
-    if (tid == 0) s_maxabs = 0u;
+    if (tid == 0) { s_maxabs = 0u; s_maxabs_z = 0u; }
     __syncthreads();
     const int *hidx = b.hyp_index + (size_t)f * H;
-    float mabs = 0.f;
+    float mabs = 0.f, mabs_z = 0.f;
     for (int r = tid; r < nv; r += blockDim.x) {
         const int h = hidx[r], m = h / J, j = h - m * J;
         atomicMin(&s_first[j], m);
         atomicMax(&s_last[j], m);
         const float *pp = b.hyp_prep + ((size_t)f * H + r) * 8;
         mabs = fmaxf(mabs, fmaxf(fabsf(pp[0]), fmaxf(fabsf(pp[1]), fabsf(pp[2]))));
+        mabs_z = fmaxf(mabs_z, fabsf(pp[2]));
     }
-    if (tid < 6 && nv > 0) mabs = fmaxf(mabs, fabsf(b.cand_stats[(size_t)f * kStatsFloats + 3 + tid]));   // point AABB
+    if (tid < 6 && nv > 0) {   // point AABB: pmin xyz, pmax xyz
+        const float v = fabsf(b.cand_stats[(size_t)f * kStatsFloats + 3 + tid]);
+        mabs = fmaxf(mabs, v);
+        if (tid == 2 || tid == 5) mabs_z = v;
+    }
     atomicMax(&s_maxabs, __float_as_uint(mabs));
+    atomicMax(&s_maxabs_z, __float_as_uint(mabs_z));
     __syncthreads();
     for (int r = tid; r < nv; r += blockDim.x) {
         const int h = hidx[r], m = h / J, j = h - m * J;
@@ -1221,7 +1227,7 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
         }
     }
     __syncthreads();
-    const float eps = sweep_eps(__uint_as_float(s_maxabs));
+    const float eps = sweep_eps(__uint_as_float(s_maxabs)), eps_z = sweep_eps_z(__uint_as_float(s_maxabs_z));
     for (int j = tid; j < J; j += blockDim.x) {
         const int m0 = s_first[j], m1 = s_last[j];
         SweepCol c;
@@ -1232,7 +1238,7 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
             const float den[3] = {__uint_as_float(s_den[3 * j]), __uint_as_float(s_den[3 * j + 1]),
                                   __uint_as_float(s_den[3 * j + 2])};
             c = sweep_col_build(m0, m1, s_c0 + 3 * j, s_c1 + 3 * j, dev, den,
-                                load_prep(b.hyp_prep, (size_t)f * H + s_r0[j]), eps);
+                                load_prep(b.hyp_prep, (size_t)f * H + s_r0[j]), eps, eps_z);
         } else {
             c = SweepCol{};
             c.m0 = 0; c.m1 = -1;

@@ -122,6 +122,16 @@ FNP_HD float sweep_eps(float maxabs)
     const float scale = fmaxf(f_mul(2.f, maxabs), 64.f);
     return f_mul(scale, 3.814697265625e-06f);
 }
+// The z axis is not rotated: its predicate |rn(z - cz)| <= hz and its solve only see z-magnitudes
+// (a few metres), so its rounding bound is taken from the largest |z|, |cz| alone: < 4 ulp of
+// 2 maxabs_z on both sides together, eps_z = 2 maxabs_z 2^-18 leaves a factor 4.  This matters
+// because the z slope is the smallest (~1 mm per depth step): eps / |slope| is the width, in
+// depth steps, of the band that takes exact predicates.
+FNP_HD float sweep_eps_z(float maxabs_z)
+{
+    const float scale = fmaxf(f_mul(2.f, maxabs_z), 1.f);
+    return f_mul(scale, 3.814697265625e-06f);
+}
 
 // Column parameters from the line fit: c0 = C at the first valid step, slope per step, dev_pos /
 // dev_neg = max of C(m) - line(m) and of line(m) - C(m) over the valid steps (both >= 0), p = any
@@ -132,17 +142,18 @@ FNP_HD float sweep_eps(float maxabs)
 // (the line then strays from the fitted one by at most travel + eps, which is added to dl), so
 // that the range solve needs no special case for constant axes.
 FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float slope[3], const float dev_pos[3],
-                                const float dev_neg[3], const BoxPrep &p, float eps)
+                                const float dev_neg[3], const BoxPrep &p, float eps_xy, float eps_z)
 {
     const float INF = INFINITY;
     SweepCol c;
     c.m0 = m0; c.m1 = m1;
     c.pseudo_mask = 0;
-    c.eps = eps; c.pad0 = 0.f; c.pad1 = 0.f;
+    c.eps = eps_xy; c.pad0 = eps_z; c.pad1 = 0.f;
     c.cosa = p.cosa; c.sina = p.sina;
     const float t[3] = {p.tx, p.ty, p.hz};
     const float span = (float)(m1 - m0);
     for (int k = 0; k < 3; k++) {
+        const float eps = k == 2 ? eps_z : eps_xy;
         float s = slope[k];
         float dl = f_add(f_mul(0.5f, f_add(dev_pos[k], dev_neg[k])), eps);
         c.c0[k] = f_add(c0[k], f_mul(0.5f, f_sub(dev_pos[k], dev_neg[k])));

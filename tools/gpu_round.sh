@@ -12,3 +12,6 @@ python tools/ncu_summary.py gpurun_out/launches.csv
 ncu --set full --clock-control none --import-source on -k 'regex:cull_|cell_table|hypotheses_|recall_|scan_|score_|sweep_|seg_nms|select_|stats_' -s 16 -c 13 -o gpurun_out/prof_all -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 python tools/ncu_kernels.py gpurun_out/prof_all.ncu-rep
 fi
+python bench.py --steps 10 --warmup 3 --config cfg1 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err; tail -c 400 gpurun_out/bench_cfg1.json
+python bench.py --steps 6 --warmup 3 --config cfg5 --frames 16 --distinct 4 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; tail -c 400 gpurun_out/bench_cfg5.json
+python bench.py --steps 10 --warmup 3 --score-mode direct --no-cpu-baseline > gpurun_out/bench_direct.json 2> gpurun_out/bench_direct.err; tail -c 300 gpurun_out/bench_direct.json

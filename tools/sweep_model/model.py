@@ -27,7 +27,7 @@ def build(force=False):
     lib = C.CDLL(SO)
     lib.sweep_model_counts.restype = C.c_int
     lib.sweep_model_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                       C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -66,8 +66,9 @@ def run_frustum(lib, xyz, prep, hidx, J, M, split=2048, cols_out=None, dev_out=N
     cs, cb = np.zeros(max(nv, 1), np.int32), np.zeros(max(nv, 1), np.int32)
     st = np.zeros(8, np.int64)
     maxabs = float(np.abs(xyz).max()) if xyz.shape[0] else 0.0
+    maxabs_z = float(np.abs(xyz[:, 2]).max()) if xyz.shape[0] else 0.0
     rc = lib.sweep_model_counts(xyz.ctypes.data, xyz.shape[0], prep.ctypes.data, hidx.ctypes.data, nv, J, M,
-                                C.c_float(maxabs), split, cs.ctypes.data, cb.ctypes.data, st.ctypes.data,
+                                C.c_float(maxabs), C.c_float(maxabs_z), split, cs.ctypes.data, cb.ctypes.data, st.ctypes.data,
                                 cols_out.ctypes.data if cols_out is not None else None,
                                 dev_out.ctypes.data if dev_out is not None else None)
     assert rc == 0

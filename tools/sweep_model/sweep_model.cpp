@@ -24,7 +24,7 @@ using namespace fnp;
 // adds, [2] (point, column) pairs, [3] constant-axis columns*axes, [4] columns, [5] pairs with a
 // definite range.  split: points per split (the splits must add up like on the device).
 extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, const int *hidx, int nv, int J, int M,
-                                  float maxabs_pts, int split, int *counts_sweep, int *counts_brute, long long *stats,
+                                  float maxabs_pts, float maxabs_pts_z, int split, int *counts_sweep, int *counts_brute, long long *stats,
                                   float *cols_out /* (J, FNP_SWEEP_COL_FLOATS) or NULL */, float *dev_out /* (J,3) or NULL */)
 {
     const int H = J * M;
@@ -33,12 +33,13 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
     // ---- sweep_prep_kernel
     std::vector<int> first(J, 0x7fffffff), last(J, -1), r0(J, 0);
     std::vector<float> c0(3 * J, 0.f), c1(3 * J, 0.f), dev(3 * J, 0.f), den(3 * J, 0.f);
-    float maxabs = maxabs_pts;
+    float maxabs = maxabs_pts, maxabs_z = maxabs_pts_z;
     for (int r = 0; r < nv; r++) {
         const int h = hidx[r], m = h / J, j = h - m * J;
         if (m < first[j]) first[j] = m;
         if (m > last[j]) last[j] = m;
         for (int k = 0; k < 3; k++) maxabs = fmaxf(maxabs, fabsf(prep[r * 8 + k]));
+        maxabs_z = fmaxf(maxabs_z, fabsf(prep[r * 8 + 2]));
     }
     for (int r = 0; r < nv; r++) {
         const int h = hidx[r], m = h / J, j = h - m * J;
@@ -63,11 +64,11 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
             if (d < 0.f) den[3 * j + k] = fmaxf(den[3 * j + k], -d);
         }
     }
-    const float eps = sweep_eps(maxabs);
+    const float eps = sweep_eps(maxabs), eps_z = sweep_eps_z(maxabs_z);
     std::vector<SweepCol> cols(J);
     for (int j = 0; j < J; j++) {
         if (last[j] >= first[j]) {
-            cols[j] = sweep_col_build(first[j], last[j], &c0[3 * j], &c1[3 * j], &dev[3 * j], &den[3 * j], load_prep(prep, r0[j]), eps);
+            cols[j] = sweep_col_build(first[j], last[j], &c0[3 * j], &c1[3 * j], &dev[3 * j], &den[3 * j], load_prep(prep, r0[j]), eps, eps_z);
             stats[4]++;
             for (int k = 0; k < 3; k++) stats[3] += (cols[j].pseudo_mask >> k) & 1;
         } else {

@@ -259,8 +259,12 @@ class SeekerEngine:
                       out=cam_cand_start[1:])
         n_tiles, tile_frame, tile_row0, frame_tile_start = self._tiles(np.ascontiguousarray(frame_row_start, np.int64))
         cand_score = np.ascontiguousarray(det_scores[sel], np.float32)
-        # stage-4 priority order inside each frame: descending 2D score, stable
-        nms_order = np.lexsort((np.arange(F), -cand_score.astype(np.float64), cand_frame)).astype(np.int32)
+        # stage-4 priority order inside each frame: descending 2D score, stable (= np.lexsort((index,
+        # -score, frame)); in C: the lexsort was 1.1 of plan's 3.9 ms per 256 frames)
+        nms_order = np.empty(max(F, 1), np.int32)[:F]
+        fcs32 = np.ascontiguousarray(frame_cand_start, np.int32)
+        _lib.check(_lib.lib.fnp_host_nms_order(cand_score.ctypes.data, fcs32.ctypes.data, B, nms_order.ctypes.data),
+                   "fnp_host_nms_order")
         return dict(
             B=B, F=F, n_tiles=n_tiles, stride=int(stride), xyz_offset=int(xyz_offset),
             total_rows=int(frame_row_start[-1]),

@@ -261,6 +261,11 @@ int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels
                                const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
                                float score_thr, int32_t *cand_det, int32_t *frame_cand_start);
 
+/* Stage-4 priority order: inside every frame the candidates by descending 2D score, ties by
+ * candidate index.  cand_score (F), frame_cand_start (n_frames+1), order (F) out. */
+int fnp_host_nms_order(const float *cand_score, const int32_t *frame_cand_start, int n_frames,
+                       int32_t *order);
+
 /* Column gather of the point table on the host: x, y, z of `rows` rows of `stride` floats (xyz at
  * column xyz_offset) into dst_host (rows,3), so that only the 12 B/point the path reads cross PCIe
  * (the reference uploads every column: pcdet/models/__init__.py:23-36).  n_threads worker threads

@@ -126,3 +126,19 @@ def test_host_pack_xyz_gathers_the_columns():
     assert _lib.lib.fnp_host_pack_xyz(src.ctypes.data, 10, 2, 0, a.ctypes.data, 1) == -1      # stride < 3
     assert _lib.lib.fnp_host_pack_xyz(src.ctypes.data, 10, 5, 3, a.ctypes.data, 1) == -1      # columns past the row
     assert _lib.lib.fnp_host_pack_xyz(None, 10, 5, 0, a.ctypes.data, 1) == -1
+
+
+def test_host_nms_order_equals_lexsort():
+    """fnp_host_nms_order: per frame, descending score, ties by index."""
+    from findnpropagate_b200 import _lib
+    rng = np.random.default_rng(5)
+    for n_frames in (0, 1, 7, 64):
+        counts = rng.integers(0, 40, n_frames)
+        fcs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        F = int(fcs[-1])
+        score = rng.choice(np.linspace(0.45, 0.95, 23).astype(np.float32), F)       # many ties
+        frame = np.repeat(np.arange(n_frames), counts)
+        order = np.full(max(F, 1), -7, np.int32)
+        assert _lib.lib.fnp_host_nms_order(score.ctypes.data, fcs.ctypes.data, n_frames, order.ctypes.data) == 0
+        ref = np.lexsort((np.arange(F), -score.astype(np.float64), frame)).astype(np.int32)
+        assert np.array_equal(order[:F], ref)

@@ -43,6 +43,7 @@ struct GreedyNms {
                 const float xx2 = std::min(ix2, x2[j]), yy2 = std::min(iy2, y2[j]);
                 const float w = std::max(0.0f, xx2 - xx1), h = std::max(0.0f, yy2 - yy1);
                 const float inter = w * h;
+                if (!(inter > 0.0f)) continue;      // disjoint: ovr is 0 (or 0/0 = NaN), never > thr; skips the division
                 const float ovr = inter / (ia + area[j] - inter);
                 if ((double)ovr > thr) dead[j] = 1;
             }

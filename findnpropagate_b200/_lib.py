@@ -97,6 +97,8 @@ lib.fnp_host_nms_order.argtypes = [_vp, _vp, _i, _vp]
 for _n in ("fnp_host_pack_xyz", "fnp_host_pack_xyz_begin"):
     getattr(lib, _n).restype = _i
     getattr(lib, _n).argtypes = [_vp, C.c_int64, _i, _i, _vp, _i]
+lib.fnp_host_pack_xyz_multi_begin.restype = _i
+lib.fnp_host_pack_xyz_multi_begin.argtypes = [_vp, _vp, _i, _i, _i, _vp, _i]
 lib.fnp_host_pack_wait.restype = _i
 lib.fnp_host_pack_wait.argtypes = [_i]
 
@@ -113,7 +115,7 @@ EXPORTED = [
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
     "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
-    "fnp_host_pack_wait", "fnp_host_nms_order",
+    "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin",
 ]
 
 

@@ -220,11 +220,38 @@ std::mutex g_jobs_mutex;
 
 }  // namespace
 
-extern "C" int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
-                                       int n_threads)
+// Worker: the rows [g0, g1) of the concatenation of the segments (segment s holds seg_rows[s] rows
+// at seg_src[s]; its first row is row seg_first[s] of dst).
+static void pack_segments(std::vector<const float *> seg_src, std::vector<int64_t> seg_first, int64_t g0, int64_t g1,
+                          int stride, int off, float *dst)
 {
-    if (rows < 0 || stride < 3 || xyz_offset < 0 || xyz_offset + 3 > stride || (rows > 0 && (!src_host || !dst_host)))
-        return FNP_EINVAL;
+    const int n_seg = (int)seg_src.size();
+    int s = (int)(std::upper_bound(seg_first.begin(), seg_first.end(), g0) - seg_first.begin()) - 1;
+    while (g0 < g1 && s < n_seg) {
+        const int64_t seg_end = (s + 1 < n_seg) ? seg_first[s + 1] : g1;
+        const int64_t e = std::min(g1, seg_end);
+        if (e > g0) pack_rows(seg_src[s], g0 - seg_first[s], e - seg_first[s], stride, off, dst + seg_first[s] * 3);
+        g0 = std::max(g0, e);
+        s++;
+    }
+}
+
+extern "C" int fnp_host_pack_xyz_multi_begin(const float *const *seg_src_host, const int64_t *seg_rows, int n_segments,
+                                             int stride, int xyz_offset, float *dst_host, int n_threads)
+{
+    if (n_segments < 0 || stride < 3 || xyz_offset < 0 || xyz_offset + 3 > stride) return FNP_EINVAL;
+    if (n_segments > 0 && (!seg_src_host || !seg_rows)) return FNP_EINVAL;
+    std::vector<const float *> src;
+    std::vector<int64_t> first;
+    int64_t rows = 0;
+    for (int s = 0; s < n_segments; s++) {
+        if (seg_rows[s] < 0 || (seg_rows[s] > 0 && !seg_src_host[s])) return FNP_EINVAL;
+        if (seg_rows[s] == 0) continue;
+        src.push_back(seg_src_host[s]);
+        first.push_back(rows);
+        rows += seg_rows[s];
+    }
+    if (rows > 0 && !dst_host) return FNP_EINVAL;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
     int ticket = -1;
@@ -235,13 +262,22 @@ extern "C" int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int 
     }
     if (ticket < 0) return FNP_EWORKSPACE;      // too many gathers in flight
     PackJob &job = g_jobs[ticket];
-    const int64_t per = (rows + n_threads - 1) / n_threads;
+    // thread shares are multiples of 4 rows so that every share but the last starts 16-byte aligned
+    const int64_t per = ((rows + n_threads - 1) / n_threads + 3) & ~(int64_t)3;
     for (int t = 0; t < n_threads; t++) {
-        const int64_t r0 = (int64_t)t * per, r1 = std::min(rows, r0 + per);
-        if (r0 >= r1) break;
-        job.threads.emplace_back(pack_rows, src_host, r0, r1, stride, xyz_offset, dst_host);
+        const int64_t g0 = (int64_t)t * per, g1 = std::min(rows, g0 + per);
+        if (g0 >= g1) break;
+        job.threads.emplace_back(pack_segments, src, first, g0, g1, stride, xyz_offset, dst_host);
     }
     return ticket;
+}
+
+extern "C" int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
+                                       int n_threads)
+{
+    if (rows < 0 || (rows > 0 && !src_host)) return FNP_EINVAL;
+    const float *srcs[1] = {src_host};
+    return fnp_host_pack_xyz_multi_begin(srcs, &rows, 1, stride, xyz_offset, dst_host, n_threads);
 }
 
 extern "C" int fnp_host_pack_wait(int ticket)

@@ -163,14 +163,7 @@ def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch
             recall[k] = recall.get(k, 0) + int(v)
 
     def stage(slot, frames):
-        rows = sum(f.points.shape[0] for f in frames)
-        width = frames[0].points.shape[1]
-        host = torch.empty((rows, width), dtype=torch.float32, pin_memory=not pack_xyz)
-        r = 0
-        for f in frames:
-            host[r:r + f.points.shape[0]] = torch.from_numpy(f.points)
-            r += f.points.shape[0]
-        feeder.submit(slot, host)
+        feeder.submit(slot, [f.points for f in frames])      # per-frame arrays, gathered back to back
 
     prev, k = None, 0
     batches = feed.prefetch(mine, detector, batch_frames=batch_frames, workers=workers)

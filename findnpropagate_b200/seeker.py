@@ -575,6 +575,7 @@ class HostPointFeeder:
         self.host = [None] * self.slots
         self.dev = [None] * self.slots
         self.src = [None] * self.slots
+        self.rows, self.width = [0] * self.slots, [0] * self.slots
         self.copied = [torch.cuda.Event() for _ in range(self.slots)]      # staging slot read by the DMA
         self.copied_valid = [False] * self.slots
 
@@ -583,28 +584,51 @@ class HostPointFeeder:
         """(stride, xyz_offset) of the device table, for SeekerEngine.plan."""
         return (3, 0) if self.pack else (None, None)
 
-    def submit(self, slot, points_host: torch.Tensor, xyz_offset=0):
-        """points_host: (rows, C) float32 CPU tensor (pinned for pack=False).  Starts the gather."""
-        assert points_host.dtype == torch.float32 and points_host.is_contiguous() and not points_host.is_cuda
-        rows, C_ = points_host.shape
-        self.src[slot] = points_host
+    def submit(self, slot, points_host, xyz_offset=0):
+        """Starts the gather of one batch into staging slot `slot`.  points_host: one (rows, C)
+        float32 CPU tensor, or a list of per-frame (n_i, C) float32 arrays / tensors as a data loader
+        leaves them (gathered back to back: no concatenated copy of the full-width rows is made).
+        With pack=False a list is concatenated into a pinned slot instead (one full-width copy)."""
+        segs = points_host if isinstance(points_host, (list, tuple)) else [points_host]
+        segs = [torch.from_numpy(np.ascontiguousarray(p, np.float32)) if isinstance(p, np.ndarray) else p for p in segs]
+        for p in segs:
+            assert p.dtype == torch.float32 and p.is_contiguous() and not p.is_cuda and p.dim() == 2
+        C_ = int(segs[0].shape[1])
+        assert all(int(p.shape[1]) == C_ for p in segs)
+        rows = int(sum(int(p.shape[0]) for p in segs))
+        self.rows[slot], self.width[slot] = rows, C_
+        if self.copied_valid[slot]:
+            self.copied[slot].synchronize()          # the DMA has read the previous contents of the slot
         if not self.pack:
+            if len(segs) == 1:
+                self.src[slot] = segs[0]
+                return
+            nbytes = rows * C_ * 4
+            if self.host[slot] is None or self.host[slot].numel() < nbytes:
+                self.host[slot] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, pin_memory=True)
+            dst = self.host[slot][:nbytes].view(torch.float32).view(rows, C_)
+            r = 0
+            for p in segs:
+                dst[r:r + p.shape[0]] = p
+                r += int(p.shape[0])
+            self.src[slot] = dst
             return
+        self.src[slot] = segs                        # keep the sources alive until the gather is done
         nbytes = rows * 12
         if self.host[slot] is None or self.host[slot].numel() < nbytes:
             self.host[slot] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, pin_memory=True)
-        if self.copied_valid[slot]:
-            self.copied[slot].synchronize()          # the DMA has read the previous contents of the slot
-        t = _lib.lib.fnp_host_pack_xyz_begin(points_host.data_ptr(), rows, C_, xyz_offset, self.host[slot].data_ptr(),
-                                             self.n_threads)
+        ptrs = (C.c_void_p * len(segs))(*[p.data_ptr() for p in segs])
+        nrow = (C.c_int64 * len(segs))(*[int(p.shape[0]) for p in segs])
+        t = _lib.lib.fnp_host_pack_xyz_multi_begin(ptrs, nrow, len(segs), C_, xyz_offset, self.host[slot].data_ptr(),
+                                                   self.n_threads)
         if t < 0:
-            _lib.check(t, "fnp_host_pack_xyz_begin")
+            _lib.check(t, "fnp_host_pack_xyz_multi_begin")
         self.ticket[slot] = t
 
     def upload(self, slot):
         """Waits for the slot's gather, enqueues its H2D copy; returns (device table, ready event)."""
         src = self.src[slot]
-        rows, C_ = src.shape
+        rows, C_ = self.rows[slot], self.width[slot]
         if self.pack:
             _lib.check(_lib.lib.fnp_host_pack_wait(self.ticket[slot]), "fnp_host_pack_wait")
             self.ticket[slot] = None

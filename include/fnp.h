@@ -277,6 +277,11 @@ int fnp_host_pack_xyz(const float *src_host, int64_t rows, int stride, int xyz_o
 int fnp_host_pack_xyz_begin(const float *src_host, int64_t rows, int stride, int xyz_offset, float *dst_host,
                             int n_threads);
 int fnp_host_pack_wait(int ticket);
+/* The same for a table that lies in n_segments pieces on the host (one per frame, as a data loader
+ * leaves them): segment s has seg_rows[s] rows at seg_src_host[s]; the pieces are gathered back to
+ * back into dst_host, so no concatenated copy of the full-width rows is ever made. */
+int fnp_host_pack_xyz_multi_begin(const float *const *seg_src_host, const int64_t *seg_rows, int n_segments,
+                                  int stride, int xyz_offset, float *dst_host, int n_threads);
 
 /* Host->device upload of a small block by a kernel instead of the copy engine: src is pinned,
  * UVA-mapped host memory (cudaHostAlloc / torch pin_memory), dst device memory, both 16-byte

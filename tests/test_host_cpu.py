@@ -142,3 +142,22 @@ def test_host_nms_order_equals_lexsort():
         assert _lib.lib.fnp_host_nms_order(score.ctypes.data, fcs.ctypes.data, n_frames, order.ctypes.data) == 0
         ref = np.lexsort((np.arange(F), -score.astype(np.float64), frame)).astype(np.int32)
         assert np.array_equal(order[:F], ref)
+
+
+def test_host_pack_xyz_multi_gathers_segments_back_to_back():
+    """fnp_host_pack_xyz_multi_begin: per-frame pieces of the point table -> one (rows,3) table,
+    including empty pieces, pieces shorter than a thread share, and odd alignments."""
+    import ctypes as C
+    from findnpropagate_b200 import _lib
+    rng = np.random.default_rng(11)
+    for sizes, stride, off, nt in (([5, 0, 1, 1000, 3, 77], 5, 0, 4), ([4096, 4097, 1], 5, 1, 7), ([0, 0], 5, 0, 2),
+                                   ([333] * 9, 6, 2, 16), ([2], 3, 0, 5)):
+        segs = [rng.random((n, stride), dtype=np.float32) for n in sizes]
+        rows = sum(sizes)
+        dst = np.full((max(rows, 1), 3), -1, np.float32)
+        ptrs = (C.c_void_p * len(segs))(*[s.ctypes.data for s in segs])
+        nrow = (C.c_int64 * len(segs))(*sizes)
+        t = _lib.lib.fnp_host_pack_xyz_multi_begin(ptrs, nrow, len(segs), stride, off, dst.ctypes.data, nt)
+        assert t >= 0 and _lib.lib.fnp_host_pack_wait(t) == 0
+        ref = np.concatenate([s[:, off:off + 3] for s in segs]) if rows else np.zeros((0, 3), np.float32)
+        assert np.array_equal(dst[:rows], ref)

@@ -1,6 +1,9 @@
-#!/bin/bash
-# quick GPU iteration: parity tests, stage times, bench (no ncu)
+set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q --timeout=900 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
-python tools/stage_times.py --frames 32 > gpurun_out/stage_times_32.json 2> gpurun_out/stage_times.err; cat gpurun_out/stage_times_32.json; tail -3 gpurun_out/stage_times.err
-python bench.py --steps ${STEPS:-10} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | grep -v "^frame #" > gpurun_out/t_final.log; tail -4 gpurun_out/t_final.log | cut -c1-300
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chk.json 2> gpurun_out/bench_chk.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_chk.json").read().strip().splitlines()[-1])
+print("value %.0f ms/step %.2f e2e %.0f (%.2f ms)"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), d["host_ms_per_step"]["resident"])
+PY

@@ -150,8 +150,6 @@ class FrustumProposerOG(nn.Module):
         assert p['nms_3d'] == 0, 'DO NOT USE!'          # the reference's own assertion (:209)
         self.params = p
         self.box_fmt = _cfg_get(model_cfg, 'BOX_FORMAT', 'xyxy')
-        if self.box_fmt != 'xyxy':
-            raise NotImplementedError("BOX_FORMAT %r (only 'xyxy' is on the shipped path)" % self.box_fmt)
         self.image_order = [2, 0, 1, 5, 3, 4]
         self.image_size = [900, 1600]
         self.topk, self.score_thr, self.max_dist = p['topk'], p['score_thr'], p['max_dist']
@@ -163,7 +161,7 @@ class FrustumProposerOG(nn.Module):
             if 'PreprocessedGLIP' not in preds_path:
                 raise NotImplementedError("only the PreprocessedGLIP feeder is on the shipped path")
             self.image_detector = PreprocessedGLIP(class_names=class_names)
-        self.engine = SeekerEngine(p, device=device)
+        self.engine = SeekerEngine(p, device=device, box_format=self.box_fmt)
         self.anchors = torch.tensor(__import__('findnpropagate_b200.seeker', fromlist=['ANCHORS']).ANCHORS,
                                     dtype=torch.float32, device=self.engine.device)
         self.base_boxes = self.engine.base_boxes

@@ -138,7 +138,7 @@ def _align(x, a=256):
 class SeekerEngine:
     """Batched Box Seeker on one GPU."""
 
-    def __init__(self, params=None, device=None, debug=False, split_points=None, score_mode="auto"):
+    def __init__(self, params=None, device=None, debug=False, split_points=None, score_mode="auto", box_format="xyxy"):
         if not torch.cuda.is_available():
             raise RuntimeError("findnpropagate_b200.SeekerEngine needs a CUDA device (no CPU fallback)")
         self.p = resolve_params(params)
@@ -163,6 +163,10 @@ class SeekerEngine:
         # "auto" | "direct" | "sweep": which stage-2b kernel counts the points (same counts either way)
         self.score_mode = {"auto": _lib.SCORE_AUTO, "direct": _lib.SCORE_DIRECT, "sweep": _lib.SCORE_SWEEP}[score_mode]
         self.last_score_mode = None
+        # MODEL.DENSE_HEAD.BOX_FORMAT (frustum_proposals_v1.py:252,597-601): 'xyxy', anything else means
+        # x, y, w, h -- the 2D NMS runs on the raw numbers (as in the reference), the corner x+w, y+h is
+        # formed afterwards in fp32
+        self.box_format = box_format
         self.pts_factor = 2.0
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.launches = 0          # kernels of ours launched (bench bookkeeping)
@@ -273,8 +277,15 @@ class SeekerEngine:
             frame_tile_start=frame_tile_start, cam_mats=np.ascontiguousarray(cam_mats, np.float32),
             frame_cand_start=frame_cand_start, cam_cand_start=cam_cand_start, cand_frame=cand_frame,
             cand_cam=cand_cam, cand_label=det_labels[sel].astype(np.int32),
-            cand_box2d=np.ascontiguousarray(det_boxes[sel], np.float32),
+            cand_box2d=self._cand_boxes(det_boxes[sel]),
             cand_score=cand_score, cand_det=sel, nms_order=nms_order)
+
+    def _cand_boxes(self, boxes):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
+        if self.box_format != "xyxy":
+            b = b.copy()
+            b[:, 2:] += b[:, 0:2]
+        return b
 
     # ------------------------------------------------------------------ device execution
     _META = ["frame_row_start", "tile_frame", "tile_row0", "frame_tile_start", "cam_mats", "frame_cand_start",

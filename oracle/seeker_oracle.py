@@ -64,7 +64,7 @@ def camera_matrices(camera2lidar, camera_intrinsics):
     return combine.numpy(), c2l[..., :3, 3].numpy().copy()
 
 
-def nms2d_candidates(det_boxes, det_labels, det_scores, det_cam_idx, nms_2d, score_thr):
+def nms2d_candidates(det_boxes, det_labels, det_scores, det_cam_idx, nms_2d, score_thr, box_format="xyxy"):
     """Frustum candidates of one frame in reference order: cameras [2,0,1,5,3,4], per-camera
     torchvision batched_nms (score-descending), then the score threshold
     (frustum_proposals_v1.py:582-595)."""
@@ -83,12 +83,15 @@ def nms2d_candidates(det_boxes, det_labels, det_scores, det_cam_idx, nms_2d, sco
         for b, l, s in zip(cb, cl, cs):
             if s < score_thr:
                 continue
+            if box_format != "xyxy":       # x, y, w, h: the 2D NMS above saw the raw numbers, the corner
+                b = b.clone()              # is formed afterwards in fp32 (frustum_proposals_v1.py:597-601)
+                b[2:] += b[0:2]
             out.append((c, b.numpy().copy(), int(l), np.float32(s.item())))
     return out
 
 
 def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, params, tables=None,
-               keep_intermediates=False):
+               keep_intermediates=False, box_format="xyxy"):
     """One frame.  points (N,>=3) xyz first; dets = (boxes, labels, scores, cam_idx).
     Returns dict(pred_boxes (K,7) f32, pred_labels (K) int32, pred_scores (K) f32,
     frustums=[per-frustum intermediates])."""
@@ -99,7 +102,7 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
     mags = torch.linspace(0.0, 1.0, p["num_mags"]).numpy() if p["num_mags"] > 0 else np.zeros(1, np.float32)
     max_dist = np.float32(p["max_dist"])
     pts = np.ascontiguousarray(points, np.float32)
-    cands = nms2d_candidates(*dets, p["nms_2d"], p["score_thr"])
+    cands = nms2d_candidates(*dets, p["nms_2d"], p["score_thr"], box_format)
     boxes_out, labels_out, scores_out, inter = [], [], [], []
     for (c, box2d, label, score) in cands:
         L = np.ascontiguousarray(lidar2image[c], np.float32)

@@ -65,7 +65,8 @@ def test_seeker_oracle_against_reference_run(path):
     params = synth.seeker_params(cfg)
     out = SO.seek_frame(g["points"], g["lidar2image"], g["camera2lidar"], g["camera_intrinsics"],
                         (g["det_boxes"], g["det_labels"], g["det_scores"], g["det_cam_idx"]), params,
-                        tables=(g["base_boxes"], g["base_corners"]), keep_intermediates=True)
+                        tables=(g["base_boxes"], g["base_corners"]), keep_intermediates=True,
+                        box_format=str(g["box_format"]) if "box_format" in g else "xyxy")
     assert out["pred_boxes"].shape == g["ref_boxes"].shape
     assert np.array_equal(out["pred_labels"], g["ref_labels"])
     assert np.array_equal(out["pred_scores"], g["ref_scores"])

@@ -32,7 +32,8 @@ def _frame_from_synth(f):
 def _oracle(fi, params, eng):
     return SO.seek_frame(fi.points, fi.lidar2image, fi.camera2lidar, fi.camera_intrinsics,
                          (fi.det_boxes, fi.det_labels, fi.det_scores, fi.det_cam_idx), params,
-                         tables=(eng.base_boxes_host.numpy(), eng.base_corners_host.numpy()), keep_intermediates=True)
+                         tables=(eng.base_boxes_host.numpy(), eng.base_corners_host.numpy()), keep_intermediates=True,
+                         box_format=eng.box_format)
 
 
 def _check_against_oracle(eng, frames, params):
@@ -94,7 +95,8 @@ def _check_against_oracle(eng, frames, params):
 def test_pipeline_vs_oracle_and_reference_golden(path):
     g = np.load(path)
     params = synth.seeker_params(synth.CONFIGS[str(g["cfg"])])
-    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    eng = SeekerEngine(params, device="cuda:0", debug=True,
+                       box_format=str(g["box_format"]) if "box_format" in g else "xyxy")     # one fixture is x, y, w, h
     fi = _frame_from_golden(g)
     res, n = _check_against_oracle(eng, [fi], params)
     assert n > 0

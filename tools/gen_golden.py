@@ -29,13 +29,16 @@ from findnpropagate_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def frame_fixture(name, index):
+def frame_fixture(name, index, box_format="xyxy"):
     cfg = synth.CONFIGS[name]
     params = synth.seeker_params(cfg)
     fr = synth.make_frame(index, cfg)
-    boxes, labels, scores, bidx, cap, head = ref_seeker.run([fr], params)
+    if box_format != "xyxy":     # BOX_FORMAT 'xywh' (frustum_proposals_v1.py:597-601): the feeder hands out x, y, w, h
+        fr.det_boxes = fr.det_boxes.copy()
+        fr.det_boxes[:, 2:] = fr.det_boxes[:, 2:] - fr.det_boxes[:, :2]
+    boxes, labels, scores, bidx, cap, head = ref_seeker.run([fr], params, box_format=box_format)
     d = dict(
-        cfg=name, index=index,
+        cfg=name, index=index, box_format=box_format,
         points=fr.points, lidar2image=fr.lidar2image, camera_intrinsics=fr.camera_intrinsics,
         camera2lidar=fr.camera2lidar, lidar_aug_matrix=fr.lidar_aug_matrix, gt_boxes=fr.gt_boxes,
         det_boxes=fr.det_boxes, det_labels=fr.det_labels, det_scores=fr.det_scores,
@@ -51,7 +54,7 @@ def frame_fixture(name, index):
         d["f%d_scores" % k] = f["scores"]
         d["f%d_keep" % k] = f["keep"]
     # reference recall record (detector3d_template.py:315) evaluated with the oracle iou3d
-    path = os.path.join(OUT, "seeker_%s_%d.npz" % (name, index))
+    path = os.path.join(OUT, "seeker_%s%s_%d.npz" % (name, "" if box_format == "xyxy" else "_" + box_format, index))
     np.savez_compressed(path, **d)
     print("wrote", path, "K =", boxes.shape[0], "frustums =", len(cap["frustums"]))
 
@@ -87,3 +90,4 @@ if __name__ == "__main__":
     for name, idxs in (("tiny", (0, 1, 2)), ("cfg1", (0,))):
         for i in idxs:
             frame_fixture(name, i)
+    frame_fixture("tiny", 3, box_format="xywh")

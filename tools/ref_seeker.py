@@ -136,10 +136,10 @@ class SyntheticFeeder:
                 torch.cat(cam))
 
 
-def build_head(params, frames):
+def build_head(params, frames, box_format="xyxy"):
     mod = load()
     mod.PreprocessedGLIP = lambda class_names=None: SyntheticFeeder(frames)
-    cfg = AttrDict(PARAMS=dict(params), PREDS_PATH="PreprocessedGLIP", BOX_FORMAT="xyxy")
+    cfg = AttrDict(PARAMS=dict(params), PREDS_PATH="PreprocessedGLIP", BOX_FORMAT=box_format)
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -148,12 +148,12 @@ def build_head(params, frames):
     return head
 
 
-def run(frames, params, capture=True):
+def run(frames, params, capture=True, box_format="xyxy"):
     """Run reference get_proposals over `frames` (one call, batch_size=len(frames)).
     Returns (boxes (K,7), labels (K), scores (K), batch_idx (K), capture dict, head)."""
     global _CAPTURE
     from findnpropagate_b200 import synth
-    head = build_head(params, frames)
+    head = build_head(params, frames, box_format)
     head.image_detector = SyntheticFeeder(frames)
     bd = synth.collate(frames)
     for k, v in list(bd.items()):

@@ -8,6 +8,7 @@ Same class names, constructor arguments, ``model_cfg.PARAMS`` keys, method names
 types and devices; the work is done by :class:`findnpropagate_b200.seeker.SeekerEngine`.
 """
 import json
+import os
 import sys
 import types
 
@@ -186,16 +187,35 @@ class FrustumProposerOG(nn.Module):
         dev = self.engine.device
         if isinstance(pts, np.ndarray):
             pts = torch.from_numpy(np.ascontiguousarray(pts, np.float32))
-        pts = pts.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-        bidx = pts[:, 0].contiguous()
-        bounds = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32)).cpu().numpy()
-        if not bool((bidx[1:] >= bidx[:-1]).all()) if bidx.numel() > 1 else False:
-            raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+        if not pts.is_cuda:
+            # host table (the collate output before load_data_to_gpu): frame bounds from the batch
+            # column on the host, then only x, y, z cross PCIe (threaded gather, fnp_host_pack_xyz)
+            pts = pts.to(torch.float32).contiguous()
+            bcol = pts[:, 0].numpy()
+            if bcol.size > 1 and not bool((bcol[1:] >= bcol[:-1]).all()):
+                raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+            bounds = np.searchsorted(bcol, np.arange(B + 1, dtype=np.float32))
+            rows = int(pts.shape[0])
+            stage = self.engine.arena.get("head_xyz_host", rows * 12, pinned=True)[:rows * 12].view(torch.float32).view(rows, 3)
+            from . import _lib
+            _lib.check(_lib.lib.fnp_host_pack_xyz(pts.data_ptr(), rows, int(pts.shape[1]), 1, stage.data_ptr(),
+                                                  max(1, min(16, len(os.sched_getaffinity(0)) - 1))),
+                       "fnp_host_pack_xyz")
+            pts = self.engine.arena.get("head_xyz_dev", rows * 12)[:rows * 12].view(torch.float32).view(rows, 3)
+            pts.copy_(stage, non_blocking=True)
+            stride, xyz_offset = 3, 0
+        else:
+            pts = pts.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+            bidx = pts[:, 0].contiguous()
+            bounds = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32)).cpu().numpy()
+            if not bool((bidx[1:] >= bidx[:-1]).all()) if bidx.numel() > 1 else False:
+                raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+            stride, xyz_offset = int(pts.shape[1]), 1
         from .seeker import camera_matrices
         cam_mats = camera_matrices(self._np(batch_dict['lidar2image']), self._np(batch_dict['camera2lidar']),
                                    self._np(batch_dict['camera_intrinsics']))
         plan = self.engine.plan_arrays(
-            bounds.astype(np.int64), pts.shape[1], 1, cam_mats, self._np(det_boxes).astype(np.float32).reshape(-1, 4),
+            bounds.astype(np.int64), stride, xyz_offset, cam_mats, self._np(det_boxes).astype(np.float32).reshape(-1, 4),
             self._np(det_labels).astype(np.int64), self._np(det_scores).astype(np.float32),
             self._np(det_batch_idx).astype(np.int64), self._np(det_cam_idx).astype(np.int64))
         while True:

@@ -12,6 +12,7 @@ field.  Nothing here reads /root/reference; the CPU arms use oracle/_ref (the re
 own ops, prebuilt) and the oracle restatement of the seeker loop.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -45,6 +46,7 @@ def parse():
                          "auto = on for one rank per host (the gather needs the host's cores and memory bandwidth: "
                          "with several ranks sharing them the plain upload, 20 B/point of DMA reads, is cheaper)")
     ap.add_argument("--pack-threads", type=int, default=None)
+    ap.add_argument("--slots", type=int, default=3, help="batches in flight on the device (streams + arenas), resident arm")
     return ap.parse_args()
 
 
@@ -278,7 +280,7 @@ def run_ours(a):
 
     # two compute streams, one per slot: consecutive batches overlap on the device, so the small
     # latency-bound kernels at the end of batch k run under the big kernels of batch k+1
-    comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    comp = [torch.cuda.Stream(device=dev) for _ in range(max(2, a.slots))]
     feeder = HostPointFeeder(eng, pack=(a.e2e_pack == "on" or (a.e2e_pack == "auto" and world == 1)),
                              n_threads=a.pack_threads)
     copy_stream = feeder.copy_stream
@@ -286,6 +288,7 @@ def run_ours(a):
 
     def step(k, resident, prev, more=True):
         """One pass of the hot path over one batch; returns the new handle."""
+        slot = k % len(comp) if resident else k % 2
         if resident:
             pts, ready = dev_pts[k % 2], None
             plan = eng.plan(batch)
@@ -297,14 +300,18 @@ def run_ours(a):
             if more:
                 feeder.submit((k + 1) % 2, pinned[(k + 1) % 2])
             plan = eng.plan(batch, stride=f_stride, xyz_offset=0 if f_stride else 0)
-        with torch.cuda.stream(comp[k % 2]):
-            h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=k % 2, points_ready=ready)
+        with torch.cuda.stream(comp[slot]):
+            h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=slot, points_ready=ready)
             if not resident:
                 feeder.mark_consumed(k % 2)
-        res = eng.finish(prev) if prev is not None else None      # overlaps the GPU work of step k
-        if res is not None and world > 1:
-            exchange_add(res, prev["plan"])
-        return h, res
+        prev.append(h)
+        res = None
+        if len(prev) >= (len(comp) if resident else 2):           # the oldest batch in flight: its result is
+            old = prev.popleft()                                  # assembled under the GPU work of the newer ones
+            res = eng.finish(old)
+            if world > 1:
+                exchange_add(res, old["plan"])
+        return res
 
     exchange_ms = [0.0]     # host + device time of that exchange in the last timed run (it is inside the timing)
 
@@ -356,18 +363,26 @@ def run_ours(a):
         dist.all_reduce(rc)
         return xbuf["allp"], xbuf["allc"], rc
 
+    def drain(prev):
+        last = None
+        while prev:
+            old = prev.popleft()
+            last = eng.finish(old)
+            if world > 1:
+                exchange_add(last, old["plan"])
+        return last
+
     def timed(resident, steps, warmup):
-        prev = None
+        prev = collections.deque()
         if world > 1:
             exchange_setup(max(warmup, 1))
         if not resident and warmup > 0:
             feeder.submit(0, pinned[0])
         for k in range(warmup):
-            prev, _ = step(k, resident, prev, more=k + 1 < warmup)
-        if prev is not None:
-            r = eng.finish(prev)
+            step(k, resident, prev, more=k + 1 < warmup)
+        if prev:
+            drain(prev)
             if world > 1:
-                exchange_add(r, prev["plan"])
                 gather_results()           # warm-up of the exchange too (NCCL connects lazily per collective)
         if world > 1:
             exchange_setup(steps)          # the slabs at their final size, outside the timing
@@ -385,13 +400,10 @@ def run_ours(a):
         h0 = dict(eng.host_s)
         if not resident:
             feeder.submit(0, pinned[0])        # the first gather is inside the timed region as well
-        prev, last = None, None
         for k in range(steps):
-            prev, r = step(k, resident, prev, more=k + 1 < steps)
-            last = r or last
-        last = eng.finish(prev)
+            step(k, resident, prev, more=k + 1 < steps)
+        last = drain(prev)
         if world > 1:
-            exchange_add(last, prev["plan"])
             t_x = time.perf_counter()
             gather_results()
             torch.cuda.synchronize()

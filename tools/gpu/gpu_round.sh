@@ -15,3 +15,4 @@ fi
 python bench.py --steps 10 --warmup 3 --config cfg1 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err; tail -c 400 gpurun_out/bench_cfg1.json
 python bench.py --steps 6 --warmup 3 --config cfg5 --frames 16 --distinct 4 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; tail -c 400 gpurun_out/bench_cfg5.json
 python bench.py --steps 10 --warmup 3 --score-mode direct --no-cpu-baseline > gpurun_out/bench_direct.json 2> gpurun_out/bench_direct.err; tail -c 300 gpurun_out/bench_direct.json
+python tools/probes/feed_probe.py > gpurun_out/feed_probe.txt 2>&1; ./tools/probes/pack_probe > gpurun_out/pack_probe.txt 2>&1

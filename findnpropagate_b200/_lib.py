@@ -26,7 +26,8 @@ class SeekerCfg(C.Structure):
     _fields_ = [("num_mags", C.c_int32), ("num_yaw_size", C.c_int32), ("n_classes", C.c_int32),
                 ("clamp_bottom", C.c_int32), ("img_w", _f), ("img_h", _f), ("lq", _f), ("uq", _f),
                 ("cq", _f), ("frustum_min", _f), ("max_dist", _f), ("min_cam_iou", _f),
-                ("dns_w", _f), ("iou_w", _f)]
+                ("dns_w", _f), ("iou_w", _f),
+                ("dst_w", _f), ("ego_w", _f), ("occl_w", _f), ("search_depth", _f), ("flags", C.c_int32)]
 
 
 class SeekerBatch(C.Structure):
@@ -48,11 +49,13 @@ class SeekerBatch(C.Structure):
         ("score_mode", C.c_int32), ("sweep_cols", _vp),
         ("out_boxes", _vp), ("out_score", _vp), ("out_best", _vp), ("out_count", _vp),
         ("status", _vp),
+        ("hyp_dist", _vp), ("hyp_nfar", _vp),
     ]
 
 
 CULL_TILE = 1024
 SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
+SEEKER_MULT, SEEKER_OCCL_MULT, SEEKER_MULTICAM_IOU = 1, 2, 4
 SWEEP_MIN_MAGS = 16
 SWEEP_COL_FLOATS = 20
 SEG_NMS_MAX = 1024
@@ -75,7 +78,7 @@ for _n in ("fnp_nms_rotated", "fnp_nms_normal"):
     getattr(lib, _n).restype = _i
     getattr(lib, _n).argtypes = [_vp, _i, _f, _vp, _vp, _vp, C.c_size_t, _vp]
 for _n in ("fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses", "fnp_seeker_score",
-           "fnp_seeker_select", "fnp_seeker_run"):
+           "fnp_seeker_occlusion", "fnp_seeker_select", "fnp_seeker_run"):
     getattr(lib, _n).restype = _i
     getattr(lib, _n).argtypes = [C.POINTER(SeekerCfg), C.POINTER(SeekerBatch), _vp]
 lib.fnp_seeker_score_mode.restype = _i
@@ -113,7 +116,7 @@ EXPORTED = [
     "fnp_version", "fnp_points_in_boxes", "fnp_count_in_boxes", "fnp_boxes_overlap_bev",
     "fnp_boxes_iou_bev", "fnp_boxes_aligned_overlap_bev", "fnp_nms_workspace_bytes", "fnp_nms_rotated",
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
-    "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
+    "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_occlusion", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
     "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin",
 ]

@@ -718,7 +718,9 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_b
 
     // ---- depth quantiles (frustum_proposals_v1.py:616-648)
     const float qmin = block_quantile(pts, S, cached, n, cfg.lq, mn[3], mx[3]);
-    const float qmax = block_quantile(pts, S, cached, n, cfg.uq, mn[3], mx[3]);
+    // search_depth (:619-623): the far end of the frustum is the near quantile + depth
+    const float qmax = (cfg.search_depth > 0.f) ? __fadd_rn(qmin, cfg.search_depth)
+                                                : block_quantile(pts, S, cached, n, cfg.uq, mn[3], mx[3]);
     const float qc = block_quantile(pts, S, cached, n, cfg.cq, mn[3], mx[3]);
     const float dmax = fminf(qmax, cfg.max_dist);
     const float dmin = fmaxf(qmin, cfg.frustum_min);
@@ -756,6 +758,13 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_b
             s_geo[a] = close;
             s_geo[3 + a] = __fsub_rn(far, close);
         }
+        if (cfg.search_depth > 0.f) {   // :841-842  center_vec / center_vec.norm() * search_depth
+            const float nv = norm3(s_geo[3], s_geo[4], s_geo[5]);
+            for (int a = 0; a < 3; a++) s_geo[3 + a] = __fmul_rn(__fdiv_rn(s_geo[3 + a], nv), cfg.search_depth);
+        }
+        // weighted_centre_xyz (:631-636): the 2D box centre at the cq depth quantile, unprojected
+        unproject(cm + 12, cm + 21, __fmul_rn(__fadd_rn(bx[0], bx[2]), 0.5f), __fmul_rn(__fadd_rn(bx[1], bx[3]), 0.5f), qc,
+                  st[10], st[11], st[12]);
         st[0] = dmin; st[1] = dmax; st[2] = qc;
         for (int a = 0; a < 3; a++) { st[3 + a] = mn[a]; st[6 + a] = mx[a]; }
         st[9] = (float)n;
@@ -773,10 +782,39 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_b
 // ======================================================================================
 // Stage 2a: hypotheses
 // ======================================================================================
+// 2D IoU of the image-plane bounding box of the 8 shifted corners with a 2D box (calc_iou, :1392-1411)
+__device__ __forceinline__ float view_iou(const float *__restrict__ L, const float4 box2d, const float (&cor)[8][3],
+                                          const float (&shift)[3], const float img_w, const float img_h)
+{
+    const float area2 = __fmul_rn(__fsub_rn(box2d.z, box2d.x), __fsub_rn(box2d.w, box2d.y));
+    const float INF = __int_as_float(0x7f800000);
+    float x1 = INF, y1 = INF, x2 = -INF, y2 = -INF;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float u, v, d;
+        project(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]),
+                __fadd_rn(cor[k][2], shift[2]), img_w, img_h, u, v, d);
+        u = fminf(fmaxf(u, 0.f), img_w);
+        v = fminf(fmaxf(v, 0.f), img_h);
+        x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+    }
+    const float area1 = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    const float lx = fmaxf(x1, box2d.x), ly = fmaxf(y1, box2d.y);
+    const float rx = fminf(x2, box2d.z), ry = fminf(y2, box2d.w);
+    const float iw = fmaxf(__fsub_rn(rx, lx), 0.f), ih = fmaxf(__fsub_rn(ry, ly), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(area1, area2), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+// EXTRAS = false is the shipped configuration (single-view IoU, no hyp_dist): the optional terms are
+// compiled out so that they cost the hot path no registers.
+template <bool EXTRAS>
 __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ int s_wcnt[4];
     __shared__ int s_base;
+    __shared__ float s_dmm[4][2];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int J = cfg.num_yaw_size, M = cfg.num_mags, H = J * M;
@@ -791,7 +829,15 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
     const int label = b.cand_label[f];
     const float *L = b.cam_mats + ((size_t)frame * 6 + b.cand_cam[f]) * 24;
     const float4 box2d = reinterpret_cast<const float4 *>(b.cand_box2d)[f];
-    const float area2 = __fmul_rn(__fsub_rn(box2d.z, box2d.x), __fsub_rn(box2d.w, box2d.y));
+    const bool multicam = EXTRAS && (cfg.flags & FNP_SEEKER_MULTICAM_IOU) != 0;
+    const int fc0 = b.frame_cand_start[frame], fc1 = b.frame_cand_start[frame + 1];
+    const bool want_dist = EXTRAS && b.hyp_dist != nullptr;
+    float wc[3] = {0.f, 0.f, 0.f};
+    if (want_dist) {
+        const float *st = b.cand_stats + (size_t)f * kStatsFloats;
+        wc[0] = st[10]; wc[1] = st[11]; wc[2] = st[12];
+    }
+    float dist_mn = __int_as_float(0x7f800000), dist_mx = -__int_as_float(0x7f800000);
     const float *bb_tab = b.base_boxes + (size_t)(label - 1) * J * 7;
     const float *bc_tab = b.base_corners + (size_t)(label - 1) * J * 24;
     if (tid == 0) s_base = 0;
@@ -801,7 +847,7 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
         const int h = h0 + tid;
         bool valid = false;
         float box[7] = {0, 0, 0, 0, 0, 0, 0};
-        float iou = 0.f;
+        float iou = 0.f, dist = 0.f;
         if (h < H) {
             const int m = h / J, j = h - m * J;
             const float *ct = b.centres + ((size_t)f * M + m) * 3;
@@ -837,24 +883,26 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
 #pragma unroll
             for (int a = 3; a < 7; a++) box[a] = __ldg(bb + a);
             const bool near_enough = norm3(front[0], front[1], front[2]) < cfg.max_dist;
-            const float INF = __int_as_float(0x7f800000);
-            float x1 = INF, y1 = INF, x2 = -INF, y2 = -INF;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                float u, v, d;
-                project(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]),
-                        __fadd_rn(cor[k][2], shift[2]), cfg.img_w, cfg.img_h, u, v, d);
-                u = fminf(fmaxf(u, 0.f), cfg.img_w);
-                v = fminf(fmaxf(v, 0.f), cfg.img_h);
-                x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+            if (!multicam) iou = view_iou(L, box2d, cor, shift, cfg.img_w, cfg.img_h);
+            else {
+                // multicam_ious (:1413-1429): every candidate of the frame with points and the same label
+                // (this one included), summed in candidate order, over (number of non-zero IoUs + 1e-6)
+                float sum_iou = 0.f;
+                int nz = 0;
+                for (int i = fc0; i < fc1; i++) {
+                    if (b.cand_label[i] != label || b.cand_npts[i] <= 0) continue;
+                    const float vi = view_iou(b.cam_mats + ((size_t)frame * 6 + b.cand_cam[i]) * 24,
+                                              reinterpret_cast<const float4 *>(b.cand_box2d)[i], cor, shift,
+                                              cfg.img_w, cfg.img_h);
+                    sum_iou = __fadd_rn(sum_iou, vi);
+                    nz += vi > 0.f;
+                }
+                iou = __fdiv_rn(sum_iou, __fadd_rn((float)nz, 1e-6f));
             }
-            const float area1 = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-            const float lx = fmaxf(x1, box2d.x), ly = fmaxf(y1, box2d.y);
-            const float rx = fminf(x2, box2d.z), ry = fminf(y2, box2d.w);
-            const float iw = fmaxf(__fsub_rn(rx, lx), 0.f), ih = fmaxf(__fsub_rn(ry, ly), 0.f);
-            const float inter = __fmul_rn(iw, ih);
-            const float uni = __fsub_rn(__fadd_rn(area1, area2), inter);
-            iou = __fdiv_rn(inter, uni);
+            if (want_dist) {   // torch.cdist(front, weighted_centre_xyz) (:889), evaluated directly
+                dist = norm3(__fsub_rn(front[0], wc[0]), __fsub_rn(front[1], wc[1]), __fsub_rn(front[2], wc[2]));
+                if (near_enough) { dist_mn = fminf(dist_mn, dist); dist_mx = fmaxf(dist_mx, dist); }
+            }
             valid = near_enough && (iou > cfg.min_cam_iou);
             if (b.hyp_boxes_dbg) {
                 float *o = b.hyp_boxes_dbg + ((size_t)f * H + h) * 7;
@@ -878,12 +926,24 @@ __global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch 
             dst[1] = make_float4(p.cosa, p.sina, p.tx, p.ty);
             b.hyp_index[(size_t)f * H + r] = h;
             b.hyp_iou[(size_t)f * H + r] = iou;
+            if (want_dist) b.hyp_dist[(size_t)f * H + r] = dist;
         }
         __syncthreads();
         if (tid == 0) s_base = base + s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
         __syncthreads();
     }
     if (tid == 0) b.hyp_nvalid[f] = s_base;
+    if (want_dist) {   // dists_ranked is normalised over the hypotheses within max_dist (:891)
+        dist_mn = warp_min(dist_mn);
+        dist_mx = warp_max(dist_mx);
+        if (lane == 0) { s_dmm[warp][0] = dist_mn; s_dmm[warp][1] = dist_mx; }
+        __syncthreads();
+        if (tid == 0) {
+            float *st = b.cand_stats + (size_t)f * kStatsFloats;
+            st[13] = fminf(fminf(s_dmm[0][0], s_dmm[1][0]), fminf(s_dmm[2][0], s_dmm[3][0]));
+            st[14] = fmaxf(fmaxf(s_dmm[0][1], s_dmm[1][1]), fmaxf(s_dmm[2][1], s_dmm[3][1]));
+        }
+    }
 }
 
 // ======================================================================================
@@ -1476,6 +1536,79 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
 // ======================================================================================
 // Stage 3: score + greedy argmax
 // ======================================================================================
+// Optional stage 2c: n_far of every compacted hypothesis = frustum points whose norm exceeds the norm of
+// the hypothesis' nearest corner (calc_occl_scores, frustum_proposals_v1.py:408-477; the corners are rebuilt
+// from the box the way boxes_to_corners_3d does, box_utils.py:28-52).  One thread per hypothesis, the
+// norms of a tile of points in shared memory, read as broadcast LDS.128.
+constexpr int kOcclThreads = 256;
+constexpr int kOcclTile = 2048;
+
+__global__ void __launch_bounds__(kOcclThreads) occl_kernel(const fnp_seeker_batch b, const int J, const int H)
+{
+    __shared__ __align__(16) float s_mag[kOcclTile];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nv = b.hyp_nvalid[f];
+    const int r = blockIdx.y * kOcclThreads + tid;
+    if ((int)(blockIdx.y * kOcclThreads) >= nv || b.status[0] != 0) return;
+    const float INF = __int_as_float(0x7f800000);
+    float m1 = INF;
+    if (r < nv) {
+        const float *pp = b.hyp_prep + ((size_t)f * H + r) * 8;
+        const int j = b.hyp_index[(size_t)f * H + r] % J;
+        const float *bb = b.base_boxes + ((size_t)(b.cand_label[f] - 1) * J + j) * 7;
+        const float ca = cosf(bb[6]), sa = sinf(bb[6]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float sx = (k == 0 || k == 1 || k == 4 || k == 5) ? 0.5f : -0.5f;   // box_utils.py:42-45
+            const float sy = (k == 0 || k == 3 || k == 4 || k == 7) ? 0.5f : -0.5f;
+            const float sz = (k >= 4) ? 0.5f : -0.5f;
+            const float x = __fmul_rn(bb[3], sx), y = __fmul_rn(bb[4], sy), z = __fmul_rn(bb[5], sz);
+            const float cx = __fadd_rn(__fmaf_rn(y, -sa, __fmul_rn(x, ca)), pp[0]);
+            const float cy = __fadd_rn(__fmaf_rn(y, ca, __fmul_rn(x, sa)), pp[1]);
+            const float cz = __fadd_rn(z, pp[2]);
+            m1 = fminf(m1, norm3(cx, cy, cz));
+        }
+    }
+    const int n = b.cand_npts[f];
+    const float *pts = b.frustum_pts + (size_t)(b.cand_pt_start[f] >> 1) * 8;
+    int cnt = 0;
+    for (int t0 = 0; t0 < n; t0 += kOcclTile) {
+        const int tn = min(kOcclTile, n - t0);
+        for (int i = tid; i < kOcclTile; i += kOcclThreads) {
+            float m = -INF;   // padding never counts
+            if (i < tn) {
+                const int p = t0 + i;
+                const float *rec = pts + (size_t)(p >> 1) * 8 + (p & 1);
+                m = norm3(rec[0], rec[2], rec[4]);
+            }
+            s_mag[i] = m;
+        }
+        __syncthreads();
+        const float4 *sm4 = reinterpret_cast<const float4 *>(s_mag);
+        const int n4 = (tn + 3) >> 2;
+#pragma unroll 4
+        for (int i = 0; i < n4; i++) {
+            const float4 m = sm4[i];
+            cnt += (m.x > m1) + (m.y > m1) + (m.z > m1) + (m.w > m1);
+        }
+        __syncthreads();
+    }
+    if (r < nv) b.hyp_nfar[(size_t)f * H + r] = cnt;
+}
+
+// ======================================================================================
+// Stage 3: second-stage score + greedy argmax
+// ======================================================================================
+__device__ __forceinline__ float block_max128(float v, float *s4, const int lane, const int warp)
+{
+    v = warp_max(v);
+    if (lane == 0) s4[warp] = v;
+    __syncthreads();
+    v = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+    __syncthreads();
+    return v;
+}
+
 __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ float s_f[4];
@@ -1493,23 +1626,52 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
         return;
     }
     const int *cbase = b.counts + (size_t)f * H;
-    int mx = 0;
-    for (int r = tid; r < nv; r += blockDim.x) mx = max(mx, cbase[r]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_i[warp] = mx;
-    __syncthreads();
-    mx = max(max(s_i[0], s_i[1]), max(s_i[2], s_i[3]));
-    __syncthreads();
-    const float den = __fadd_rn((float)mx, 1e-8f);
+    const float *pbase = b.hyp_prep + (size_t)f * H * 8;
+    const bool mult = (cfg.flags & FNP_SEEKER_MULT) != 0, occl_mult = (cfg.flags & FNP_SEEKER_OCCL_MULT) != 0;
+    const bool use_dist = (cfg.dst_w != 0.f) || mult;
+    const bool use_fail = (cfg.occl_w > 0.f) || occl_mult;
+    const bool use_ego = cfg.ego_w > 0.f;
+    const long long npts = b.cand_npts[f];
+    const int *nfar = use_fail ? b.hyp_nfar + (size_t)f * H : nullptr;
+    // the reference's occlusion score: n_far * n_out (a (P,1) & (P,) broadcast, :453), stored as float
+#define FNP_FAIL(r) __ll2float_rn((long long)nfar[r] * (npts - (long long)cbase[r]))
+    int mxi = 0;
+    float fmx = 0.f, emx = 0.f;
+    for (int r = tid; r < nv; r += blockDim.x) {
+        mxi = max(mxi, cbase[r]);
+        if (use_fail) fmx = fmaxf(fmx, FNP_FAIL(r));
+        if (use_ego) emx = fmaxf(emx, norm3(pbase[r * 8], pbase[r * 8 + 1], pbase[r * 8 + 2]));
+    }
+    const float den = __fadd_rn(block_max128((float)mxi, s_f, lane, warp), 1e-8f);
+    float fden = 1.f, dmin = 0.f, dden = 1.f;
+    if (use_fail) fden = __fadd_rn(block_max128(fmx, s_f, lane, warp), 1e-6f);
+    if (use_ego) emx = block_max128(emx, s_f, lane, warp);
+    if (use_dist) {
+        const float *st = b.cand_stats + (size_t)f * kStatsFloats;
+        dmin = st[13];
+        dden = __fadd_rn(__fsub_rn(st[14], dmin), 1e-8f);
+    }
     // argmax of score, lowest index wins ties (stable descending sort + top-1)
     float best = -__int_as_float(0x7f800000);
     int besti = 0x7fffffff;
     for (int r = tid; r < nv; r += blockDim.x) {
         const float dens = __fdiv_rn((float)cbase[r], den);
-        const float sc = __fadd_rn(__fmul_rn(dens, cfg.dns_w), __fmul_rn(b.hyp_iou[(size_t)f * H + r], cfg.iou_w));
+        const float iou = b.hyp_iou[(size_t)f * H + r];
+        const float dr = use_dist ? __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(b.hyp_dist[(size_t)f * H + r], dmin), dden)) : 1.0f;
+        float sc;
+        if (mult)
+            sc = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(dens, cfg.dns_w), iou), cfg.iou_w), dr), cfg.dst_w);
+        else {
+            sc = __fadd_rn(__fmul_rn(dens, cfg.dns_w), __fmul_rn(iou, cfg.iou_w));
+            if (cfg.dst_w != 0.f) sc = __fadd_rn(sc, __fmul_rn(dr, cfg.dst_w));
+        }
+        if (cfg.occl_w > 0.f) sc = __fadd_rn(sc, __fmul_rn(cfg.occl_w, __fsub_rn(1.0f, __fdiv_rn(FNP_FAIL(r), fden))));
+        if (use_ego)
+            sc = __fadd_rn(sc, __fmul_rn(cfg.ego_w, __fdiv_rn(norm3(pbase[r * 8], pbase[r * 8 + 1], pbase[r * 8 + 2]), emx)));
+        if (occl_mult) sc = __fmul_rn(__fmul_rn(dens, iou), FNP_FAIL(r));
         if (sc > best || besti == 0x7fffffff) { best = sc; besti = r; }
     }
+#undef FNP_FAIL
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -1633,7 +1795,10 @@ extern "C" int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker
     int rc = check_batch(cfg, b);
     if (rc) return rc;
     if (b->n_cands == 0) return FNP_OK;
-    hypotheses_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    if ((cfg->flags & FNP_SEEKER_MULTICAM_IOU) || b->hyp_dist)
+        hypotheses_kernel<true><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    else
+        hypotheses_kernel<false><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }
@@ -1711,8 +1876,23 @@ extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_bat
 {
     int rc = check_batch(cfg, b);
     if (rc) return rc;
+    if (((cfg->dst_w != 0.f) || (cfg->flags & FNP_SEEKER_MULT)) && !b->hyp_dist) return FNP_EINVAL;
+    if (((cfg->occl_w > 0.f) || (cfg->flags & FNP_SEEKER_OCCL_MULT)) && !b->hyp_nfar) return FNP_EINVAL;
     if (b->n_cands == 0) return FNP_OK;
     select_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_seeker_occlusion(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
+{
+    int rc = check_batch(cfg, b);
+    if (rc) return rc;
+    if (!(cfg->occl_w > 0.f) && !(cfg->flags & FNP_SEEKER_OCCL_MULT)) return FNP_OK;
+    if (!b->hyp_nfar) return FNP_EINVAL;
+    if (b->n_cands == 0) return FNP_OK;
+    const int J = cfg->num_yaw_size, H = J * cfg->num_mags;
+    occl_kernel<<<dim3(b->n_cands, divup(H, kOcclThreads)), kOcclThreads, 0, (cudaStream_t)stream>>>(*b, J, H);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }
@@ -1724,5 +1904,6 @@ extern "C" int fnp_seeker_run(const fnp_seeker_cfg *cfg, const fnp_seeker_batch 
     if ((rc = fnp_seeker_frustum_stats(cfg, b, stream))) return rc;
     if ((rc = fnp_seeker_hypotheses(cfg, b, stream))) return rc;
     if ((rc = fnp_seeker_score(cfg, b, stream))) return rc;
+    if ((rc = fnp_seeker_occlusion(cfg, b, stream))) return rc;
     return fnp_seeker_select(cfg, b, stream);
 }

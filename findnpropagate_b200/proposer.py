@@ -145,9 +145,10 @@ class FrustumProposerOG(nn.Module):
             for k in list(DEFAULTS) + ['aln_w', 'ego_w', 'occl_w', 'rand_center', 'search_depth']:
                 if k in params:
                     p[k] = params[k]
-        for flag in ('SAVE_BLEND', 'MULTICAM_IOU', 'OCCL_MULT', 'MULT'):
-            if _cfg_get(model_cfg, flag, False):
-                raise NotImplementedError("%s is outside the shipped Box Seeker config" % flag)
+        if _cfg_get(model_cfg, 'SAVE_BLEND', False):
+            raise NotImplementedError("SAVE_BLEND (Blender visualisation dumps) is outside the Box Seeker path")
+        for flag in ('MULTICAM_IOU', 'OCCL_MULT', 'MULT'):      # model_cfg-level switches (:154-156)
+            p[flag] = bool(_cfg_get(model_cfg, flag, False))
         assert p['nms_3d'] == 0, 'DO NOT USE!'          # the reference's own assertion (:209)
         self.params = p
         self.box_fmt = _cfg_get(model_cfg, 'BOX_FORMAT', 'xyxy')

@@ -43,8 +43,16 @@ RECALL_KEYS = ["gt", "num_3known", "num_6known", "num_4unknown", "num_7unknown"]
 RECALL_PER_THRESH = ["rcnn", "rcnn_3known", "rcnn_6known", "rcnn_4unknown", "rcnn_7unknown"]
 
 
+FLAG_KEYS = ("MULT", "OCCL_MULT", "MULTICAM_IOU")     # MODEL.DENSE_HEAD switches, frustum_proposals_v1.py:154-156
+
+
 def resolve_params(params: Optional[dict]) -> dict:
+    """PARAMS of the head (frustum_proposals_v1.py:167-195) over the constructor defaults.  Besides the
+    shipped option set, the optional terms of SURVEY.md 8 row f3 are supported: dst_w, ego_w, occl_w,
+    search_depth and the switches MULT / OCCL_MULT / MULTICAM_IOU (keys of the same dict)."""
     p = dict(DEFAULTS)
+    p.update(ego_w=0, occl_w=0, aln_w=0, rand_center=False, search_depth=None)      # :160-165
+    p.update({k: False for k in FLAG_KEYS})
     if params:
         p.update(params)
     unsupported = []
@@ -52,13 +60,14 @@ def resolve_params(params: Optional[dict]) -> dict:
         unsupported.append("topk != 1")
     if p["nms_3d"] != 0:
         unsupported.append("nms_3d != 0 (the reference asserts it too, :209)")
-    if p["dst_w"] != 0:
-        unsupported.append("dst_w != 0")
-    for k in ("aln_w", "ego_w", "occl_w", "rand_center", "search_depth"):
-        if p.get(k):
-            unsupported.append(k)
+    if p.get("aln_w"):
+        unsupported.append("aln_w (torch.pca_lowrank draws a random projection: not reproducible in the reference)")
+    if p.get("rand_center"):
+        unsupported.append("rand_center (torch.randn centres: not reproducible in the reference)")
+    if p["search_depth"] is not None and not p["search_depth"] > 0:
+        unsupported.append("search_depth <= 0")
     if unsupported:
-        raise NotImplementedError("Box Seeker options outside the shipped config: " + ", ".join(unsupported))
+        raise NotImplementedError("Box Seeker options outside the supported set: " + ", ".join(unsupported))
     return p
 
 
@@ -157,7 +166,14 @@ class SeekerEngine:
             num_mags=self.M, num_yaw_size=self.J, n_classes=bb.shape[0], clamp_bottom=int(self.p["clamp_bottom"]),
             img_w=float(IMAGE_SIZE[1]), img_h=float(IMAGE_SIZE[0]), lq=float(self.p["lq"]), uq=float(self.p["uq"]),
             cq=float(self.p["cq"]), frustum_min=FRUSTUM_MIN, max_dist=float(self.p["max_dist"]),
-            min_cam_iou=float(self.p["min_cam_iou"]), dns_w=float(self.p["dns_w"]), iou_w=float(self.p["iou_w"]))
+            min_cam_iou=float(self.p["min_cam_iou"]), dns_w=float(self.p["dns_w"]), iou_w=float(self.p["iou_w"]),
+            dst_w=float(self.p["dst_w"]), ego_w=float(self.p["ego_w"] or 0), occl_w=float(self.p["occl_w"] or 0),
+            search_depth=float(self.p["search_depth"] or 0),
+            flags=(_lib.SEEKER_MULT if self.p["MULT"] else 0) | (_lib.SEEKER_OCCL_MULT if self.p["OCCL_MULT"] else 0)
+            | (_lib.SEEKER_MULTICAM_IOU if self.p["MULTICAM_IOU"] else 0))
+        # workspaces of the optional score terms (include/fnp.h: hyp_dist, hyp_nfar)
+        self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"])
+        self.use_occl = self.cfg.occl_w > 0 or bool(self.p["OCCL_MULT"])
         self.arena = _Arena(self.device)
         self.fixed_split_points = split_points
         # "auto" | "direct" | "sweep": which stage-2b kernel counts the points (same counts either way)
@@ -358,6 +374,10 @@ class SeekerEngine:
             off_recall = 4 * (12 * F + 8)
             off_keep = off_recall + 8 * self.N_COUNTERS
             sizes["out"] = off_keep + _align(F, 8)
+            if self.use_dist:
+                sizes["hyp_dist"] = 4 * H * F
+            if self.use_occl:
+                sizes["hyp_nfar"] = 4 * H * F
             if self.debug:
                 sizes.update(frustum_idx=4 * cap, stage_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
             # every slot owns its intermediates, so that batches of different slots may be in flight on
@@ -389,12 +409,13 @@ class SeekerEngine:
                 split_points=sp, max_items=max_items,
                 cand_item_start=ptr["cand_item_start"], items=ptr["items"],
                 counts=ptr["counts"], score_mode=self.score_mode, sweep_cols=ptr["sweep_cols"],
-                out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status)
+                out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status,
+                hyp_dist=ptr.get("hyp_dist"), hyp_nfar=ptr.get("hyp_nfar"))
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
             mode = _lib.lib.fnp_seeker_score_mode(C.byref(self.cfg), C.byref(b))
             self.last_score_mode = {_lib.SCORE_DIRECT: "direct", _lib.SCORE_SWEEP: "sweep"}.get(mode)
-            self.launches += (11 + (mode == _lib.SCORE_SWEEP)) if F and plan["n_tiles"] else 0
+            self.launches += (11 + (mode == _lib.SCORE_SWEEP) + self.use_occl) if F and plan["n_tiles"] else 0
             handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta,
                           off_recall=off_recall, off_keep=off_keep, has_nms=False, has_recall=False,
                           recall_thresh=tuple(recall_thresh))
@@ -548,7 +569,13 @@ class SeekerEngine:
         sel = np.concatenate([np.arange(padded_start[f], padded_start[f] + npts[f]) for f in range(F)]
                              + [np.zeros(0, np.int64)]).astype(np.int64)
         pt_start = np.concatenate([[0], np.cumsum(npts)]).astype(np.int32)
+        extra = {}
+        if self.use_dist:
+            extra["hyp_dist"] = view("hyp_dist", torch.float32, (F, H))
+        if self.use_occl:
+            extra["hyp_nfar"] = view("hyp_nfar", torch.int32, (F, H))
         return dict(
+            **extra,
             pt_start=pt_start,
             frustum_pts=np.ascontiguousarray(rows[sel]),
             frustum_idx=np.ascontiguousarray(idx[sel]),

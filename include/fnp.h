@@ -100,7 +100,17 @@ typedef struct fnp_seeker_cfg {
     float max_dist;          /* 50                                                       */
     float min_cam_iou;       /* 0.3                                                      */
     float dns_w, iou_w;      /* score weights                                            */
+    /* ---- optional terms of FrustumProposerOG; all zero = the shipped YAML ---- */
+    float dst_w;             /* weight of dists_ranked (frustum_proposals_v1.py:889-893,996-999)           */
+    float ego_w;             /* weight of |centre| / max |centre| (:1016-1020)                              */
+    float occl_w;            /* weight of 1 - fail / (max fail + 1e-6), calc_occl_scores (:408-477,1007-1014) */
+    float search_depth;      /* PARAMS search_depth (:619-623,841-842); <= 0: not set                       */
+    int32_t flags;           /* FNP_SEEKER_MULT | FNP_SEEKER_OCCL_MULT | FNP_SEEKER_MULTICAM_IOU            */
 } fnp_seeker_cfg;
+
+#define FNP_SEEKER_MULT 1          /* MODEL.DENSE_HEAD.MULT: product of the score terms (:998-999)             */
+#define FNP_SEEKER_OCCL_MULT 2     /* OCCL_MULT: score = density * iou * occlusion fail score (:1022-1026)      */
+#define FNP_SEEKER_MULTICAM_IOU 4  /* MULTICAM_IOU: 2D IoU averaged over the frame's same-label boxes (:1413-1429) */
 
 typedef struct fnp_seeker_batch {
     /* ---- inputs ---- */
@@ -150,7 +160,9 @@ typedef struct fnp_seeker_batch {
     int32_t *frustum_idx;            /* (pts_capacity) source row within the frame, or NULL */
     int64_t pts_capacity;            /* points; even */
     float *cand_stats;               /* (F,40): [0]dmin [1]dmax [2]dcentre [3..5]pmin [6..8]pmax
-                                        [9]n_points [16..39] clamped frustum corners (8,3)  */
+                                        [9]n_points [10..12] weighted_centre_xyz [13]/[14] min/max of
+                                        hyp_dist over the hypotheses within max_dist
+                                        [16..39] clamped frustum corners (8,3)  */
     float *centres;                  /* (F,M,3) */
     float *hyp_prep;                 /* (F,H,8) compacted valid hypotheses, H = M*J:
                                         cx,cy,cz,hz, cosa,sina,tx,ty                       */
@@ -179,6 +191,11 @@ typedef struct fnp_seeker_batch {
                                         bit1: items overflow ([2] items needed);
                                         [4] work-item counter of the scoring kernel; [5] staging
                                         cursor of stage 1; [6..7] spare                     */
+    /* ---- workspaces of the optional terms (may be NULL when the term is off) ---- */
+    float *hyp_dist;                 /* (F,H) |front - weighted_centre_xyz| of each compacted hypothesis;
+                                        required iff dst_w != 0 or FNP_SEEKER_MULT          */
+    int32_t *hyp_nfar;               /* (F,H) frustum points beyond the nearest corner of each compacted
+                                        hypothesis; required iff occl_w > 0 or FNP_SEEKER_OCCL_MULT */
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024
@@ -217,9 +234,13 @@ int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void 
 /* The scoring kernel fnp_seeker_score runs for this batch: FNP_SCORE_DIRECT or FNP_SCORE_SWEEP
  * (FNP_EINVAL if the requested mode cannot run).  Host-only query, enqueues nothing. */
 int fnp_seeker_score_mode(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b);
-/* Stage 3: density + IoU score and greedy argmax per frustum. */
+/* Optional stage 2c (occl_w > 0 or FNP_SEEKER_OCCL_MULT; a no-op otherwise): hyp_nfar.  The reference's
+ * occlusion score of a hypothesis is hyp_nfar * (P_f - count) (calc_occl_scores broadcasts a (P,1)
+ * against a (P,) mask, :453); fnp_seeker_select forms the product. */
+int fnp_seeker_occlusion(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
+/* Stage 3: second-stage score (density + IoU and the optional terms) and greedy argmax per frustum. */
 int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
-/* All five stages back to back on `stream`. */
+/* All stages back to back on `stream`. */
 int fnp_seeker_run(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 
 /* Stage 4: batched rotated-BEV bitmask NMS in shared memory.  Segment s covers boxes

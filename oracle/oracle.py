@@ -74,6 +74,16 @@ def lib():
         L.fnp_o_hypotheses.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _f, _f, _f, _f, _fp, _fp, _bp]
         L.fnp_o_select.restype = C.c_int
         L.fnp_o_select.argtypes = [_ip, _fp, _bp, C.c_int, _f, _f, _fp]
+        L.fnp_o_centre_line_ex.restype = None
+        L.fnp_o_centre_line_ex.argtypes = [_fp, _f, _f, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, _f, _fp, _fp]
+        L.fnp_o_hypotheses_ex.restype = None
+        L.fnp_o_hypotheses_ex.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _f, _f, _f, _f,
+                                          C.c_int, _fp, _fp, _fp, _fp, _fp, _bp, _bp, _fp]
+        L.fnp_o_occl_fail.restype = None
+        L.fnp_o_occl_fail.argtypes = [C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _ip]
+        L.fnp_o_select_ex.restype = C.c_int
+        L.fnp_o_select_ex.argtypes = [_ip, _fp, _bp, C.c_int, _fp, _bp, _fp, _fp, _f, _f, _f, _f, _f, C.c_int,
+                                      _fp, _fp]
     return _lib
 
 
@@ -219,14 +229,22 @@ def quantile(x, q):
     return np.float32(lib().fnp_o_quantile(_p(x), x.shape[0], np.float32(q)))
 
 
-def centre_line(box2d, dmin, dmax, combine, trans, pmin, pmax, clamp_bottom, mags):
+def centre_line(box2d, dmin, dmax, combine, trans, pmin, pmax, clamp_bottom, mags, search_depth=None):
     box2d, combine, trans, pmin, pmax, mags = (_f32(x).reshape(-1) for x in (box2d, combine, trans, pmin, pmax, mags))
     M = mags.shape[0]
     centres = np.empty((M, 3), np.float32)
     corners = np.empty((8, 3), np.float32)
-    lib().fnp_o_centre_line(_p(box2d), np.float32(dmin), np.float32(dmax), _p(combine), _p(trans),
-                            _p(pmin), _p(pmax), int(clamp_bottom), _p(mags), M, _p(centres), _p(corners))
+    lib().fnp_o_centre_line_ex(_p(box2d), np.float32(dmin), np.float32(dmax), _p(combine), _p(trans),
+                               _p(pmin), _p(pmax), int(clamp_bottom), _p(mags), M,
+                               np.float32(search_depth or 0.0), _p(centres), _p(corners))
     return centres, corners
+
+
+def unproject(combine, trans, u, v, d):
+    combine, trans = _f32(combine).reshape(-1), _f32(trans).reshape(-1)
+    out = np.empty(3, np.float32)
+    lib().fnp_o_unproject(_p(combine), _p(trans), np.float32(u), np.float32(v), np.float32(d), _p(out))
+    return out
 
 
 def hypotheses(base_boxes, base_corners, centres, L, box2d, max_dist, min_iou,
@@ -242,6 +260,63 @@ def hypotheses(base_boxes, base_corners, centres, L, box2d, max_dist, min_iou,
                            img_w, img_h, np.float32(max_dist), np.float32(min_iou),
                            _p(boxes), _p(iou), _p(valid, _bp))
     return boxes, iou, valid.astype(bool)
+
+
+def hypotheses_ex(base_boxes, base_corners, centres, L, box2d, max_dist, min_iou, views=None, wc=None,
+                  img_w=1600.0, img_h=900.0):
+    """hypotheses() with the optional parts: views = (Ls (n,4,4), boxes2d (n,4)) for MULTICAM_IOU,
+    wc (3) the weighted centre -> also returns near (H) and dist (H)."""
+    base_boxes, base_corners, centres = _f32(base_boxes), _f32(base_corners), _f32(centres)
+    L, box2d = _f32(L).reshape(-1), _f32(box2d).reshape(-1)
+    J, M = base_boxes.shape[0], centres.shape[0]
+    H = J * M
+    boxes = np.empty((H, 7), np.float32)
+    iou = np.empty((H,), np.float32)
+    valid = np.empty((H,), np.uint8)
+    near = np.empty((H,), np.uint8)
+    dist = np.zeros((H,), np.float32)
+    n_views, vL, vb = 0, None, None
+    if views is not None:
+        vL, vb = _f32(views[0]).reshape(-1, 16), _f32(views[1]).reshape(-1, 4)
+        n_views = vL.shape[0]
+    wcv = _f32(wc).reshape(-1) if wc is not None else None
+    lib().fnp_o_hypotheses_ex(_p(base_boxes), _p(base_corners), J, _p(centres), M, _p(L), _p(box2d),
+                              img_w, img_h, np.float32(max_dist), np.float32(min_iou), n_views,
+                              _p(vL) if n_views else None, _p(vb) if n_views else None,
+                              _p(wcv) if wcv is not None else None, _p(boxes), _p(iou), _p(valid, _bp),
+                              _p(near, _bp), _p(dist) if wcv is not None else None)
+    return boxes, iou, valid.astype(bool), near.astype(bool), dist
+
+
+def occl_fail(points, boxes):
+    """calc_occl_scores restated: points (P,>=3), boxes (H,7) -> fail (H,) f32 (= n_far * n_out), n_far (H,) int32."""
+    points, boxes = _f32(points), _f32(boxes)
+    out = np.empty((boxes.shape[0],), np.float32)
+    nfar = np.empty((boxes.shape[0],), np.int32)
+    lib().fnp_o_occl_fail(points.shape[0], _p(points), points.shape[1], boxes.shape[0], _p(boxes), _p(out),
+                          _p(nfar, _ip))
+    return out, nfar
+
+
+def select_ex(counts, iou, valid, dist=None, near=None, fail=None, boxes=None, dns_w=1.0, iou_w=1.0, dst_w=0.0,
+              occl_w=0.0, ego_w=0.0, mult=False, occl_mult=False):
+    """Score with the optional terms + argmax; returns (h, best score, scores (H) [valid entries])."""
+    counts = np.ascontiguousarray(counts, np.int32)
+    iou = _f32(iou)
+    valid = np.ascontiguousarray(valid, np.uint8)
+    H = counts.shape[0]
+    dist = _f32(dist) if dist is not None else None
+    near = np.ascontiguousarray(near, np.uint8) if near is not None else None
+    fail = _f32(fail) if fail is not None else None
+    boxes = _f32(boxes) if boxes is not None else None
+    scores = np.zeros((H,), np.float32)
+    s = C.c_float(0)
+    h = lib().fnp_o_select_ex(_p(counts, _ip), _p(iou), _p(valid, _bp), H,
+                              _p(dist) if dist is not None else None, _p(near, _bp) if near is not None else None,
+                              _p(fail) if fail is not None else None, _p(boxes) if boxes is not None else None,
+                              np.float32(dns_w), np.float32(iou_w), np.float32(dst_w), np.float32(occl_w),
+                              np.float32(ego_w), int(bool(mult)) | (int(bool(occl_mult)) << 1), _p(scores), C.byref(s))
+    return h, np.float32(s.value), scores
 
 
 def select(counts, iou, valid, dns_w=1.0, iou_w=1.0):

@@ -3,8 +3,9 @@
 Restates FrustumProposerOG.get_proposals (reference:
 pcdet/models/dense_heads/frustum_proposals_v1.py:523-1067) on top of the C oracle
 (fnp_oracle.c) with the shipped option set of
-tools/cfgs/nuscenes_box_seeker_proposals.yaml:83 (no img/lidar augmentation, dst_w = 0,
-nms_3d = 0, topk = 1, no search_depth / rand_center / occl / aln / ego terms).
+tools/cfgs/nuscenes_box_seeker_proposals.yaml:83 (no img/lidar augmentation, nms_3d = 0, topk = 1),
+plus the optional terms of SURVEY.md 8 row f3: dst_w, ego_w, occl_w, search_depth and the flags
+MULT, OCCL_MULT, MULTICAM_IOU (passed as keys of `params`).
 
 Never imported by the product package.  Used by tests/ (as the checker of the CUDA
 pipeline), tools/gen_golden.py and the CPU-baseline legs of bench.py.
@@ -96,33 +97,69 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
     Returns dict(pred_boxes (K,7) f32, pred_labels (K) int32, pred_scores (K) f32,
     frustums=[per-frustum intermediates])."""
     p = dict(DEFAULTS); p.update(params)
-    assert p["topk"] == 1 and p["nms_3d"] == 0 and p["dst_w"] == 0.0
+    assert p["topk"] == 1 and p["nms_3d"] == 0
+    # optional terms (SURVEY 8 row f3): dst_w, ego_w, occl_w, search_depth, MULT, OCCL_MULT, MULTICAM_IOU;
+    # aln_w (randomised pca_lowrank) and rand_center (randn) are not deterministic in the reference
+    assert not p.get("aln_w") and not p.get("rand_center")
+    dst_w, ego_w, occl_w = float(p["dst_w"]), float(p.get("ego_w") or 0), float(p.get("occl_w") or 0)
+    mult, occl_mult, multicam = bool(p.get("MULT")), bool(p.get("OCCL_MULT")), bool(p.get("MULTICAM_IOU"))
+    sdepth = p.get("search_depth")
+    use_dist, use_fail = dst_w != 0 or mult, occl_w > 0 or occl_mult
+    extras = use_dist or use_fail or ego_w > 0 or multicam
     base_boxes, base_corners = tables if tables is not None else build_tables(p)
     combine, trans = camera_matrices(camera2lidar, camera_intrinsics)
     mags = torch.linspace(0.0, 1.0, p["num_mags"]).numpy() if p["num_mags"] > 0 else np.zeros(1, np.float32)
     max_dist = np.float32(p["max_dist"])
     pts = np.ascontiguousarray(points, np.float32)
     cands = nms2d_candidates(*dets, p["nms_2d"], p["score_thr"], box_format)
+    culls = [O.frustum_cull(pts, np.ascontiguousarray(lidar2image[c], np.float32), combine[c], trans[c], box2d,
+                            IMG_W, IMG_H) for (c, box2d, _, _) in cands]
     boxes_out, labels_out, scores_out, inter = [], [], [], []
-    for (c, box2d, label, score) in cands:
+    for k, (c, box2d, label, score) in enumerate(cands):
         L = np.ascontiguousarray(lidar2image[c], np.float32)
-        idx, uvd, xyz = O.frustum_cull(pts, L, combine[c], trans[c], box2d, IMG_W, IMG_H)
+        idx, uvd, xyz = culls[k]
         rec = dict(cam=c, box2d=box2d, label=label, score=score, n_points=int(idx.shape[0]))
         if idx.shape[0] == 0:
             if keep_intermediates:
                 inter.append(rec)
             continue
         d = uvd[:, 2]
-        dmin = np.maximum(O.quantile(d, p["lq"]), FRUSTUM_MIN)
-        dmax = np.minimum(O.quantile(d, p["uq"]), max_dist)
+        qmin = O.quantile(d, p["lq"])
+        # search_depth (:619-623): the far end is the near quantile + depth
+        qmax = O.quantile(d, p["uq"]) if sdepth is None else np.float32(qmin + np.float32(sdepth))
+        dmin = np.maximum(qmin, FRUSTUM_MIN)
+        dmax = np.minimum(qmax, max_dist)
         centres, corners = O.centre_line(box2d, dmin, dmax, combine[c], trans[c], xyz.min(0), xyz.max(0),
-                                         p["clamp_bottom"], mags)
-        hb, iou, valid = O.hypotheses(base_boxes[label - 1], base_corners[label - 1], centres, L, box2d,
-                                      max_dist, p["min_cam_iou"], IMG_W, IMG_H)
+                                         p["clamp_bottom"], mags, search_depth=sdepth)
+        if not extras:
+            hb, iou, valid = O.hypotheses(base_boxes[label - 1], base_corners[label - 1], centres, L, box2d,
+                                          max_dist, p["min_cam_iou"], IMG_W, IMG_H)
+            near = dist = None
+        else:
+            # weighted_centre_xyz (:631-636): box centre at the cq depth quantile, unprojected
+            wc = O.unproject(combine[c], trans[c], (box2d[0] + box2d[2]) / np.float32(2), (box2d[1] + box2d[3]) / np.float32(2),
+                             O.quantile(d, p["cq"]))
+            views = None
+            if multicam:   # every candidate of the frame with points and the same label, itself included (:879-880)
+                same = [i for i, cd in enumerate(cands) if cd[2] == label and culls[i][0].shape[0] > 0]
+                views = (np.stack([lidar2image[cands[i][0]] for i in same]), np.stack([cands[i][1] for i in same]))
+            hb, iou, valid, near, dist = O.hypotheses_ex(base_boxes[label - 1], base_corners[label - 1], centres, L,
+                                                         box2d, max_dist, p["min_cam_iou"], views=views, wc=wc)
+            rec.update(wc=wc, near=near, dist=dist)
         counts = np.zeros(hb.shape[0], np.int32)
+        fail = np.zeros(hb.shape[0], np.float32) if use_fail else None
+        nfar = np.zeros(hb.shape[0], np.int32)
         if valid.any():
             counts[valid] = O.count_in_boxes(xyz, hb[valid])
-        h, s = O.select(counts, iou, valid, p["dns_w"], p["iou_w"])
+            if use_fail:
+                fail[valid], nfar[valid] = O.occl_fail(xyz, hb[valid])
+        if not extras:
+            h, s = O.select(counts, iou, valid, p["dns_w"], p["iou_w"])
+        else:
+            h, s, sc = O.select_ex(counts, iou, valid, dist=dist, near=near, fail=fail, boxes=hb, dns_w=p["dns_w"],
+                                   iou_w=p["iou_w"], dst_w=dst_w, occl_w=occl_w, ego_w=ego_w, mult=mult,
+                                   occl_mult=occl_mult)
+            rec.update(scores=sc, fail=fail, nfar=nfar)
         rec.update(idx=idx, uvd=uvd, xyz=xyz, dmin=dmin, dmax=dmax, centres=centres, corners=corners,
                    hyp_boxes=hb, iou=iou, valid=valid, counts=counts, best=h, best_score=s)
         if keep_intermediates:

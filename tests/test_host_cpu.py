@@ -26,9 +26,13 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from findnpropagate_b200 import _lib
-    # 14 x 4-byte fields
-    assert ctypes.sizeof(_lib.SeekerCfg) == 56
+    # 19 x 4-byte fields, in the header's order
+    assert ctypes.sizeof(_lib.SeekerCfg) == 76
     hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
+    cbody = hdr[hdr.index("typedef struct fnp_seeker_cfg"):hdr.index("} fnp_seeker_cfg;")]
+    cbody = re.sub(r"/\*.*?\*/", "", cbody, flags=re.S)
+    cnames = [n for grp in re.findall(r"(?:int32_t|float)\s+([a-z_0-9,\s]+);", cbody) for n in re.split(r",\s*", grp.strip())]
+    assert cnames == [f[0] for f in _lib.SeekerCfg._fields_]
     body = hdr[hdr.index("typedef struct fnp_seeker_batch"):hdr.index("} fnp_seeker_batch;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"[\*\s]([a-z_0-9]+)(?:,\s*([a-z_0-9]+))?;", body)
@@ -101,8 +105,13 @@ def test_unsupported_options_raise():
     from findnpropagate_b200 import seeker
     with pytest.raises(NotImplementedError):
         seeker.resolve_params(dict(topk=2, nms_3d=0, dst_w=0))
-    with pytest.raises(NotImplementedError):
-        seeker.resolve_params(dict(nms_3d=0, dst_w=0.2))
+    for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(nms_3d=0.5), dict(search_depth=0.0)):
+        with pytest.raises(NotImplementedError):
+            seeker.resolve_params(dict(dict(nms_3d=0), **bad))
+    # the optional terms of SURVEY.md 8 row f3 are accepted
+    p = seeker.resolve_params(dict(nms_3d=0, dst_w=0.2, ego_w=0.1, occl_w=0.3, search_depth=4.0, MULT=True,
+                                   OCCL_MULT=True, MULTICAM_IOU=True))
+    assert p["MULT"] and p["search_depth"] == 4.0
 
 
 def test_host_pack_xyz_gathers_the_columns():

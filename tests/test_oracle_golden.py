@@ -1,6 +1,7 @@
 """CPU tests: the oracle against the golden vectors produced by the reference itself
 (tools/gen_golden.py): compiled reference CPU ops + the reference's own get_proposals."""
 import glob
+import json
 import os
 
 import numpy as np
@@ -63,6 +64,8 @@ def test_seeker_oracle_against_reference_run(path):
     g = np.load(path)
     cfg = synth.CONFIGS[str(g["cfg"])]
     params = synth.seeker_params(cfg)
+    opts = json.loads(str(g["opts"])) if "opts" in g else {}      # row f3 option sets (tools/gen_golden.py)
+    params.update(opts)
     out = SO.seek_frame(g["points"], g["lidar2image"], g["camera2lidar"], g["camera_intrinsics"],
                         (g["det_boxes"], g["det_labels"], g["det_scores"], g["det_cam_idx"]), params,
                         tables=(g["base_boxes"], g["base_corners"]), keep_intermediates=True,
@@ -72,9 +75,10 @@ def test_seeker_oracle_against_reference_run(path):
     assert np.array_equal(out["pred_scores"], g["ref_scores"])
     rel = np.abs(out["pred_boxes"] - g["ref_boxes"]) / np.maximum(np.abs(g["ref_boxes"]), 1e-3)
     twins = 0
+    tol = 1e-5 if not opts else 3e-5     # the option terms add torch ops whose CPU rounding differs (cdist, norm)
     for k in range(rel.shape[0]):
-        if rel[k].max() > 1e-5:
-            assert rel[k, :6].max() <= 1e-5
+        if rel[k].max() > tol:
+            assert rel[k, :6].max() <= tol
             assert abs(abs(out["pred_boxes"][k, 6] - g["ref_boxes"][k, 6]) - np.pi) < 1e-5
             twins += 1
     assert twins <= max(1, rel.shape[0] // 5)
@@ -89,7 +93,9 @@ def test_seeker_oracle_against_reference_run(path):
         assert vb.shape == g["f%d_boxes" % k].shape                           # same valid set size
         assert np.allclose(vb, g["f%d_boxes" % k], rtol=1e-5, atol=1e-5)
         assert np.array_equal(f["counts"][f["valid"]], g["f%d_counts" % k])   # per-hypothesis counts
-        assert np.allclose(f["best_score"], g["f%d_scores" % k].max(), rtol=1e-5)
+        assert np.allclose(f["best_score"], g["f%d_scores" % k].max(), rtol=1e-5 if not opts else 1e-4)
+        if "scores" in f:      # second-stage score of every valid hypothesis, optional terms included
+            assert np.allclose(f["scores"][f["valid"]], g["f%d_scores" % k], rtol=1e-4, atol=1e-4)
 
 
 def test_oracle_trig_close_to_libm():

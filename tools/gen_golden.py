@@ -29,9 +29,26 @@ from findnpropagate_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def frame_fixture(name, index, box_format="xyxy"):
+# option sets of SURVEY.md 8 row f3 (PARAMS keys and the MULT / OCCL_MULT / MULTICAM_IOU switches of
+# the head's model_cfg), each pinned by a reference run on a tiny frame
+OPTION_SETS = {
+    "dst": dict(dst_w=0.226, iou_w=0.95, dns_w=0.05),          # the constructor's own defaults (:146)
+    "ego": dict(ego_w=0.3),
+    "mult": dict(MULT=True, dst_w=0.7, iou_w=0.9),
+    "occl": dict(occl_w=0.5),
+    "occlmult": dict(OCCL_MULT=True),
+    "multicam": dict(MULTICAM_IOU=True),
+    "sdepth": dict(search_depth=4.0),
+    "all": dict(dst_w=0.2, ego_w=0.1, occl_w=0.3, MULTICAM_IOU=True, search_depth=6.0),
+}
+
+
+def frame_fixture(name, index, box_format="xyxy", opts=None):
+    import json
     cfg = synth.CONFIGS[name]
     params = synth.seeker_params(cfg)
+    if opts is not None:
+        params.update(OPTION_SETS[opts])
     fr = synth.make_frame(index, cfg)
     if box_format != "xyxy":     # BOX_FORMAT 'xywh' (frustum_proposals_v1.py:597-601): the feeder hands out x, y, w, h
         fr.det_boxes = fr.det_boxes.copy()
@@ -46,6 +63,7 @@ def frame_fixture(name, index, box_format="xyxy"):
         ref_boxes=boxes, ref_labels=labels.astype(np.int32), ref_scores=scores,
         base_boxes=head.base_boxes.numpy(), base_corners=head.base_corners.numpy(),
         n_frustums=len(cap["frustums"]),
+        opts=json.dumps(OPTION_SETS[opts] if opts is not None else {}),
     )
     for k, f in enumerate(cap["frustums"]):
         d["f%d_points" % k] = f["points"]
@@ -54,7 +72,8 @@ def frame_fixture(name, index, box_format="xyxy"):
         d["f%d_scores" % k] = f["scores"]
         d["f%d_keep" % k] = f["keep"]
     # reference recall record (detector3d_template.py:315) evaluated with the oracle iou3d
-    path = os.path.join(OUT, "seeker_%s%s_%d.npz" % (name, "" if box_format == "xyxy" else "_" + box_format, index))
+    tag = ("" if box_format == "xyxy" else "_" + box_format) + ("" if opts is None else "_opt-" + opts)
+    path = os.path.join(OUT, "seeker_%s%s_%d.npz" % (name, tag, index))
     np.savez_compressed(path, **d)
     print("wrote", path, "K =", boxes.shape[0], "frustums =", len(cap["frustums"]))
 
@@ -91,3 +110,5 @@ if __name__ == "__main__":
         for i in idxs:
             frame_fixture(name, i)
     frame_fixture("tiny", 3, box_format="xywh")
+    for k, o in enumerate(OPTION_SETS):
+        frame_fixture("tiny", k % 3, opts=o)

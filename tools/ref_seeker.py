@@ -62,9 +62,12 @@ def _emul_nms_normal_gpu(boxes, scores, thresh, **kw):
     if _CAPTURE is not None:
         calls = _CAPTURE["pib_calls"]
         n = b.shape[0]
+        # the density loop makes the first n calls of a frustum; calc_occl_scores (occl_w / OCCL_MULT) makes
+        # n more per use, after it
+        assert len(calls) % n == 0 and len(calls) >= n
         _CAPTURE["frustums"].append(dict(
             boxes=b.copy(), scores=s.copy(), keep=keep.copy(),
-            counts=np.array([c for _, c in calls[-n:]], np.int32),
+            counts=np.array([c for _, c in calls[:n]], np.int32),
             points=_CAPTURE.get("last_points", np.zeros((0, 3), np.float32)).copy()))
         _CAPTURE["pib_calls"] = []
     return torch.from_numpy(keep), None
@@ -139,7 +142,9 @@ class SyntheticFeeder:
 def build_head(params, frames, box_format="xyxy"):
     mod = load()
     mod.PreprocessedGLIP = lambda class_names=None: SyntheticFeeder(frames)
-    cfg = AttrDict(PARAMS=dict(params), PREDS_PATH="PreprocessedGLIP", BOX_FORMAT=box_format)
+    flags = {k: bool(params.get(k)) for k in ("MULT", "OCCL_MULT", "MULTICAM_IOU")}   # model_cfg-level switches
+    cfg = AttrDict(PARAMS={k: v for k, v in params.items() if k not in flags}, PREDS_PATH="PreprocessedGLIP",
+                   BOX_FORMAT=box_format, **flags)
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):

@@ -27,7 +27,8 @@ class SeekerCfg(C.Structure):
                 ("clamp_bottom", C.c_int32), ("img_w", _f), ("img_h", _f), ("lq", _f), ("uq", _f),
                 ("cq", _f), ("frustum_min", _f), ("max_dist", _f), ("min_cam_iou", _f),
                 ("dns_w", _f), ("iou_w", _f),
-                ("dst_w", _f), ("ego_w", _f), ("occl_w", _f), ("search_depth", _f), ("flags", C.c_int32)]
+                ("dst_w", _f), ("ego_w", _f), ("occl_w", _f), ("search_depth", _f), ("flags", C.c_int32),
+                ("topk", C.c_int32), ("nms_normal", _f)]
 
 
 class SeekerBatch(C.Structure):
@@ -49,7 +50,7 @@ class SeekerBatch(C.Structure):
         ("score_mode", C.c_int32), ("sweep_cols", _vp),
         ("out_boxes", _vp), ("out_score", _vp), ("out_best", _vp), ("out_count", _vp),
         ("status", _vp),
-        ("hyp_dist", _vp), ("hyp_nfar", _vp),
+        ("hyp_dist", _vp), ("hyp_nfar", _vp), ("hyp_score", _vp),
     ]
 
 

@@ -87,6 +87,20 @@ __device__ __forceinline__ float fnp_exp(float x)
     return __fmul_rn(e, __int_as_float((ni + 127) << 23));
 }
 
+// axis-aligned BEV IoU (iou_normal): Sa + Sb is one fma, x -+ dx/2 are exact-half fmas
+__device__ __forceinline__ float iou_normal(const float *__restrict__ a, const float *__restrict__ b)
+{
+    // a, b: x, y, (z), dx, dy at [0], [1], [3], [4] (iou3d_nms_kernel.cu:327-338)
+    const float left = fmaxf(__fmaf_rn(a[3], -0.5f, a[0]), __fmaf_rn(b[3], -0.5f, b[0]));
+    const float right = fminf(__fmaf_rn(a[3], 0.5f, a[0]), __fmaf_rn(b[3], 0.5f, b[0]));
+    const float top = fmaxf(__fmaf_rn(a[4], -0.5f, a[1]), __fmaf_rn(b[4], -0.5f, b[1]));
+    const float bottom = fminf(__fmaf_rn(a[4], 0.5f, a[1]), __fmaf_rn(b[4], 0.5f, b[1]));
+    const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
+    const float inter = __fmul_rn(width, height);
+    const float sasb = __fmaf_rn(b[3], b[4], __fmul_rn(a[3], a[4]));
+    return __fdiv_rn(inter, fmaxf(__fsub_rn(sasb, inter), 1e-8f));
+}
+
 // LiDAR -> image (frustum_proposals_v1.py:1431-1475 without augmentation).  L = rows 0..2 of
 // lidar2image, 12 floats row-major [r0c0 r0c1 r0c2 r0c3 | r1.. | r2..].
 __device__ __forceinline__ bool project(const float *__restrict__ L, float x, float y, float z,

@@ -234,19 +234,6 @@ __device__ __forceinline__ float iou_bev(const RBox &A, const RBox &B)
     return __fdiv_rn(ov, fmaxf(__fsub_rn(__fadd_rn(A.area, B.area), ov), 1e-8f));
 }
 
-// axis-aligned BEV IoU (iou_normal): Sa + Sb is one fma, x -+ dx/2 are exact-half fmas
-__device__ __forceinline__ float iou_normal(const float *__restrict__ a, const float *__restrict__ b)
-{
-    const float left = fmaxf(__fmaf_rn(a[3], -0.5f, a[0]), __fmaf_rn(b[3], -0.5f, b[0]));
-    const float right = fminf(__fmaf_rn(a[3], 0.5f, a[0]), __fmaf_rn(b[3], 0.5f, b[0]));
-    const float top = fmaxf(__fmaf_rn(a[4], -0.5f, a[1]), __fmaf_rn(b[4], -0.5f, b[1]));
-    const float bottom = fminf(__fmaf_rn(a[4], 0.5f, a[1]), __fmaf_rn(b[4], 0.5f, b[1]));
-    const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
-    const float inter = __fmul_rn(width, height);
-    const float sasb = __fmaf_rn(b[3], b[4], __fmul_rn(a[3], a[4]));
-    return __fdiv_rn(inter, fmaxf(__fsub_rn(sasb, inter), 1e-8f));
-}
-
 template <bool IOU>
 __global__ void __launch_bounds__(256) pairwise_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                                        float *__restrict__ out, int N, int M)

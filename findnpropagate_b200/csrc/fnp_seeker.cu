@@ -1609,20 +1609,45 @@ __device__ __forceinline__ float block_max128(float v, float *s4, const int lane
     return v;
 }
 
+// Block-wide arg-max of (score, index) over 128 threads, lowest index on ties; every thread gets the result.
+// besti == 0x7fffffff means "no entry".
+__device__ __forceinline__ void block_argmax128(float &best, int &besti, float *s_f, int *s_i, const int lane,
+                                                const int warp)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    if (lane == 0) { s_f[warp] = best; s_i[warp] = besti; }
+    __syncthreads();
+    best = s_f[0]; besti = s_i[0];
+#pragma unroll
+    for (int w = 1; w < 4; w++) {
+        const float ob = s_f[w];
+        const int oi = s_i[w];
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    __syncthreads();
+}
+
+constexpr int kSelectMaxTopkH = 32768;   // hypotheses per frustum the suppression bitmask of topk > 1 covers
+
 __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ float s_f[4];
     __shared__ int s_i[4];
+    __shared__ unsigned s_dead[kSelectMaxTopkH / 32];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int J = cfg.num_yaw_size, H = J * cfg.num_mags;
+    const int T = max(cfg.topk, 1);
     const int nv = b.hyp_nvalid[f];
-    if (nv <= 0) {
-        if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
-        return;
-    }
-    if (b.status[0] & 2) {
-        if (tid == 0) { b.out_best[f] = -1; b.out_score[f] = 0.f; b.out_count[f] = 0; }
+    if (nv <= 0 || (b.status[0] & 2)) {
+        for (int k = tid; k < T; k += blockDim.x) {
+            b.out_best[(size_t)f * T + k] = -1; b.out_score[(size_t)f * T + k] = 0.f; b.out_count[(size_t)f * T + k] = 0;
+        }
         return;
     }
     const int *cbase = b.counts + (size_t)f * H;
@@ -1669,33 +1694,52 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
         if (use_ego)
             sc = __fadd_rn(sc, __fmul_rn(cfg.ego_w, __fdiv_rn(norm3(pbase[r * 8], pbase[r * 8 + 1], pbase[r * 8 + 2]), emx)));
         if (occl_mult) sc = __fmul_rn(__fmul_rn(dens, iou), FNP_FAIL(r));
+        if (T > 1) b.hyp_score[(size_t)f * H + r] = sc;
         if (sc > best || besti == 0x7fffffff) { best = sc; besti = r; }
     }
 #undef FNP_FAIL
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    if (T > 1) {
+        for (int i = tid; i < (nv + 31) >> 5; i += blockDim.x) s_dead[i] = 0u;
     }
-    if (lane == 0) { s_f[warp] = best; s_i[warp] = besti; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 4; w++) {
-            const float ob = s_f[w];
-            const int oi = s_i[w];
-            if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    block_argmax128(best, besti, s_f, s_i, lane, warp);     // also orders the hyp_score / s_dead writes
+    const float *bb_tab = b.base_boxes + (size_t)(b.cand_label[f] - 1) * J * 7;
+    for (int k = 0;;) {
+        const float *pp = pbase + (size_t)besti * 8;
+        const float *bb = bb_tab + (size_t)(b.hyp_index[(size_t)f * H + besti] % J) * 7;
+        if (tid == 0) {
+            float *o = b.out_boxes + ((size_t)f * T + k) * 7;
+            o[0] = pp[0]; o[1] = pp[1]; o[2] = pp[2];
+            o[3] = bb[3]; o[4] = bb[4]; o[5] = bb[5]; o[6] = bb[6];
+            b.out_best[(size_t)f * T + k] = besti;
+            b.out_score[(size_t)f * T + k] = best;
+            b.out_count[(size_t)f * T + k] = cbase[besti];
         }
-        const int h = b.hyp_index[(size_t)f * H + besti];
-        const int j = h % J;
-        const float *pp = b.hyp_prep + ((size_t)f * H + besti) * 8;
-        const float *bb = b.base_boxes + ((size_t)(b.cand_label[f] - 1) * J + j) * 7;
-        float *o = b.out_boxes + (size_t)f * 7;
-        o[0] = pp[0]; o[1] = pp[1]; o[2] = pp[2];
-        o[3] = bb[3]; o[4] = bb[4]; o[5] = bb[5]; o[6] = bb[6];
-        b.out_best[f] = besti;
-        b.out_score[f] = best;
-        b.out_count[f] = cbase[besti];
+        if (++k >= T) break;
+        // nms_normal_gpu (:1030, iou3d_nms.cpp:162-209): the kept box suppresses every later one with an
+        // axis-aligned BEV IoU above the threshold; the next kept box is the best survivor
+        const float abox[5] = {pp[0], pp[1], 0.f, bb[3], bb[4]};
+        if (tid == 0) atomicOr(&s_dead[besti >> 5], 1u << (besti & 31));
+        for (int r = tid; r < nv; r += blockDim.x) {
+            if ((s_dead[r >> 5] >> (r & 31)) & 1u) continue;
+            const float *bq = bb_tab + (size_t)(b.hyp_index[(size_t)f * H + r] % J) * 7;
+            const float qbox[5] = {pbase[r * 8], pbase[r * 8 + 1], 0.f, bq[3], bq[4]};
+            if (r != besti && iou_normal(abox, qbox) > cfg.nms_normal) atomicOr(&s_dead[r >> 5], 1u << (r & 31));
+        }
+        __syncthreads();
+        best = -__int_as_float(0x7f800000);
+        besti = 0x7fffffff;
+        for (int r = tid; r < nv; r += blockDim.x) {
+            if ((s_dead[r >> 5] >> (r & 31)) & 1u) continue;
+            const float sc = b.hyp_score[(size_t)f * H + r];
+            if (sc > best || besti == 0x7fffffff) { best = sc; besti = r; }
+        }
+        block_argmax128(best, besti, s_f, s_i, lane, warp);
+        if (besti == 0x7fffffff) {       // fewer survivors than topk: the remaining slots stay empty
+            for (int kk = k + tid; kk < T; kk += blockDim.x) {
+                b.out_best[(size_t)f * T + kk] = -1; b.out_score[(size_t)f * T + kk] = 0.f; b.out_count[(size_t)f * T + kk] = 0;
+            }
+            break;
+        }
     }
 }
 
@@ -1878,6 +1922,7 @@ extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_bat
     if (rc) return rc;
     if (((cfg->dst_w != 0.f) || (cfg->flags & FNP_SEEKER_MULT)) && !b->hyp_dist) return FNP_EINVAL;
     if (((cfg->occl_w > 0.f) || (cfg->flags & FNP_SEEKER_OCCL_MULT)) && !b->hyp_nfar) return FNP_EINVAL;
+    if (cfg->topk > 1 && (!b->hyp_score || cfg->num_yaw_size * cfg->num_mags > kSelectMaxTopkH)) return FNP_EINVAL;
     if (b->n_cands == 0) return FNP_OK;
     select_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
     FNP_LAUNCH_CHECK();

@@ -56,8 +56,8 @@ def resolve_params(params: Optional[dict]) -> dict:
     if params:
         p.update(params)
     unsupported = []
-    if p["topk"] != 1:
-        unsupported.append("topk != 1")
+    if int(p["topk"]) < 1:
+        unsupported.append("topk < 1")
     if p["nms_3d"] != 0:
         unsupported.append("nms_3d != 0 (the reference asserts it too, :209)")
     if p.get("aln_w"):
@@ -170,7 +170,9 @@ class SeekerEngine:
             dst_w=float(self.p["dst_w"]), ego_w=float(self.p["ego_w"] or 0), occl_w=float(self.p["occl_w"] or 0),
             search_depth=float(self.p["search_depth"] or 0),
             flags=(_lib.SEEKER_MULT if self.p["MULT"] else 0) | (_lib.SEEKER_OCCL_MULT if self.p["OCCL_MULT"] else 0)
-            | (_lib.SEEKER_MULTICAM_IOU if self.p["MULTICAM_IOU"] else 0))
+            | (_lib.SEEKER_MULTICAM_IOU if self.p["MULTICAM_IOU"] else 0),
+            topk=int(self.p["topk"]), nms_normal=float(self.p["nms_normal"]))
+        self.T = int(self.p["topk"])       # proposal slots per candidate frustum (NMS order), :1040-1046
         # workspaces of the optional score terms (include/fnp.h: hyp_dist, hyp_nfar)
         self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"])
         self.use_occl = self.cfg.occl_w > 0 or bool(self.p["OCCL_MULT"])
@@ -285,7 +287,15 @@ class SeekerEngine:
         fcs32 = np.ascontiguousarray(frame_cand_start, np.int32)
         _lib.check(_lib.lib.fnp_host_nms_order(cand_score.ctypes.data, fcs32.ctypes.data, B, nms_order.ctypes.data),
                    "fnp_host_nms_order")
+        extra = {}
+        if self.T > 1:
+            # topk > 1: every candidate owns T consecutive proposal slots; per-frame slot ranges and the
+            # stage-4 order over slots (a candidate's slots stay together, best first)
+            T = self.T
+            extra = dict(frame_prop_start=(fcs32 * T).astype(np.int32),
+                         prop_order=(nms_order[:, None] * T + np.arange(T, dtype=np.int32)[None, :]).reshape(-1).astype(np.int32))
         return dict(
+            **extra,
             B=B, F=F, n_tiles=n_tiles, stride=int(stride), xyz_offset=int(xyz_offset),
             total_rows=int(frame_row_start[-1]),
             max_cands=int(np.diff(frame_cand_start).max()) if B else 0,
@@ -309,12 +319,13 @@ class SeekerEngine:
 
     def _upload_meta(self, plan, stream, slot=0):
         offs, total = {}, 0
-        for k in self._META:
+        keys = self._META + (["frame_prop_start", "prop_order"] if self.T > 1 else [])
+        for k in keys:
             offs[k] = total
             total = _align(total + plan[k].nbytes)
         host = self.arena.get("meta_host%d" % slot, total, pinned=True)
         hv = host.numpy()
-        for k in self._META:
+        for k in keys:
             a = plan[k]
             hv[offs[k]:offs[k] + a.nbytes] = a.reshape(-1).view(np.uint8)
         dev = self.arena.get("meta_dev%d" % slot, total)
@@ -369,11 +380,15 @@ class SeekerEngine:
                 hyp_iou=4 * H * F, counts=4 * H * F, items=16 * max_items,
                 cand_item_start=4 * (F + 1), sweep_cols=4 * _lib.SWEEP_COL_FLOATS * self.J * F,
                 )
-            # outputs, one D2H: boxes(7) score best count npts nvalid per candidate, status(4) + pad(4),
-            # recall counters (20 x int64), stage-4 keep flags (F bytes)
-            off_recall = 4 * (12 * F + 8)
+            # outputs, one D2H: boxes(7) score best count per proposal slot (T per candidate), npts nvalid
+            # per candidate, status(4) + pad(4), recall counters (20 x int64), stage-4 keep flags (F T bytes)
+            T = self.T
+            FT = F * T
+            off_recall = 4 * (10 * FT + 2 * F + 8)
             off_keep = off_recall + 8 * self.N_COUNTERS
-            sizes["out"] = off_keep + _align(F, 8)
+            sizes["out"] = off_keep + _align(FT, 8)
+            if T > 1:
+                sizes["hyp_score"] = 4 * H * F
             if self.use_dist:
                 sizes["hyp_dist"] = 4 * H * F
             if self.use_occl:
@@ -386,8 +401,8 @@ class SeekerEngine:
             ptr = {k: self.arena.get(k + sfx, v).data_ptr() for k, v in sizes.items() if k != "out"}
             out_dev = self.arena.get("out%d" % slot, sizes["out"])
             ob = out_dev.data_ptr()
-            o_boxes, o_score, o_best, o_count = ob, ob + 28 * F, ob + 32 * F, ob + 36 * F
-            o_npts, o_nvalid, o_status = ob + 40 * F, ob + 44 * F, ob + 48 * F
+            o_boxes, o_score, o_best, o_count = ob, ob + 28 * FT, ob + 32 * FT, ob + 36 * FT
+            o_npts, o_nvalid, o_status = ob + 40 * FT, ob + 40 * FT + 4 * F, ob + 40 * FT + 8 * F
             o_ptstart = self.arena.get("cand_pt_start" + sfx, 4 * (F + 1)).data_ptr()
             b = _lib.SeekerBatch(
                 n_frames=B, n_cands=F, n_tiles=plan["n_tiles"], max_cands_per_frame=Cmax,
@@ -410,7 +425,7 @@ class SeekerEngine:
                 cand_item_start=ptr["cand_item_start"], items=ptr["items"],
                 counts=ptr["counts"], score_mode=self.score_mode, sweep_cols=ptr["sweep_cols"],
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status,
-                hyp_dist=ptr.get("hyp_dist"), hyp_nfar=ptr.get("hyp_nfar"))
+                hyp_dist=ptr.get("hyp_dist"), hyp_nfar=ptr.get("hyp_nfar"), hyp_score=ptr.get("hyp_score"))
             rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
             _lib.check(rc, "fnp_seeker_run")
             mode = _lib.lib.fnp_seeker_score_mode(C.byref(self.cfg), C.byref(b))
@@ -438,8 +453,12 @@ class SeekerEngine:
     def _stage4_nms(self, plan, meta, o_boxes, o_best, thresh, stream, keep_ptr):
         """Rotated-BEV NMS of each frame's proposals in 2D-score order (the dedup
         PseudoLoader applies later on the CPU, pseudo_loader.py:29-55,755)."""
-        rc = _lib.lib.fnp_seg_nms_rotated(o_boxes, None, meta["nms_order"], o_best, meta["frame_cand_start"], plan["B"],
-                                          int(min(max(plan["max_cands"], 1), _lib.SEG_NMS_MAX)), thresh,
+        T = self.T
+        if plan["max_cands"] * T > _lib.SEG_NMS_MAX:
+            raise ValueError("stage-4 NMS handles at most %d proposals per frame" % _lib.SEG_NMS_MAX)
+        rc = _lib.lib.fnp_seg_nms_rotated(o_boxes, None, meta["nms_order" if T == 1 else "prop_order"], o_best,
+                                          meta["frame_cand_start" if T == 1 else "frame_prop_start"], plan["B"],
+                                          int(min(max(plan["max_cands"] * T, 1), _lib.SEG_NMS_MAX)), thresh,
                                           keep_ptr, stream)
         _lib.check(rc, "fnp_seg_nms_rotated")
         self.launches += 1
@@ -449,8 +468,9 @@ class SeekerEngine:
         assert len(thresh) == 3
         out_dev[off:off + 8 * self.N_COUNTERS].zero_()
         th = (C.c_float * len(thresh))(*[float(t) for t in thresh])
-        rc = _lib.lib.fnp_recall_counters(o_boxes, o_best, meta["frame_cand_start"], gt_boxes.data_ptr(),
-                                          gt_start.data_ptr(), plan["B"], max(plan["max_cands"], 1), int(max_gt), th, len(thresh),
+        rc = _lib.lib.fnp_recall_counters(o_boxes, o_best, meta["frame_cand_start" if self.T == 1 else "frame_prop_start"],
+                                          gt_boxes.data_ptr(), gt_start.data_ptr(), plan["B"],
+                                          max(plan["max_cands"] * self.T, 1), int(max_gt), th, len(thresh),
                                           out_dev.data_ptr() + off, stream)
         _lib.check(rc, "fnp_recall_counters")
         self.launches += 1
@@ -464,13 +484,15 @@ class SeekerEngine:
         raw = handle["out_host"].numpy()[:handle["out_bytes"]]
         f32 = raw.view(np.float32)
         i32 = raw.view(np.int32)
-        boxes = f32[0:7 * F].reshape(F, 7)
-        score = f32[7 * F:8 * F]
-        best = i32[8 * F:9 * F]
-        count = i32[9 * F:10 * F]
-        npts = i32[10 * F:11 * F]
-        nvalid = i32[11 * F:12 * F]
-        status = i32[12 * F:12 * F + 4]
+        T = self.T
+        FT = F * T
+        boxes = f32[0:7 * FT].reshape(FT, 7)
+        score = f32[7 * FT:8 * FT]
+        best = i32[8 * FT:9 * FT]
+        count = i32[9 * FT:10 * FT]
+        npts = i32[10 * FT:10 * FT + F]
+        nvalid = i32[10 * FT + F:10 * FT + 2 * F]
+        status = i32[10 * FT + 2 * F:10 * FT + 2 * F + 4]
         if status[0] & 1:
             raise OverflowError(int(status[1]))
         if status[0] & 2:
@@ -480,10 +502,11 @@ class SeekerEngine:
         # compact once, then hand every frame a slice (views of the compacted arrays: no per-frame
         # boolean indexing -- 128 frames: 1.4 ms -> 0.4 ms of host time per batch)
         idx = np.flatnonzero(ok)
-        c_boxes, c_scores = boxes[idx], plan["cand_score"][idx]
-        c_labels = plan["cand_label"][idx].astype(np.int32)
-        c_keep = raw[handle["off_keep"]:handle["off_keep"] + F][idx].astype(bool) if handle["has_nms"] else None
-        st = np.searchsorted(idx, fcs).tolist()
+        cand_of = idx if T == 1 else idx // T      # slot -> candidate: 2D score and label repeat (:1048-1052)
+        c_boxes, c_scores = boxes[idx], plan["cand_score"][cand_of]
+        c_labels = plan["cand_label"][cand_of].astype(np.int32)
+        c_keep = raw[handle["off_keep"]:handle["off_keep"] + FT][idx].astype(bool) if handle["has_nms"] else None
+        st = np.searchsorted(idx, fcs * T).tolist()
         frames = []
         for b in range(B):
             d = dict(pred_boxes=c_boxes[st[b]:st[b + 1]], pred_scores=c_scores[st[b]:st[b + 1]],
@@ -491,9 +514,13 @@ class SeekerEngine:
             if c_keep is not None:
                 d["nms_keep"] = c_keep[st[b]:st[b + 1]]
             frames.append(d)
-        res = dict(frames=frames, cand_valid=ok.copy(), cand_best=best.copy(), cand_score2=score.copy(),
-                   cand_count=count.copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),
-                   cand_boxes=boxes.copy())
+        # per-candidate views: the best proposal of each (slot 0); cand_topk has every slot
+        res = dict(frames=frames, cand_valid=ok[::T].copy(), cand_best=best[::T].copy(), cand_score2=score[::T].copy(),
+                   cand_count=count[::T].copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),
+                   cand_boxes=boxes[::T].copy())
+        if T > 1:
+            res["cand_topk"] = dict(best=best.reshape(F, T).copy(), score2=score.reshape(F, T).copy(),
+                                    boxes=boxes.reshape(F, T, 7).copy(), count=count.reshape(F, T).copy())
         if handle["has_recall"]:
             o = handle["off_recall"]
             res["recall"] = self.recall_dict(raw[o:o + 8 * self.N_COUNTERS].view(np.int64), handle["recall_thresh"])
@@ -565,7 +592,7 @@ class SeekerEngine:
         rec = view("frustum_pts", torch.float32, (total // 2, 4, 2))
         rows = rec.transpose(0, 2, 1).reshape(total, 4)
         idx = view("frustum_idx", torch.int32, (total,))
-        npts = handle["out_host"].numpy()[:handle["out_bytes"]].view(np.int32)[10 * F:11 * F]
+        npts = handle["out_host"].numpy()[:handle["out_bytes"]].view(np.int32)[10 * F * self.T:10 * F * self.T + F]
         sel = np.concatenate([np.arange(padded_start[f], padded_start[f] + npts[f]) for f in range(F)]
                              + [np.zeros(0, np.int64)]).astype(np.int64)
         pt_start = np.concatenate([[0], np.cumsum(npts)]).astype(np.int32)

@@ -106,6 +106,9 @@ typedef struct fnp_seeker_cfg {
     float occl_w;            /* weight of 1 - fail / (max fail + 1e-6), calc_occl_scores (:408-477,1007-1014) */
     float search_depth;      /* PARAMS search_depth (:619-623,841-842); <= 0: not set                       */
     int32_t flags;           /* FNP_SEEKER_MULT | FNP_SEEKER_OCCL_MULT | FNP_SEEKER_MULTICAM_IOU            */
+    int32_t topk;            /* proposals per frustum (:1040-1046); 0 and 1 both mean the single best one  */
+    float nms_normal;        /* axis-aligned BEV IoU threshold of the per-frustum NMS (:1030); only matters
+                                for topk > 1 (the first survivor is the arg-max whatever the threshold)    */
 } fnp_seeker_cfg;
 
 #define FNP_SEEKER_MULT 1          /* MODEL.DENSE_HEAD.MULT: product of the score terms (:998-999)             */
@@ -182,11 +185,11 @@ typedef struct fnp_seeker_batch {
     int32_t score_mode;              /* FNP_SCORE_AUTO / FNP_SCORE_DIRECT / FNP_SCORE_SWEEP */
     float *sweep_cols;               /* (F,J,FNP_SWEEP_COL_FLOATS) per (frustum, yaw-size column) depth-
                                         sweep parameters; required for the sweep mode       */
-    /* ---- outputs ---- */
-    float *out_boxes;                /* (F,7) selected box per candidate                   */
-    float *out_score;                /* (F)   its second-stage score                       */
-    int32_t *out_best;               /* (F)   compacted index of the winner, -1 if none    */
-    int32_t *out_count;              /* (F)   point count of the winner                    */
+    /* ---- outputs (T = max(cfg.topk, 1) slots per candidate, in NMS order: slot f*T + k) ---- */
+    float *out_boxes;                /* (F*T,7) selected boxes per candidate               */
+    float *out_score;                /* (F*T)   their second-stage scores                  */
+    int32_t *out_best;               /* (F*T)   compacted index of the hypothesis, -1 for an unused slot */
+    int32_t *out_count;              /* (F*T)   its point count                            */
     int32_t *status;                 /* (8)   [0] bit0: frustum_pts overflow (needed points in [1]),
                                         bit1: items overflow ([2] items needed);
                                         [4] work-item counter of the scoring kernel; [5] staging
@@ -196,6 +199,8 @@ typedef struct fnp_seeker_batch {
                                         required iff dst_w != 0 or FNP_SEEKER_MULT          */
     int32_t *hyp_nfar;               /* (F,H) frustum points beyond the nearest corner of each compacted
                                         hypothesis; required iff occl_w > 0 or FNP_SEEKER_OCCL_MULT */
+    float *hyp_score;                /* (F,H) second-stage score of each compacted hypothesis; required iff
+                                        topk > 1 (needs H <= 32768)                          */
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024

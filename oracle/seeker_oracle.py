@@ -3,9 +3,9 @@
 Restates FrustumProposerOG.get_proposals (reference:
 pcdet/models/dense_heads/frustum_proposals_v1.py:523-1067) on top of the C oracle
 (fnp_oracle.c) with the shipped option set of
-tools/cfgs/nuscenes_box_seeker_proposals.yaml:83 (no img/lidar augmentation, nms_3d = 0, topk = 1),
+tools/cfgs/nuscenes_box_seeker_proposals.yaml:83 (no img/lidar augmentation, nms_3d = 0),
 plus the optional terms of SURVEY.md 8 row f3: dst_w, ego_w, occl_w, search_depth and the flags
-MULT, OCCL_MULT, MULTICAM_IOU (passed as keys of `params`).
+MULT, OCCL_MULT, MULTICAM_IOU (passed as keys of `params`), topk > 1 with nms_normal.
 
 Never imported by the product package.  Used by tests/ (as the checker of the CUDA
 pipeline), tools/gen_golden.py and the CPU-baseline legs of bench.py.
@@ -97,7 +97,8 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
     Returns dict(pred_boxes (K,7) f32, pred_labels (K) int32, pred_scores (K) f32,
     frustums=[per-frustum intermediates])."""
     p = dict(DEFAULTS); p.update(params)
-    assert p["topk"] == 1 and p["nms_3d"] == 0
+    assert p["nms_3d"] == 0
+    topk = int(p["topk"])
     # optional terms (SURVEY 8 row f3): dst_w, ego_w, occl_w, search_depth, MULT, OCCL_MULT, MULTICAM_IOU;
     # aln_w (randomised pca_lowrank) and rand_center (randn) are not deterministic in the reference
     assert not p.get("aln_w") and not p.get("rand_center")
@@ -153,7 +154,7 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
             counts[valid] = O.count_in_boxes(xyz, hb[valid])
             if use_fail:
                 fail[valid], nfar[valid] = O.occl_fail(xyz, hb[valid])
-        if not extras:
+        if not extras and topk == 1:
             h, s = O.select(counts, iou, valid, p["dns_w"], p["iou_w"])
         else:
             h, s, sc = O.select_ex(counts, iou, valid, dist=dist, near=near, fail=fail, boxes=hb, dns_w=p["dns_w"],
@@ -166,7 +167,16 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
             inter.append(rec)
         if h < 0:
             continue
-        boxes_out.append(hb[h]); labels_out.append(label); scores_out.append(score)
+        if topk == 1:
+            boxes_out.append(hb[h]); labels_out.append(label); scores_out.append(score)
+        else:
+            # nms_normal_gpu over the valid hypotheses in descending second-stage score (stable), the first
+            # topk survivors in that order (:1030-1046); the frustum's 2D score and label repeat (:1048-1052)
+            vi = np.flatnonzero(valid)
+            keep = O.nms_normal(hb[vi], rec["scores"][vi], p["nms_normal"])[:topk]
+            rec["topk"] = vi[keep]
+            for hh in vi[keep]:
+                boxes_out.append(hb[hh]); labels_out.append(label); scores_out.append(score)
     return dict(
         pred_boxes=np.asarray(boxes_out, np.float32).reshape(-1, 7),
         pred_labels=np.asarray(labels_out, np.int32),

@@ -26,8 +26,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from findnpropagate_b200 import _lib
-    # 19 x 4-byte fields, in the header's order
-    assert ctypes.sizeof(_lib.SeekerCfg) == 76
+    # 21 x 4-byte fields, in the header's order
+    assert ctypes.sizeof(_lib.SeekerCfg) == 84
     hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
     cbody = hdr[hdr.index("typedef struct fnp_seeker_cfg"):hdr.index("} fnp_seeker_cfg;")]
     cbody = re.sub(r"/\*.*?\*/", "", cbody, flags=re.S)
@@ -104,7 +104,7 @@ def test_synth_frame_is_deterministic_and_well_formed(golden_dir):
 def test_unsupported_options_raise():
     from findnpropagate_b200 import seeker
     with pytest.raises(NotImplementedError):
-        seeker.resolve_params(dict(topk=2, nms_3d=0, dst_w=0))
+        seeker.resolve_params(dict(topk=0, nms_3d=0, dst_w=0))
     for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(nms_3d=0.5), dict(search_depth=0.0)):
         with pytest.raises(NotImplementedError):
             seeker.resolve_params(dict(dict(nms_3d=0), **bad))

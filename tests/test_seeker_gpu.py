@@ -92,6 +92,13 @@ def _check_against_oracle(eng, frames, params):
                 assert dbg["hyp_index"][f, res["cand_best"][f]] == rec["best"]
                 assert res["cand_score2"][f].tobytes() == np.float32(rec["best_score"]).tobytes()
                 assert np.array_equal(res["cand_boxes"][f].view(np.uint32), rec["hyp_boxes"][rec["best"]].view(np.uint32))
+                if eng.T > 1:    # topk > 1: the first T survivors of the per-frustum nms_normal, in order
+                    tk, want = res["cand_topk"]["best"][f], rec["topk"]
+                    assert np.array_equal(dbg["hyp_index"][f, tk[:len(want)]], want) and (tk[len(want):] == -1).all()
+                    assert np.array_equal(res["cand_topk"]["boxes"][f, :len(want)].view(np.uint32),
+                                          rec["hyp_boxes"][want].view(np.uint32))
+                    assert np.array_equal(res["cand_topk"]["score2"][f, :len(want)].view(np.uint32),
+                                          rec["scores"][want].view(np.uint32))
             n_checked += 1
         out = res["frames"][b]
         assert np.array_equal(out["pred_boxes"].view(np.uint32), ora["pred_boxes"].view(np.uint32))
@@ -368,6 +375,8 @@ def test_sweep_and_direct_scoring_give_identical_counts(cfg_name, override, n_fr
     (dict(MULT=True, dst_w=0.6, OCCL_MULT=True), None, "direct"),
     (dict(dst_w=0.3, ego_w=0.2, occl_w=0.5, MULTICAM_IOU=True), dict(num_mags=24, num_sizes=2), "sweep"),
     (dict(MULT=True, dst_w=0.8, search_depth=7.5), dict(num_mags=17), "sweep"),
+    (dict(topk=3, nms_normal=0.5), None, "direct"),
+    (dict(topk=4, nms_normal=0.3, occl_w=0.2, dst_w=0.1), dict(num_mags=20), "sweep"),
 ])
 def test_optional_score_terms_vs_oracle(opts, override, mode):
     """dst_w / ego_w / occl_w / search_depth and MULT / OCCL_MULT / MULTICAM_IOU
@@ -387,14 +396,31 @@ def test_optional_score_terms_vs_oracle(opts, override, mode):
     p0 = synth.seeker_params(cfg)
     if override:
         p0.update(override)
+    r0 = SeekerEngine(p0, device="cuda:0").run(frames)
     if "search_depth" not in opts and "MULTICAM_IOU" not in opts:
-        r0 = SeekerEngine(p0, device="cuda:0").run(frames)
         assert np.array_equal(r0["cand_nvalid"], res["cand_nvalid"])
-        assert not np.array_equal(r0["cand_best"], res["cand_best"])
+        if set(opts) & {"dst_w", "ego_w", "occl_w", "MULT", "OCCL_MULT"}:
+            assert not np.array_equal(r0["cand_best"], res["cand_best"])
+        else:
+            assert np.array_equal(r0["cand_best"], res["cand_best"])
+    if eng.T > 1:
+        # more than one proposal per frustum comes out, and stage-4 NMS / recall run over all of them
+        assert sum(f["pred_boxes"].shape[0] for f in res["frames"]) > sum(f["pred_boxes"].shape[0] for f in r0["frames"])
+        r2 = eng.run(frames, nms_thresh=0.1, with_recall=True)
+        exp = None
+        for b, fr in enumerate(r2["frames"]):
+            assert np.array_equal(fr["pred_boxes"], res["frames"][b]["pred_boxes"])
+            kept = O.nms_rotated(fr["pred_boxes"], fr["pred_scores"], 0.1)
+            m = np.zeros(fr["pred_boxes"].shape[0], bool)
+            m[kept] = True
+            assert np.array_equal(fr["nms_keep"], m)
+            rd = SO.recall_record(fr["pred_boxes"], frames[b].gt_boxes)
+            exp = rd if exp is None else {k: exp[k] + rd[k] for k in rd}
+        assert r2["recall"] == exp
 
 
 def test_unsupported_options_raise():
-    for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(topk=2), dict(nms_3d=0.5), dict(search_depth=0.0)):
+    for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(topk=0), dict(nms_3d=0.5), dict(search_depth=0.0)):
         with pytest.raises(NotImplementedError):
             SeekerEngine(dict(synth.seeker_params(synth.CONFIGS["tiny"]), **bad), device="cuda:0")
 

@@ -40,6 +40,8 @@ OPTION_SETS = {
     "multicam": dict(MULTICAM_IOU=True),
     "sdepth": dict(search_depth=4.0),
     "all": dict(dst_w=0.2, ego_w=0.1, occl_w=0.3, MULTICAM_IOU=True, search_depth=6.0),
+    "topk": dict(topk=3, nms_normal=0.5),                      # :1030-1046: NMS over the hypotheses, first 3 survivors
+    "topkdst": dict(topk=2, nms_normal=0.7, dst_w=0.226, iou_w=0.95, dns_w=0.05),
 }
 
 

@@ -439,6 +439,21 @@ def test_optional_score_terms_vs_oracle(opts, override, mode):
         assert r2["recall"] == exp
 
 
+def test_optional_score_terms_full_size_frame():
+    """The same on a cfg2 frame (BASELINE.json configs[1]: ~322k points, 58 frustums of up to 1e4 points,
+    768 hypotheses each): occl_kernel runs several point tiles and hypothesis blocks per frustum, the
+    per-frustum NMS works on hundreds of valid hypotheses."""
+    cfg = synth.CONFIGS["cfg2"]
+    params = synth.seeker_params(cfg)
+    params.update(occl_w=0.3, dst_w=0.2, ego_w=0.1, topk=3, nms_normal=0.6, MULTICAM_IOU=True)
+    frames = [_frame_from_synth(synth.make_frame(1, cfg, device="cuda:0"))]
+    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    res, n = _check_against_oracle(eng, frames, params)
+    assert eng.last_score_mode == "sweep" and n > 30
+    assert res["cand_npts"].max() > 4096 and res["cand_nvalid"].max() > 256
+    assert (res["cand_topk"]["best"][:, 1] >= 0).sum() > 2      # the axis-aligned IoU ignores yaw: few survivors
+
+
 def test_unsupported_options_raise():
     for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(topk=0), dict(nms_3d=0.5), dict(search_depth=0.0)):
         with pytest.raises(NotImplementedError):

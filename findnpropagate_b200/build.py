@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfnp_sm100.so")
 SOURCES = ["fnp_ops.cu", "fnp_seeker.cu", "fnp_host.cpp"]
-HEADERS = ["fnp_common.cuh", os.path.join("..", "..", "include", "fnp.h")]
+HEADERS = ["fnp_common.cuh", "fnp_sweep.cuh", os.path.join("..", "..", "include", "fnp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -1307,7 +1307,10 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
     }
 }
 
-constexpr int kSweepThreads = 256;
+#ifndef FNP_SWEEP_THREADS
+#define FNP_SWEEP_THREADS 256
+#endif
+constexpr int kSweepThreads = FNP_SWEEP_THREADS;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kSweepChunk = 256;   // points per (column, chunk) warp item
 

@@ -1448,7 +1448,7 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                         } else {   // queue full: take the exact predicates here
                             const int cnt = sweep_uncertain_count(wa);
                             for (int k = 0; k < cnt; k++)
-                                sweep_exact_step(xa, ya, za, sweep_uncertain_step(wa, k), D, diff, slot_col, J, prep_f, red);
+                                sweep_exact_step_col(xa, ya, za, sweep_uncertain_step(wa, k), D, diff, slot_col, J, prep_f, c.cosa, c.sina, c.tx, c.ty, red);
                         }
                     }
                     if (wb) {
@@ -1457,7 +1457,7 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                         } else {
                             const int cnt = sweep_uncertain_count(wb);
                             for (int k = 0; k < cnt; k++)
-                                sweep_exact_step(xb, yb, zb, sweep_uncertain_step(wb, k), D, diff, slot_col, J, prep_f, red);
+                                sweep_exact_step_col(xb, yb, zb, sweep_uncertain_step(wb, k), D, diff, slot_col, J, prep_f, c.cosa, c.sina, c.tx, c.ty, red);
                         }
                     }
                 }
@@ -1499,9 +1499,10 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                 const int first = __shfl_sync(0xffffffffu, incl - cnt, own);
                 if (t < total) {
                     const int i = (int)(e0 & 0xffffu), j = (int)(e0 >> 16);
+                    const float4 rot = *reinterpret_cast<const float4 *>(&s_col[j].cosa);     // cosa, sina, tx, ty
                     const int m0 = s_col[j].m0, D = s_col[j].m1 - m0;
-                    sweep_exact_step(s_x[i], s_y[i], s_z[i], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
-                                     s_slot + m0 * J + j, J, prep_f, red);
+                    sweep_exact_step_col(s_x[i], s_y[i], s_z[i], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
+                                         s_slot + m0 * J + j, J, prep_f, rot.x, rot.y, rot.z, rot.w, red);
                 }
             }
         }

@@ -96,14 +96,15 @@ FNP_HD BoxPrep load_prep(const float *hyp_prep, size_t idx)
 // A column in which t - dl < 0 has no definite range and degrades to exact tests of the possible
 // range, so the result is correct for any geometry and fast for the seeker's.
 struct SweepCol {
-    float cosa, sina;
+    float cosa, sina, tx, ty;   // rotation and x/y thresholds shared by the column's hypotheses (one 16-byte load:
+                                // with the centre + hz of a hypothesis they are its whole BoxPrep)
     int m0, m1;          // first / last valid depth step of the column (m0 > m1: none)
+    int pseudo_mask;     // bit k: axis k does not travel; it carries a pseudo slope (statistics only)
+    float eps;           // rounding bound used for the x/y axes (statistics only)
     float c0[3];         // Cu, Cv, Cz at m0
     float inv_s[3];      // 1 / slope per depth step
     float w_in[3];       // (t - dl) |inv_s|  (depth steps; -inf when t < dl)
     float w_p[3];        // (t + dl) |inv_s|
-    int pseudo_mask;     // bit k: axis k does not travel; it carries a pseudo slope (statistics only)
-    float eps, pad0, pad1;
 };
 static_assert(sizeof(SweepCol) == FNP_SWEEP_COL_FLOATS * 4, "SweepCol layout is part of the ABI workspace size");
 
@@ -148,8 +149,8 @@ FNP_HD SweepCol sweep_col_build(int m0, int m1, const float c0[3], const float s
     SweepCol c;
     c.m0 = m0; c.m1 = m1;
     c.pseudo_mask = 0;
-    c.eps = eps_xy; c.pad0 = eps_z; c.pad1 = 0.f;
-    c.cosa = p.cosa; c.sina = p.sina;
+    c.eps = eps_xy;
+    c.cosa = p.cosa; c.sina = p.sina; c.tx = p.tx; c.ty = p.ty;
     const float t[3] = {p.tx, p.ty, p.hz};
     const float span = (float)(m1 - m0);
     for (int k = 0; k < 3; k++) {
@@ -228,6 +229,29 @@ FNP_HD void sweep_exact_step(const float x, const float y, const float z, const 
     g_exact_tests++;   // host model only: how many exact predicates the sweep takes
 #endif
     if (in_box(x, y, z, load_prep(prep_f, (size_t)r))) {
+        add(diff + dm, 1);
+        if (dm < D) add(diff + dm + 1, -1);
+    }
+}
+
+// The same with the column's shared parameters supplied by the caller (cosa, sina, tx, ty are equal, bit for
+// bit, for all hypotheses of a column: prep_box computes them from the same row of the prior table), so that
+// only the 16 bytes {cx, cy, cz, hz} of the hypothesis are loaded.
+template <class Add>
+FNP_HD void sweep_exact_step_col(const float x, const float y, const float z, const int dm, const int D, int *diff,
+                                 const short *slot_col, const int J, const float *prep_f, const float cosa,
+                                 const float sina, const float tx, const float ty, Add add)
+{
+    const int r = slot_col[dm * J];
+    if (r < 0) return;
+#ifdef FNP_SWEEP_MODEL
+    g_exact_tests++;
+#endif
+    const float4 a = ld4(reinterpret_cast<const float4 *>(prep_f + (size_t)r * 8));
+    BoxPrep p;
+    p.cx = a.x; p.cy = a.y; p.cz = a.z; p.hz = a.w;
+    p.cosa = cosa; p.sina = sina; p.tx = tx; p.ty = ty;
+    if (in_box(x, y, z, p)) {
         add(diff + dm, 1);
         if (dm < D) add(diff + dm + 1, -1);
     }

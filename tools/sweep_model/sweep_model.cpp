@@ -104,7 +104,7 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
                 const unsigned w = sweep_pack_uncertain(r);
                 const int cnt = sweep_uncertain_count(w);
                 for (int k = 0; k < cnt; k++)
-                    sweep_exact_step(p[0], p[1], p[2], sweep_uncertain_step(w, k), D, d, sl, J, prep, add);
+                    sweep_exact_step_col(p[0], p[1], p[2], sweep_uncertain_step(w, k), D, d, sl, J, prep, c.cosa, c.sina, c.tx, c.ty, add);
                 stats[5] += (r.a <= r.e);
                 stats[6] += (w != 0);
                 stats[2]++;

@@ -1638,15 +1638,18 @@ __device__ __forceinline__ void block_argmax128(float &best, int &besti, float *
 
 constexpr int kSelectMaxTopkH = 32768;   // hypotheses per frustum the suppression bitmask of topk > 1 covers
 
+// EXTRAS = false is the shipped configuration (density + IoU, top-1): the optional terms, the score table and
+// the suppression bitmask of topk > 1 are compiled out.
+template <bool EXTRAS>
 __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ float s_f[4];
     __shared__ int s_i[4];
-    __shared__ unsigned s_dead[kSelectMaxTopkH / 32];
+    __shared__ unsigned s_dead[EXTRAS ? kSelectMaxTopkH / 32 : 1];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int J = cfg.num_yaw_size, H = J * cfg.num_mags;
-    const int T = max(cfg.topk, 1);
+    const int T = EXTRAS ? max(cfg.topk, 1) : 1;
     const int nv = b.hyp_nvalid[f];
     if (nv <= 0 || (b.status[0] & 2)) {
         for (int k = tid; k < T; k += blockDim.x) {
@@ -1656,10 +1659,11 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
     }
     const int *cbase = b.counts + (size_t)f * H;
     const float *pbase = b.hyp_prep + (size_t)f * H * 8;
-    const bool mult = (cfg.flags & FNP_SEEKER_MULT) != 0, occl_mult = (cfg.flags & FNP_SEEKER_OCCL_MULT) != 0;
-    const bool use_dist = (cfg.dst_w != 0.f) || mult;
-    const bool use_fail = (cfg.occl_w > 0.f) || occl_mult;
-    const bool use_ego = cfg.ego_w > 0.f;
+    const bool mult = EXTRAS && (cfg.flags & FNP_SEEKER_MULT) != 0, occl_mult = EXTRAS && (cfg.flags & FNP_SEEKER_OCCL_MULT) != 0;
+    const bool use_dist = EXTRAS && ((cfg.dst_w != 0.f) || mult);
+    const bool use_fail = EXTRAS && ((cfg.occl_w > 0.f) || occl_mult);
+    const bool use_ego = EXTRAS && cfg.ego_w > 0.f;
+    const bool use_occl_w = EXTRAS && cfg.occl_w > 0.f;
     const long long npts = b.cand_npts[f];
     const int *nfar = use_fail ? b.hyp_nfar + (size_t)f * H : nullptr;
     // the reference's occlusion score: n_far * n_out (a (P,1) & (P,) broadcast, :453), stored as float
@@ -1692,9 +1696,9 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
             sc = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(dens, cfg.dns_w), iou), cfg.iou_w), dr), cfg.dst_w);
         else {
             sc = __fadd_rn(__fmul_rn(dens, cfg.dns_w), __fmul_rn(iou, cfg.iou_w));
-            if (cfg.dst_w != 0.f) sc = __fadd_rn(sc, __fmul_rn(dr, cfg.dst_w));
+            if (use_dist) sc = __fadd_rn(sc, __fmul_rn(dr, cfg.dst_w));
         }
-        if (cfg.occl_w > 0.f) sc = __fadd_rn(sc, __fmul_rn(cfg.occl_w, __fsub_rn(1.0f, __fdiv_rn(FNP_FAIL(r), fden))));
+        if (use_occl_w) sc = __fadd_rn(sc, __fmul_rn(cfg.occl_w, __fsub_rn(1.0f, __fdiv_rn(FNP_FAIL(r), fden))));
         if (use_ego)
             sc = __fadd_rn(sc, __fmul_rn(cfg.ego_w, __fdiv_rn(norm3(pbase[r * 8], pbase[r * 8 + 1], pbase[r * 8 + 2]), emx)));
         if (occl_mult) sc = __fmul_rn(__fmul_rn(dens, iou), FNP_FAIL(r));
@@ -1928,7 +1932,11 @@ extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_bat
     if (((cfg->occl_w > 0.f) || (cfg->flags & FNP_SEEKER_OCCL_MULT)) && !b->hyp_nfar) return FNP_EINVAL;
     if (cfg->topk > 1 && (!b->hyp_score || cfg->num_yaw_size * cfg->num_mags > kSelectMaxTopkH)) return FNP_EINVAL;
     if (b->n_cands == 0) return FNP_OK;
-    select_kernel<<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    const bool extras = cfg->dst_w != 0.f || cfg->ego_w > 0.f || cfg->occl_w > 0.f || cfg->flags != 0 || cfg->topk > 1;
+    if (extras)
+        select_kernel<true><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    else
+        select_kernel<false><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }

@@ -258,9 +258,13 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    frames_d, params = make_frames(a.config, rank * a.distinct, a.distinct, str(dev))
+    # weak scaling: every rank gets the same amount of work per step -- the same pool of distinct synthetic
+    # frames, taken in a rank-dependent rotation (a pool of only `distinct` frames per rank, each repeated
+    # B / distinct times, would otherwise turn the frame-to-frame spread of the work into a rank imbalance
+    # that B distinct frames per rank would average out)
+    frames_d, params = make_frames(a.config, 0, a.distinct, str(dev))
     B = a.frames
-    batch = [frames_d[i % a.distinct] for i in range(B)]
+    batch = [frames_d[(i + rank) % a.distinct] for i in range(B)]
     eng = SeekerEngine(params, device=dev, score_mode=a.score_mode, split_points=a.split_points)
     H = eng.H
     # two input sets (A/B) so that consecutive steps never touch the same HBM lines; each is
@@ -314,6 +318,7 @@ def run_ours(a):
         return res
 
     exchange_ms = [0.0]     # host + device time of that exchange in the last timed run (it is inside the timing)
+    ms_by_rank = {}         # per-rank ms/step of the last timed runs (the reported time is their maximum)
 
     xbuf = {}               # exchange slabs (pinned host + device), sized before the timing starts
 
@@ -415,8 +420,10 @@ def run_ours(a):
         ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_host) if not resident else 0.0)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(every, t)
+            ms_by_rank[("resident" if resident else "e2e")] = [round(float(x) / steps, 4) for x in every.tolist()]
+            ms = float(every.max().item())
             dist.barrier()
         host_ms = {k: 1e3 * (eng.host_s[k] - h0[k]) / steps for k in h0}
         return ms, last, eng.launches - l0, host_ms
@@ -536,6 +543,7 @@ def run_ours(a):
                     "host_pack": ("x,y,z gathered on the host by %d threads (fnp_host_pack_xyz), 12 B/point uploaded"
                                   % feeder.n_threads) if feeder.pack else "off: all %d columns uploaded" % batch[0].points.shape[1]},
             "gpu_launches": int(launches),
+            "ms_per_step_by_rank": ms_by_rank if world > 1 else None,
             "host_ms_per_step": {"resident": host_res, "e2e": host_e2e,
                                  "note": "main-thread time in SeekerEngine.plan / execute / finish (after its event wait) per step"},
             "clocks": clocks,

@@ -5,5 +5,5 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/bench_n2.json").read().strip().splitlines()[-1])
-print("n2 value %.0f ms/step %.2f e2e %.0f (%.2f ms)"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), d["host_ms_per_step"], d["config"]["sharding"])
+print("n2 value %.0f ms/step %.2f e2e %.0f (%.2f ms)"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), d.get("ms_per_step_by_rank"), d["config"]["sharding"])
 PY

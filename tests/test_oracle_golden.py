@@ -121,3 +121,35 @@ def test_recall_record_counts():
     pred = np.array([[0.1, 0, 0, 4, 2, 1.5, 0.2]], np.float32)
     rd = SO.recall_record(pred, gt)
     assert rd["gt"] == 2 and rd["rcnn_0.5"] == 1 and rd["num_3known"] == 1 and rd["rcnn_7unknown_0.3"] == 0
+
+
+def test_occlusion_score_is_the_reference_broadcast_product():
+    """calc_occl_scores (frustum_proposals_v1.py:408-477) forms ((cur_mags > m1) & (~real_mask)).sum() with a
+    (P,1) tensor against a (P,) mask; the oracle restates the resulting (P,P) count as n_far * n_out.  Checked
+    against that very torch expression (box_utils.boxes_to_corners_3d restated with torch ops)."""
+    import torch
+    rng = np.random.default_rng(11)
+    pts = (rng.normal(0, 1, (300, 3)) * [3, 3, 0.6] + [12, 4, -0.5]).astype(np.float32)
+    boxes = np.zeros((9, 7), np.float32)
+    boxes[:, :3] = rng.normal(0, 1.5, (9, 3)) * [1, 1, 0.2] + [12, 4, -0.5]
+    boxes[:, 3:6] = synth.PRIORS[rng.integers(0, 10, 9)]
+    boxes[:, 6] = rng.uniform(0, np.pi, 9)
+    fail, nfar = O.occl_fail(pts, boxes)
+    counts = O.count_in_boxes(pts, boxes)
+    tp = torch.from_numpy(pts)
+    mags = tp.norm(dim=-1, keepdim=True)                       # (P,1), as pts_mags at :1008
+    template = torch.tensor([[1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1],
+                             [1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, 1]], dtype=torch.float32) / 2
+    for i in range(9):
+        b = torch.from_numpy(boxes[i])
+        c, s = torch.cos(b[6]), torch.sin(b[6])
+        rot = torch.stack([c, s, torch.zeros(()), -s, c, torch.zeros(()), torch.zeros(()), torch.zeros(()), torch.ones(())]).view(3, 3)
+        corners = (b[3:6] * template) @ rot + b[:3]
+        m1 = corners.norm(dim=-1).min()
+        real_mask = torch.from_numpy(O.points_in_boxes_gpu(pts[None], boxes[i][None, None])[0] >= 0)   # (P,)
+        ref = int(((mags > m1) & (~real_mask)).sum())          # broadcasts to (P,P)
+        assert ref == int((mags[:, 0] > m1).sum()) * int((~real_mask).sum())
+        assert abs(int(nfar[i]) - int((mags[:, 0] > m1).sum())) <= 1     # torch's CPU cos/sin/norm may differ in the last ulp
+        if int(nfar[i]) == int((mags[:, 0] > m1).sum()):
+            assert float(fail[i]) == float(np.float32(ref))
+        assert int(nfar[i]) * (pts.shape[0] - int(counts[i])) == int(round(float(fail[i]))) or fail[i] > 2 ** 24

@@ -2,7 +2,7 @@
 
 Reference: pcdet/models/dense_heads/frustum_proposals_v1.py:142-318 (constructor),
 :523-1067 (get_proposals), :1547-1573 (forward / get_bboxes) and
-pcdet/models/preprocessed_detector.py:7-106 (PreprocessedGLIP).
+pcdet/models/preprocessed_detector.py:7-106 (PreprocessedGLIP), :111-290 (PreprocessedDetector).
 
 Same class names, constructor arguments, ``model_cfg.PARAMS`` keys, method names, return
 types and devices; the work is done by :class:`findnpropagate_b200.seeker.SeekerEngine`.
@@ -98,6 +98,93 @@ class PreprocessedGLIP:
         raise TypeError('need kitti / nusc batch dict!')
 
 
+class PreprocessedDetector:
+    """The head's other feeder: COCO-format result files, one per camera view (``PREDS_PATHS`` / ``PREDS_PATH`` +
+    camera name, frustum_proposals_v1.py:262-268), served per batch with the same 5-tensor contract --
+    pcdet/models/preprocessed_detector.py:111-290.
+
+    The files are indexed once: per image name the boxes / class ids / scores of the wanted categories as
+    arrays, in annotation order (file after file), so that a batch is a handful of concatenations.  Boxes are
+    handed out as they are stored (COCO x, y, w, h: such configs set ``BOX_FORMAT`` accordingly)."""
+
+    def __init__(self, cam_jsons=(), class_names=None):
+        assert len(cam_jsons) > 0
+        self.infer_cam = len(cam_jsons) == 1
+        self.categories = None
+        views = []
+        for path in cam_jsons:
+            with open(path, 'r') as f:
+                d = json.load(f)
+            assert self.categories is None or self.categories == d['categories'], 'categories differ!'
+            self.categories = d['categories']
+            views.append(d)
+        self.class_names = [c['name'] for c in self.categories] if not class_names else list(class_names)
+        cat_ids = {c['id'] for c in self.categories}
+        # category id -> class id (1-based position of the category's name in class_names); other categories
+        # are dropped (:149-150)
+        self.catid_to_classid = {c['id']: i + 1 for c in self.categories
+                                 for i, n in enumerate(self.class_names) if n == c['name']}
+        self.wanted_catids = list(self.catid_to_classid)
+        if not self.catid_to_classid:
+            raise ValueError("none of the class names %r is a category of the result files" % (self.class_names,))
+        rows = {}                       # image name -> list of (bbox, class id, score)
+        for d in views:
+            name_of = {}
+            for img in d['images']:
+                name = img['name'] if 'name' in img else os.path.basename(img['file_name'])     # :132-135
+                name_of[img['id']] = name
+                rows.setdefault(name, [])
+            for ann in d['annotations']:
+                cat = ann['category_id']
+                if cat not in cat_ids:                      # files with 1-based ids over 0-based categories (:176-177)
+                    cat -= 1
+                assert cat in cat_ids, '%r not valid' % (ann,)
+                if cat in self.catid_to_classid:
+                    rows[name_of[ann['image_id']]].append(
+                        (ann['bbox'], self.catid_to_classid[cat], 1.0 if 'score' not in ann else ann['score']))
+        self.img_names = set(rows)
+        first = next(iter(rows))
+        self.incl_ext = '.jpg' in first or '.png' in first
+        self.by_name = {n: (np.asarray([r[0] for r in v], np.float32).reshape(-1, 4),
+                            np.asarray([r[1] for r in v], np.int64), np.asarray([r[2] for r in v], np.float32))
+                        for n, v in rows.items()}
+
+    def _collect(self, names_per_frame, cams_per_frame, strict=False):
+        boxes, labels, scores, idx, cam = [], [], [], [], []
+        for b, (names, cams) in enumerate(zip(names_per_frame, cams_per_frame)):
+            for name, c in zip(names, cams):
+                ent = self.by_name.get(name)
+                if ent is None:
+                    if strict:
+                        raise ValueError('frame_id=%s did not exist in preprocessing' % name)
+                    continue
+                boxes.append(ent[0]); labels.append(ent[1]); scores.append(ent[2])
+                idx.append(np.full(ent[1].shape[0], b, np.int64)); cam.append(np.full(ent[1].shape[0], c, np.int64))
+        if not boxes or sum(x.shape[0] for x in labels) == 0:
+            # the reference builds its tensors from empty lists here: five float tensors of shape (0,)
+            return tuple(torch.tensor([]) for _ in range(5))
+        return (torch.from_numpy(np.concatenate(boxes)), torch.from_numpy(np.concatenate(labels)),
+                torch.from_numpy(np.concatenate(scores)), torch.from_numpy(np.concatenate(idx)),
+                torch.from_numpy(np.concatenate(cam)))
+
+    def infer_nusc(self, batch_dict):
+        names = [[(os.path.basename(str(p)) if self.incl_ext else os.path.splitext(os.path.basename(str(p)))[0])
+                  for p in batch_dict['image_paths'][b]] for b in range(batch_dict['batch_size'])]
+        return self._collect(names, [range(len(n)) for n in names])
+
+    def infer_kitti(self, batch_dict):
+        names = [[(batch_dict['frame_id'][b] + '.png') if self.incl_ext else batch_dict['frame_id'][b]]
+                 for b in range(batch_dict['batch_size'])]
+        return self._collect(names, [[0]] * len(names), strict=True)
+
+    def __call__(self, batch_dict):
+        if 'image_paths' in batch_dict:
+            return self.infer_nusc(batch_dict)
+        if 'frame_id' in batch_dict:
+            return self.infer_kitti(batch_dict)
+        raise TypeError('need kitti / nusc batch dict!')
+
+
 class SyntheticGLIP:
     """Feeder with the PreprocessedGLIP return contract over synthetic frames
     (findnpropagate_b200.synth.Frame), keyed by the first image path of each frame."""
@@ -160,9 +247,13 @@ class FrustumProposerOG(nn.Module):
             self.image_detector = image_detector
         else:
             preds_path = _cfg_get(model_cfg, 'PREDS_PATH', 'PreprocessedGLIP')
-            if 'PreprocessedGLIP' not in preds_path:
-                raise NotImplementedError("only the PreprocessedGLIP feeder is on the shipped path")
-            self.image_detector = PreprocessedGLIP(class_names=class_names)
+            if 'PreprocessedGLIP' in preds_path:
+                self.image_detector = PreprocessedGLIP(class_names=class_names)
+            else:      # one COCO result file per camera view (:262-268)
+                camera_names = ['CAM_BACK', 'CAM_BACK_LEFT', 'CAM_BACK_RIGHT', 'CAM_FRONT', 'CAM_FRONT_LEFT',
+                                'CAM_FRONT_RIGHT']
+                preds_paths = _cfg_get(model_cfg, 'PREDS_PATHS', [preds_path + "%s.json" % c for c in camera_names])
+                self.image_detector = PreprocessedDetector(preds_paths, class_names=class_names)
         self.engine = SeekerEngine(p, device=device, box_format=self.box_fmt)
         self.anchors = torch.tensor(__import__('findnpropagate_b200.seeker', fromlist=['ANCHORS']).ANCHORS,
                                     dtype=torch.float32, device=self.engine.device)

@@ -106,3 +106,34 @@ def test_frame_input_and_prefetch(gold, tree):
     assert [i for b in got for i in b[1]] == [Path(i["lidar_path"]).stem for i in gold["infos"]]
     ref = feed.frame_input(2, detector)[0]
     assert np.array_equal(got[1][0][0].points, ref.points)
+
+
+def test_preprocessed_detector_matches_reference_feeder(golden_dir, tmp_path):
+    """proposer.PreprocessedDetector (per-camera COCO result files, the head's other feeder) against what the
+    reference's own class returned for the same files (tools/gen_golden_detector.py): values, order, dtypes, a
+    single-frame batch, unknown images, and the empty batch's (0,)-shaped tensors."""
+    import json
+    import torch
+    from findnpropagate_b200.proposer import PreprocessedDetector
+    cams = ['CAM_BACK', 'CAM_BACK_LEFT', 'CAM_BACK_RIGHT', 'CAM_FRONT', 'CAM_FRONT_LEFT', 'CAM_FRONT_RIGHT']
+    cases = json.load(open(os.path.join(golden_dir, "preprocessed_detector.json")))
+    assert len(cases) == 3
+    for case in cases:
+        files = []
+        for cam, v in zip(cams, case["views"]):
+            files.append(str(tmp_path / ("%s_%s.json" % (case["name"], cam))))
+            json.dump(v, open(files[-1], "w"))
+        det = PreprocessedDetector(files, class_names=case["class_names"])
+        out = det({"image_paths": case["image_paths"], "batch_size": len(case["image_paths"])})
+        assert len(out) == 5 and len(out[1]) > 10
+        for got, want, dt in zip(out, case["out"], case["out_dtypes"]):
+            assert str(got.dtype) == dt
+            assert torch.equal(got, torch.tensor(want, dtype=got.dtype))
+        one = det({"image_paths": [case["image_paths"][1]], "batch_size": 1})
+        for got, want in zip(one, case["out_frame1"]):
+            assert got.tolist() == want
+        missing = det({"image_paths": [["x/unknown_%d.jpg" % c for c in range(6)]], "batch_size": 1})
+        assert [list(t.shape) for t in missing] == case["missing_shapes"]
+        assert [str(t.dtype) for t in missing] == case["missing_dtypes"]
+    with pytest.raises(TypeError):
+        det({"points": None})

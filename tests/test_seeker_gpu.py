@@ -332,6 +332,37 @@ def test_reference_compatible_head_and_extraction(tmp_path):
         assert np.array_equal(out3[b]["pred_boxes"].cpu().numpy().view(np.uint32), ora["pred_boxes"].view(np.uint32))
         assert np.array_equal(out3[b]["pred_labels"].numpy(), ora["pred_labels"])
     assert sum(o["pred_boxes"].shape[0] for o in out3) > sum(o["pred_boxes"].shape[0] for o in out)
+    # the head's other feeder: one COCO result file per camera view (PREDS_PATHS, x, y, w, h boxes ->
+    # BOX_FORMAT), preprocessed_detector.py:111-290
+    import json
+    names = ['car', 'truck', 'construction_vehicle', 'bus', 'trailer', 'barrier', 'motorcycle', 'bicycle',
+             'pedestrian', 'traffic_cone']
+    files = []
+    for c in range(6):
+        images, anns = [], []
+        for b, f in enumerate(sf):
+            images.append({"id": b, "file_name": f.image_paths[c]})
+            for k in np.flatnonzero(f.det_cam_idx == c):
+                x1, y1, x2, y2 = (float(v) for v in f.det_boxes[k])
+                anns.append({"id": len(anns), "image_id": b, "category_id": int(f.det_labels[k]) - 1,
+                             "bbox": [x1, y1, x2 - x1, y2 - y1], "score": float(f.det_scores[k])})
+        files.append(str(tmp_path / ("OWL_%d.json" % c)))
+        json.dump({"images": images, "annotations": anns,
+                   "categories": [{"id": i, "name": n} for i, n in enumerate(names)]}, open(files[-1], "w"))
+    head4 = proposer.FrustumProposerOG(model_cfg=dict(PARAMS=params, PREDS_PATH=str(tmp_path / "OWL_"), PREDS_PATHS=files,
+                                                      BOX_FORMAT='xywh'), class_names=names)
+    assert isinstance(head4.image_detector, proposer.PreprocessedDetector)
+    out4 = head4.get_bboxes(bd)
+    db, dl, ds, di, dc = head4.image_detector(bd)
+    e4 = SeekerEngine(params, device="cuda:0", box_format="xywh")
+    for b, f in enumerate(sf):
+        m = (di == b).numpy()
+        ora = SO.seek_frame(f.points, f.lidar2image, f.camera2lidar, f.camera_intrinsics,
+                            (db.numpy()[m], dl.numpy()[m], ds.numpy()[m], dc.numpy()[m]), params,
+                            tables=(e4.base_boxes_host.numpy(), e4.base_corners_host.numpy()), box_format="xywh")
+        assert ora["pred_boxes"].shape[0] > 0
+        assert np.array_equal(out4[b]["pred_boxes"].cpu().numpy().view(np.uint32), ora["pred_boxes"].view(np.uint32))
+        assert np.array_equal(out4[b]["pred_labels"].numpy(), ora["pred_labels"])
     # extraction driver: one .pth per frame, reference format, recall counters
     frames = [_frame_from_synth(f) for f in sf]
     merged, total, ar = extract.extract(frames, lambda fs: eng.run(fs, with_recall=True), folder=str(tmp_path),

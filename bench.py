@@ -35,16 +35,18 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU (BASELINE.json configs[2]: batches of 256 frames)")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated per rank")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames per rank (weak scaling) / in the pool (--total-frames)")
+    ap.add_argument("--total-frames", type=int, default=0,
+                    help="strong scaling, BASELINE.json configs[3]: this many frames in all, sharded rank::world "
+                         "(6019 = the nuScenes val sweep); steps = ceil(shard / frames), --steps is ignored")
+    ap.add_argument("--layout", default="xyz", choices=["xyz", "rows"],
+                    help="point table the loader hands over: x,y,z as its own array (12 B/point, no gather) or the "
+                         "reference's rows (5 columns; the e2e arm gathers x,y,z on the host)")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-mode", default="auto", choices=["auto", "direct", "sweep"],
                     help="stage-2b kernel (include/fnp.h FNP_SCORE_*); both give the same counts")
     ap.add_argument("--split-points", type=int, default=None)
-    ap.add_argument("--e2e-pack", default="auto", choices=["auto", "on", "off"],
-                    help="e2e arm: gather x,y,z on the host (threaded) and upload 12 B/point instead of all columns; "
-                         "auto = on for one rank per host (the gather needs the host's cores and memory bandwidth: "
-                         "with several ranks sharing them the plain upload, 20 B/point of DMA reads, is cheaper)")
     ap.add_argument("--pack-threads", type=int, default=None)
     ap.add_argument("--slots", type=int, default=3, help="batches in flight on the device (streams + arenas), resident arm")
     return ap.parse_args()
@@ -120,9 +122,28 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- data
-def make_frames(cfg_name, first_index, n, device):
-    from findnpropagate_b200 import synth
-    from findnpropagate_b200.seeker import FrameInput
+def _synth_standalone():
+    """The synthetic-frame generator loaded from its file, WITHOUT importing the findnpropagate_b200 package:
+    the reference arm must not map the product's library (synth.py itself needs numpy and torch only)."""
+    import importlib.util
+    name = "fnp_bench_synth"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "findnpropagate_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_frames(cfg_name, first_index, n, device, standalone=False):
+    if standalone:
+        import types
+        synth = _synth_standalone()
+        FrameInput = lambda **kw: types.SimpleNamespace(**kw)      # noqa: E731
+    else:
+        from findnpropagate_b200 import synth
+        from findnpropagate_b200.seeker import FrameInput
     cfg = synth.CONFIGS[cfg_name]
     out = []
     for i in range(n):
@@ -214,7 +235,8 @@ def run_reference_arm(a):
     cores = len(os.sched_getaffinity(0))
     kind = cpu_kind()
     procs = max(1, min(cores, 16))
-    frames, params = make_frames(a.config, 0, min(a.distinct, procs), "cpu")
+    frames, params = make_frames(a.config, 0, min(a.distinct, procs), "cpu", standalone=True)
+    assert not any("findnpropagate_b200" in m for m in sys.modules), "the reference arm must not import the product"
     per_step = procs                              # bounded sample: one frame per process and step
     ctx = mp.get_context("spawn")
     with ctx.Pool(processes=procs, initializer=_ref_init, initargs=(frames, params, kind)) as pool:
@@ -242,6 +264,33 @@ def run_reference_arm(a):
 
 
 # --------------------------------------------------------------------------- ours
+def bind_numa(local):
+    """Pins this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory
+    is allocated (first touch), so that the H2D DMA of every rank reads node-local DRAM.  Best effort."""
+    info = {"node": None, "cpus": None}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return info
+        cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"node": node, "cpus": len(allowed)}
+    except Exception as e:          # containers without sysfs / a restricted cpuset: leave the affinity alone
+        info["error"] = type(e).__name__
+    return info
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -255,55 +304,78 @@ def run_ours(a):
         raise RuntimeError("bench.py (ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_numa(local) if world > 1 else {"node": None, "cpus": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: every rank gets the same amount of work per step -- the same pool of distinct synthetic
-    # frames, taken in a rank-dependent rotation (a pool of only `distinct` frames per rank, each repeated
-    # B / distinct times, would otherwise turn the frame-to-frame spread of the work into a rank imbalance
-    # that B distinct frames per rank would average out)
-    frames_d, params = make_frames(a.config, 0, a.distinct, str(dev))
-    B = a.frames
-    batch = [frames_d[(i + rank) % a.distinct] for i in range(B)]
-    eng = SeekerEngine(params, device=dev, score_mode=a.score_mode, split_points=a.split_points)
+    B, D = a.frames, a.distinct
+    strong = a.total_frames > 0
+    if strong:
+        # BASELINE.json configs[3]: a FIXED set of frames sharded rank::world (extract.shard_indices, the reference's
+        # rule, pcdet/datasets/__init__.py:43-48), fill/drain, the ragged last batch and the gather inside the timing.
+        # Global frame i carries synthetic frame i % D; every rank generates the pool, so that rank 0 can re-run any
+        # other rank's frames for the gather check.  (W B) % D == 0 makes every batch of a rank the same table.
+        assert (world * B) % D == 0, "--total-frames needs (world * frames) % distinct == 0"
+        pool, params = make_frames(a.config, 0, D, str(dev))
+        n_mine = len(range(rank, a.total_frames, world))
+        n_steps = max(1, -(-n_mine // B))
+        tail = n_mine - (n_steps - 1) * B
+
+        def content(r, j):
+            return (r + world * j) % D
+    else:
+        # weak scaling: the same NUMBER of frames per rank and step, but every rank works on its own D distinct
+        # synthetic frames (indices rank D .. rank D + D - 1)
+        pool, params = make_frames(a.config, rank * D, D, str(dev))
+        n_steps, tail = a.steps, B
+
+        def content(r, j):
+            return j % D
+    batch = [pool[content(rank, j)] for j in range(B)]
+    eng = SeekerEngine(params, device=dev, score_mode=a.score_mode, split_points=a.split_points, host_cache=False)
     H = eng.H
-    # two input sets (A/B) so that consecutive steps never touch the same HBM lines; each is
-    # B x ~7.7 MB of points, well above the 126 MB L2 for the default B
+    # ---- the batch's point table on the host (pinned) and on the device, two copies of each (A/B) so that
+    # consecutive steps never touch the same HBM lines; each is B x ~4 MB, well above the 126 MB L2.
+    # layout "xyz": the loader keeps x, y, z as their own (rows,3) array (nuscenes_feed.py emits it while it
+    # concatenates the sweeps), so 12 B/point cross PCIe with no gather pass; "rows": the reference's full rows
+    # (5 columns) on the host, gathered to 12 B/point by HostPointFeeder's threads (round-1 path).
+    width = 3 if a.layout == "xyz" else batch[0].points.shape[1]
+    row_end = np.zeros(B + 1, np.int64)
+    np.cumsum([f.points.shape[0] for f in batch], out=row_end[1:])
+    rows = int(row_end[-1])
     pinned = []
     for s in range(2):
-        rows = sum(f.points.shape[0] for f in batch)
-        t = torch.empty((rows, batch[0].points.shape[1]), dtype=torch.float32, pin_memory=True)
-        r = 0
-        for f in batch:
-            t[r:r + f.points.shape[0]] = torch.from_numpy(f.points)
-            r += f.points.shape[0]
+        t = torch.empty((rows, width), dtype=torch.float32, pin_memory=True)
+        for j, f in enumerate(batch):
+            t[row_end[j]:row_end[j + 1]] = torch.from_numpy(np.ascontiguousarray(f.points[:, :width]))
         pinned.append(t)
     dev_pts = [p.to(dev) for p in pinned]
     gt = eng.upload_gt(batch)
     in_bytes = pinned[0].numel() * 4
 
-    # two compute streams, one per slot: consecutive batches overlap on the device, so the small
-    # latency-bound kernels at the end of batch k run under the big kernels of batch k+1
     comp = [torch.cuda.Stream(device=dev) for _ in range(max(2, a.slots))]
-    feeder = HostPointFeeder(eng, pack=(a.e2e_pack == "on" or (a.e2e_pack == "auto" and world == 1)),
-                             n_threads=a.pack_threads)
+    feeder = HostPointFeeder(eng, pack=(a.layout == "rows"), n_threads=a.pack_threads)
     copy_stream = feeder.copy_stream
-    f_stride, f_off = feeder.layout
 
-    def step(k, resident, prev, more=True):
-        """One pass of the hot path over one batch; returns the new handle."""
+    def nf_of(k):
+        """frames of timed step k: full batches, then the ragged tail of the shard (strong scaling only)"""
+        return B if k < n_steps - 1 else tail
+
+    def step(k, resident, prev, nf=B, nf_next=None):
+        """One pass of the hot path over one batch of nf frames; nf_next: frames of the step after it (None: this is
+        the last one).  Returns the result of the oldest batch in flight, if any."""
+        fk = batch if nf == B else batch[:nf]
         slot = k % len(comp) if resident else k % 2
         if resident:
-            pts, ready = dev_pts[k % 2], None
-            plan = eng.plan(batch)
+            pts, ready = dev_pts[k % 2][:row_end[len(fk)]], None
+            plan = eng.plan(fk, stride=width, xyz_offset=0)
         else:
-            # this step's points come from (pinned) host memory inside the timed region: threaded gather
-            # of x,y,z into a pinned staging slot (started one step ahead), H2D on a copy stream so that
-            # it overlaps the previous step's kernels
+            # this step's points come from (pinned) host memory inside the timed region, H2D on a copy stream so
+            # that it overlaps the previous step's kernels
             pts, ready = feeder.upload(k % 2)
-            if more:
-                feeder.submit((k + 1) % 2, pinned[(k + 1) % 2])
-            plan = eng.plan(batch, stride=f_stride, xyz_offset=0 if f_stride else 0)
+            if nf_next is not None:
+                feeder.submit((k + 1) % 2, pinned[(k + 1) % 2][:row_end[nf_next]])
+            plan = eng.plan(fk, stride=3, xyz_offset=0)
         with torch.cuda.stream(comp[slot]):
             h = eng.execute(plan, pts, nms_thresh=0.1, gt=gt, slot=slot, points_ready=ready)
             if not resident:
@@ -319,23 +391,21 @@ def run_ours(a):
 
     exchange_ms = [0.0]     # host + device time of that exchange in the last timed run (it is inside the timing)
     ms_by_rank = {}         # per-rank ms/step of the last timed runs (the reported time is their maximum)
-
     xbuf = {}               # exchange slabs (pinned host + device), sized before the timing starts
 
-    def exchange_setup(n_steps):
+    def exchange_setup(n):
         cap = B * 64
-        xbuf["n"], xbuf["cap"], xbuf["i"] = n_steps, cap, 0
-        xbuf["pack"] = eng.arena.get("gather_pack", n_steps * cap * 9 * 4, pinned=True)[:n_steps * cap * 9 * 4] \
-            .view(torch.float32).view(n_steps, cap, 9)
-        xbuf["cnt"] = eng.arena.get("gather_cnt", n_steps * B * 4, pinned=True)[:n_steps * B * 4] \
-            .view(torch.int32).view(n_steps, B)
-        xbuf["tp"] = eng.arena.get("gather_pack_dev", n_steps * cap * 9 * 4)[:n_steps * cap * 9 * 4] \
-            .view(torch.float32).view(n_steps, cap, 9)
-        xbuf["tc"] = eng.arena.get("gather_cnt_dev", n_steps * B * 4)[:n_steps * B * 4].view(torch.int32).view(n_steps, B)
-        xbuf["allp"] = eng.arena.get("gather_all_pack", world * n_steps * cap * 9 * 4)[:world * n_steps * cap * 9 * 4] \
-            .view(torch.float32).view(world, n_steps, cap, 9)
-        xbuf["allc"] = eng.arena.get("gather_all_cnt", world * n_steps * B * 4)[:world * n_steps * B * 4] \
-            .view(torch.int32).view(world, n_steps, B)
+        xbuf["n"], xbuf["cap"], xbuf["i"] = n, cap, 0
+        xbuf["pack"] = eng.arena.get("gather_pack", n * cap * 9 * 4, pinned=True)[:n * cap * 9 * 4] \
+            .view(torch.float32).view(n, cap, 9)
+        xbuf["cnt"] = eng.arena.get("gather_cnt", n * B * 4, pinned=True)[:n * B * 4].view(torch.int32).view(n, B)
+        xbuf["cnt"].zero_()
+        xbuf["tp"] = eng.arena.get("gather_pack_dev", n * cap * 9 * 4)[:n * cap * 9 * 4].view(torch.float32).view(n, cap, 9)
+        xbuf["tc"] = eng.arena.get("gather_cnt_dev", n * B * 4)[:n * B * 4].view(torch.int32).view(n, B)
+        xbuf["allp"] = eng.arena.get("gather_all_pack", world * n * cap * 9 * 4)[:world * n * cap * 9 * 4] \
+            .view(torch.float32).view(world, n, cap, 9)
+        xbuf["allc"] = eng.arena.get("gather_all_cnt", world * n * B * 4)[:world * n * B * 4] \
+            .view(torch.int32).view(world, n, B)
         xbuf["recall"] = None
 
     def exchange_add(res, plan):
@@ -350,7 +420,8 @@ def run_ours(a):
         pk[i, :n, 7] = plan["cand_score"][m]
         pk[i, :n, 8] = plan["cand_label"][m]
         csum = np.concatenate([[0], np.cumsum(m)])
-        xbuf["cnt"].numpy()[i] = np.diff(csum[plan["frame_cand_start"]])
+        per_frame = np.diff(csum[plan["frame_cand_start"]])
+        xbuf["cnt"].numpy()[i, :per_frame.shape[0]] = per_frame
         rc = res["recall"]
         xbuf["recall"] = dict(rc) if xbuf["recall"] is None else {k: xbuf["recall"][k] + rc[k] for k in rc}
         xbuf["i"] = i + 1
@@ -377,6 +448,8 @@ def run_ours(a):
                 exchange_add(last, old["plan"])
         return last
 
+    gathered = {}
+
     def timed(resident, steps, warmup):
         prev = collections.deque()
         if world > 1:
@@ -384,7 +457,7 @@ def run_ours(a):
         if not resident and warmup > 0:
             feeder.submit(0, pinned[0])
         for k in range(warmup):
-            step(k, resident, prev, more=k + 1 < warmup)
+            step(k, resident, prev, B, B if k + 1 < warmup else None)
         if prev:
             drain(prev)
             if world > 1:
@@ -404,15 +477,17 @@ def run_ours(a):
         t_host = time.perf_counter()
         h0 = dict(eng.host_s)
         if not resident:
-            feeder.submit(0, pinned[0])        # the first gather is inside the timed region as well
+            feeder.submit(0, pinned[0][:row_end[nf_of(0)]])   # the first upload is inside the timed region too
         for k in range(steps):
-            step(k, resident, prev, more=k + 1 < steps)
+            step(k, resident, prev, nf_of(k), nf_of(k + 1) if k + 1 < steps else None)
         last = drain(prev)
         if world > 1:
             t_x = time.perf_counter()
-            gather_results()
+            g = gather_results()
             torch.cuda.synchronize()
             exchange_ms[0] = 1e3 * (time.perf_counter() - t_x)
+            if resident:
+                gathered["allp"], gathered["allc"] = g[0].cpu().numpy().copy(), g[1].cpu().numpy().copy()
         for st in comp + [copy_stream]:
             cur.wait_stream(st)                # e1 after everything the timed region enqueued
         e1.record()
@@ -428,15 +503,75 @@ def run_ours(a):
         host_ms = {k: 1e3 * (eng.host_s[k] - h0[k]) / steps for k in h0}
         return ms, last, eng.launches - l0, host_ms
 
+    def gather_check():
+        """Rank 0 re-runs frames of every rank's shard alone (one batch, same engine code) and compares them with
+        what arrived through the all_gather: boxes bit for bit, 2D scores, labels, per-frame counts."""
+        checked = 0
+        chk = SeekerEngine(params, device=dev, score_mode=a.score_mode)
+        for r in range(world):
+            pos = list(range(0, B, max(1, B // 16))) if strong else [0, D // 2, D - 1]
+            if strong:      # frames of rank r's first batch
+                pos = [j for j in pos if j < min(B, len(range(r, a.total_frames, world)))]
+            if strong:
+                fr = [pool[content(r, j)] for j in pos]
+            elif r == rank:
+                fr = [pool[j % D] for j in pos]
+            else:
+                fr = [make_frames(a.config, r * D + (j % D), 1, str(dev))[0][0] for j in pos]
+            res = chk.run(fr, nms_thresh=0.1, with_recall=True)
+            cnt = gathered["allc"][r, 0]
+            off = np.concatenate([[0], np.cumsum(cnt)])
+            for i, j in enumerate(pos):
+                got = gathered["allp"][r, 0, off[j]:off[j + 1]]
+                want = res["frames"][i]
+                if got.shape[0] != want["pred_boxes"].shape[0] or \
+                        not np.array_equal(got[:, :7].view(np.uint32), want["pred_boxes"].view(np.uint32)) or \
+                        not np.array_equal(got[:, 7], want["pred_scores"]) or \
+                        not np.array_equal(got[:, 8].astype(np.int32), want["pred_labels"]):
+                    return "MISMATCH rank %d frame %d" % (r, j)
+                checked += 1
+        return "ok (%d frames of %d ranks re-run on rank 0, bit-equal to the gathered proposals)" % (checked, world)
+
+    def h2d_ceiling(iters=4):
+        """Pinned -> device copies of this rank's point table, all ranks at the same time: what the link (and the
+        host memory behind it) delivers with nothing else going on."""
+        dst = torch.empty_like(dev_pts[0])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            dst.copy_(pinned[0], non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        with torch.cuda.stream(copy_stream):
+            e0.record(copy_stream)
+            for i in range(iters):
+                dst.copy_(pinned[i % 2], non_blocking=True)
+            e1.record(copy_stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        per_rank = [ms]
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            every = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(every, t)
+            per_rank = every.tolist()
+        gbs = [in_bytes * iters / (m * 1e-3) / 1e9 for m in per_rank]
+        return {"per_rank_gbs": [round(g, 2) for g in gbs], "aggregate_gbs": world * in_bytes * iters / (max(per_rank) * 1e-3) / 1e9}
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_res, last, launches, host_res = timed(True, a.steps, a.warmup)
-    ms_e2e, _, _, host_e2e = timed(False, a.steps, a.warmup)
+    ms_res, last, launches, host_res = timed(True, n_steps, a.warmup)
+    ms_e2e, _, _, host_e2e = timed(False, n_steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    check = None
+    if world > 1:
+        check = gather_check() if rank == 0 else None
+        dist.barrier()
+    ceiling = h2d_ceiling()
 
     # ---- the two heaviest stages in isolation, CUDA events on the launching stream, L2 flushed
-    plan = eng.plan(batch)
+    plan = eng.plan(batch, stride=width, xyz_offset=0)
     h = eng.execute(plan, dev_pts[0])
     res = eng.finish(h)
     score_mode = eng.last_score_mode
@@ -460,9 +595,10 @@ def run_ours(a):
         return tot / iters
 
     cull_ms = stage_ms(_lib.lib.fnp_seeker_cull)          # later stages read what cull leaves: run it first
-    for fn in (_lib.lib.fnp_seeker_frustum_stats, _lib.lib.fnp_seeker_hypotheses):
-        fn(C.byref(eng.cfg), C.byref(h["batch"]), stream)
+    stats_ms = stage_ms(_lib.lib.fnp_seeker_frustum_stats)
+    hyp_ms = stage_ms(_lib.lib.fnp_seeker_hypotheses)
     score_ms = stage_ms(_lib.lib.fnp_seeker_score)
+    select_ms = stage_ms(_lib.lib.fnp_seeker_select)
     npts = res["cand_npts"].astype(np.int64)
     nval = res["cand_nvalid"].astype(np.int64)
     n_rows = int(plan["total_rows"])
@@ -483,7 +619,7 @@ def run_ours(a):
     traffic = {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
-        if tj.get("config") == a.config and tj.get("frames") == B:
+        if tj.get("config") == a.config and tj.get("frames") == B and tj.get("layout") == a.layout:
             traffic = tj.get("dram_bytes_per_launch", {})
     except Exception:
         pass
@@ -502,8 +638,8 @@ def run_ours(a):
                       if score_mode == "sweep" else
                       "stage 2b, direct kernel: bound by the SM's ALU/FMA pipes, not by HBM (DESIGN.md section 4)"),
         "cull": roof("cull", "fnp::cull_stage_kernel", cull_ms,
-                     "stage 1 (projection x 6 cameras + frustum cull + ordered compaction), timed through "
-                     "fnp_seeker_cull (five launches); HBM-bound by design, instruction-issue-bound as measured"),
+                     "stage 1 (projection + frustum cull + ordered compaction), timed through fnp_seeker_cull (all its "
+                     "launches); HBM-bound by design, instruction-issue-bound as measured"),
     }
     dominant = "score" if score_ms >= cull_ms else "cull"
     other = "cull" if dominant == "score" else "score"
@@ -512,13 +648,16 @@ def run_ours(a):
         "point_column_range_solves_per_launch": float(npts[nval > 0].sum() * J) if score_mode == "sweep" else None})
 
     if rank == 0:
-        n_frames = B * world
+        total = a.total_frames if strong else B * world * n_steps
         F_step = plan["F"]
         cpu = None if (a.no_cpu_baseline or world > 1) else cpu_baseline(batch, params, a.cpu_sample_frames)
+        h2d_step = int(n_rows * 12 + sum(plan[k].nbytes for k in eng._META))
+        e2e_fps = total / (ms_e2e * 1e-3)
         line = {
-            "metric": "box_seeker_frames_per_s", "value": n_frames * a.steps / (ms_res * 1e-3), "unit": "frames/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_res / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": "box_seeker_frames_per_s", "value": total / (ms_res * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": n_steps, "warmup": a.warmup, "ms_per_step": ms_res / n_steps,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {
                 "workload": "%s frames (%s: ~%dk points, 6 cameras, ~%d 2D boxes, "
                             "%d depths x %d yaws = %d hypotheses/frustum), batch of %d frames per step per GPU"
@@ -526,30 +665,54 @@ def run_ours(a):
                                           "cfg2": "BASELINE.json configs[1] shape, 10 sweeps",
                                           "cfg5": "BASELINE.json configs[4] shape, 128 beams"}.get(a.config, "custom"),
                                int(np.mean([f.points.shape[0] for f in batch]) / 1000), F_step // B,
-                               params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B),
-                "frames_per_step_per_gpu": B, "distinct_frames": a.distinct,
+                               params["num_mags"], params["num_rotations"] * params["num_sizes"], H, B)
+                            + ("; BASELINE.json configs[3]: %d frames in all, sharded rank::world, ragged last batch, "
+                               "fill/drain and the gather inside the timing" % a.total_frames if strong else ""),
+                "frames_per_step_per_gpu": B,
+                "distinct_frames": ("%d in the pool, global frame i = pool[i %% %d]" % (D, D)) if strong else
+                                   "%d per rank, different on every rank (synthetic indices rank*%d ..)" % (D, D),
+                "host_caches": "off (tile table and camera matrices recomputed for every batch)",
+                "point_layout": "x,y,z as its own (rows,3) array on the host and on the device (the loader splits the "
+                                "columns while it concatenates the sweeps)" if a.layout == "xyz" else
+                                "reference rows (5 columns) on the host and on the device",
                 "l2_policy": "inputs larger than L2: %.0f MB of points per step, two alternating input sets" % (in_bytes / 1e6),
                 "sharding": ("frame-wise, no data-path collective; one all_gather of packed proposals + one "
                              "all_reduce of recall counters per run, inside the timed region (%.2f ms of the run)"
-                             % exchange_ms[0]) if world > 1 else "single GPU"},
-            "hypotheses_per_s": F_step * H * world * a.steps / (ms_res * 1e-3),
+                             % exchange_ms[0]) if world > 1 else "single GPU",
+                "numa": numa},
+            "hypotheses_per_s": (total / B) * F_step * H / (ms_res * 1e-3),
             "point_box_tests_equivalent_per_s_scoring_stage": tests / (score_ms * 1e-3),
-            "e2e": {"value": n_frames * a.steps / (ms_e2e * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int((n_rows * 12 if feeder.pack else in_bytes)
-                                              + sum(plan[k].nbytes for k in eng._META)),
+            "e2e": {"value": e2e_fps, "unit": "frames/s",
+                    "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": int(4 * (12 * plan["F"] + 8) + plan["F"]),
-                    "ms_per_step": ms_e2e / a.steps,
+                    "ms_per_step": ms_e2e / n_steps,
                     "host_input_bytes_per_step": int(in_bytes),
-                    "host_pack": ("x,y,z gathered on the host by %d threads (fnp_host_pack_xyz), 12 B/point uploaded"
-                                  % feeder.n_threads) if feeder.pack else "off: all %d columns uploaded" % batch[0].points.shape[1]},
+                    "host_pack": ("rows on the host: x,y,z gathered by %d threads (fnp_host_pack_xyz), 12 B/point uploaded"
+                                  % feeder.n_threads) if feeder.pack else
+                                 "none: the loader's (rows,3) x,y,z array is uploaded as is, 12 B/point, same at every N",
+                    "h2d_ceiling": ceiling,
+                    "frac_of_h2d_ceiling": (world * h2d_step / (ms_e2e / n_steps * 1e-3) / 1e9) / ceiling["aggregate_gbs"]},
             "gpu_launches": int(launches),
+            "gather_check": check,
             "ms_per_step_by_rank": ms_by_rank if world > 1 else None,
             "host_ms_per_step": {"resident": host_res, "e2e": host_e2e,
                                  "note": "main-thread time in SeekerEngine.plan / execute / finish (after its event wait) per step"},
+            "stage_ms": {"cull": cull_ms, "frustum_stats": stats_ms, "hypotheses": hyp_ms, "score": score_ms,
+                         "select": select_ms, "note": "each stage alone through its C-ABI call, L2 flushed, CUDA events"},
             "clocks": clocks,
             "roofline": roofs[dominant],
             "roofline_second_kernel": roofs[other],
         }
+        ref_gpu = os.path.join(ROOT, "profiles", "r02_reference_gpu.json")
+        if os.path.exists(ref_gpu):
+            try:
+                rg = json.load(open(ref_gpu))
+                line["reference_gpu"] = {
+                    "source": "profiles/r02_reference_gpu.json (tools/ref_gpu_bench.py: the reference's own head + "
+                              "kernels compiled for sm_100a, run on a B200 of this pool)",
+                    "frames_per_s": {hd["config"]: hd["reference_gpu_frames_per_s"] for hd in rg.get("heads", [])}}
+            except Exception:
+                pass
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

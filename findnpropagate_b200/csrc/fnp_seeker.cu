@@ -1881,11 +1881,15 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     const int mode = resolve_score_mode(cfg, b);
     if (mode < 0) return FNP_EINVAL;
     const int sweep = mode == FNP_SCORE_SWEEP;
-    static int n_sms = 0;
-    if (n_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    // per device: a process may run engines on several GPUs (function attributes and the SM count are per device)
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n_sms = 0;
+    if (dev >= 0 && dev < 64 && sms_of[dev]) n_sms = sms_of[dev];
+    else {
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (dev >= 0 && dev < 64) sms_of[dev] = n_sms;
     }
     cudaMemsetAsync(b->counts, 0, sizeof(int32_t) * (size_t)b->n_cands * H, st);
     if (sweep) sweep_prep_kernel<<<b->n_cands, 128, (size_t)15 * J * 4, st>>>(*b, J, M);
@@ -1895,10 +1899,10 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
         // persistent CTAs: a whole number of CTAs per SM (148 SMs on B200), capped by the item capacity
         if (sweep) {
             const size_t smem = sweep_smem_bytes(b->split_points, H, J);
-            static size_t smem_set = 0;
-            if (smem > smem_set) {
+            static size_t smem_set[64] = {0};
+            if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
                 cudaFuncSetAttribute(sweep_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                smem_set = smem;
+                if (dev >= 0 && dev < 64) smem_set[dev] = smem;
             }
             int per_sm = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_score_kernel, kSweepThreads, smem);

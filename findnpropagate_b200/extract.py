@@ -125,7 +125,7 @@ def extract(frames, compute_fn: Callable, folder: Optional[str] = None, batch_fr
 
 def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch_frames: int = 32, rank: int = 0,
                      world: int = 1, nms_thresh: Optional[float] = None, workers: int = 4, pack_xyz: bool = True,
-                     device=None):
+                     device=None, loader_xyz: bool = True):
     """tools/extract_pseudo_labels.py:113-146 over a nuScenes info list, pipelined end to end:
 
         worker threads   NuScenesFeed.prefetch: read + transform + filter the next batch of frames
@@ -135,7 +135,12 @@ def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch
         this thread      per-frame .pth files (``save_frame``), recall bookkeeping
 
     Batch k+1 is read, gathered and uploaded while batch k is in the kernels.  Frames are sharded
-    by rank as in ``extract``; returns (all_preds in dataset order, recall dict, AR per threshold)."""
+    by rank as in ``extract``; returns (all_preds in dataset order, recall dict, AR per threshold).
+
+    loader_xyz: the loader's worker threads hand over x, y, z as their own (n,3) arrays (the seeker reads
+    nothing else), so the host threads only concatenate 12 B/point instead of gathering columns out of full rows.
+    For the recall numbers the reference tool logs, build ``feed`` with ``training=True`` -- the mode
+    tools/extract_pseudo_labels.py:47-58 runs its loader in (see NuScenesFeed)."""
     import torch
     from .seeker import HostPointFeeder
     n = len(feed)
@@ -166,10 +171,24 @@ def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch
         feeder.submit(slot, [f.points for f in frames])      # per-frame arrays, gathered back to back
 
     prev, k = None, 0
-    batches = feed.prefetch(mine, detector, batch_frames=batch_frames, workers=workers)
-    cur = next(batches, None)
-    if cur is not None:
-        stage(0, cur[0])
+    batches = feed.prefetch(mine, detector, batch_frames=batch_frames, workers=workers, xyz_only=loader_xyz)
+    try:
+        cur = next(batches, None)
+        if cur is not None:
+            stage(0, cur[0])
+        prev = _pipeline(cur, batches, feeder, engine, stride, stage, finish, nms_thresh)
+    finally:
+        feeder.close()          # an exception between submit and upload must not leak a gather ticket
+    if prev is not None:
+        finish(prev)
+    merged, total = gather_shards(local, recall, n, rank, world, device=device or "cpu")
+    ar = {("rcnn_%s" % t): (total.get("rcnn_%s" % t, 0) / max(total.get("gt", 0), 1)) for t in THRESH}
+    return merged, total, ar
+
+
+def _pipeline(cur, batches, feeder, engine, stride, stage, finish, nms_thresh):
+    """The steady state of extract_nuscenes; returns the last job in flight (not yet finished)."""
+    prev, k = None, 0
     while cur is not None:
         frames, ids, _ = cur
         slot = k % 2
@@ -187,8 +206,4 @@ def extract_nuscenes(feed, detector, engine, folder: Optional[str] = None, batch
         if prev is not None:
             finish(prev)                                    # overlaps the kernels of this batch
         prev, cur, k = (h, ids, run), nxt, k + 1
-    if prev is not None:
-        finish(prev)
-    merged, total = gather_shards(local, recall, n, rank, world, device=device or "cpu")
-    ar = {("rcnn_%s" % t): (total.get("rcnn_%s" % t, 0) / max(total.get("gt", 0), 1)) for t in THRESH}
-    return merged, total, ar
+    return prev

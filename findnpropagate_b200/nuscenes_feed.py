@@ -12,7 +12,15 @@ NuScenesDataset.get_sweep (nuscenes_dataset.py:85-103)             load_sweep
 NuScenesDataset.get_lidar_with_sweeps (:105-124)                   lidar_with_sweeps
 NuScenesDataset.load_camera_info (:172-233, CAM_WITHOUT_IMAGE)     camera_info
 NuScenesDataset.__getitem__ (:241-279)                             NuScenesFeed.__getitem__
-DatasetTemplate.prepare_data, test mode (dataset.py:159-220)       NuScenesFeed._prepare
+DatasetTemplate.prepare_data (dataset.py:159-220)                  NuScenesFeed._prepare
+  test mode, and the mode the extraction tool really runs in:        training=True
+  tools/extract_pseudo_labels.py:47-58 builds its loader with
+  training=True and an EMPTY augmentation list, so that
+  DataAugmentor.forward (data_augmentor.py:362-395) only wraps the
+  headings, REMOVE_OUTSIDE_BOXES drops GT whose centre is outside
+  POINT_CLOUD_RANGE (data_processor.py:88-93, box_utils.py:93-114)
+  and frames left without GT are re-drawn (SKIP_NO_GT, dataset.py:
+  23,213-215)
   DataProcessor.mask_points_and_boxes_outside_range                  (data_processor.py:80-94,
   (shuffle disabled, yaml:46-50)                                      common_utils.py:78-81)
 DatasetTemplate.collate_batch (dataset.py:222-344)                 collate_batch
@@ -143,14 +151,38 @@ def collate_batch(batch_list: List[dict]) -> dict:
     return ret
 
 
+def limit_period(val: np.ndarray, offset: float = 0.5, period: float = np.pi) -> np.ndarray:
+    """common_utils.py:21-24 (the reference computes it through a float32 torch tensor; so does this)."""
+    import torch
+    v = torch.from_numpy(np.ascontiguousarray(val)).float()
+    return (v - torch.floor(v / period + offset) * period).numpy()
+
+
+def mask_boxes_outside_range(boxes: np.ndarray, limit_range) -> np.ndarray:
+    """box_utils.mask_boxes_outside_range_numpy with USE_CENTER_TO_FILTER (its default, box_utils.py:93-107):
+    keep a box when its centre lies inside the range, both ends included."""
+    c = boxes[:, 0:3]
+    return ((c >= limit_range[0:3]) & (c <= limit_range[3:6])).all(axis=-1)
+
+
 class NuScenesFeed:
-    """Map-style producer of the seeker's per-frame ``data_dict`` (test mode)."""
+    """Map-style producer of the seeker's per-frame ``data_dict``.
+
+    training=False is the reference's test mode; training=True is the mode tools/extract_pseudo_labels.py
+    builds its loader in (:47-58, with an empty augmentation list): GT headings are wrapped to [-pi, pi), GT
+    boxes whose centre is outside POINT_CLOUD_RANGE are dropped, and a frame left without GT is replaced by
+    a randomly drawn one (SKIP_NO_GT).  The points and camera matrices -- everything the proposals depend on --
+    are the same in both modes; what changes is the gt_boxes the recall counters see."""
 
     def __init__(self, root_path, infos, class_names: Sequence[str] = CLASS_NAMES, max_sweeps: int = 1,
                  point_cloud_range=POINT_CLOUD_RANGE, filter_min_points_in_gt: int = 1, pred_velocity: bool = True,
-                 set_nan_velocity_to_zeros: bool = True, final_dim=(900, 1600), resize_lim_test=(1.0, 1.0), rng=None):
+                 set_nan_velocity_to_zeros: bool = True, final_dim=(900, 1600), resize_lim_test=(1.0, 1.0), rng=None,
+                 training: bool = False, skip_no_gt: bool = True):
         """infos: list of info dicts, or path(s) of nuscenes_infos_*.pkl files (nuscenes_dataset.py:39-51).
-        max_sweeps: MAX_SWEEPS (1 in the seeker yaml:12, 10 in the dataset base config)."""
+        max_sweeps: MAX_SWEEPS (1 in the seeker yaml:12, 10 in the dataset base config).
+        rng: private generator for the sweep draw and the SKIP_NO_GT re-draw (None: numpy's global one, as in
+        the reference)."""
+        self.training, self.skip_no_gt = bool(training), bool(skip_no_gt)
         self.root = Path(root_path)
         if isinstance(infos, (str, Path)):
             infos = [infos]
@@ -174,7 +206,14 @@ class NuScenesFeed:
         return len(self.infos)
 
     def _prepare(self, d: dict) -> dict:
-        """DatasetTemplate.prepare_data in test mode (dataset.py:159-220)."""
+        """DatasetTemplate.prepare_data (dataset.py:159-220); returns None when the frame has to be re-drawn."""
+        if self.training:
+            assert 'gt_boxes' in d, 'gt_boxes should be provided for training'      # dataset.py:182
+            # DataAugmentor.forward with an empty queue (data_augmentor.py:380-394): headings wrapped, then the
+            # class mask computed at dataset.py:183 applied
+            keep = np.array([n in self.class_names for n in d['gt_names']], dtype=np.bool_)
+            d['gt_boxes'][:, 6] = limit_period(d['gt_boxes'][:, 6], offset=0.5, period=2 * np.pi)
+            d['gt_boxes'], d['gt_names'] = d['gt_boxes'][keep], d['gt_names'][keep]
         d['lidar_aug_matrix'] = np.eye(4)                                   # set_lidar_aug_matrix, no augmentation
         if d.get('gt_boxes', None) is not None:
             sel = np.array([i for i, n in enumerate(d['gt_names']) if n in self.class_names], dtype=np.int64)
@@ -184,6 +223,10 @@ class NuScenesFeed:
             d['gt_boxes'] = np.concatenate((d['gt_boxes'], cls.reshape(-1, 1).astype(np.float32)), axis=1)
         d['use_lead_xyz'] = True                                            # absolute_coordinates_encoding
         d['points'] = d['points'][mask_points_by_range(d['points'], self.range)]
+        if self.training and d.get('gt_boxes', None) is not None:          # REMOVE_OUTSIDE_BOXES, data_processor.py:88-93
+            d['gt_boxes'] = d['gt_boxes'][mask_boxes_outside_range(d['gt_boxes'], self.range)]
+        if self.training and len(d['gt_boxes']) == 0 and self.skip_no_gt:   # dataset.py:213-215
+            return None
         d.pop('gt_names', None)
         return d
 
@@ -200,6 +243,8 @@ class NuScenesFeed:
         d['ori_shape'] = [fW, fH]
         d['img_process_infos'] = [[float(np.mean(self.resize_lim_test)), (0, 0, fW, fH), False, 0] for _ in range(6)]
         d = self._prepare(d)
+        if d is None:        # SKIP_NO_GT: the reference returns another, randomly drawn frame in this one's place
+            d = self[int((np.random if self.rng is None else self.rng).randint(len(self)))]
         if self.set_nan_velocity_to_zeros and 'gt_boxes' in info:
             g = d['gt_boxes']
             g[np.isnan(g)] = 0
@@ -209,13 +254,17 @@ class NuScenesFeed:
         return d
 
     # ---------------------------------------------------------------- seeker inputs
-    def frame_input(self, index: int, detector):
+    def frame_input(self, index: int, detector, xyz_only: bool = False):
         """One frame as the engine wants it: the data_dict of ``__getitem__`` plus the frame's
         GLIP boxes.  ``detector`` has the reference feeder's contract (preprocessed_detector.py:47-106,
         e.g. ``proposer.PreprocessedGLIP``): called with a batch_dict holding ``batch_size``,
         ``image_paths`` and ``metadata`` it returns (boxes, labels, scores, batch_idx, cam_idx)."""
         from .seeker import FrameInput
         d = self[index]
+        if xyz_only:
+            # the seeker reads x, y, z only: split the columns here, on the loader's worker thread, so that the
+            # host table that crosses PCIe is 12 B/point and no separate gather pass over full rows is needed
+            d['points'] = np.ascontiguousarray(d['points'][:, :3], np.float32)
         boxes, labels, scores, _, cam_idx = detector(
             {'batch_size': 1, 'image_paths': [d['image_paths']], 'metadata': [d['metadata']]})
         fi = FrameInput(points=np.ascontiguousarray(d['points'], np.float32),
@@ -227,7 +276,8 @@ class NuScenesFeed:
                         gt_boxes=d.get('gt_boxes'))
         return fi, d['frame_id'], d['metadata']
 
-    def prefetch(self, indices: Iterable[int], detector, batch_frames: int = 32, workers: int = 4):
+    def prefetch(self, indices: Iterable[int], detector, batch_frames: int = 32, workers: int = 4,
+                 xyz_only: bool = False):
         """Yields (frame_inputs, frame_ids, metadata) per batch of ``batch_frames`` frames, loading
         the NEXT batch on worker threads while the caller runs the current one on the GPU (file
         reads and numpy release the GIL).  The reference gets the same overlap from DataLoader
@@ -238,7 +288,7 @@ class NuScenesFeed:
             return
         with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
             def submit(b):
-                return [pool.submit(self.frame_input, i, detector) for i in b]
+                return [pool.submit(self.frame_input, i, detector, xyz_only) for i in b]
             pending = submit(batches[0])
             for k in range(len(batches)):
                 nxt = submit(batches[k + 1]) if k + 1 < len(batches) else None

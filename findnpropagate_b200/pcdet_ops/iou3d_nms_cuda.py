@@ -15,7 +15,10 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.type, device.index)
+    """NMS scratch (bitmask + prepared boxes), one buffer per (device, stream): calls enqueued on different
+    streams of one device must not share it.  A buffer that is outgrown is handed back to torch's caching
+    allocator, which is stream-ordered, so kernels still reading it are not overtaken."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)

@@ -15,6 +15,14 @@ and `bench.py --impl reference` uses `points_in_boxes_cpu` as the timed CPU base
 /root/reference does not exist on the GPU box: only the prebuilt `.so` files are used
 there.
 
+It also installs the ten Python files of the reference that `FrustumProposerOG` needs at import
+time (the head, its op wrappers and utils), byte for byte, under `oracle/_ref/pysrc/pcdet/...`
+-- the equivalent of `pip install --target` for the slice of the package on this path
+(the full package needs spconv / SharedArray / kornia and is not installable here).  Like the
+`.so` files they are git-ignored build outputs that travel with the gpurun snapshot, so that
+`tests/test_reference_gpu.py` and `tools/ref_gpu_bench.py` can run the reference's own
+`get_proposals` on the B200.  They are never imported by the product.
+
 Usage:  python oracle/build_ref.py [--force]
 """
 import os
@@ -39,6 +47,47 @@ MODULES = {
         "pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu",
     ],
 }
+
+
+# reference Python files FrustumProposerOG imports (tools/ref_seeker.py lists why each one is needed)
+PY_FILES = [
+    "pcdet/models/dense_heads/frustum_proposals_v1.py",
+    "pcdet/models/dense_heads/frustum_proposals_v1_kitti.py",
+    "pcdet/models/dense_heads/target_assigner/hungarian_assigner.py",
+    "pcdet/models/model_utils/centernet_utils.py",
+    "pcdet/models/model_utils/model_nms_utils.py",
+    "pcdet/models/preprocessed_detector.py",
+    "pcdet/utils/box_utils.py",
+    "pcdet/utils/common_utils.py",
+    "pcdet/utils/loss_utils.py",
+    "pcdet/utils/calibration_kitti.py",
+    "pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py",
+    "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
+]
+PYSRC = os.path.join(OUT, "pysrc")
+
+
+def install_py(force=False):
+    """Copies PY_FILES (unmodified) to oracle/_ref/pysrc/; a no-op without the reference tree."""
+    import shutil
+    if not os.path.isdir(REF):
+        return
+    for rel in PY_FILES:
+        src, dst = os.path.join(REF, rel), os.path.join(PYSRC, rel)
+        if not os.path.exists(src):
+            continue
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+
+
+def py_root():
+    """Root of the reference's Python files: the reference tree itself where it exists, else the installed copy."""
+    if os.path.isdir(os.path.join(REF, "pcdet")):
+        return REF
+    if os.path.isdir(os.path.join(PYSRC, "pcdet")):
+        return PYSRC
+    raise ImportError("neither %s nor oracle/_ref/pysrc holds the reference's Python files" % REF)
 
 
 def _flags(name):
@@ -84,6 +133,7 @@ def build(force=False):
             raise RuntimeError("reference tree %s absent and oracle/_ref lacks %s" % (REF, missing))
         return
     os.makedirs(OUT, exist_ok=True)
+    install_py(force)
     jobs, links = [], []
     for name, srcs in MODULES.items():
         so = os.path.join(OUT, name + ".so")

@@ -52,10 +52,13 @@ def _same(a, b, key):
         assert a == b, (key, a, b)
 
 
-@pytest.mark.parametrize("case", ["seeker_yaml", "ten_sweeps", "no_velocity"])
+@pytest.mark.parametrize("case", ["seeker_yaml", "ten_sweeps", "no_velocity", "seeker_yaml_extract", "no_velocity_extract"])
 def test_samples_and_collated_batch_equal_the_reference(gold, tree, case):
+    """*_extract: training=True, the mode tools/extract_pseudo_labels.py builds its loader in -- GT outside the
+    range dropped, headings wrapped, the frame without GT re-drawn (SKIP_NO_GT) from numpy's global generator."""
     c = gold["cases"][case]
-    feed = NF.NuScenesFeed(tree, gold["infos"], max_sweeps=c["max_sweeps"], pred_velocity=c["pred_velocity"])
+    feed = NF.NuScenesFeed(tree, gold["infos"], max_sweeps=c["max_sweeps"], pred_velocity=c["pred_velocity"],
+                           training=c["training"])
     np.random.seed(gold["seed"])                 # the reference draws the sweeps from the global generator
     samples = [feed[i] for i in range(len(feed))]
     assert len(samples) == len(c["samples"])

@@ -501,8 +501,8 @@ def test_score_mode_auto_picks_sweep_for_deep_grids_only():
         assert (eng.M >= _lib.SWEEP_MIN_MAGS) == (want == "sweep")
 
 
-@pytest.mark.parametrize("pack_xyz", [True, False])
-def test_nuscenes_feed_to_pth_pipeline(tmp_path, pack_xyz):
+@pytest.mark.parametrize("pack_xyz,loader_xyz", [(True, True), (False, True), (True, False), (False, False)])
+def test_nuscenes_feed_to_pth_pipeline(tmp_path, pack_xyz, loader_xyz):
     """Row f2 end to end: nuScenes-format files -> NuScenesFeed (prefetch threads) -> HostPointFeeder
     (threaded x,y,z gather, double-buffered H2D) -> the five stages -> one .pth per frame.  The
     pipelined driver must give what the plain per-batch path gives on the same frames, bit for
@@ -517,7 +517,7 @@ def test_nuscenes_feed_to_pth_pipeline(tmp_path, pack_xyz):
     eng = SeekerEngine(params, device="cuda:0")
     out_dir = tmp_path / "pl"
     merged, total, ar = extract.extract_nuscenes(feed, glip, eng, folder=str(out_dir), batch_frames=2, nms_thresh=0.1,
-                                                 pack_xyz=pack_xyz, workers=2)
+                                                 pack_xyz=pack_xyz, workers=2, loader_xyz=loader_xyz)
     assert len(merged) == 5
     frames = [feed.frame_input(i, glip)[0] for i in range(5)]
     ref = SeekerEngine(params, device="cuda:0").run(frames, with_recall=True, nms_thresh=0.1)

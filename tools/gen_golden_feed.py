@@ -125,17 +125,24 @@ def make_fixture(root, rng, n_frames=3, n_sweeps=3, n_pts=260):
         G = 5 + i
         names = np.array(rng.choice(CLASS_NAMES + ["animal", "debris"], G))
         gt = rng.uniform(-60, 60, (G, 9)).astype(np.float32)
+        gt[:, 2] = rng.uniform(-6, 4, G)                       # most centres inside the z range, some outside
+        gt[:, 6] = rng.uniform(-9, 9, G)                       # headings beyond +-pi: wrapped in training mode
+        if i == 1:
+            gt[:, 0] = rng.choice([-58.0, 57.5], G)            # no GT centre inside the range: SKIP_NO_GT re-draws
         gt[0, 7] = np.nan
         infos.append(dict(lidar_path=key, token="token%d" % i, sweeps=sweeps, cams=cams, gt_boxes=gt, gt_names=names,
                           num_lidar_pts=rng.integers(0, 4, G)))
     return infos, files
 
 
-def reference_outputs(root, infos, max_sweeps, pred_velocity):
+def reference_outputs(root, infos, max_sweeps, pred_velocity, training=False):
     g = dict(np=np, Path=Path, copy=copy, defaultdict=defaultdict, partial=partial, torch=torch, Quaternion=Quaternion)
-    cu = types.SimpleNamespace(**lift("pcdet/utils/common_utils.py", ["mask_points_by_range", "keep_arrays_by_name"], g))
+    cu = types.SimpleNamespace(**lift("pcdet/utils/common_utils.py",
+                                      ["mask_points_by_range", "keep_arrays_by_name", "limit_period", "check_numpy_to_torch"], g))
     g["common_utils"] = cu
-    g["box_utils"] = types.SimpleNamespace()
+    g["check_numpy_to_torch"] = cu.check_numpy_to_torch
+    g["box_utils"] = types.SimpleNamespace(**lift("pcdet/utils/box_utils.py", ["mask_boxes_outside_range_numpy"], g))
+    aug = lift("pcdet/datasets/augmentor/data_augmentor.py", ["forward"], g, cls="DataAugmentor")
     pfe_ns = dict(np=np)
     exec(compile(open(os.path.join(REF, "pcdet/datasets/processor/point_feature_encoder.py")).read(), "pfe", "exec"), pfe_ns)
     ds = lift("pcdet/datasets/nuscenes/nuscenes_dataset.py",
@@ -149,7 +156,7 @@ def reference_outputs(root, infos, max_sweeps, pred_velocity):
         pass
     proc = Proc()
     proc.point_cloud_range = np.array([-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], dtype=np.float32)
-    proc.training, proc.mode = False, 'test'
+    proc.training, proc.mode = training, ('train' if training else 'test')
     for k, f in dp.items():
         setattr(Proc, k, f)
     proc.data_processor_queue = [
@@ -163,7 +170,13 @@ def reference_outputs(root, infos, max_sweeps, pred_velocity):
         setattr(DS, k, staticmethod(f) if k == "collate_batch" else f)
     d = DS()
     d.infos, d.root_path = infos, Path(root)
-    d.training, d.class_names = False, CLASS_NAMES
+    d.training, d.class_names = training, CLASS_NAMES
+    d.skip_no_gt = True                                  # DatasetTemplate.__init__, dataset.py:23 (SKIP_NO_GT default)
+
+    class Aug:                                           # DataAugmentor with AUG_CONFIG_LIST = [] (extract_pseudo_labels.py:50)
+        data_augmentor_queue = []
+    Aug.forward = aug["forward"]
+    d.data_augmentor = Aug()
     d._merge_all_iters_to_one_epoch = False
     d.use_camera, d.cam_without_image = True, True
     d.camera_image_config = AttrDict(FINAL_DIM=[900, 1600], RESIZE_LIM_TEST=[1.0, 1.0])
@@ -173,7 +186,7 @@ def reference_outputs(root, infos, max_sweeps, pred_velocity):
         AttrDict(encoding_type='absolute_coordinates_encoding', used_feature_list=['x', 'y', 'z', 'intensity', 'timestamp'],
                  src_feature_list=['x', 'y', 'z', 'intensity', 'timestamp']), point_cloud_range=proc.point_cloud_range)
     d.data_processor = proc
-    d.__len__ = lambda: len(infos)
+    DS.__len__ = lambda self: len(infos)
     np.random.seed(1234)                                # the reference draws the sweeps from the global generator
     samples = [d.__getitem__(i) for i in range(len(infos))]
     batch = DS.collate_batch([copy.deepcopy(s) for s in samples])
@@ -186,9 +199,12 @@ def main():
     with tempfile.TemporaryDirectory() as root:
         infos, files = make_fixture(root, rng)
         cases = {}
-        for name, (ms, pv) in {"seeker_yaml": (1, True), "ten_sweeps": (4, True), "no_velocity": (2, False)}.items():
-            samples, batch = reference_outputs(root, copy.deepcopy(infos), ms, pv)
-            cases[name] = dict(max_sweeps=ms, pred_velocity=pv, samples=samples, batch=batch)
+        # *_extract: training=True, the mode tools/extract_pseudo_labels.py:47-58 builds its loader in
+        for name, (ms, pv, tr) in {"seeker_yaml": (1, True, False), "ten_sweeps": (4, True, False),
+                                   "no_velocity": (2, False, False), "seeker_yaml_extract": (1, True, True),
+                                   "no_velocity_extract": (3, False, True)}.items():
+            samples, batch = reference_outputs(root, copy.deepcopy(infos), ms, pv, tr)
+            cases[name] = dict(max_sweeps=ms, pred_velocity=pv, training=tr, samples=samples, batch=batch)
     with open(os.path.join(OUT, "nuscenes_feed.pkl"), "wb") as f:
         pickle.dump(dict(infos=infos, files=files, cases=cases, seed=1234), f, protocol=4)
     for name, c in cases.items():

@@ -54,6 +54,20 @@ class SeekerBatch(C.Structure):
     ]
 
 
+class HostFrame(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("det_boxes", _vp), ("det_labels", _vp), ("det_scores", _vp), ("det_cam", _vp),
+                ("cam_mats", _vp), ("n_dets", C.c_int32), ("reserved", C.c_int32)]
+
+
+class HostPlanOut(C.Structure):
+    _fields_ = [("frame_row_start", _vp), ("tile_frame", _vp), ("tile_row0", _vp), ("frame_tile_start", _vp),
+                ("cam_mats", _vp), ("frame_cand_start", _vp), ("cam_cand_start", _vp), ("cand_frame", _vp),
+                ("cand_cam", _vp), ("cand_label", _vp), ("cand_box2d", _vp), ("nms_order", _vp),
+                ("frame_prop_start", _vp), ("prop_order", _vp), ("cand_score", _vp), ("cand_det", _vp),
+                ("n_cands", C.c_int32), ("n_tiles", C.c_int32), ("max_cands_per_frame", C.c_int32),
+                ("reserved", C.c_int32), ("total_rows", C.c_int64)]
+
+
 CULL_TILE = 1024
 SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
 SEEKER_MULT, SEEKER_OCCL_MULT, SEEKER_MULTICAM_IOU = 1, 2, 4
@@ -96,6 +110,10 @@ lib.fnp_recall_counters.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINT
 lib.fnp_host_select_candidates.restype = _i
 lib.fnp_host_select_candidates.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
 
+lib.fnp_host_plan_sizes.restype = _i
+lib.fnp_host_plan_sizes.argtypes = [_vp, _i, _vp]
+lib.fnp_host_plan.restype = _i
+lib.fnp_host_plan.argtypes = [_vp, _i, _f, _f, _i, _i, C.POINTER(HostPlanOut)]
 lib.fnp_host_nms_order.restype = _i
 lib.fnp_host_nms_order.argtypes = [_vp, _vp, _i, _vp]
 for _n in ("fnp_host_pack_xyz", "fnp_host_pack_xyz_begin"):
@@ -119,7 +137,7 @@ EXPORTED = [
     "fnp_nms_normal", "fnp_seeker_cull", "fnp_seeker_frustum_stats", "fnp_seeker_hypotheses",
     "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_occlusion", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
-    "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin",
+    "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin", "fnp_host_plan_sizes", "fnp_host_plan",
 ]
 
 

@@ -155,6 +155,106 @@ extern "C" int fnp_host_nms_order(const float *cand_score, const int32_t *frame_
 }
 
 // ---------------------------------------------------------------------------------------
+// Whole-batch planning in one call (what SeekerEngine.plan used to do in numpy, 3 ms per 256 frames
+// on the main thread): candidate selection as above over the frames' own detection arrays, the
+// per-(frame, camera rank) candidate ranges, the stage-4 priority order, the point-tile table and
+// the camera-matrix block, written straight into caller-provided arrays.
+// ---------------------------------------------------------------------------------------
+extern "C" int fnp_host_plan_sizes(const fnp_host_frame *frames, int n_frames, int64_t *sizes3)
+{
+    if (n_frames < 0 || !sizes3 || (n_frames > 0 && !frames)) return FNP_EINVAL;
+    int64_t n_dets = 0, n_tiles = 0, rows = 0;
+    for (int b = 0; b < n_frames; b++) {
+        if (frames[b].n_rows < 0 || frames[b].n_dets < 0) return FNP_EINVAL;
+        n_dets += frames[b].n_dets;
+        n_tiles += (frames[b].n_rows + FNP_CULL_TILE - 1) / FNP_CULL_TILE;
+        rows += frames[b].n_rows;
+    }
+    if (n_dets > 0x7fffffff || n_tiles > 0x7fffffff) return FNP_EINVAL;
+    sizes3[0] = n_dets; sizes3[1] = n_tiles; sizes3[2] = rows;
+    return FNP_OK;
+}
+
+extern "C" int fnp_host_plan(const fnp_host_frame *frames, int n_frames, float nms_2d, float score_thr, int box_xywh,
+                             int topk, fnp_host_plan_out *out)
+{
+    if (n_frames < 0 || !out || (n_frames > 0 && !frames)) return FNP_EINVAL;
+    int64_t sz[3];
+    int rc = fnp_host_plan_sizes(frames, n_frames, sz);
+    if (rc) return rc;
+    const int n_dets = (int)sz[0];
+    if (!out->frame_row_start || !out->frame_tile_start || !out->frame_cand_start || !out->cam_cand_start) return FNP_EINVAL;
+    if (sz[1] > 0 && (!out->tile_frame || !out->tile_row0)) return FNP_EINVAL;
+    if (n_frames > 0 && !out->cam_mats) return FNP_EINVAL;
+    // ---- rows, tiles (tiles never straddle a frame), camera matrices
+    int64_t row = 0;
+    int tile = 0;
+    for (int b = 0; b < n_frames; b++) {
+        out->frame_row_start[b] = row;
+        out->frame_tile_start[b] = tile;
+        const int nt = (int)((frames[b].n_rows + FNP_CULL_TILE - 1) / FNP_CULL_TILE);
+        for (int t = 0; t < nt; t++) { out->tile_frame[tile + t] = b; out->tile_row0[tile + t] = t * FNP_CULL_TILE; }
+        tile += nt;
+        row += frames[b].n_rows;
+        if (!frames[b].cam_mats) return FNP_EINVAL;
+        std::copy(frames[b].cam_mats, frames[b].cam_mats + 144, out->cam_mats + (size_t)b * 144);
+    }
+    out->frame_row_start[n_frames] = row;
+    out->frame_tile_start[n_frames] = tile;
+    out->n_tiles = tile;
+    out->total_rows = row;
+    // ---- detections of the batch, flat (a few thousand rows)
+    std::vector<float> boxes((size_t)n_dets * 4), scores(n_dets);
+    std::vector<int64_t> labels(n_dets), dframe(n_dets), dcam(n_dets);
+    int d0 = 0;
+    for (int b = 0; b < n_frames; b++) {
+        const fnp_host_frame &f = frames[b];
+        if (f.n_dets > 0 && (!f.det_boxes || !f.det_labels || !f.det_scores || !f.det_cam)) return FNP_EINVAL;
+        for (int i = 0; i < f.n_dets; i++) {
+            for (int k = 0; k < 4; k++) boxes[(size_t)(d0 + i) * 4 + k] = f.det_boxes[(size_t)i * 4 + k];
+            scores[d0 + i] = f.det_scores[i];
+            labels[d0 + i] = f.det_labels[i];
+            dcam[d0 + i] = f.det_cam[i];
+            dframe[d0 + i] = b;
+        }
+        d0 += f.n_dets;
+    }
+    if (n_dets > 0 && (!out->cand_det || !out->cand_frame || !out->cand_cam || !out->cand_label || !out->cand_box2d ||
+                       !out->cand_score || !out->nms_order))
+        return FNP_EINVAL;
+    const int F = fnp_host_select_candidates(boxes.data(), labels.data(), scores.data(), dframe.data(), dcam.data(), n_dets,
+                                             n_frames, nms_2d, score_thr, out->cand_det, out->frame_cand_start);
+    if (F < 0) return F;
+    out->n_cands = F;
+    for (int g = 0; g <= n_frames * 6; g++) out->cam_cand_start[g] = 0;
+    int max_c = 0;
+    for (int b = 0; b < n_frames; b++) max_c = std::max(max_c, out->frame_cand_start[b + 1] - out->frame_cand_start[b]);
+    out->max_cands_per_frame = max_c;
+    for (int i = 0; i < F; i++) {
+        const int d = out->cand_det[i];
+        const int fr = (int)dframe[d], cam = (int)dcam[d];
+        out->cand_frame[i] = fr;
+        out->cand_cam[i] = cam;
+        out->cand_label[i] = (int32_t)labels[d];
+        out->cand_score[i] = scores[d];
+        float *bx = out->cand_box2d + (size_t)i * 4;
+        for (int k = 0; k < 4; k++) bx[k] = boxes[(size_t)d * 4 + k];
+        if (box_xywh) { bx[2] = bx[2] + bx[0]; bx[3] = bx[3] + bx[1]; }   // frustum_proposals_v1.py:597-601, after the NMS
+        out->cam_cand_start[fr * 6 + kCamRank[cam] + 1]++;                 // candidates are already in this order
+    }
+    for (int g = 0; g < n_frames * 6; g++) out->cam_cand_start[g + 1] += out->cam_cand_start[g];
+    rc = fnp_host_nms_order(out->cand_score, out->frame_cand_start, n_frames, out->nms_order);
+    if (rc) return rc;
+    if (topk > 1) {   // every candidate owns topk consecutive proposal slots; a candidate's slots stay together, best first
+        if (!out->frame_prop_start || (F > 0 && !out->prop_order)) return FNP_EINVAL;
+        for (int b = 0; b <= n_frames; b++) out->frame_prop_start[b] = out->frame_cand_start[b] * topk;
+        for (int i = 0; i < F; i++)
+            for (int k = 0; k < topk; k++) out->prop_order[(size_t)i * topk + k] = out->nms_order[i] * topk + k;
+    }
+    return FNP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Host-side column gather of the point table.
 //
 // The reference uploads every column of `points` ([batch_idx,] x, y, z, intensity, time:

@@ -287,6 +287,54 @@ int fnp_host_select_candidates(const float *det_boxes, const int64_t *det_labels
                                const int64_t *det_cam, int n_dets, int n_frames, float nms_2d,
                                float score_thr, int32_t *cand_det, int32_t *frame_cand_start);
 
+/* Whole-batch planning in one call: everything SeekerEngine.plan contributes to a batch.  One
+ * fnp_host_frame per frame points at the frame's own host arrays (nothing is concatenated by the
+ * caller); every output array is caller-allocated with the capacities fnp_host_plan_sizes reports
+ * (sizes3 = {detections, point tiles, point rows} of the batch): arrays indexed by candidate have
+ * room for `detections` entries, tile arrays for `point tiles`.  box_xywh: the 2D boxes are x, y, w, h
+ * (BOX_FORMAT other than 'xyxy', frustum_proposals_v1.py:597-601: the 2D NMS runs on the raw numbers,
+ * the corner is formed afterwards).  topk > 1 also fills frame_prop_start / prop_order (slot tables of
+ * stage 4).  Returns FNP_OK / FNP_EINVAL. */
+typedef struct fnp_host_frame {
+    int64_t n_rows;              /* points of the frame                                    */
+    const float *det_boxes;      /* (n_dets,4) fp32                                        */
+    const int64_t *det_labels;   /* (n_dets) 1..A                                          */
+    const float *det_scores;     /* (n_dets)                                               */
+    const int64_t *det_cam;      /* (n_dets) 0..5                                          */
+    const float *cam_mats;       /* (6,24): lidar2image rows 0..2 | combine | cam2lidar_t  */
+    int32_t n_dets;
+    int32_t reserved;
+} fnp_host_frame;
+
+typedef struct fnp_host_plan_out {
+    /* the batch metadata the device reads (fnp_seeker_batch fields of the same names) */
+    int64_t *frame_row_start;    /* (n_frames+1)   */
+    int32_t *tile_frame;         /* (tiles)        */
+    int32_t *tile_row0;          /* (tiles)        */
+    int32_t *frame_tile_start;   /* (n_frames+1)   */
+    float *cam_mats;             /* (n_frames,6,24)*/
+    int32_t *frame_cand_start;   /* (n_frames+1)   */
+    int32_t *cam_cand_start;     /* (6 n_frames+1) */
+    int32_t *cand_frame;         /* (detections)   */
+    int32_t *cand_cam;
+    int32_t *cand_label;
+    float *cand_box2d;           /* (detections,4) */
+    int32_t *nms_order;          /* (detections) stage-4 priority order                    */
+    int32_t *frame_prop_start;   /* (n_frames+1), topk > 1 only (else may be NULL)         */
+    int32_t *prop_order;         /* (detections * topk), topk > 1 only                     */
+    /* host-side bookkeeping */
+    float *cand_score;           /* (detections) 2D score of each candidate                */
+    int32_t *cand_det;           /* (detections) index of each candidate among the batch's detections, frames
+                                    back to back                                           */
+    /* written by the call */
+    int32_t n_cands, n_tiles, max_cands_per_frame, reserved;
+    int64_t total_rows;
+} fnp_host_plan_out;
+
+int fnp_host_plan_sizes(const fnp_host_frame *frames, int n_frames, int64_t *sizes3);
+int fnp_host_plan(const fnp_host_frame *frames, int n_frames, float nms_2d, float score_thr, int box_xywh,
+                  int topk, fnp_host_plan_out *out);
+
 /* Stage-4 priority order: inside every frame the candidates by descending 2D score, ties by
  * candidate index.  cand_score (F), frame_cand_start (n_frames+1), order (F) out. */
 int fnp_host_nms_order(const float *cand_score, const int32_t *frame_cand_start, int n_frames,

@@ -92,6 +92,7 @@ def head_table(ref_seeker, cfg_name, n_frames, ref_frames):
     # --- drop-in head, batch size 1 (the reference's operating point), device-resident batch_dict
     ours = proposer.FrustumProposerOG(model_cfg=dict(PARAMS=params), image_detector=proposer.SyntheticGLIP(frames[:1]),
                                       device="cuda:0")
+    ours.eval()
     bds = []
     for fr in frames:
         bd = synth.collate([fr])

@@ -77,10 +77,21 @@ extern "C" int fnp_host_select_candidates(const float *det_boxes, const int64_t 
     for (int g = 0; g < n_groups; g++) gstart[g + 1] += gstart[g];
     std::vector<int32_t> order(n_dets), fill(gstart.begin(), gstart.end() - 1);
     for (int i = 0; i < n_dets; i++) order[fill[group[i]]++] = i;
-    for (int g = 0; g < n_groups; g++)
-        if (gstart[g + 1] - gstart[g] > 1)
-            std::stable_sort(order.begin() + gstart[g], order.begin() + gstart[g + 1],
-                             [&](int32_t a, int32_t b) { return det_scores[a] > det_scores[b]; });
+    for (int g = 0; g < n_groups; g++) {
+        const int n = gstart[g + 1] - gstart[g];
+        int32_t *o = order.data() + gstart[g];
+        if (n > 1 && n <= 48) {          // the usual case: a stable insertion sort, no temporary buffer
+            for (int i = 1; i < n; i++) {
+                const int32_t v = o[i];
+                const float sv = det_scores[v];
+                int j = i - 1;
+                while (j >= 0 && det_scores[o[j]] < sv) { o[j + 1] = o[j]; j--; }
+                o[j + 1] = v;
+            }
+        } else if (n > 1) {
+            std::stable_sort(o, o + n, [&](int32_t a, int32_t b) { return det_scores[a] > det_scores[b]; });
+        }
+    }
     GreedyNms nms;
     std::vector<uint8_t> keep, keep_l;
     std::vector<int> idx_l;

@@ -118,6 +118,31 @@ class FrameInput:
     det_scores: np.ndarray        # (D,)
     det_cam_idx: np.ndarray       # (D,) 0..5
     gt_boxes: Optional[np.ndarray] = None   # (G,>=8): box7 ... class label last
+    _prep: Optional[dict] = None            # per-frame host preparation (prepare()); assigning any field drops it
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name != "_prep":
+            object.__setattr__(self, "_prep", None)
+
+    def prepare(self):
+        """Per-FRAME host work, done once (by the loader's worker threads, or lazily by the first plan()):
+        typed contiguous detection arrays, the frame's (6,24) camera-matrix block (inverse(K), combine --
+        frustum_proposals_v1.py:1442-1452, 1512-1535) and the fnp_host_frame record fnp_host_plan reads.
+        SeekerEngine.plan() then only joins the records of a batch and makes one C call."""
+        if self._prep is None:
+            boxes = np.ascontiguousarray(self.det_boxes, np.float32).reshape(-1, 4)
+            labels = np.ascontiguousarray(self.det_labels, np.int64).reshape(-1)
+            scores = np.ascontiguousarray(self.det_scores, np.float32).reshape(-1)
+            cam = np.ascontiguousarray(self.det_cam_idx, np.int64).reshape(-1)
+            assert boxes.shape[0] == labels.shape[0] == scores.shape[0] == cam.shape[0]
+            cm = np.ascontiguousarray(camera_matrices(self.lidar2image, self.camera2lidar, self.camera_intrinsics), np.float32)
+            assert cm.shape == (6, 24)
+            rec = _lib.HostFrame(n_rows=int(self.points.shape[0]), det_boxes=boxes.ctypes.data, det_labels=labels.ctypes.data,
+                                 det_scores=scores.ctypes.data, det_cam=cam.ctypes.data, cam_mats=cm.ctypes.data,
+                                 n_dets=int(scores.shape[0]), reserved=0)
+            self._prep = dict(blob=bytes(rec), keep=(boxes, labels, scores, cam, cm))
+        return self._prep
 
 
 class _Arena:
@@ -196,6 +221,17 @@ class SeekerEngine:
         self.host_s = dict(plan=0.0, execute=0.0, finish=0.0)   # host time spent per call kind (bench bookkeeping)
 
     # ------------------------------------------------------------------ host planning
+    @classmethod
+    def host_planner(cls, params=None, box_format="xyxy"):
+        """The planning half only (plan / plan_flat / plan_arrays), without a device: for loaders that plan ahead
+        of the GPU process, and for the CPU tests."""
+        self = object.__new__(cls)
+        self.p = resolve_params(params)
+        self.T, self.box_format = int(self.p["topk"]), box_format
+        self._cam_cache, self._tile_cache, self.host_cache = {}, {}, True
+        self.host_s = dict(plan=0.0, execute=0.0, finish=0.0)
+        return self
+
     def _cam_mats(self, frames):
         """(B,6,24) camera matrices; calibration repeats from frame to frame (it is fixed per
         scene), so the torch.inverse/matmul result is cached by the content of its inputs."""
@@ -225,8 +261,54 @@ class SeekerEngine:
     def plan(self, frames: List[FrameInput], xyz_offset=0, stride=None):
         """Everything the host contributes to a batch, as numpy arrays.  stride / xyz_offset describe
         the DEVICE point table handed to execute() (default: the frames' own row layout; (3, 0) for
-        a table gathered by HostPointFeeder)."""
+        a table gathered by HostPointFeeder).  One call into the C-ABI library (fnp_host_plan) over the
+        frames' prepared records; the arrays are views of one block that execute() uploads as it is."""
         t0 = time.perf_counter()
+        B = len(frames)
+        if stride is None:
+            stride = int(frames[0].points.shape[1]) if B else 5
+        blob = b"".join([f.prepare()["blob"] for f in frames])
+        sz = (C.c_int64 * 3)()
+        _lib.check(_lib.lib.fnp_host_plan_sizes(blob, B, sz), "fnp_host_plan_sizes")
+        D, n_tiles = int(sz[0]), int(sz[1])
+        T = self.T
+        spec = [("frame_row_start", np.int64, B + 1), ("tile_frame", np.int32, n_tiles), ("tile_row0", np.int32, n_tiles),
+                ("frame_tile_start", np.int32, B + 1), ("cam_mats", np.float32, B * 144), ("frame_cand_start", np.int32, B + 1),
+                ("cam_cand_start", np.int32, 6 * B + 1), ("cand_frame", np.int32, D), ("cand_cam", np.int32, D),
+                ("cand_label", np.int32, D), ("cand_box2d", np.float32, 4 * D), ("nms_order", np.int32, D)]
+        if T > 1:
+            spec += [("frame_prop_start", np.int32, B + 1), ("prop_order", np.int32, D * T)]
+        n_dev = len(spec)
+        spec += [("cand_score", np.float32, D), ("cand_det", np.int32, D)]        # host-side bookkeeping, not uploaded
+        offs, total, dev_bytes = {}, 0, 0
+        for i, (k, dt, n) in enumerate(spec):
+            offs[k] = total
+            total = _align(total + np.dtype(dt).itemsize * max(n, 1))
+            if i + 1 == n_dev:
+                dev_bytes = total
+        block = np.empty(total, np.uint8)
+        base = block.ctypes.data
+        out = _lib.HostPlanOut(**{k: base + offs[k] for k, _, _ in spec})
+        _lib.check(_lib.lib.fnp_host_plan(blob, B, float(self.p["nms_2d"]), float(self.p["score_thr"]),
+                                          int(self.box_format != "xyxy"), T, C.byref(out)), "fnp_host_plan")
+        F = int(out.n_cands)
+
+        def view(k, dt, n):
+            return block[offs[k]:offs[k] + np.dtype(dt).itemsize * n].view(dt)
+        plan = dict(B=B, F=F, n_tiles=int(out.n_tiles), stride=int(stride), xyz_offset=int(xyz_offset),
+                    total_rows=int(out.total_rows), max_cands=int(out.max_cands_per_frame),
+                    meta_block=block, meta_offs=offs, meta_dev_bytes=dev_bytes)
+        for k, dt, n in spec:
+            n_used = F if k.startswith("cand_") or k == "nms_order" else F * T if k == "prop_order" else n
+            plan[k] = view(k, dt, n_used)
+        plan["cand_box2d"] = view("cand_box2d", np.float32, 4 * F).reshape(F, 4)
+        plan["cam_mats"] = plan["cam_mats"].reshape(B, 6, 24)
+        self.host_s["plan"] += time.perf_counter() - t0
+        return plan
+
+    def plan_flat(self, frames: List[FrameInput], xyz_offset=0, stride=None):
+        """The same plan from flat numpy arrays (plan_arrays): the path FrustumProposerOG.get_proposals takes with
+        the detections of a collated batch_dict.  Kept equal to plan() by tests/test_host_cpu.py."""
         B = len(frames)
         n_rows = np.array([f.points.shape[0] for f in frames], dtype=np.int64)
         frame_row_start = np.zeros(B + 1, np.int64)
@@ -245,10 +327,8 @@ class SeekerEngine:
             det_boxes, det_labels = np.zeros((0, 4), np.float32), np.zeros(0, np.int64)
             det_scores, det_cam = np.zeros(0, np.float32), np.zeros(0, np.int64)
             cam_mats = np.zeros((0, 6, 24), np.float32)
-        out = self.plan_arrays(frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
-                               det_frame, det_cam)
-        self.host_s["plan"] += time.perf_counter() - t0
-        return out
+        return self.plan_arrays(frame_row_start, stride, xyz_offset, cam_mats, det_boxes, det_labels, det_scores,
+                                det_frame, det_cam)
 
     def _tiles(self, frame_row_start):
         key = frame_row_start.tobytes()
@@ -322,6 +402,16 @@ class SeekerEngine:
              "cam_cand_start", "cand_frame", "cand_cam", "cand_label", "cand_box2d", "nms_order"]
 
     def _upload_meta(self, plan, stream, slot=0):
+        if "meta_block" in plan:       # plan(): the arrays already lie in one block with these offsets
+            total = int(plan["meta_dev_bytes"])
+            host = self.arena.get("meta_host%d" % slot, total, pinned=True)
+            host.numpy()[:total] = plan["meta_block"][:total]
+            dev = self.arena.get("meta_dev%d" % slot, total)
+            _lib.check(_lib.lib.fnp_upload_from_pinned(dev.data_ptr(), host.data_ptr(), total, stream),
+                       "fnp_upload_from_pinned")
+            self.launches += 1
+            base = dev.data_ptr()
+            return {k: base + o for k, o in plan["meta_offs"].items()}
         offs, total = {}, 0
         keys = self._META + (["frame_prop_start", "prop_order"] if self.T > 1 else [])
         for k in keys:

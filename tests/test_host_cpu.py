@@ -170,3 +170,35 @@ def test_host_pack_xyz_multi_gathers_segments_back_to_back():
         assert t >= 0 and _lib.lib.fnp_host_pack_wait(t) == 0
         ref = np.concatenate([s[:, off:off + 3] for s in segs]) if rows else np.zeros((0, 3), np.float32)
         assert np.array_equal(dst[:rows], ref)
+
+
+def test_batch_planner_in_c_equals_the_numpy_path():
+    """SeekerEngine.plan (one fnp_host_plan call over the frames' prepared records) against plan_flat (numpy +
+    fnp_host_select_candidates on flat arrays): every array of the plan, for xyxy / xywh boxes, topk 1 and 3,
+    frames without detections, and an empty batch."""
+    from findnpropagate_b200.seeker import FrameInput, SeekerEngine
+    cfg = synth.SynthConfig("plan", 8, 180, 1, 40, 16, 6, 1)
+    sf = [synth.make_frame(i, cfg) for i in range(6)]
+    fis = [FrameInput(points=f.points, lidar2image=f.lidar2image, camera2lidar=f.camera2lidar,
+                      camera_intrinsics=f.camera_intrinsics, det_boxes=f.det_boxes, det_labels=f.det_labels,
+                      det_scores=f.det_scores, det_cam_idx=f.det_cam_idx, gt_boxes=f.gt_boxes) for f in sf]
+    fis[2].det_boxes, fis[2].det_labels = np.zeros((0, 4), np.float32), np.zeros(0, np.int64)
+    fis[2].det_scores, fis[2].det_cam_idx = np.zeros(0, np.float32), np.zeros(0, np.int64)
+    batch = [fis[i % 6] for i in range(17)]
+    for topk, fmt in ((1, "xyxy"), (3, "xywh")):
+        eng = SeekerEngine.host_planner(dict(synth.seeker_params(cfg), topk=topk), box_format=fmt)
+        for frames in (batch, batch[:1], [fis[2]], []):
+            a, b = eng.plan(frames, stride=3), eng.plan_flat(frames, stride=3)
+            assert a["F"] == b["F"] and (a["F"] > 0 or len(frames) < 2)
+            for k, vb in b.items():
+                va = a[k]
+                if isinstance(vb, np.ndarray):
+                    assert np.array_equal(np.asarray(va), vb), k
+                    assert va.dtype == vb.dtype or k == "cand_det", (k, va.dtype, vb.dtype)
+                else:
+                    assert va == vb, (k, va, vb)
+    # the prepared record follows the fields: assigning one drops it
+    p0 = fis[0].prepare()
+    assert fis[0].prepare() is p0
+    fis[0].det_scores = fis[0].det_scores.copy()
+    assert fis[0]._prep is None and fis[0].prepare() is not p0

@@ -40,9 +40,9 @@ class SeekerBatch(C.Structure):
         ("cam_mats", _vp), ("frame_cand_start", _vp), ("cam_cand_start", _vp), ("cand_frame", _vp), ("cand_cam", _vp),
         ("cand_label", _vp), ("cand_box2d", _vp), ("base_boxes", _vp), ("base_corners", _vp),
         ("mags", _vp),
-        ("tile_counts", _vp), ("tile_dst", _vp), ("tile_base", _vp), ("cell_masks", _vp), ("mask_words", C.c_int32),
-        ("stage_pts", _vp), ("stage_idx", _vp), ("cand_npts", _vp), ("cand_pt_start", _vp), ("frustum_pts", _vp),
-        ("frustum_idx", _vp), ("pts_capacity", C.c_int64), ("cand_stats", _vp), ("centres", _vp),
+        ("cell_masks", _vp), ("mask_words", C.c_int32), ("cand_npts", _vp), ("page_tab", _vp),
+        ("page_tab_stride", C.c_int32), ("page_planes", C.c_int32), ("frustum_pts", _vp),
+        ("pts_capacity", C.c_int64), ("cand_stats", _vp), ("centres", _vp),
         ("hyp_prep", _vp), ("hyp_index", _vp), ("hyp_iou", _vp), ("hyp_nvalid", _vp),
         ("hyp_boxes_dbg", _vp), ("hyp_iou_dbg", _vp), ("hyp_valid_dbg", _vp),
         ("split_points", C.c_int32), ("max_items", C.c_int32),
@@ -69,6 +69,7 @@ class HostPlanOut(C.Structure):
 
 
 CULL_TILE = 1024
+PAGE_POINTS = 256
 SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
 SEEKER_MULT, SEEKER_OCCL_MULT, SEEKER_MULTICAM_IOU = 1, 2, 4
 SWEEP_MIN_MAGS = 16
@@ -85,6 +86,14 @@ lib.fnp_count_in_boxes.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _vp]
 for _n in ("fnp_boxes_overlap_bev", "fnp_boxes_iou_bev"):
     getattr(lib, _n).restype = _i
     getattr(lib, _n).argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+lib.fnp_boxes_iou3d.restype = _i
+lib.fnp_boxes_iou3d.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+lib.fnp_boxes_aligned_iou3d.restype = _i
+lib.fnp_boxes_aligned_iou3d.argtypes = [_vp, _vp, _vp, _i, _vp]
+lib.fnp_points_in_boxes_matrix.restype = _i
+lib.fnp_points_in_boxes_matrix.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+lib.fnp_host_prep_boxes_cpu.restype = _i
+lib.fnp_host_prep_boxes_cpu.argtypes = [_vp, _vp, _i]
 lib.fnp_boxes_aligned_overlap_bev.restype = _i
 lib.fnp_boxes_aligned_overlap_bev.argtypes = [_vp, _vp, _vp, _i, _vp]
 lib.fnp_nms_workspace_bytes.restype = C.c_size_t
@@ -127,6 +136,8 @@ lib.fnp_host_pack_wait.argtypes = [_i]
 lib.fnp_upload_from_pinned.restype = _i
 lib.fnp_upload_from_pinned.argtypes = [_vp, _vp, C.c_size_t, _vp]
 
+lib.fnp_set_option.restype = _i
+lib.fnp_set_option.argtypes = [C.c_char_p, _i]
 lib.fnp_dbg_math.restype = _i
 lib.fnp_dbg_math.argtypes = [_vp, _vp, _vp, _i, _vp]
 
@@ -138,6 +149,7 @@ EXPORTED = [
     "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_occlusion", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
     "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin", "fnp_host_plan_sizes", "fnp_host_plan",
+    "fnp_points_in_boxes_matrix", "fnp_host_prep_boxes_cpu", "fnp_boxes_iou3d", "fnp_boxes_aligned_iou3d", "fnp_set_option",
 ]
 
 

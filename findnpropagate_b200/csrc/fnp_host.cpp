@@ -166,6 +166,46 @@ extern "C" int fnp_host_nms_order(const float *cand_score, const int32_t *frame_
 }
 
 // ---------------------------------------------------------------------------------------
+// Per-box constants of the reference's CPU point-in-box predicate (roiaware_pool3d.cpp:121-140), computed
+// where the reference computes them -- on the host, with the host's libm:
+//     cosa = cos(-rz), sina = sin(-rz)                        (float overloads: glibc cosf / sinf)
+//     in_z  = !(fabsf(z - cz) > dz / 2.0)                     (fp64 compare)
+//     in_xy = fabs(lx) < dx / 2.0 + MARGIN, MARGIN = 1e-2f    (fp64 compare, MARGIN a float constant)
+// The fp64 compares are hoisted into fp32 thresholds exactly:  |l| < t  <=>  |l| <= pred(t), pred(t) the
+// largest float strictly below t;  |sz| > h  <=>  |sz| > rd(h), rd = round down to float.
+// ---------------------------------------------------------------------------------------
+#include <cmath>
+#include <cstring>
+
+static float strict_below(double t)
+{
+    if (!(t > 0.0)) return (t != t) ? std::nanf("") : -1.0f;      // nothing is inside
+    float f = (float)t;                                           // round to nearest
+    if ((double)f >= t) f = std::nextafterf(f, -INFINITY);        // largest float < t
+    return f;
+}
+
+extern "C" int fnp_host_prep_boxes_cpu(const float *boxes_host, float *prep_host, int N)
+{
+    if (N < 0 || (N > 0 && (!boxes_host || !prep_host))) return FNP_EINVAL;
+    for (int i = 0; i < N; i++) {
+        const float *b = boxes_host + (size_t)i * 7;
+        float *q = prep_host + (size_t)i * 8;
+        const float rz = b[6];
+        q[0] = b[0]; q[1] = b[1]; q[2] = b[2];
+        const double h = (double)b[5] / 2.0;
+        float hz = (float)h;
+        if ((double)hz > h) hz = std::nextafterf(hz, -INFINITY);  // rd(h): |sz| > h  <=>  |sz| > rd(h) for float |sz|
+        q[3] = hz;
+        q[4] = cosf(-rz);
+        q[5] = sinf(-rz);
+        q[6] = strict_below((double)b[3] / 2.0 + (double)1e-2f);
+        q[7] = strict_below((double)b[4] / 2.0 + (double)1e-2f);
+    }
+    return FNP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Whole-batch planning in one call (what SeekerEngine.plan used to do in numpy, 3 ms per 256 frames
 // on the main thread): candidate selection as above over the frames' own detection arrays, the
 // per-(frame, camera rank) candidate ranges, the stage-4 priority order, the point-tile table and

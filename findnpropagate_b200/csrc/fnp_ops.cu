@@ -80,6 +80,40 @@ __global__ void __launch_bounds__(kCntThreads) count_segments_kernel(const float
 }
 
 // ======================================================================================
+// points_in_boxes_cpu semantics on the device: the (N, P) 0/1 matrix of the reference's CPU op
+// (roiaware_pool3d.cpp:121-168).  Its predicate is NOT the GPU op's: MARGIN is 1e-2 (1 cm) instead of
+// 1e-5, and the host compiler evaluates  lx = sx*cosa + sy*(-sina),  ly = sx*sina + sy*cosa  with every
+// product rounded (no fma on x86-64 without -mfma), with glibc's cosf/sinf.  The per-box constants
+// therefore come from the HOST (fnp_host_prep_boxes_cpu: glibc trig, the fp64 compares hoisted into fp32
+// thresholds exactly as for the GPU predicate); this kernel only does the rounded fp32 arithmetic.
+//   prep (N,8): cx, cy, cz, hz, cosa, sina, tx, ty   with  |l| < t  <=>  |l| <= t_prepared
+// ======================================================================================
+constexpr int kMatThreads = 256;
+constexpr int kMatBoxes = 16;     // boxes per CTA (rows of the output a CTA writes)
+
+__global__ void __launch_bounds__(kMatThreads) pib_matrix_kernel(const float *__restrict__ prep, const float *__restrict__ pts,
+                                                                 int32_t *__restrict__ out, int N, int P)
+{
+    __shared__ float s_box[kMatBoxes][8];
+    const int n0 = blockIdx.y * kMatBoxes;
+    const int nb = min(kMatBoxes, N - n0);
+    for (int i = threadIdx.x; i < nb * 8; i += kMatThreads) s_box[i / 8][i % 8] = prep[(size_t)n0 * 8 + i];
+    __syncthreads();
+    const int j = blockIdx.x * kMatThreads + threadIdx.x;
+    if (j >= P) return;
+    const float x = pts[(size_t)j * 3], y = pts[(size_t)j * 3 + 1], z = pts[(size_t)j * 3 + 2];
+    for (int k = 0; k < nb; k++) {
+        const float *q = s_box[k];
+        const float sz = __fsub_rn(z, q[2]);
+        const float sx = __fsub_rn(x, q[0]), sy = __fsub_rn(y, q[1]);
+        const float lx = __fadd_rn(__fmul_rn(sx, q[4]), __fmul_rn(sy, -q[5]));
+        const float ly = __fadd_rn(__fmul_rn(sx, q[5]), __fmul_rn(sy, q[4]));
+        const bool in = !(fabsf(sz) > q[3]) && (fabsf(lx) <= q[6]) && (fabsf(ly) <= q[7]);
+        out[(size_t)(n0 + k) * P + j] = in ? 1 : 0;      // coalesced along the points
+    }
+}
+
+// ======================================================================================
 // Rotated BEV overlap
 // ======================================================================================
 struct RBox {
@@ -262,6 +296,53 @@ __global__ void __launch_bounds__(128) aligned_overlap_kernel(const float *__res
     out[i] = box_overlap(A, B);
 }
 
+// 3D IoU from a BEV overlap (iou3d_nms_utils.py:48-81 / :83-117): height overlap, volumes, clamp and
+// division, every step one rounded fp32 operation in torch's order.
+__device__ __forceinline__ float iou3d_from_overlap(const float *__restrict__ a, const float *__restrict__ b, const float ov_bev)
+{
+    const float a_hi = __fadd_rn(a[2], __fmul_rn(a[5], 0.5f)), a_lo = __fsub_rn(a[2], __fmul_rn(a[5], 0.5f));
+    const float b_hi = __fadd_rn(b[2], __fmul_rn(b[5], 0.5f)), b_lo = __fsub_rn(b[2], __fmul_rn(b[5], 0.5f));
+    const float ov_h = fmaxf(__fsub_rn(fminf(a_hi, b_hi), fmaxf(a_lo, b_lo)), 0.f);
+    const float ov3 = __fmul_rn(ov_bev, ov_h);
+    const float va = __fmul_rn(__fmul_rn(a[3], a[4]), a[5]);
+    const float vb = __fmul_rn(__fmul_rn(b[3], b[4]), b[5]);
+    return __fdiv_rn(ov3, fmaxf(__fsub_rn(__fadd_rn(va, vb), ov3), 1e-6f));
+}
+
+__global__ void __launch_bounds__(256) pairwise_iou3d_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                             float *__restrict__ out, int N, int M)
+{
+    __shared__ RBox s_a[16], s_b[16];
+    __shared__ float s_ra[16][7], s_rb[16][7];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    if (threadIdx.x < 16) {
+        if (a0 + (int)threadIdx.x < N) {
+            s_a[threadIdx.x] = prep_rbox(a + (size_t)(a0 + threadIdx.x) * 7);
+            for (int k = 0; k < 7; k++) s_ra[threadIdx.x][k] = a[(size_t)(a0 + threadIdx.x) * 7 + k];
+        }
+    } else if (threadIdx.x < 32) {
+        const int k = threadIdx.x - 16;
+        if (b0 + k < M) {
+            s_b[k] = prep_rbox(b + (size_t)(b0 + k) * 7);
+            for (int c = 0; c < 7; c++) s_rb[k][c] = b[(size_t)(b0 + k) * 7 + c];
+        }
+    }
+    __syncthreads();
+    const int ai = a0 + ty, bi = b0 + tx;
+    if (ai >= N || bi >= M) return;
+    out[(size_t)ai * M + bi] = iou3d_from_overlap(s_ra[ty], s_rb[tx], box_overlap(s_a[ty], s_b[tx]));
+}
+
+__global__ void __launch_bounds__(128) aligned_iou3d_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                            float *__restrict__ out, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const RBox A = prep_rbox(a + (size_t)i * 7), B = prep_rbox(b + (size_t)i * 7);
+    out[i] = iou3d_from_overlap(a + (size_t)i * 7, b + (size_t)i * 7, box_overlap(A, B));
+}
+
 // ======================================================================================
 // NMS: 64x64 bitmask tiles + on-device greedy scan
 // ======================================================================================
@@ -305,44 +386,62 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float *__restrict__ 
     mask[(size_t)cur * cb + col_blk] = bits;
 }
 
-// one warp; remv (cb words) lives in dynamic shared memory
-__global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long *__restrict__ mask, int N,
-                                                      int64_t *__restrict__ keep, int32_t *__restrict__ num_keep)
+// Greedy scan over the bitmask, one CTA.  Per 64-box block: warp 0 resolves the block's own 64 boxes in order
+// (the only sequential part), then every thread ORs the kept rows' masks into one later block's "removed"
+// word -- loads coalesced along the blocks, four independent accumulators per thread.  remv (cb words) lives
+// in dynamic shared memory.
+constexpr int kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned long long *__restrict__ mask, int N,
+                                                                int64_t *__restrict__ keep, int32_t *__restrict__ num_keep)
 {
     extern __shared__ unsigned long long s_remv[];
-    const int lane = threadIdx.x;
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_nkeep;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int cb = divup(N, 64);
-    for (int j = lane; j < cb; j += 32) s_remv[j] = 0ULL;
-    __syncwarp();
-    int nkeep = 0;
+    for (int j = tid; j < cb; j += kScanThreads) s_remv[j] = 0ULL;
+    if (tid == 0) s_nkeep = 0;
+    __syncthreads();
     for (int b = 0; b < cb; b++) {
         const int n_in = min(64, N - b * 64);
-        const unsigned long long d0 = (lane < n_in) ? mask[(size_t)(b * 64 + lane) * cb + b] : 0ULL;
-        const unsigned long long d1 = (lane + 32 < n_in) ? mask[(size_t)(b * 64 + lane + 32) * cb + b] : 0ULL;
-        unsigned long long cur = s_remv[b];
-        unsigned long long kept = 0ULL;
-        for (int r = 0; r < n_in; r++) {
-            const unsigned long long d = __shfl_sync(0xffffffffu, (r < 32) ? d0 : d1, r & 31);
-            if (!((cur >> r) & 1ULL)) { kept |= 1ULL << r; cur |= d; }
-        }
-        // emit kept indices in order
-        for (int r = lane; r < n_in; r += 32)
-            if ((kept >> r) & 1ULL) keep[nkeep + __popcll(kept & ((1ULL << r) - 1ULL))] = (int64_t)b * 64 + r;
-        nkeep += __popcll(kept);
-        // propagate the kept rows' masks to later blocks
-        for (int j = b + 1 + lane; j < cb; j += 32) {
-            unsigned long long acc = s_remv[j];
-            unsigned long long k2 = kept;
-            while (k2) {
-                const int r = __ffsll((long long)k2) - 1;
-                k2 &= k2 - 1;
-                acc |= mask[(size_t)(b * 64 + r) * cb + j];
+        if (tid < 32) {
+            const unsigned long long d0 = (lane < n_in) ? mask[(size_t)(b * 64 + lane) * cb + b] : 0ULL;
+            const unsigned long long d1 = (lane + 32 < n_in) ? mask[(size_t)(b * 64 + lane + 32) * cb + b] : 0ULL;
+            unsigned long long cur = s_remv[b];
+            unsigned long long kept = 0ULL;
+            for (int r = 0; r < n_in; r++) {
+                const unsigned long long d = __shfl_sync(0xffffffffu, (r < 32) ? d0 : d1, r & 31);
+                if (!((cur >> r) & 1ULL)) { kept |= 1ULL << r; cur |= d; }
             }
-            s_remv[j] = acc;
+            const int nkeep = s_nkeep;
+            for (int r = lane; r < n_in; r += 32)      // emit kept indices in order
+                if ((kept >> r) & 1ULL) keep[nkeep + __popcll(kept & ((1ULL << r) - 1ULL))] = (int64_t)b * 64 + r;
+            __syncwarp();
+            if (lane == 0) { s_kept = kept; s_nkeep = nkeep + __popcll(kept); }
         }
-        __syncwarp();
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        for (int j = b + 1 + tid; j < cb; j += kScanThreads) {     // propagate the kept rows' masks to later blocks
+            unsigned long long a0 = 0ULL, a1 = 0ULL, a2 = 0ULL, a3 = 0ULL, k2 = kept;
+            const unsigned long long *col = mask + (size_t)(b * 64) * cb + j;
+            while (k2) {
+                int r = __ffsll((long long)k2) - 1; k2 &= k2 - 1;
+                a0 |= col[(size_t)r * cb];
+                if (!k2) break;
+                r = __ffsll((long long)k2) - 1; k2 &= k2 - 1;
+                a1 |= col[(size_t)r * cb];
+                if (!k2) break;
+                r = __ffsll((long long)k2) - 1; k2 &= k2 - 1;
+                a2 |= col[(size_t)r * cb];
+                if (!k2) break;
+                r = __ffsll((long long)k2) - 1; k2 &= k2 - 1;
+                a3 |= col[(size_t)r * cb];
+            }
+            s_remv[j] |= (a0 | a1) | (a2 | a3);
+        }
+        __syncthreads();
     }
-    if (lane == 0) *num_keep = nkeep;
+    if (tid == 0) *num_keep = s_nkeep;
 }
 
 // ======================================================================================
@@ -583,6 +682,40 @@ extern "C" int fnp_boxes_aligned_overlap_bev(const float *a, const float *b, flo
     return FNP_OK;
 }
 
+extern "C" int fnp_points_in_boxes_matrix(const float *box_prep, const float *pts, int32_t *out, int N, int P, void *stream)
+{
+    if (N < 0 || P < 0) return FNP_EINVAL;
+    if (N == 0 || P == 0) return FNP_OK;
+    if (!box_prep || !pts || !out) return FNP_EINVAL;
+    if (divup(N, kMatBoxes) > 65535) return FNP_EINVAL;
+    dim3 grid(divup(P, kMatThreads), divup(N, kMatBoxes));
+    pib_matrix_kernel<<<grid, kMatThreads, 0, (cudaStream_t)stream>>>(box_prep, pts, out, N, P);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_boxes_iou3d(const float *a, const float *b, float *out, int N, int M, void *stream)
+{
+    if (N < 0 || M < 0) return FNP_EINVAL;
+    if (N == 0 || M == 0) return FNP_OK;
+    if (!a || !b || !out) return FNP_EINVAL;
+    if (divup(N, 16) > 65535) return FNP_EINVAL;
+    dim3 grid(divup(M, 16), divup(N, 16));
+    pairwise_iou3d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, out, N, M);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
+extern "C" int fnp_boxes_aligned_iou3d(const float *a, const float *b, float *out, int N, void *stream)
+{
+    if (N < 0) return FNP_EINVAL;
+    if (N == 0) return FNP_OK;
+    if (!a || !b || !out) return FNP_EINVAL;
+    aligned_iou3d_kernel<<<divup(N, 128), 128, 0, (cudaStream_t)stream>>>(a, b, out, N);
+    FNP_LAUNCH_CHECK();
+    return FNP_OK;
+}
+
 extern "C" size_t fnp_nms_workspace_bytes(int N)
 {
     if (N <= 0) return 16;
@@ -614,7 +747,7 @@ static int nms_impl(const float *boxes, int N, float thresh, int64_t *keep, int3
     const size_t smem = (size_t)cb * 8;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_scan_kernel<<<1, 32, smem, st>>>(mask, N, keep, num_keep);
+    nms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, N, keep, num_keep);
     FNP_LAUNCH_CHECK();
     return FNP_OK;
 }

@@ -8,37 +8,48 @@
 //   stage 2a  :851-911,:1392-1411 hypothesis grid, softmin front shift, distance/IoU filters
 //   stage 2b  :930-932            one points_in_boxes_gpu launch + sum + D2H per hypothesis
 //   stage 3   :994-1053           density+IoU score, sort, nms_normal(thresh 1), top-1
+#include <string>
+
 #include "fnp_common.cuh"
 
 namespace fnp {
 
 constexpr int kCullThreads = 256;                       // one point per thread per sub-tile
 constexpr int kCullSub = FNP_CULL_TILE / kCullThreads;  // sub-tiles of one CTA tile
-constexpr int kCullWarps = kCullThreads / 32;
-constexpr int kCullVW = kCullSub * kCullWarps;          // "virtual warps" of a tile, in row order
 constexpr int kStatsFloats = 40;
 static_assert(FNP_CULL_TILE % kCullThreads == 0, "tile must be a whole number of sub-tiles");
 
 // ======================================================================================
-// Stage 1: projection + frustum cull + ordered compaction
-//   cell_table_kernel:  per (frame, camera rank) a grid of 64-px image cells, each holding the
-//       bitmask of the rank's candidates whose 2D box touches the cell (conservative);
-//   cull_stage_kernel:  reads every point ONCE.  Per camera a division-free "certainly off
-//       this image" test on packed point pairs, the reference's exact IEEE u, v only for the
-//       survivors, one cell lookup, exact box tests for the few bits set there.  Membership
-//       stays in registers; ballot/popc give per-(warp, candidate) populations, one atomicAdd
-//       per tile reserves the tile's slice of a staging buffer, and member points are written
-//       there as (x, y, z, depth) of the *unprojected* point, candidate-major, in input order;
-//   scans (scan_tiles_kernel, scan_cands_kernel): exclusive prefixes of the per-tile
-//       populations -> where every tile's slice lands inside every frustum;
-//   cull_gather_kernel: copies the slices to their final, input-ordered position in the
-//       pair-interleaved frustum buffer (deterministic, whatever order the tiles ran in).
+// Frustum point storage: pages.
+//   A frustum's points live in pages of FNP_PAGE_POINTS (256) points, SoA inside the page:
+//   x[256] | y[256] | z[256] | d[256] (| source row[256] with page_planes == 5), xyz of the *unprojected*
+//   point and its camera depth.  Point i of frustum f is slot i & 255 of page page_tab[f][i >> 8].  Pages are
+//   handed out from one pool by an atomic cursor while stage 1 runs, so stage 1 needs no counting pass, no
+//   scan and no reordering pass: a tile reserves a range of the frustum's point indices with one atomic on
+//   the frustum's fill counter and writes its members there.
+//   The ORDER of a frustum's points is therefore whatever order the tiles got to it.  Nothing downstream
+//   depends on it: the depth quantiles are exact order statistics, the AABB is min/max, the per-hypothesis
+//   counts are integer sums -- every output is bit-identical whatever the order (the debug view sorts by
+//   source row).  A page of one plane is 1 KB contiguous: x, y, z of a page are one 3 KB TMA bulk copy for
+//   the scoring kernels, and (x0,x1) of neighbouring points are one 64-bit shared-memory word, the operand
+//   of the packed fp32x2 instructions.
 // ======================================================================================
-// Frustum points are stored pair-interleaved: points 2p and 2p+1 of the buffer share one 32-byte
-// record {x0,x1, y0,y1, z0,z1, d0,d1}, so that the scoring kernel reads (x0,x1) / (y0,y1) /
-// (z0,z1) as the 64-bit operands of Blackwell's packed fp32x2 instructions.  Every frustum
-// starts at an even point index.  pair_slot(i) = float offset of x of point i.
-__device__ __forceinline__ size_t pair_slot(int64_t i) { return (size_t)(i >> 1) * 8 + (size_t)(i & 1); }
+constexpr int kPage = FNP_PAGE_POINTS;
+static_assert(kPage == 256, "page = 256 points: the stats kernel's block size, the sweep kernel's chunk");
+
+__device__ __forceinline__ int ld_volatile(const int *p)
+{
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Page k of frustum f (nullptr: the pool overflowed).  Only for kernels that run AFTER stage 1.
+__device__ __forceinline__ const float *page_of(const fnp_seeker_batch &b, int f, int k)
+{
+    const int pg = b.page_tab[(size_t)f * b.page_tab_stride + k];
+    return b.frustum_pts + (size_t)(pg - 1) * (size_t)(b.page_planes * kPage);
+}
 
 __device__ __constant__ int kImageOrder[6] = {2, 0, 1, 5, 3, 4};   // frustum_proposals_v1.py:201
 
@@ -48,27 +59,106 @@ constexpr float kCellInv = 1.0f / kCellPx;
 __host__ __device__ inline int cell_cols(float img_w) { return (int)((img_w + kCellPx - 1) / kCellPx); }
 __host__ __device__ inline int cell_rows(float img_h) { return (int)((img_h + kCellPx - 1) / kCellPx); }
 
+constexpr int kCullList = 1280;      // member entries a tile can hold in shared memory (typical: ~300)
+
 struct alignas(16) CullSmem {
     float cam[6][24];       // by camera index
     int cs[8];              // candidate range per camera RANK, local to the frame: [cs[r], cs[r+1])
-    int tile_base;          // first staging slot of this tile
-    int tile_total;
+    int n_list;             // entries pushed (may exceed kCullList: then the tile takes the direct pass)
+    unsigned all_ranks;     // bit r: camera rank r has candidates in this frame
+    int pad[2];
+    unsigned sect[64];      // the frame's sector table: camera ranks that can see a point of the sector
 };
-static_assert(sizeof(CullSmem) % 16 == 0, "the float4 box table follows this struct in shared memory");
+static_assert(sizeof(CullSmem) % 16 == 0, "the float4 tables follow this struct in shared memory");
 
-// bits [lo, hi) of word w (bit j of word w = candidate 32 w + j)
-__device__ __forceinline__ unsigned range_bits(int lo, int hi, int w)
+// --------------------------------------------------------------------------------------
+// Azimuth sectors: which cameras can see a point at all.
+//   The horizontal plane around the LiDAR is cut into 64 sectors (4 quadrants x 16 steps of the "diamond
+//   angle" |y| / (|x| + |y|), which needs no atan).  Per frame a 64-entry table holds, for every sector, the
+//   set of camera ranks that can possibly see a point of that sector; the membership pass then projects a
+//   point into those cameras only (1-2 instead of 6).  The table is CONSERVATIVE: camera c is dropped from a
+//   sector only if no point p of the sector's region
+//        R = { rho >= kSecRho0, theta in the sector widened by kSecMargin, |z| <= kSecZ }
+//   can pass the exact on-image test, proved with interval bounds on the linear forms wx, wy, wz of
+//   lidar2image (in fp64, with a slack kSecSlack that is > 20x the fp32 rounding error of the forms):
+//        front of the camera:  sup wx >= -slack, sup (W' wz - wx) >= -slack, sup wy >= -slack,
+//                              sup (H' wz - wy) >= -slack, sup wz >= 0              (each is necessary)
+//        behind it (depth clamps to 1e-5, so u = wx / 1e-5: a thin tube through the camera centre can still
+//        land on the image):  |wx| <= slack, |wy| <= slack feasible and inf wz <= 1.
+//   Points outside R (closer than kSecRho0, |z| > kSecZ, non-finite) take all cameras.  A wrong table could
+//   only ADD work, never change a result, as long as it is a superset; tests/test_seeker_gpu.py runs stage 1
+//   with and without the table on adversarial points (near the cameras, on the tubes, on sector borders).
+// --------------------------------------------------------------------------------------
+constexpr int kSectors = 64;
+constexpr float kSecRho0 = 3.0f, kSecZ = 16.0f;
+constexpr double kSecMargin = 0.02, kSecSlack = 1.0;
+
+__device__ __forceinline__ int sector_of(const float x, const float y)
 {
-    const int a = min(max(lo - 32 * w, 0), 32), b = min(max(hi - 32 * w, 0), 32);
-    const unsigned below_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-    const unsigned below_a = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
-    return below_b & ~below_a;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float q = __fdividef(ay, ax + ay);                      // in [0, 1]; any rounding is far inside kSecMargin
+    const int iq = min((int)(q * 16.0f), 15);
+    return ((x < 0.f) ? 32 : 0) | ((y < 0.f) ? 16 : 0) | iq;
+}
+
+__device__ bool angle_in(double a, double t0, double t1)
+{
+    const double two_pi = 6.283185307179586;
+    double d = fmod(a - t0, two_pi);
+    if (d < 0) d += two_pi;
+    return d <= t1 - t0;
+}
+
+// sup / inf over the sector region of the linear form a x + b y + c z + e
+__device__ void form_range(double a, double b, double c, double e, double t0, double t1, double &sup, double &inf)
+{
+    const double r = hypot(a, b), phi = atan2(b, a);
+    const double h0 = a * cos(t0) + b * sin(t0), h1 = a * cos(t1) + b * sin(t1);
+    double hmax = fmax(h0, h1), hmin = fmin(h0, h1);
+    if (angle_in(phi, t0, t1)) hmax = r;
+    if (angle_in(phi + 3.141592653589793, t0, t1)) hmin = -r;
+    const double INF = 1e300;
+    sup = (hmax > 0 ? INF : (double)kSecRho0 * hmax) + fabs(c) * (double)kSecZ + e;
+    inf = (hmin < 0 ? -INF : (double)kSecRho0 * hmin) - fabs(c) * (double)kSecZ + e;
+}
+
+__device__ bool sector_sees(const float *__restrict__ L, const int s, const float img_w, const float img_h)
+{
+    const double PI = 3.141592653589793;
+    const int iq = s & 15;
+    const double q0 = iq / 16.0, q1 = (iq + 1) / 16.0;
+    const double a0 = atan2(q0, 1.0 - q0), a1 = atan2(q1, 1.0 - q1);      // angles of (|x|, |y|), a0 < a1
+    double t0, t1;
+    switch (s >> 4) {
+        case 0: t0 = a0; t1 = a1; break;                 // x >= 0, y >= 0
+        case 1: t0 = -a1; t1 = -a0; break;               // x >= 0, y <  0
+        case 2: t0 = PI - a1; t1 = PI - a0; break;       // x <  0, y >= 0
+        default: t0 = -PI + a0; t1 = -PI + a1; break;    // x <  0, y <  0
+    }
+    t0 -= kSecMargin; t1 += kSecMargin;
+    const double W = (double)img_w * 1.001, H = (double)img_h * 1.001;
+    double sup[5], inf[5];
+    // forms: wx, wy, wz, W wz - wx, H wz - wy
+    const double f[5][4] = {
+        {L[0], L[1], L[2], L[3]}, {L[4], L[5], L[6], L[7]}, {L[8], L[9], L[10], L[11]},
+        {W * L[8] - L[0], W * L[9] - L[1], W * L[10] - L[2], W * L[11] - L[3]},
+        {H * L[8] - L[4], H * L[9] - L[5], H * L[10] - L[6], H * L[11] - L[7]}};
+    for (int k = 0; k < 5; k++) {
+        if (!(isfinite(f[k][0]) && isfinite(f[k][1]) && isfinite(f[k][2]) && isfinite(f[k][3]))) return true;
+        form_range(f[k][0], f[k][1], f[k][2], f[k][3], t0, t1, sup[k], inf[k]);
+    }
+    const bool front = sup[0] >= -kSecSlack && sup[1] >= -kSecSlack && sup[2] >= 0.0 && sup[3] >= -kSecSlack &&
+                       sup[4] >= -kSecSlack;
+    const bool back = inf[0] <= kSecSlack && sup[0] >= -kSecSlack && inf[1] <= kSecSlack && sup[1] >= -kSecSlack &&
+                      inf[2] <= 1.0;
+    return front || back;
 }
 
 // One CTA per (frame, camera rank): cell -> candidates of that rank whose box may contain a
-// pixel of the cell.  Conservative (a superset); the exact test follows in cull_stage_kernel.
+// pixel of the cell.  Conservative (a superset); the exact test follows in cull_kernel.
 template <int W>
-__global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch b, const int n_cu, const int n_cv)
+__global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch b, const int n_cu, const int n_cv,
+                                                         const float img_w, const float img_h)
 {
     extern __shared__ unsigned s_cells[];                 // [n_cu * n_cv][W]
     const int frame = blockIdx.x / 6, r = blockIdx.x % 6;
@@ -91,6 +181,12 @@ __global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch 
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_cells * W; i += blockDim.x) out[i] = s_cells[i];
+    // sector table of the frame (after the cell masks of all frames; zeroed by the host call): bit r of entry s
+    if (hi > lo && (int)threadIdx.x < kSectors) {
+        unsigned *sect = b.cell_masks + (size_t)b.n_frames * 6 * n_cells * W + (size_t)frame * kSectors;
+        const float *L = b.cam_mats + ((size_t)frame * 6 + kImageOrder[r]) * 24;
+        if (sector_sees(L, threadIdx.x, img_w, img_h)) atomicOr(&sect[threadIdx.x], 1u << r);
+    }
 }
 
 // wx, wy, wz of two points against one camera: the three rows of lidar2image, each
@@ -119,20 +215,121 @@ __device__ __forceinline__ unsigned long long row2(const float *__restrict__ a, 
 
 constexpr int kPtsPerThread = kCullSub;   // a thread owns row (sub * kCullThreads + tid) of every sub-tile
 
+// Writes one member point to slot v of frustum f (global candidate index).  Spins (briefly) if the page
+// that holds the slot is being handed out by another tile at this moment.
+__device__ __forceinline__ void store_member(const fnp_seeker_batch &b, const int f, const int v, const float X,
+                                             const float Y, const float Z, const float d, const int row)
+{
+    const int *slot_of_page = b.page_tab + (size_t)f * b.page_tab_stride + (v >> 8);
+    int pg = ld_volatile(slot_of_page);
+    while (pg == 0) pg = ld_volatile(slot_of_page);
+    if (pg < 0) return;                       // pool exhausted: the batch is re-run with a larger pool
+    float *base = b.frustum_pts + (size_t)(pg - 1) * (size_t)(b.page_planes * kPage) + (v & (kPage - 1));
+    base[0] = X; base[kPage] = Y; base[2 * kPage] = Z; base[3 * kPage] = d;
+    if (b.page_planes > 4) reinterpret_cast<int *>(base)[4 * kPage] = row;
+}
+
+// The membership pass of a tile.  Per camera a division-free "certainly off this image" test on packed
+// point pairs, the reference's exact IEEE u, v only for the survivors, one lookup in the camera's cell
+// table, exact half-open box tests for the few bits set there.  A member (point, candidate) pair gets its
+// rank among the tile's members of that candidate from a shared-memory atomic and
+//   DIRECT == false: is appended to the tile's member list (unprojected point, candidate, rank);
+//   DIRECT == true : is written to its final place at once (s_base[] = the tile's reservation).
+template <bool DIRECT, int W>
+__device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem &S, const float4 *s_box, int *s_cnt,
+                                             const int *s_base, float4 *s_ent, int *s_key, int *s_row,
+                                             const float (&x)[kPtsPerThread], const float (&y)[kPtsPerThread],
+                                             const float (&z)[kPtsPerThread], const bool (&live)[kPtsPerThread],
+                                             const int frame, const int c0, const int row0, const float img_w,
+                                             const float img_h, const int n_cu, const int n_cv, const bool use_sectors)
+{
+    const int tid = threadIdx.x;
+    // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
+    const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
+    const int n_cells = n_cu * n_cv;
+#pragma unroll
+    for (int s = 0; s < kPtsPerThread; s++) {
+        // cameras (ranks) that can see this point at all: the frame's sector table, or every rank with candidates
+        unsigned cams = 0u;
+        if (live[s]) {
+            const float rho2 = __fmaf_rn(y[s], y[s], __fmul_rn(x[s], x[s]));
+            const bool in_region = use_sectors & (rho2 >= kSecRho0 * kSecRho0) & (rho2 < 1e12f) & (fabsf(z[s]) <= kSecZ);
+            cams = in_region ? S.sect[sector_of(x[s], y[s])] : S.all_ranks;
+        }
+        // the 32 points of a warp's sub-tile are neighbours in the sweep: their camera sets nearly coincide
+        unsigned todo = __reduce_or_sync(0xffffffffu, cams);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float *L = S.cam[kImageOrder[r]];
+            const float wx = __fadd_rn(dot3(L + 0, x[s], y[s], z[s]), L[3]);
+            const float wy = __fadd_rn(dot3(L + 4, x[s], y[s], z[s]), L[7]);
+            const float wz = __fadd_rn(dot3(L + 8, x[s], y[s], z[s]), L[11]);
+            const float d = fminf(fmaxf(wz, 1e-5f), 1e5f);
+            // cheap, division-free "certainly off this image" test
+            const bool off = (wx < -1e-30f) | (wy < -1e-30f) | (wx > __fmul_rn(w_hi, d)) | (wy > __fmul_rn(h_hi, d));
+            if (!live[s] | off) continue;
+            // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
+            const float u = __fdiv_rn(wx, d), v = __fdiv_rn(wy, d);
+            if (!((v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f))) continue;
+            const int cell = min((int)(v * kCellInv), n_cv - 1) * n_cu + min((int)(u * kCellInv), n_cu - 1);
+            const unsigned *cm = b.cell_masks + (((size_t)frame * 6 + r) * n_cells + cell) * W;
+            bool have = false;
+            float X = 0.f, Y = 0.f, Z = 0.f;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                unsigned m = __ldg(cm + w);
+                while (m) {
+                    const int jb = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j = 32 * w + jb;
+                    const float4 bx = s_box[j];
+                    if (!((v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x))) continue;
+                    if (!have) {     // the reference tests unproject(project(p)) (:812-815): one per (point, camera)
+                        unproject(L + 12, L + 21, u, v, d, X, Y, Z);
+                        have = true;
+                    }
+                    const int rank = atomicAdd(&s_cnt[j], 1);
+                    const int row = row0 + s * kCullThreads + tid;
+                    if (DIRECT) {
+                        store_member(b, c0 + j, s_base[j] + rank, X, Y, Z, d, row);
+                    } else {
+                        const int e = atomicAdd(&S.n_list, 1);
+                        if (e < kCullList) {
+                            s_ent[e] = make_float4(X, Y, Z, d);
+                            s_key[e] = (j << 16) | rank;
+                            s_row[e] = row;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Stage 1 proper: one CTA per 1024-point tile; reads every point ONCE.
+//   1. membership pass -> member list in shared memory, per-candidate populations;
+//   2. one atomic per (tile, candidate with members) on the frustum's fill counter reserves a range of its
+//      point indices; the reservation that contains the first slot of a page takes that page from the pool;
+//   3. the list is flushed to the reserved slots by full warps.
+// A tile whose members do not fit the list (kCullList) repeats the membership pass with direct writes.
 template <int W>
-__global__ void __launch_bounds__(kCullThreads, 5) cull_stage_kernel(const fnp_seeker_batch b, const float img_w,
-                                                                  const float img_h, const int n_cu, const int n_cv)
+__global__ void __launch_bounds__(kCullThreads, 5) cull_kernel(const fnp_seeker_batch b, const float img_w,
+                                                            const float img_h, const int n_cu, const int n_cv,
+                                                            const int use_sectors)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CullSmem &S = *reinterpret_cast<CullSmem *>(smem_raw);
     const int Cmax = b.max_cands_per_frame;
     float4 *s_box = reinterpret_cast<float4 *>(smem_raw + sizeof(CullSmem));            // [Cmax]
-    int *s_cnt = reinterpret_cast<int *>(s_box + Cmax);                                  // [kCullVW][Cmax]
-    int *s_off = s_cnt + kCullVW * Cmax;                                                 // [Cmax] slice offset of a candidate
-    unsigned *s_rm = reinterpret_cast<unsigned *>(s_off + Cmax);                         // [6][W] rank bit ranges
+    float4 *s_ent = s_box + Cmax;                                                        // [kCullList]
+    int *s_key = reinterpret_cast<int *>(s_ent + kCullList);                             // [kCullList]
+    int *s_row = s_key + kCullList;                                                      // [kCullList]
+    int *s_cnt = s_row + kCullList;                                                      // [Cmax] members of a candidate in this tile
+    int *s_base = s_cnt + Cmax;                                                          // [Cmax] first reserved slot
 
     const int tile = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int frame = b.tile_frame[tile];
     const int row0 = b.tile_row0[tile];
     const int64_t frow = b.frame_row_start[frame];
@@ -157,286 +354,72 @@ __global__ void __launch_bounds__(kCullThreads, 5) cull_stage_kernel(const fnp_s
     }
 
     // ---- per-CTA setup
-    for (int i = tid; i < 6 * 24; i += kCullThreads) S.cam[i / 24][i % 24] = b.cam_mats[(size_t)frame * 144 + i];
-    for (int j = tid; j < nc; j += kCullThreads) s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
-    for (int i = tid; i < kCullVW * Cmax; i += kCullThreads) s_cnt[i] = 0;
+    if (tid < 6 * 24) (&S.cam[0][0])[tid] = b.cam_mats[(size_t)frame * 144 + tid];
+    for (int j = tid; j < nc; j += kCullThreads) { s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j]; s_cnt[j] = 0; }
     if (tid < 7) S.cs[tid] = b.cam_cand_start[frame * 6 + tid] - c0;
-    __syncthreads();
-    if (tid < 6 * W) s_rm[tid] = range_bits(S.cs[tid / W], S.cs[tid / W + 1], tid % W);
-
-    unsigned mask[kPtsPerThread][W];
-#pragma unroll
-    for (int s = 0; s < kPtsPerThread; s++)
-#pragma unroll
-        for (int w = 0; w < W; w++) mask[s][w] = 0u;
-
-    // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
-    const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
-    const int n_cells = n_cu * n_cv;
-
-    // ---- membership
-#pragma unroll 1
-    for (int r = 0; r < 6; r++) {
-        if (S.cs[r] == S.cs[r + 1]) continue;                       // camera without candidates
-        const float *L = S.cam[kImageOrder[r]];
-        float wx[kPtsPerThread], wy[kPtsPerThread], d[kPtsPerThread];
-        bool maybe[kPtsPerThread];
-        bool any_maybe = false;
-#pragma unroll
-        for (int s = 0; s < kPtsPerThread; s += 2) {
-            const unsigned long long x2 = pack2(x[s], x[s + 1]), y2 = pack2(y[s], y[s + 1]), z2 = pack2(z[s], z[s + 1]);
-            float wz0, wz1;
-            unpack2(row2(L + 0, x2, y2, z2), wx[s], wx[s + 1]);
-            unpack2(row2(L + 4, x2, y2, z2), wy[s], wy[s + 1]);
-            unpack2(row2(L + 8, x2, y2, z2), wz0, wz1);
-            d[s] = fminf(fmaxf(wz0, 1e-5f), 1e5f);
-            d[s + 1] = fminf(fmaxf(wz1, 1e-5f), 1e5f);
-        }
-#pragma unroll
-        for (int s = 0; s < kPtsPerThread; s++) {
-            // cheap, division-free "certainly off this image" test
-            const bool off = (wx[s] < -1e-30f) | (wy[s] < -1e-30f) | (wx[s] > __fmul_rn(w_hi, d[s])) |
-                             (wy[s] > __fmul_rn(h_hi, d[s]));
-            maybe[s] = live[s] & !off;
-            any_maybe |= maybe[s];
-        }
-        if (!__any_sync(0xffffffffu, any_maybe)) continue;
-        const unsigned *cells = b.cell_masks + ((size_t)frame * 6 + r) * n_cells * W;
-#pragma unroll
-        for (int s = 0; s < kPtsPerThread; s++) {
-            if (!maybe[s]) continue;
-            // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
-            const float u = __fdiv_rn(wx[s], d[s]), v = __fdiv_rn(wy[s], d[s]);
-            if (!((v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f))) continue;
-            const int cell = min((int)(v * kCellInv), n_cv - 1) * n_cu + min((int)(u * kCellInv), n_cu - 1);
-            const unsigned *cm = cells + (size_t)cell * W;
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                unsigned m = __ldg(cm + w);
-                while (m) {
-                    const int jb = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float4 bx = s_box[32 * w + jb];
-                    const bool in = (v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x);
-                    mask[s][w] |= (in ? 1u : 0u) << jb;
-                }
-            }
-        }
-    }
-
-    // ---- populations per (virtual warp, candidate)
-#pragma unroll
-    for (int s = 0; s < kPtsPerThread; s++) {
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            unsigned any = __reduce_or_sync(0xffffffffu, mask[s][w]);
-            while (any) {
-                const int j = __ffs(any) - 1;
-                any &= any - 1;
-                const unsigned m = __ballot_sync(0xffffffffu, (mask[s][w] >> j) & 1u);
-                if (lane == 0) s_cnt[(s * kCullWarps + warp) * Cmax + 32 * w + j] = __popc(m);
-            }
-        }
+    if (tid == 7) S.n_list = 0;
+    if (tid >= 32 && tid < 32 + kSectors)
+        S.sect[tid - 32] = b.cell_masks[(size_t)b.n_frames * 6 * n_cu * n_cv * W + (size_t)frame * kSectors + (tid - 32)];
+    if (tid == 8) {
+        unsigned all = 0u;
+        for (int r = 0; r < 6; r++)
+            if (b.cam_cand_start[frame * 6 + r + 1] > b.cam_cand_start[frame * 6 + r]) all |= 1u << r;
+        S.all_ranks = all;
     }
     __syncthreads();
-    // exclusive prefix over the virtual warps of every candidate; the tile's population of it
+
+    cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+                           n_cu, n_cv, use_sectors != 0);
+    __syncthreads();
+    const int n_list = S.n_list;
+    if (n_list == 0) return;
+
+    // ---- reserve slots; hand out the pages whose first slot lies in the reservation
+    const int n_pages_cap = (int)(b.pts_capacity / kPage);
     for (int j = tid; j < nc; j += kCullThreads) {
-        int run = 0;
-#pragma unroll
-        for (int vw = 0; vw < kCullVW; vw++) {
-            const int c = s_cnt[vw * Cmax + j];
-            s_cnt[vw * Cmax + j] = run;
-            run += c;
-        }
-        b.tile_counts[(size_t)tile * Cmax + j] = run;
-        s_off[j] = run;
-    }
-    __syncthreads();
-    // exclusive prefix over candidates (one warp), then reserve the tile's staging slice
-    if (warp == 0) {
-        int carry = 0;
-        for (int j0 = 0; j0 < nc; j0 += 32) {
-            const int j = j0 + lane;
-            const int val = (j < nc) ? s_off[j] : 0;
-            int inc = val;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += n;
+        const int c = s_cnt[j];
+        if (c == 0) continue;
+        const int f = c0 + j;
+        const int base = atomicAdd(&b.cand_npts[f], c);
+        s_base[j] = base;
+        int *tab = b.page_tab + (size_t)f * b.page_tab_stride;
+        for (int k = (base + kPage - 1) / kPage; k * kPage < base + c; k++) {
+            const int pg = atomicAdd(&b.status[5], 1);
+            int val = pg + 1;
+            if (pg >= n_pages_cap || k >= b.page_tab_stride) { val = -1; atomicOr(&b.status[0], 1); }
+            if (k < b.page_tab_stride) {
+                __threadfence();
+                atomicExch(&tab[k], val);
             }
-            if (j < nc) s_off[j] = carry + inc - val;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) {
-            S.tile_total = carry;
-            S.tile_base = carry ? atomicAdd(&b.status[5], carry) : 0;
-            b.tile_base[tile] = S.tile_base;
         }
     }
     __syncthreads();
-    const int total = S.tile_total;
-    if (total == 0) return;
-    const int64_t base = S.tile_base;
-    if (base + total > b.pts_capacity) return;      // overflow: scan_cands_kernel raises the flag
 
-    // ---- re-project members into their camera, unproject, ordered write into the slice
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int s = 0; s < kPtsPerThread; s++) {
-        unsigned sub_any = 0u;
-#pragma unroll
-        for (int w = 0; w < W; w++) sub_any |= mask[s][w];
-        if (!__any_sync(0xffffffffu, sub_any != 0u)) continue;
-        const int row = row0 + s * kCullThreads + tid;
-        const int *cnt_vw = s_cnt + (s * kCullWarps + warp) * Cmax;
-#pragma unroll 1
-        for (int r = 0; r < 6; r++) {
-            unsigned rm[W];
-            unsigned has = 0u;
-#pragma unroll
-            for (int w = 0; w < W; w++) { rm[w] = mask[s][w] & s_rm[r * W + w]; has |= rm[w]; }
-            if (!__any_sync(0xffffffffu, has != 0u)) continue;
-            const float *cm = S.cam[kImageOrder[r]];
-            float u, v, dd, X = 0.f, Y = 0.f, Z = 0.f;
-            project(cm, x[s], y[s], z[s], img_w, img_h, u, v, dd);
-            unproject(cm + 12, cm + 21, u, v, dd, X, Y, Z);
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                unsigned any = __reduce_or_sync(0xffffffffu, rm[w]);
-                while (any) {
-                    const int jb = __ffs(any) - 1;
-                    any &= any - 1;
-                    const bool in = (rm[w] >> jb) & 1u;
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (in) {
-                        const int j = 32 * w + jb;
-                        const int64_t pos = base + s_off[j] + cnt_vw[j] + __popc(m & lt);
-                        reinterpret_cast<float4 *>(b.stage_pts)[pos] = make_float4(X, Y, Z, dd);
-                        if (b.stage_idx) b.stage_idx[pos] = row;
-                    }
-                }
-            }
+    if (n_list <= kCullList) {
+        // ---- flush the list: full warps, four 4-byte stores per member
+        for (int e = tid; e < n_list; e += kCullThreads) {
+            const int key = s_key[e];
+            const int j = key >> 16;
+            const float4 p = s_ent[e];
+            store_member(b, c0 + j, s_base[j] + (key & 0xffff), p.x, p.y, p.z, p.w, s_row[e]);
         }
+    } else {
+        // ---- more members than the list holds (dense overlapping boxes): repeat the pass with direct writes;
+        // the ranks are handed out again, any assignment of a candidate's members to its reserved slots will do
+        for (int j = tid; j < nc; j += kCullThreads) s_cnt[j] = 0;
+        __syncthreads();
+        cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+                              n_cu, n_cv, use_sectors != 0);
     }
 }
 
-// One CTA per tile: move the tile's staging slice to its final place in every frustum.
-__global__ void __launch_bounds__(256) cull_gather_kernel(const fnp_seeker_batch b)
+// After the tiles: pages needed (for the host's retry), overflow flag.
+__global__ void cull_finish_kernel(const fnp_seeker_batch b)
 {
-    extern __shared__ int s_o[];                           // [Cmax + 1] slice offsets, then [Cmax] destinations
-    const int Cmax = b.max_cands_per_frame;
-    int *s_dst = s_o + Cmax + 1;
-    __shared__ int s_total;
-    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int frame = b.tile_frame[tile];
-    const int c0 = b.frame_cand_start[frame];
-    const int nc = b.frame_cand_start[frame + 1] - c0;
-    if (nc == 0 || b.status[0] != 0) return;
-    if (tid < 32) {
-        int carry = 0;
-        for (int j0 = 0; j0 < nc; j0 += 32) {
-            const int j = j0 + lane;
-            const int val = (j < nc) ? b.tile_counts[(size_t)tile * Cmax + j] : 0;
-            int inc = val;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += n;
-            }
-            if (j < nc) {
-                s_o[j] = carry + inc - val;
-                s_dst[j] = b.cand_pt_start[c0 + j] + b.tile_dst[(size_t)tile * Cmax + j];
-            }
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) { s_o[nc] = carry; s_total = carry; }
-    }
-    __syncthreads();
-    const int total = s_total;
-    if (total == 0) return;
-    const int64_t base = b.tile_base[tile];
-    for (int k = tid; k < total; k += blockDim.x) {
-        // candidate of slot k: the last j with s_o[j] <= k
-        int lo = 0, hi = nc;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_o[mid] <= k) lo = mid; else hi = mid;
-        }
-        const int64_t pos = (int64_t)s_dst[lo] + (k - s_o[lo]);
-        const float4 rec = reinterpret_cast<const float4 *>(b.stage_pts)[base + k];
-        float *dst = b.frustum_pts + pair_slot(pos);
-        dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
-        if (b.frustum_idx) b.frustum_idx[pos] = b.stage_idx[base + k];
-    }
-}
-
-// exclusive prefix of one candidate's tile counts (one warp per candidate)
-__global__ void __launch_bounds__(128) scan_tiles_kernel(const fnp_seeker_batch b)
-{
-    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= b.n_cands) return;
-    const int frame = b.cand_frame[f];
-    const int j = f - b.frame_cand_start[frame];
-    const int t0 = b.frame_tile_start[frame], t1 = b.frame_tile_start[frame + 1];
-    int carry = 0;
-    for (int t = t0; t < t1; t += 32) {
-        const int i = t + lane;
-        const size_t cell = (size_t)i * b.max_cands_per_frame + j;
-        const int val = (i < t1) ? b.tile_counts[cell] : 0;
-        int inc = val;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        if (i < t1) b.tile_dst[cell] = carry + inc - val;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) b.cand_npts[f] = carry;
-}
-
-// exclusive prefix over candidates -> cand_pt_start, capacity check
-__global__ void __launch_bounds__(1024) scan_cands_kernel(const fnp_seeker_batch b)
-{
-    __shared__ int s_warp[32];
-    __shared__ long long s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < b.n_cands; base += 1024) {
-        const int i = base + tid;
-        const int val = (i < b.n_cands) ? ((b.cand_npts[i] + 1) & ~1) : 0;   // frustums start on a pair boundary
-        int inc = val;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += n;
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const long long carry = s_carry;
-        const long long excl = carry + (warp ? s_warp[warp - 1] : 0) + inc - val;
-        if (i < b.n_cands) b.cand_pt_start[i] = (int)min(excl, (long long)0x7fffffff);
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const long long total = s_carry;
-        b.cand_pt_start[b.n_cands] = (int)min(total, (long long)0x7fffffff);
-        b.status[0] = (total > b.pts_capacity) ? 1 : 0;
-        b.status[1] = (int)min(total, (long long)0x7fffffff);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long pages = b.status[5];
+        b.status[1] = (int)min(pages * (long long)kPage, (long long)0x7fffffff);   // points of capacity needed
+        if (pages * kPage > b.pts_capacity) b.status[0] |= 1;
     }
 }
 
@@ -468,11 +451,6 @@ constexpr int kSelList = 512;      // keys finished by rank counting
 constexpr int kStatsCache = 4096;  // depth keys cached in shared memory
 constexpr int kStatsThreads = 256;
 
-__device__ __forceinline__ float pt_depth(const float *__restrict__ pts, int i)
-{
-    return pts[(size_t)(i >> 1) * 8 + 6 + (i & 1)];
-}
-
 struct SelSmem {
     unsigned hist[kSelBins];
     unsigned list[kSelList];
@@ -481,38 +459,47 @@ struct SelSmem {
     unsigned misc[8];   // 0 bin, 1 keys below it, 2 keys in it, 3 next non-empty bin, 4 list fill, 5 min key above, 6/7 results
 };
 
-// Calls f(key) for every depth key of the frustum, block-strided.  Uncached frustums (the few
-// large ones, which set the duration of the whole kernel) are read as pair records with four
-// independent 16-byte loads in flight per thread.
+// Calls f(key) for every depth key of the frustum.  Cached frustums (<= kStatsCache points) read the keys
+// from shared memory; the few large ones, which set the duration of the whole kernel, stream the depth plane
+// of their pages, one point per thread and page, four pages in flight.
+struct FrustumPages {
+    const int *tab;          // page table row of the frustum
+    const float *pool;
+    int page_floats;
+    __device__ __forceinline__ const float *page(int k) const { return pool + (size_t)(tab[k] - 1) * (size_t)page_floats; }
+};
+
 template <typename F>
-__device__ __forceinline__ void for_each_key(const float *__restrict__ pts, const SelSmem &S, bool cached, int n, F f)
+__device__ __forceinline__ void for_each_key(const FrustumPages &P, const SelSmem &S, bool cached, int n, F f)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (cached) {
         for (int i = tid; i < n; i += nt) f(S.key[i]);
         return;
     }
-    const float4 *rec = reinterpret_cast<const float4 *>(pts);
-    const int np = (n + 1) >> 1;                         // pair records
-    for (int p0 = tid; p0 < np; p0 += 4 * nt) {
-        float4 c[4];
+    // thread t: 16-byte vector t & 63 of the depth plane of page k0 + (t >> 6); two such loads in flight
+    const int n_pg = (n + kPage - 1) / kPage;
+    const int sub = tid >> 6, i4 = (tid & 63) * 4;
+    for (int k0 = 0; k0 < n_pg; k0 += 8) {
+        float4 c[2];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int p = p0 + u * nt;
-            if (p < np) c[u] = __ldg(rec + 2 * p + 1);   // z0 z1 d0 d1
+        for (int u = 0; u < 2; u++) {
+            const int k = k0 + 4 * u + sub;
+            if (k < n_pg && k * kPage + i4 < n) c[u] = __ldg(reinterpret_cast<const float4 *>(P.page(k) + 3 * kPage + i4));
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int p = p0 + u * nt;
-            if (p < np) {
-                f(__float_as_uint(c[u].z));
-                if (2 * p + 1 < n) f(__float_as_uint(c[u].w));
-            }
+        for (int u = 0; u < 2; u++) {
+            const int k = k0 + 4 * u + sub, p = k * kPage + i4;
+            if (k >= n_pg || p >= n) continue;
+            f(__float_as_uint(c[u].x));
+            if (p + 1 < n) f(__float_as_uint(c[u].y));
+            if (p + 2 < n) f(__float_as_uint(c[u].z));
+            if (p + 3 < n) f(__float_as_uint(c[u].w));
         }
     }
 }
 
-__device__ void select_pair(const float *__restrict__ pts, SelSmem &S, bool cached, int n, int k, unsigned kmin,
+__device__ void select_pair(const FrustumPages &pts, SelSmem &S, bool cached, int n, int k, unsigned kmin,
                             unsigned kmax, float &v_lo, float &v_hi)
 {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -634,7 +621,7 @@ __device__ void select_pair(const float *__restrict__ pts, SelSmem &S, bool cach
 }
 
 // torch.quantile(depth, q), linear interpolation (ATen Sorting.cpp quantile_compute + lerp)
-__device__ float block_quantile(const float *__restrict__ pts, SelSmem &S, bool cached, int n, float q, float dmin,
+__device__ float block_quantile(const FrustumPages &pts, SelSmem &S, bool cached, int n, float q, float dmin,
                                 float dmax)
 {
     const float pos = __fmul_rn(q, (float)(n - 1));
@@ -665,54 +652,48 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_b
         if (tid == 0) { st[9] = 0.f; }
         return;
     }
-    const float *pts = b.frustum_pts + (size_t)(b.cand_pt_start[f] >> 1) * 8;   // starts are even
+    FrustumPages pts;
+    pts.tab = b.page_tab + (size_t)f * b.page_tab_stride;
+    pts.pool = b.frustum_pts;
+    pts.page_floats = b.page_planes * kPage;
 
-    // ---- min / max of depth and of x, y, z: one 32-byte pair record per thread and iteration
+    // ---- min / max of depth and of x, y, z.  A page is 4 planes of 64 16-byte vectors: thread t takes vector
+    // t & 63 of plane t >> 6 (warps 0-1: x, 2-3: y, 4-5: z, 6-7: depth), four pages in flight per thread.
     const float INF = __int_as_float(0x7f800000);
     float mn[4] = {INF, INF, INF, INF}, mx[4] = {-INF, -INF, -INF, -INF};
-    const float4 *rec = reinterpret_cast<const float4 *>(pts);
     const bool cached = n <= kStatsCache;                         // depth keys stay in shared memory
-    const int np = (n + 1) >> 1;
-    for (int p0 = tid; p0 < np; p0 += 4 * kStatsThreads) {        // four records (8 loads) in flight per thread
-        float4 ra[4], rc[4];
+    const int n_pg = (n + kPage - 1) / kPage;
+    {
+        const int plane = tid >> 6, i4 = (tid & 63) * 4;
+        float lo = INF, hi = -INF;
+        for (int k0 = 0; k0 < n_pg; k0 += 4) {
+            float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int p = p0 + u * kStatsThreads;
-            if (p < np) { ra[u] = rec[2 * p]; rc[u] = rec[2 * p + 1]; }   // x0 x1 y0 y1 | z0 z1 d0 d1
-        }
+            for (int u = 0; u < 4; u++)
+                if (k0 + u < n_pg && (k0 + u) * kPage + i4 < n)
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(pts.page(k0 + u) + plane * kPage + i4));
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int p = p0 + u * kStatsThreads;
-            if (p >= np) continue;
-            const float4 a = ra[u], c = rc[u];
-            if (cached) {
-                S.key[2 * p] = __float_as_uint(c.z);
-                if (2 * p + 1 < n) S.key[2 * p + 1] = __float_as_uint(c.w);
-            }
-            mn[0] = fminf(mn[0], a.x); mx[0] = fmaxf(mx[0], a.x);
-            mn[1] = fminf(mn[1], a.z); mx[1] = fmaxf(mx[1], a.z);
-            mn[2] = fminf(mn[2], c.x); mx[2] = fmaxf(mx[2], c.x);
-            mn[3] = fminf(mn[3], c.z); mx[3] = fmaxf(mx[3], c.z);
-            if (2 * p + 1 < n) {
-                mn[0] = fminf(mn[0], a.y); mx[0] = fmaxf(mx[0], a.y);
-                mn[1] = fminf(mn[1], a.w); mx[1] = fmaxf(mx[1], a.w);
-                mn[2] = fminf(mn[2], c.y); mx[2] = fmaxf(mx[2], c.y);
-                mn[3] = fminf(mn[3], c.w); mx[3] = fmaxf(mx[3], c.w);
+            for (int u = 0; u < 4; u++) {
+                const int p = (k0 + u) * kPage + i4;            // first of the vector's four points
+                if (k0 + u >= n_pg || p >= n) continue;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (p + c < n) {                            // the tail of the last page is not initialised
+                        lo = fminf(lo, e[c]); hi = fmaxf(hi, e[c]);
+                        if (cached && plane == 3) S.key[p + c] = __float_as_uint(e[c]);
+                    }
             }
         }
-    }
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        mn[a] = warp_min(mn[a]);
-        mx[a] = warp_max(mx[a]);
-        if (lane == 0) { s_red[warp][a] = mn[a]; s_red[warp][4 + a] = mx[a]; }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lane == 0) { s_red[warp][0] = lo; s_red[warp][1] = hi; }
     }
     __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-        float m0 = INF, m1 = -INF;
-        for (int w = 0; w < 8; w++) { m0 = fminf(m0, s_red[w][a]); m1 = fmaxf(m1, s_red[w][4 + a]); }
-        mn[a] = m0; mx[a] = m1;
+        mn[a] = fminf(s_red[2 * a][0], s_red[2 * a + 1][0]);
+        mx[a] = fmaxf(s_red[2 * a][1], s_red[2 * a + 1][1]);
     }
     __syncthreads();
 
@@ -1083,10 +1064,11 @@ __device__ __forceinline__ void count_pair(int &cnt, unsigned long long xx, unsi
 // Persistent CTAs pull (frustum, hypothesis chunk, point split) work items off a device
 // counter.  A CTA keeps K hypotheses per thread in registers for the whole item and streams
 // the item's points through a two-stage shared-memory ring filled by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx); every thread reads every staged pair record with
-// broadcast LDS.128.
+// (cp.async.bulk + mbarrier complete_tx): the x, y, z planes of a page are 3 KB contiguous, one
+// copy per page; every thread reads every staged point pair with broadcast LDS.64.
+constexpr int kScorePages = kScoreTile / kPage;      // pages per TMA stage
 struct ScoreSmem {
-    float4 tile[2][kScoreTile / 2][2];   // [stage][pair][x0x1y0y1 | z0z1d0d1]
+    float tile[2][kScorePages][3][kPage];   // [stage][page][x | y | z][slot]
     uint64_t bar[2];
     int item;
 };
@@ -1098,21 +1080,22 @@ __device__ __forceinline__ void score_item(const fnp_seeker_batch &b, const int 
     const int tid = threadIdx.x;
     const int nv = b.hyp_nvalid[f];
     const int npts = b.cand_npts[f];
-    const int p0 = split * b.split_points;                    // even: split_points is even
+    const int p0 = split * b.split_points;                    // a multiple of the page size
     const int n = min(npts, p0 + b.split_points) - p0;
-    const int n_rec = (n + 1) >> 1;                           // pair records of this item
-    const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
-    constexpr int kRecTile = kScoreTile / 2;
-    const int n_tiles = (n_rec + kRecTile - 1) / kRecTile;
+    const int n_tiles = (n + kScoreTile - 1) / kScoreTile;
+    const int *tab = b.page_tab + (size_t)f * b.page_tab_stride + p0 / kPage;
+    const size_t page_floats = (size_t)b.page_planes * kPage;
 
-    if (tid == 0) {
-        for (int t = 0; t < 2 && t < n_tiles; t++) {
-            const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - t * kRecTile) * 32u;
-            const unsigned st = (it + t) & 1u;
-            mbar_expect_tx(&S.bar[st], bytes);
-            tma_load_1d(S.tile[st], grec + (size_t)t * kRecTile * 2, bytes, &S.bar[st]);
-        }
-    }
+    auto issue = [&](int t) {      // one thread: the pages of tile t into stage (it + t) & 1
+        const int pages = min(kScorePages, (n - t * kScoreTile + kPage - 1) / kPage);
+        const unsigned st = (it + t) & 1u;
+        mbar_expect_tx(&S.bar[st], (uint32_t)pages * 3u * kPage * 4u);
+        for (int q = 0; q < pages; q++)
+            tma_load_1d(S.tile[st][q], b.frustum_pts + (size_t)(tab[t * kScorePages + q] - 1) * page_floats, 3u * kPage * 4u,
+                        &S.bar[st]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < 2 && t < n_tiles; t++) issue(t);
 
     HypPacked hp[K];
     int cnt[K];
@@ -1130,45 +1113,47 @@ __device__ __forceinline__ void score_item(const fnp_seeker_batch &b, const int 
         hp[k].tx = c.z; hp[k].ty = c.w;
     }
 
-    for (int t = 0; t < n_tiles; t++, it++) {
-        const unsigned st = it & 1u;
-        mbar_wait(&S.bar[st], (it >> 1) & 1u);
-        const int m_pts = min(kScoreTile, n - t * kScoreTile);   // points in this tile
-        const int m_full = m_pts >> 1;                            // complete pairs
-        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(S.tile[st]);
-        int i = 0;
-        for (; i + 2 <= m_full; i += 2) {
-            const ulonglong2 xy0 = tp[2 * i], zd0 = tp[2 * i + 1];
-            const ulonglong2 xy1 = tp[2 * i + 2], zd1 = tp[2 * i + 3];
+    for (int t = 0; t < n_tiles; t++) {
+        const unsigned st = (it + t) & 1u;
+        mbar_wait(&S.bar[st], ((it + t) >> 1) & 1u);
+        const int m_tile = min(kScoreTile, n - t * kScoreTile);   // points in this tile
+        for (int q = 0; q * kPage < m_tile; q++) {
+            const int m_pts = min(kPage, m_tile - q * kPage);
+            const int m_full = m_pts >> 1;                         // complete pairs
+            const unsigned long long *xs = reinterpret_cast<const unsigned long long *>(S.tile[st][q][0]);
+            const unsigned long long *ys = reinterpret_cast<const unsigned long long *>(S.tile[st][q][1]);
+            const unsigned long long *zs = reinterpret_cast<const unsigned long long *>(S.tile[st][q][2]);
+            int i = 0;
+            for (; i + 2 <= m_full; i += 2) {
+                const unsigned long long x0 = xs[i], y0 = ys[i], z0 = zs[i];
+                const unsigned long long x1 = xs[i + 1], y1 = ys[i + 1], z1 = zs[i + 1];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                count_pair(cnt[k], xy0.x, xy0.y, zd0.x, hp[k]);
-                count_pair(cnt[k], xy1.x, xy1.y, zd1.x, hp[k]);
+                for (int k = 0; k < K; k++) {
+                    count_pair(cnt[k], x0, y0, z0, hp[k]);
+                    count_pair(cnt[k], x1, y1, z1, hp[k]);
+                }
             }
-        }
-        for (; i < m_full; i++) {
-            const ulonglong2 xy = tp[2 * i], zd = tp[2 * i + 1];
+            for (; i < m_full; i++) {
+                const unsigned long long x0 = xs[i], y0 = ys[i], z0 = zs[i];
 #pragma unroll
-            for (int k = 0; k < K; k++) count_pair(cnt[k], xy.x, xy.y, zd.x, hp[k]);
-        }
-        if (m_pts & 1) {   // last point of the frustum: lane 0 of a half-filled record
-            const float4 xy = S.tile[st][m_full][0], zd = S.tile[st][m_full][1];
+                for (int k = 0; k < K; k++) count_pair(cnt[k], x0, y0, z0, hp[k]);
+            }
+            if (m_pts & 1) {   // last point of the frustum
+                const float px = S.tile[st][q][0][m_pts - 1], py = S.tile[st][q][1][m_pts - 1], pz = S.tile[st][q][2][m_pts - 1];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                BoxPrep bp;
-                bp.cx = lo_half(hp[k].cx2); bp.cy = lo_half(hp[k].cy2); bp.cz = lo_half(hp[k].cz2);
-                bp.cosa = lo_half(hp[k].cosa2); bp.sina = lo_half(hp[k].sina2);
-                bp.hz = hp[k].hz; bp.tx = hp[k].tx; bp.ty = hp[k].ty;
-                count_if(cnt[k], in_box(xy.x, xy.z, zd.x, bp));
+                for (int k = 0; k < K; k++) {
+                    BoxPrep bp;
+                    bp.cx = lo_half(hp[k].cx2); bp.cy = lo_half(hp[k].cy2); bp.cz = lo_half(hp[k].cz2);
+                    bp.cosa = lo_half(hp[k].cosa2); bp.sina = lo_half(hp[k].sina2);
+                    bp.hz = hp[k].hz; bp.tx = hp[k].tx; bp.ty = hp[k].ty;
+                    count_if(cnt[k], in_box(px, py, pz, bp));
+                }
             }
         }
         __syncthreads();  // everyone is done with stage st
-        if (tid == 0 && t + 2 < n_tiles) {
-            const uint32_t bytes = (uint32_t)min(kRecTile, n_rec - (t + 2) * kRecTile) * 32u;
-            mbar_expect_tx(&S.bar[st], bytes);
-            tma_load_1d(S.tile[st], grec + (size_t)(t + 2) * kRecTile * 2, bytes, &S.bar[st]);
-        }
+        if (tid == 0 && t + 2 < n_tiles) issue(t + 2);
     }
+    it += (unsigned)n_tiles;
 
     int *out = b.counts + (size_t)f * H;
 #pragma unroll
@@ -1312,7 +1297,7 @@ __global__ void __launch_bounds__(128) sweep_prep_kernel(const fnp_seeker_batch 
 #endif
 constexpr int kSweepThreads = FNP_SWEEP_THREADS;
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kSweepChunk = 256;   // points per (column, chunk) warp item
+constexpr int kSweepChunk = kPage;   // points per (column, chunk) warp item = one page
 
 // Entries of the uncertain-step queue of a CTA: (point | column << 16, packed steps).
 __host__ __device__ inline int sweep_queue_cap(int SP, int J)
@@ -1350,10 +1335,8 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
     const int QCAP = sweep_queue_cap(SP, J);
     SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
     uint2 *s_q = reinterpret_cast<uint2 *>(s_col + J);                          // [QCAP] uncertain-step queue
-    float *s_x = reinterpret_cast<float *>(s_q + QCAP);                         // [SP]  (SP is even: 8 B aligned rows)
-    float *s_y = s_x + SP;
-    float *s_z = s_y + SP;
-    int *s_diff = reinterpret_cast<int *>(s_z + SP);                            // [J][M] difference array, then counts
+    float *s_pts = reinterpret_cast<float *>(s_q + QCAP);                       // [SP / 256][x | y | z][256]: the split's pages
+    int *s_diff = reinterpret_cast<int *>(s_pts + 3 * SP);                      // [J][M] difference array, then counts
     short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
     int *s_ctl = reinterpret_cast<int *>(s_slot + ((H + 3) & ~3));              // [0] item [1] next piece [2] queue size [3] queue head
 
@@ -1384,13 +1367,14 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
             const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
             float4 *dst = reinterpret_cast<float4 *>(s_col);
             for (int i = tid; i < J * (FNP_SWEEP_COL_FLOATS / 4); i += kSweepThreads) dst[i] = __ldg(src + i);
-            const float4 *grec = reinterpret_cast<const float4 *>(b.frustum_pts) + (size_t)(b.cand_pt_start[f] + p0);
-            const int n_rec = (n + 1) >> 1;
-            for (int r = tid; r < n_rec; r += kSweepThreads) {
-                const float4 xy = __ldg(grec + 2 * r), zd = __ldg(grec + 2 * r + 1);
-                reinterpret_cast<float2 *>(s_x)[r] = make_float2(xy.x, xy.y);
-                reinterpret_cast<float2 *>(s_y)[r] = make_float2(xy.z, xy.w);
-                reinterpret_cast<float2 *>(s_z)[r] = make_float2(zd.x, zd.y);
+            // the x, y, z planes of the split's pages, as they lie in the pool (coalesced, no transposition)
+            const int *tab = b.page_tab + (size_t)f * b.page_tab_stride + p0 / kPage;
+            const int n_pg = (n + kPage - 1) / kPage;
+            constexpr int kVec = 3 * kPage / 4;        // 16-byte vectors of a page's x, y, z planes
+            for (int i = tid; i < n_pg * kVec; i += kSweepThreads) {
+                const int q = i / kVec;
+                const float4 *page = reinterpret_cast<const float4 *>(b.frustum_pts + (size_t)(tab[q] - 1) * (size_t)(b.page_planes * kPage));
+                reinterpret_cast<float4 *>(s_pts)[i] = __ldg(page + (i - q * kVec));
             }
             for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
         }
@@ -1417,13 +1401,14 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
             const short *slot_col = s_slot + c.m0 * J + j;
             int base_cnt = 0;
             const int i_end = min(n, (ch + 1) * kSweepChunk);
+            const float *pg = s_pts + ch * (3 * kPage) - ch * kSweepChunk;   // chunk ch is page ch: x of point i at pg[i]
             // two points per lane and pass: the two range solves are independent instruction chains
             for (int i0 = ch * kSweepChunk; i0 < i_end; i0 += 64) {
                 int ia = i0 + lane, ib = i0 + 32 + lane;
                 const bool live_a = ia < i_end, live_b = ib < i_end;
                 ia = min(ia, i_end - 1); ib = min(ib, i_end - 1);
-                const float xa = s_x[ia], ya = s_y[ia], za = s_z[ia];
-                const float xb = s_x[ib], yb = s_y[ib], zb = s_z[ib];
+                const float xa = pg[ia], ya = pg[kPage + ia], za = pg[2 * kPage + ia];
+                const float xb = pg[ib], yb = pg[kPage + ib], zb = pg[2 * kPage + ib];
                 const SweepRanges ra = sweep_solve(c, xa, ya, za);
                 const SweepRanges rb = sweep_solve(c, xb, yb, zb);
                 unsigned wa = 0, wb = 0;
@@ -1501,7 +1486,8 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                     const int i = (int)(e0 & 0xffffu), j = (int)(e0 >> 16);
                     const float4 rot = *reinterpret_cast<const float4 *>(&s_col[j].cosa);     // cosa, sina, tx, ty
                     const int m0 = s_col[j].m0, D = s_col[j].m1 - m0;
-                    sweep_exact_step_col(s_x[i], s_y[i], s_z[i], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
+                    const float *pp = s_pts + (i >> 8) * (3 * kPage) + (i & (kPage - 1));
+                    sweep_exact_step_col(pp[0], pp[kPage], pp[2 * kPage], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
                                          s_slot + m0 * J + j, J, prep_f, rot.x, rot.y, rot.z, rot.w, red);
                 }
             }
@@ -1574,7 +1560,6 @@ __global__ void __launch_bounds__(kOcclThreads) occl_kernel(const fnp_seeker_bat
         }
     }
     const int n = b.cand_npts[f];
-    const float *pts = b.frustum_pts + (size_t)(b.cand_pt_start[f] >> 1) * 8;
     int cnt = 0;
     for (int t0 = 0; t0 < n; t0 += kOcclTile) {
         const int tn = min(kOcclTile, n - t0);
@@ -1582,8 +1567,8 @@ __global__ void __launch_bounds__(kOcclThreads) occl_kernel(const fnp_seeker_bat
             float m = -INF;   // padding never counts
             if (i < tn) {
                 const int p = t0 + i;
-                const float *rec = pts + (size_t)(p >> 1) * 8 + (p & 1);
-                m = norm3(rec[0], rec[2], rec[4]);
+                const float *rec = page_of(b, f, p >> 8) + (p & (kPage - 1));
+                m = norm3(rec[0], rec[kPage], rec[2 * kPage]);
             }
             s_mag[i] = m;
         }
@@ -1763,29 +1748,40 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
     if (!cfg || !b) return FNP_EINVAL;
     if (b->n_frames < 0 || b->n_cands < 0 || b->n_tiles < 0) return FNP_EINVAL;
     if (cfg->num_mags < 1 || cfg->num_yaw_size < 1) return FNP_EINVAL;
-    if (b->max_items < 0 || b->split_points < 2 || (b->split_points & 1)) return FNP_EINVAL;
+    if (b->max_items < 0 || b->split_points < FNP_PAGE_POINTS || (b->split_points % FNP_PAGE_POINTS) != 0) return FNP_EINVAL;
     return FNP_OK;
 }
 
-static size_t cull_stage_smem(const fnp_seeker_batch *b, int W)
+// Tuning / test switches (fnp_set_option): not part of the stable ABI.
+static int g_opt_cull_sectors = 1;      // stage 1 consults the per-frame sector table (0: every camera for every point)
+static int g_opt_sweep_variant = 0;
+
+extern "C" int fnp_set_option(const char *name, int value)
 {
-    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 * kCullVW + 4) + (size_t)6 * W * 4 + 16;
+    if (!name) return FNP_EINVAL;
+    const std::string n(name);
+    if (n == "cull_sectors") { g_opt_cull_sectors = value; return FNP_OK; }
+    if (n == "sweep_variant") { g_opt_sweep_variant = value; return FNP_OK; }
+    return FNP_EINVAL;
+}
+
+static size_t cull_smem(const fnp_seeker_batch *b)
+{
+    return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 + 4) + (size_t)kCullList * (16 + 4 + 4) + 16;
 }
 
 template <int W>
 static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
 {
     const int n_cu = cell_cols(cfg->img_w), n_cv = cell_rows(cfg->img_h);
-    const size_t sa = cull_stage_smem(b, W), sc = (size_t)n_cu * n_cv * W * 4;
-    const size_t sg = ((size_t)2 * b->max_cands_per_frame + 1) * 4;
+    const size_t sa = cull_smem(b), sc = (size_t)n_cu * n_cv * W * 4;
     if (sa > 200 * 1024 || sc > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cull_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
     cudaFuncSetAttribute(cell_table_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
-    cell_table_kernel<W><<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv);
-    cull_stage_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv);
-    scan_tiles_kernel<<<divup(b->n_cands, 4), 128, 0, st>>>(*b);
-    scan_cands_kernel<<<1, 1024, 0, st>>>(*b);
-    cull_gather_kernel<<<b->n_tiles, 256, sg, st>>>(*b);
+    cudaMemsetAsync(b->cell_masks + (size_t)b->n_frames * 6 * n_cu * n_cv * W, 0, (size_t)b->n_frames * kSectors * 4, st);
+    cell_table_kernel<W><<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h);
+    cull_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
+    cull_finish_kernel<<<1, 32, 0, st>>>(*b);
     return FNP_OK;
 }
 
@@ -1793,7 +1789,8 @@ extern "C" size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_fr
 {
     const int W = fnp_seeker_mask_words(max_cands_per_frame);
     if (!cfg || n_frames < 0 || W < 0) return 0;
-    return (size_t)n_frames * 6 * cell_cols(cfg->img_w) * cell_rows(cfg->img_h) * W * 4;
+    // per (frame, camera rank, cell) W words, then the 64-entry sector table of every frame
+    return (size_t)n_frames * 6 * cell_cols(cfg->img_w) * cell_rows(cfg->img_h) * W * 4 + (size_t)n_frames * kSectors * 4;
 }
 
 extern "C" int fnp_seeker_mask_words(int max_cands_per_frame)
@@ -1809,16 +1806,17 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
     cudaStream_t st = (cudaStream_t)stream;
     if (b->n_cands == 0 || b->n_tiles == 0) {
         cudaMemsetAsync(b->status, 0, 8 * sizeof(int32_t), st);
-        cudaMemsetAsync(b->cand_pt_start, 0, sizeof(int32_t) * (size_t)(b->n_cands + 1), st);
         if (b->n_cands) cudaMemsetAsync(b->cand_npts, 0, sizeof(int32_t) * (size_t)b->n_cands, st);
         FNP_LAUNCH_CHECK();
         return FNP_OK;
     }
-    if (!b->points || !b->tile_counts || !b->tile_dst || !b->tile_base || !b->frustum_pts || !b->stage_pts ||
-        !b->cell_masks || !b->cam_cand_start || b->point_stride < 3 || b->xyz_offset < 0 ||
-        b->xyz_offset + 3 > b->point_stride || (b->frustum_idx && !b->stage_idx))
+    if (!b->points || !b->page_tab || !b->frustum_pts || !b->cell_masks || !b->cam_cand_start || b->point_stride < 3 ||
+        b->xyz_offset < 0 || b->xyz_offset + 3 > b->point_stride || (b->page_planes != 4 && b->page_planes != 5) ||
+        b->page_tab_stride < 1 || b->pts_capacity < FNP_PAGE_POINTS || (b->pts_capacity % FNP_PAGE_POINTS) != 0)
         return FNP_EINVAL;
-    cudaMemsetAsync(b->status, 0, 8 * sizeof(int32_t), st);      // [5] = staging cursor
+    cudaMemsetAsync(b->status, 0, 8 * sizeof(int32_t), st);      // [5] = page cursor
+    cudaMemsetAsync(b->cand_npts, 0, sizeof(int32_t) * (size_t)b->n_cands, st);
+    cudaMemsetAsync(b->page_tab, 0, sizeof(int32_t) * (size_t)b->n_cands * (size_t)b->page_tab_stride, st);
     const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
     if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 256 candidates in one frame
     switch (W) {

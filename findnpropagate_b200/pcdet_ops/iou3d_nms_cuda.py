@@ -60,6 +60,25 @@ def boxes_aligned_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
     return 1
 
 
+def boxes_iou3d_gpu(boxes_a, boxes_b, ans_iou):
+    """(N,7),(M,7) -> (N,M) 3D IoU in one kernel (no counterpart in the reference's pybind module: the reference
+    composes it from boxes_overlap_bev_gpu and a dozen eager torch ops, iou3d_nms_utils.py:48-81)."""
+    return _pair(_lib.lib.fnp_boxes_iou3d, "fnp_boxes_iou3d", boxes_a, boxes_b, ans_iou)
+
+
+def boxes_aligned_iou3d_gpu(boxes_a, boxes_b, ans_iou):
+    _check_f32_cuda(boxes_a, "boxes_a", 7)
+    _check_f32_cuda(boxes_b, "boxes_b", 7)
+    N = boxes_a.shape[0]
+    if boxes_b.shape[0] != N or ans_iou.numel() != N:
+        raise ValueError("aligned iou3d: shape mismatch")
+    with torch.cuda.device(boxes_a.device):
+        rc = _lib.lib.fnp_boxes_aligned_iou3d(_ptr(boxes_a), _ptr(boxes_b), _ptr(ans_iou), N,
+                                              _lib.current_stream(boxes_a.device))
+    _lib.check(rc, "fnp_boxes_aligned_iou3d")
+    return 1
+
+
 def _nms(fn, name, boxes, keep, thresh):
     _check_f32_cuda(boxes, "boxes", 7)
     if keep.dtype != torch.int64 or not keep.is_contiguous() or keep.numel() < boxes.shape[0]:

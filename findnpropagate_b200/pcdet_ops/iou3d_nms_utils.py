@@ -12,7 +12,11 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
         boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]   (numpy or CPU tensor)
         boxes_b: (M, 7)
     Returns:
-        ans_iou: (N, M), same kind as the inputs.  Executed on the GPU (no CPU path here).
+        ans_iou: (N, M), same kind as the inputs.  Executed on the GPU (no CPU path here) with the arithmetic of
+        the reference's CUDA kernel (fused multiply-adds as in its sm_100a SASS), NOT of iou3d_cpu.cpp:232, whose
+        host-compiled arithmetic rounds every product: values agree with the CPU op to a few ulp (<= 2e-6
+        absolute in tests/test_ops_gpu.py), not bit for bit.  A caller that thresholds these IoUs can see a pair
+        within that distance of its threshold decided differently.
     """
     boxes_a, is_numpy = check_numpy_to_torch(boxes_a)
     boxes_b, is_numpy = check_numpy_to_torch(boxes_b)
@@ -32,41 +36,20 @@ def boxes_iou_bev(boxes_a, boxes_b):
 
 
 def boxes_iou3d_gpu(boxes_a, boxes_b):
-    """(N,7),(M,7) CUDA -> (N,M) 3D IoU (iou3d_nms_utils.py:48-81)."""
+    """(N,7),(M,7) CUDA -> (N,M) 3D IoU.  Same values as the reference's composition of boxes_overlap_bev_gpu and
+    eager torch arithmetic (iou3d_nms_utils.py:48-81), computed by one kernel (fnp_boxes_iou3d)."""
     assert boxes_a.shape[1] == boxes_b.shape[1] == 7
-    boxes_a_height_max = (boxes_a[:, 2] + boxes_a[:, 5] / 2).view(-1, 1)
-    boxes_a_height_min = (boxes_a[:, 2] - boxes_a[:, 5] / 2).view(-1, 1)
-    boxes_b_height_max = (boxes_b[:, 2] + boxes_b[:, 5] / 2).view(1, -1)
-    boxes_b_height_min = (boxes_b[:, 2] - boxes_b[:, 5] / 2).view(1, -1)
-    overlaps_bev = boxes_a.new_empty((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32)
-    iou3d_nms_cuda.boxes_overlap_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), overlaps_bev)
-    max_of_min = torch.max(boxes_a_height_min, boxes_b_height_min)
-    min_of_max = torch.min(boxes_a_height_max, boxes_b_height_max)
-    overlaps_h = torch.clamp(min_of_max - max_of_min, min=0)
-    overlaps_3d = overlaps_bev * overlaps_h
-    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
-    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(1, -1)
-    iou3d = overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-6)
+    iou3d = boxes_a.new_empty((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32)
+    iou3d_nms_cuda.boxes_iou3d_gpu(boxes_a.contiguous(), boxes_b.contiguous(), iou3d)
     return iou3d
 
 
 def boxes_aligned_iou3d_gpu(boxes_a, boxes_b):
-    """(N,7),(N,7) CUDA -> (N,1) aligned 3D IoU (iou3d_nms_utils.py:83-117)."""
+    """(N,7),(N,7) CUDA -> (N,1) aligned 3D IoU (iou3d_nms_utils.py:83-117), one kernel."""
     assert boxes_a.shape[0] == boxes_b.shape[0]
     assert boxes_a.shape[1] == boxes_b.shape[1] == 7
-    boxes_a_height_max = (boxes_a[:, 2] + boxes_a[:, 5] / 2).view(-1, 1)
-    boxes_a_height_min = (boxes_a[:, 2] - boxes_a[:, 5] / 2).view(-1, 1)
-    boxes_b_height_max = (boxes_b[:, 2] + boxes_b[:, 5] / 2).view(-1, 1)
-    boxes_b_height_min = (boxes_b[:, 2] - boxes_b[:, 5] / 2).view(-1, 1)
-    overlaps_bev = boxes_a.new_empty((boxes_a.shape[0], 1), dtype=torch.float32)
-    iou3d_nms_cuda.boxes_aligned_overlap_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), overlaps_bev)
-    max_of_min = torch.max(boxes_a_height_min, boxes_b_height_min)
-    min_of_max = torch.min(boxes_a_height_max, boxes_b_height_max)
-    overlaps_h = torch.clamp(min_of_max - max_of_min, min=0)
-    overlaps_3d = overlaps_bev * overlaps_h
-    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
-    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(-1, 1)
-    iou3d = overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-6)
+    iou3d = boxes_a.new_empty((boxes_a.shape[0], 1), dtype=torch.float32)
+    iou3d_nms_cuda.boxes_aligned_iou3d_gpu(boxes_a.contiguous(), boxes_b.contiguous(), iou3d)
     return iou3d
 
 

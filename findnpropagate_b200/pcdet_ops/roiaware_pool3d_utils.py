@@ -35,22 +35,33 @@ def points_in_boxes_cpu(points, boxes, device=None):
     Returns:
         point_indices: (N, num_points) int32 0/1, numpy in -> numpy out
 
-    Same contract as the reference (roiaware_pool3d_utils.py:9-25) but executed on the GPU
-    (no CPU compute path in this build): one single-box points_in_boxes launch per box
-    batch.  NOTE the reference CPU op uses MARGIN 1e-2 (roiaware_pool3d.cpp:131) while the
-    GPU predicate uses 1e-5; this function keeps the GPU predicate, so points within 1 cm
-    outside a face differ from the reference CPU op.
+    The reference's CPU op (roiaware_pool3d_utils.py:9-25, roiaware_pool3d.cpp:121-168) with ITS predicate --
+    MARGIN 1e-2 (not the GPU op's 1e-5), products rounded individually, the host libm's cosf/sinf -- executed on
+    the GPU (no CPU compute path in this build): the per-box constants are formed on the host
+    (fnp_host_prep_boxes_cpu), the N x P tests run in one kernel (fnp_points_in_boxes_matrix) that writes the
+    matrix row by row; no (N, P, 3) expansion of the points is made.  Bit-equal to the reference-compiled op,
+    including points within 1 cm of a face (tests/test_ops_gpu.py).
     """
+    import ctypes as C
+
+    from .. import _lib
     assert boxes.shape[1] == 7
     assert points.shape[1] == 3
     points, is_numpy = check_numpy_to_torch(points)
     boxes, is_numpy = check_numpy_to_torch(boxes)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    p = points.float().to(dev).contiguous()
-    b = boxes.float().to(dev).contiguous()
-    n, m = b.shape[0], p.shape[0]
-    # (N,1,7) boxes against (N,M,3) broadcast points: index 0 where inside, -1 otherwise
-    idx = points_in_boxes_gpu(p.unsqueeze(0).expand(n, m, 3).contiguous(), b.view(n, 1, 7)) if n and m else \
-        torch.full((n, m), -1, dtype=torch.int, device=dev)
-    out = (idx >= 0).to(torch.int).cpu()
+    b_host = boxes.detach().float().cpu().contiguous()
+    n, m = int(b_host.shape[0]), int(points.shape[0])
+    prep = torch.empty((n, 8), dtype=torch.float32)
+    _lib.check(_lib.lib.fnp_host_prep_boxes_cpu(C.c_void_p(b_host.data_ptr()), C.c_void_p(prep.data_ptr()), n),
+               "fnp_host_prep_boxes_cpu")
+    p = points.detach().float().to(dev).contiguous()
+    out = torch.empty((n, m), dtype=torch.int32, device=dev)
+    if n and m:
+        prep_d = prep.to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.fnp_points_in_boxes_matrix(C.c_void_p(prep_d.data_ptr()), C.c_void_p(p.data_ptr()),
+                                                           C.c_void_p(out.data_ptr()), n, m, _lib.current_stream(dev)),
+                       "fnp_points_in_boxes_matrix")
+    out = out.cpu()
     return out.numpy() if is_numpy else out

@@ -449,9 +449,14 @@ class SeekerEngine:
             if points_ready is not None:
                 torch.cuda.current_stream(dev).wait_event(points_ready)
             chunks = -(-H // 512)      # hypothesis chunks per frustum (csrc: score_chunks)
-            cap = int(max(plan["total_rows"] * self.pts_factor, 4096) + 2 * F + 2) & ~1
+            PG = _lib.PAGE_POINTS
+            # page pool: pts_factor x the batch's rows, plus the half-empty last page of every frustum
+            cap = (int(max(plan["total_rows"] * self.pts_factor, 4096)) + PG * (F + 1) + PG - 1) // PG * PG
+            max_rows = int(np.diff(plan["frame_row_start"]).max()) if B else 0
+            tab_stride = (max_rows + PG - 1) // PG + 1
+            planes = 5 if self.debug else 4
             if self.fixed_split_points is not None:
-                sp = max(2, (int(self.fixed_split_points) + 1) & ~1)      # splits start on a pair boundary
+                sp = max(PG, (int(self.fixed_split_points) + PG - 1) // PG * PG)      # splits are whole pages
             else:
                 # point splits small enough to balance the persistent CTAs (measured on cfg2, 32 frames,
                 # direct kernel: 2048 -> 0.737 ms, 512 -> 0.666 ms, 256 -> 0.663 ms), large enough to amortise
@@ -467,9 +472,8 @@ class SeekerEngine:
             if W < 0:
                 raise ValueError("more than 256 candidate frustums in one frame (%d) are not supported" % Cmax)
             sizes = dict(
-                tile_counts=4 * plan["n_tiles"] * Cmax, tile_dst=4 * plan["n_tiles"] * Cmax,
-                tile_base=4 * plan["n_tiles"], cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
-                frustum_pts=16 * cap, stage_pts=16 * cap,
+                page_tab=4 * max(F, 1) * tab_stride, cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
+                frustum_pts=4 * planes * cap,
                 cand_stats=4 * _lib.STATS_FLOATS * F, centres=12 * M * F, hyp_prep=32 * H * F, hyp_index=4 * H * F,
                 hyp_iou=4 * H * F, counts=4 * H * F, items=16 * max_items,
                 cand_item_start=4 * (F + 1), sweep_cols=4 * _lib.SWEEP_COL_FLOATS * self.J * F,
@@ -488,7 +492,7 @@ class SeekerEngine:
             if self.use_occl:
                 sizes["hyp_nfar"] = 4 * H * F
             if self.debug:
-                sizes.update(frustum_idx=4 * cap, stage_idx=4 * cap, hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
+                sizes.update(hyp_boxes_dbg=28 * H * F, hyp_iou_dbg=4 * H * F, hyp_valid_dbg=H * F)
             # every slot owns its intermediates, so that batches of different slots may be in flight on
             # different streams at the same time (slot 0 keeps the plain names: debug_views reads them)
             sfx = "" if slot == 0 else "@%d" % slot
@@ -497,7 +501,6 @@ class SeekerEngine:
             ob = out_dev.data_ptr()
             o_boxes, o_score, o_best, o_count = ob, ob + 28 * FT, ob + 32 * FT, ob + 36 * FT
             o_npts, o_nvalid, o_status = ob + 40 * FT, ob + 40 * FT + 4 * F, ob + 40 * FT + 8 * F
-            o_ptstart = self.arena.get("cand_pt_start" + sfx, 4 * (F + 1)).data_ptr()
             b = _lib.SeekerBatch(
                 n_frames=B, n_cands=F, n_tiles=plan["n_tiles"], max_cands_per_frame=Cmax,
                 points=points_dev.data_ptr(), point_stride=plan["stride"], xyz_offset=plan["xyz_offset"],
@@ -508,9 +511,8 @@ class SeekerEngine:
                 cand_label=meta["cand_label"], cand_box2d=meta["cand_box2d"],
                 base_boxes=self.base_boxes.data_ptr(), base_corners=self.base_corners.data_ptr(),
                 mags=self.mags.data_ptr(),
-                tile_counts=ptr["tile_counts"], tile_dst=ptr["tile_dst"], tile_base=ptr["tile_base"],
-                cell_masks=ptr["cell_masks"], mask_words=W, stage_pts=ptr["stage_pts"], stage_idx=ptr.get("stage_idx"), cand_npts=o_npts, cand_pt_start=o_ptstart,
-                frustum_pts=ptr["frustum_pts"], frustum_idx=ptr.get("frustum_idx"), pts_capacity=cap,
+                cell_masks=ptr["cell_masks"], mask_words=W, cand_npts=o_npts, page_tab=ptr["page_tab"],
+                page_tab_stride=tab_stride, page_planes=planes, frustum_pts=ptr["frustum_pts"], pts_capacity=cap,
                 cand_stats=ptr["cand_stats"], centres=ptr["centres"], hyp_prep=ptr["hyp_prep"],
                 hyp_index=ptr["hyp_index"], hyp_iou=ptr["hyp_iou"], hyp_nvalid=o_nvalid,
                 hyp_boxes_dbg=ptr.get("hyp_boxes_dbg"), hyp_iou_dbg=ptr.get("hyp_iou_dbg"),
@@ -524,8 +526,9 @@ class SeekerEngine:
             _lib.check(rc, "fnp_seeker_run")
             mode = _lib.lib.fnp_seeker_score_mode(C.byref(self.cfg), C.byref(b))
             self.last_score_mode = {_lib.SCORE_DIRECT: "direct", _lib.SCORE_SWEEP: "sweep"}.get(mode)
-            self.launches += (11 + (mode == _lib.SCORE_SWEEP) + self.use_occl) if F and plan["n_tiles"] else 0
+            self.launches += (9 + (mode == _lib.SCORE_SWEEP) + self.use_occl) if F and plan["n_tiles"] else 0
             handle = dict(plan=plan, batch=b, sp=sp, cap=cap, out_dev=out_dev, out_bytes=sizes["out"], meta=meta,
+                          tab_stride=tab_stride, planes=planes,
                           off_recall=off_recall, off_keep=off_keep, has_nms=False, has_recall=False,
                           recall_thresh=tuple(recall_thresh))
             if nms_thresh is not None and F:
@@ -680,15 +683,25 @@ class SeekerEngine:
         def view(name, dtype, shape):
             n = int(np.prod(shape)) * torch.tensor([], dtype=dtype).element_size()
             return self.arena.bufs[name][:n].view(dtype).view(*shape).cpu().numpy()
-        padded_start = view("cand_pt_start", torch.int32, (F + 1,))
-        total = int(padded_start[-1])
-        # pair-interleaved records {x0,x1,y0,y1,z0,z1,d0,d1} -> one (x,y,z,d) row per point, padding removed
-        rec = view("frustum_pts", torch.float32, (total // 2, 4, 2))
-        rows = rec.transpose(0, 2, 1).reshape(total, 4)
-        idx = view("frustum_idx", torch.int32, (total,))
+        # the page pool -> one (x, y, z, d) row per point, frustum by frustum, sorted by source row (stage 1 fills
+        # a frustum in whatever order the tiles reach it; no result depends on that order, this view fixes one)
+        PG, planes, ts = _lib.PAGE_POINTS, handle["planes"], handle["tab_stride"]
         npts = handle["out_host"].numpy()[:handle["out_bytes"]].view(np.int32)[10 * F * self.T:10 * F * self.T + F]
-        sel = np.concatenate([np.arange(padded_start[f], padded_start[f] + npts[f]) for f in range(F)]
-                             + [np.zeros(0, np.int64)]).astype(np.int64)
+        tab = view("page_tab", torch.int32, (F, ts))
+        n_pages = int(tab.max()) if F else 0
+        pool = view("frustum_pts", torch.float32, (max(n_pages, 1), planes, PG))
+        rows_l, idx_l = [], []
+        for f in range(F):
+            n = int(npts[f])
+            k = (n + PG - 1) // PG
+            pg = pool[tab[f, :k] - 1]                                   # (k, planes, PG)
+            xyzd = pg[:, :4].transpose(0, 2, 1).reshape(-1, 4)[:n]
+            src = pg[:, 4].reshape(-1)[:n].view(np.int32)
+            o = np.argsort(src, kind="stable")
+            rows_l.append(xyzd[o])
+            idx_l.append(src[o])
+        rows = np.concatenate(rows_l + [np.zeros((0, 4), np.float32)])
+        idx = np.concatenate(idx_l + [np.zeros(0, np.int32)])
         pt_start = np.concatenate([[0], np.cumsum(npts)]).astype(np.int32)
         extra = {}
         if self.use_dist:
@@ -698,8 +711,8 @@ class SeekerEngine:
         return dict(
             **extra,
             pt_start=pt_start,
-            frustum_pts=np.ascontiguousarray(rows[sel]),
-            frustum_idx=np.ascontiguousarray(idx[sel]),
+            frustum_pts=np.ascontiguousarray(rows),
+            frustum_idx=np.ascontiguousarray(idx),
             stats=view("cand_stats", torch.float32, (F, _lib.STATS_FLOATS)),
             centres=view("centres", torch.float32, (F, M, 3)),
             hyp_boxes=view("hyp_boxes_dbg", torch.float32, (F, H, 7)),

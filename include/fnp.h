@@ -64,6 +64,22 @@ int fnp_points_in_boxes(const float *boxes, const float *pts, int32_t *out, int 
 int fnp_count_in_boxes(const float *pts4, const int32_t *pt_start, const float *boxes,
                        const int32_t *box_start, int n_segments, int32_t *counts, void *stream);
 
+/* The (N, P) 0/1 matrix of the reference's CPU op points_in_boxes_cpu (roiaware_pool3d.cpp:121-168): NOT
+ * the GPU predicate -- the margin is 1e-2 instead of 1e-5 and the products are rounded individually, with
+ * the host libm's cosf / sinf.  box_prep (N,8) device = fnp_host_prep_boxes_cpu(boxes) uploaded (the per-box
+ * constants are formed on the host, where the reference forms them); pts (P,3); out (N,P) int32, every
+ * entry written. */
+int fnp_points_in_boxes_matrix(const float *box_prep, const float *pts, int32_t *out, int N, int P,
+                               void *stream);
+/* HOST pointers: boxes_host (N,7) -> prep_host (N,8) = cx, cy, cz, hz, cosa, sina, tx, ty. */
+int fnp_host_prep_boxes_cpu(const float *boxes_host, float *prep_host, int N);
+
+/* 3D IoU (iou3d_nms_utils.py:48-81 boxes_iou3d_gpu / :83-117 boxes_aligned_iou3d_gpu): rotated BEV overlap
+ * x height overlap over the union volume, every step rounded like the reference's torch expressions, in ONE
+ * kernel.  (N,7) x (M,7) -> (N,M);  aligned: (N,7),(N,7) -> (N). */
+int fnp_boxes_iou3d(const float *boxes_a, const float *boxes_b, float *out, int N, int M, void *stream);
+int fnp_boxes_aligned_iou3d(const float *boxes_a, const float *boxes_b, float *out, int N, void *stream);
+
 /* Rotated BEV overlap area / IoU, (N,7) x (M,7) -> (N,M). */
 int fnp_boxes_overlap_bev(const float *boxes_a, const float *boxes_b, float *out, int N, int M,
                           void *stream);
@@ -141,27 +157,24 @@ typedef struct fnp_seeker_batch {
     const float *base_corners;       /* (A,J,8,3)                                          */
     const float *mags;               /* (M) linspace(0,1,M)                                */
     /* ---- workspaces / intermediates (caller allocated) ---- */
-    int32_t *tile_counts;            /* (n_tiles, max_cands_per_frame) members of every candidate in
-                                        every tile                                          */
-    int32_t *tile_dst;               /* (n_tiles, max_cands_per_frame) their exclusive prefix over
-                                        the tiles of the frame                              */
-    int32_t *tile_base;              /* (n_tiles) first staging slot of the tile            */
     uint32_t *cell_masks;            /* fnp_seeker_cell_mask_bytes(): per (frame, camera rank, 64-px
                                         image cell) the bitmask (mask_words words) of the rank's
                                         candidates whose 2D box touches the cell            */
     int32_t mask_words;              /* = fnp_seeker_mask_words(max_cands_per_frame)        */
-    float *stage_pts;                /* (pts_capacity, 4) staging: the members of a tile, candidate-
-                                        major, as x,y,z,depth                               */
-    int32_t *stage_idx;              /* (pts_capacity) their source rows; required iff frustum_idx */
-    int32_t *cand_npts;              /* (F)   P_f                                          */
-    int32_t *cand_pt_start;          /* (F+1) start of each frustum in frustum_pts         */
-    float *frustum_pts;              /* (pts_capacity/2, 8) frustum points, pair-interleaved: points 2p
-                                        and 2p+1 of the buffer share the record {x0,x1,y0,y1,z0,z1,
-                                        d0,d1} (xyz of the unprojected point, camera depth); every
-                                        frustum starts at an even point index, so cand_pt_start[f+1]
-                                        - cand_pt_start[f] = cand_npts[f] rounded up to even  */
-    int32_t *frustum_idx;            /* (pts_capacity) source row within the frame, or NULL */
-    int64_t pts_capacity;            /* points; even */
+    int32_t *cand_npts;              /* (F)   P_f: the frustum's fill counter while stage 1 runs, its
+                                        point count afterwards                              */
+    int32_t *page_tab;               /* (F, page_tab_stride) page of point block k of frustum f, + 1
+                                        (0: not handed out, < 0: pool exhausted); zeroed by stage 1 */
+    int32_t page_tab_stride;         /* >= ceil(largest frame's points / FNP_PAGE_POINTS) + 1 */
+    int32_t page_planes;             /* 4: x | y | z | d per page; 5: + source row within the frame
+                                        (debug)                                             */
+    float *frustum_pts;              /* the page pool: (pts_capacity / FNP_PAGE_POINTS pages, page_planes,
+                                        FNP_PAGE_POINTS) -- point i of frustum f is slot i % 256 of
+                                        page page_tab[f][i / 256] - 1; xyz of the unprojected point and
+                                        its camera depth, SoA inside the page.  The ORDER of a
+                                        frustum's points is unspecified (whatever order the tiles
+                                        reached it in); no output depends on it                */
+    int64_t pts_capacity;            /* points the pool holds; a multiple of FNP_PAGE_POINTS */
     float *cand_stats;               /* (F,40): [0]dmin [1]dmax [2]dcentre [3..5]pmin [6..8]pmax
                                         [9]n_points [10..12] weighted_centre_xyz [13]/[14] min/max of
                                         hyp_dist over the hypotheses within max_dist
@@ -175,7 +188,8 @@ typedef struct fnp_seeker_batch {
     float *hyp_boxes_dbg;            /* (F,H,7) all hypothesis boxes by original index, or NULL */
     float *hyp_iou_dbg;              /* (F,H) or NULL                                      */
     uint8_t *hyp_valid_dbg;          /* (F,H) or NULL                                      */
-    int32_t split_points;            /* points per scoring work item (point split); even   */
+    int32_t split_points;            /* points per scoring work item (point split); a multiple of
+                                        FNP_PAGE_POINTS                                     */
     int32_t max_items;               /* capacity of `items`                                */
     int32_t *cand_item_start;        /* (F+1) first work item of each frustum              */
     int32_t *items;                  /* (max_items,4) work items: frustum, first hypothesis, split,
@@ -190,9 +204,9 @@ typedef struct fnp_seeker_batch {
     float *out_score;                /* (F*T)   their second-stage scores                  */
     int32_t *out_best;               /* (F*T)   compacted index of the hypothesis, -1 for an unused slot */
     int32_t *out_count;              /* (F*T)   its point count                            */
-    int32_t *status;                 /* (8)   [0] bit0: frustum_pts overflow (needed points in [1]),
-                                        bit1: items overflow ([2] items needed);
-                                        [4] work-item counter of the scoring kernel; [5] staging
+    int32_t *status;                 /* (8)   [0] bit0: page pool overflow (capacity needed, in points,
+                                        in [1]), bit1: items overflow ([2] items needed);
+                                        [4] work-item counter of the scoring kernel; [5] page
                                         cursor of stage 1; [6..7] spare                     */
     /* ---- workspaces of the optional terms (may be NULL when the term is off) ---- */
     float *hyp_dist;                 /* (F,H) |front - weighted_centre_xyz| of each compacted hypothesis;
@@ -204,6 +218,7 @@ typedef struct fnp_seeker_batch {
 } fnp_seeker_batch;
 
 #define FNP_CULL_TILE 1024
+#define FNP_PAGE_POINTS 256
 /* Scoring modes (fnp_seeker_batch.score_mode).  Both produce the same counts, bit for bit.
  *   DIRECT: every valid hypothesis tests every frustum point (P_f * nv_f in-box predicates).
  *   SWEEP : the M hypotheses of one (yaw, size) column share rotation and size and their centres
@@ -225,9 +240,10 @@ int fnp_seeker_mask_words(int max_cands_per_frame);
 /* Bytes of fnp_seeker_batch.cell_masks for a batch (0 on bad arguments). */
 size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_frames, int max_cands_per_frame);
 
-/* Stage 1: fused LiDAR->camera projection + per-2D-box frustum cull + ordered compaction.
- * Cell table, one pass over the points (membership, per-tile populations, member points into a
- * per-tile staging slice), two scans, an ordered gather: five launches, no host sync. */
+/* Stage 1: fused LiDAR->camera projection + per-2D-box frustum cull + compaction into pages.
+ * Cell table, then ONE pass over the points: membership, a reservation per (tile, candidate) on the
+ * frustum's fill counter, member points written to their final page slots.  No counting pass, no
+ * scan, no reordering pass, no host sync. */
 int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
 /* Stage 1b: per-frustum depth quantiles, point AABB, frustum corners, centre line. */
 int fnp_seeker_frustum_stats(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream);
@@ -362,6 +378,11 @@ int fnp_host_pack_xyz_multi_begin(const float *const *seg_src_host, const int64_
  * aligned, bytes a multiple of 16.  The per-batch metadata goes this way so that it cannot queue
  * behind a large point copy of another stream in the H2D engine. */
 int fnp_upload_from_pinned(void *dst, const void *src_pinned_host, size_t bytes, void *stream);
+
+/* Tuning / test switches, process-wide; not part of the stable surface.  "cull_sectors" (default 1): stage 1
+ * consults the per-frame azimuth-sector table to skip cameras that cannot see a point (0: every camera for
+ * every point -- same results, the tests compare the two).  Returns FNP_EINVAL for an unknown name. */
+int fnp_set_option(const char *name, int value);
 
 /* Test hook: out (4,n) = sinf(x), cosf(x), atan2f(y,x), fnp_exp(x) as evaluated on the
  * device by this library's build (checked against the oracle's restatements). */

@@ -202,3 +202,40 @@ def test_batch_planner_in_c_equals_the_numpy_path():
     assert fis[0].prepare() is p0
     fis[0].det_scores = fis[0].det_scores.copy()
     assert fis[0]._prep is None and fis[0].prepare() is not p0
+
+
+def test_cpu_op_box_constants_reproduce_the_reference_cpu_op(ref_ops):
+    """fnp_host_prep_boxes_cpu (the host half of the device-executed points_in_boxes_cpu): with its constants, the
+    rounded fp32 arithmetic the device kernel performs -- emulated here in numpy, one rounding per operation --
+    gives the reference-compiled CPU op's matrix bit for bit, also for points within a few ulp of dx/2 + 1e-2."""
+    import ctypes as C
+    from findnpropagate_b200 import _lib
+    ref_rp, _ = ref_ops
+    rng = np.random.default_rng(3)
+    n = 40
+    boxes = np.zeros((n, 7), np.float32)
+    boxes[:, :3] = rng.uniform(-20, 20, (n, 3))
+    boxes[:, 3:6] = rng.uniform(0.3, 12, (n, 3))
+    boxes[:, 6] = rng.uniform(-7, 7, n)
+    k = rng.integers(0, n, 4000)
+    b = boxes[k].astype(np.float64)
+    eps = np.concatenate([rng.uniform(-0.012, 0.012, 2000), 0.01 + rng.integers(-6, 7, 2000) * 1e-7])
+    sgn = rng.choice([-1.0, 1.0], 4000)
+    lx, ly = sgn * (b[:, 3] / 2 + eps), rng.uniform(-0.45, 0.45, 4000) * b[:, 4]
+    ca, sa = np.cos(b[:, 6]), np.sin(b[:, 6])
+    pts = np.stack([b[:, 0] + lx * ca - ly * sa, b[:, 1] + lx * sa + ly * ca, b[:, 2] + rng.uniform(-0.5, 0.5, 4000) * b[:, 5]], 1)
+    pts = np.concatenate([pts, rng.uniform(-25, 25, (4000, 3))]).astype(np.float32)
+    want = torch.zeros((n, pts.shape[0]), dtype=torch.int32)
+    ref_rp.points_in_boxes_cpu(torch.from_numpy(boxes), torch.from_numpy(pts), want)
+    prep = np.zeros((n, 8), np.float32)
+    assert _lib.lib.fnp_host_prep_boxes_cpu(C.c_void_p(boxes.ctypes.data), C.c_void_p(prep.ctypes.data), n) == 0
+    f = np.float32
+    sx = (pts[None, :, 0] - prep[:, None, 0]).astype(f)
+    sy = (pts[None, :, 1] - prep[:, None, 1]).astype(f)
+    sz = (pts[None, :, 2] - prep[:, None, 2]).astype(f)
+    cosa, sina = prep[:, None, 4], prep[:, None, 5]
+    lxx = ((sx * cosa).astype(f) + (sy * -sina).astype(f)).astype(f)
+    lyy = ((sx * sina).astype(f) + (sy * cosa).astype(f)).astype(f)
+    got = ~(np.abs(sz) > prep[:, None, 3]) & (np.abs(lxx) <= prep[:, None, 6]) & (np.abs(lyy) <= prep[:, None, 7])
+    assert np.array_equal(got.astype(np.int32), want.numpy()), int((got.astype(np.int32) != want.numpy()).sum())
+    assert want.numpy().sum() > 2000

@@ -180,6 +180,94 @@ def test_many_candidates_per_frame_mask_words(n_boxes):
     assert n > n_boxes // 2
 
 
+def test_dense_overlapping_boxes_take_the_direct_pass_of_stage_one():
+    """Nested 2D boxes in every label: a point is a member of dozens of candidates, so the members of a
+    1024-point tile exceed the shared-memory member list of stage 1 and the tile repeats its membership pass
+    with direct writes.  Bit-exact against the oracle like any other frame."""
+    cfg = synth.SynthConfig("nested", 16, 720, 1, 8, 4, 6, 1)
+    params = synth.seeker_params(cfg)
+    frames = []
+    for i in range(2):
+        f = _frame_from_synth(synth.make_frame(i, cfg))
+        boxes, labels, scores, cams = [], [], [], []
+        for cam in range(6):
+            for lab in range(1, 11):
+                for k, w in enumerate((90.0, 240.0, 620.0, 1600.0)):        # mutual IoU < 0.4: all survive the 2D NMS
+                    boxes.append([0.0, 0.0, w, 900.0 - 3.0 * lab])
+                    labels.append(lab); scores.append(0.5 + 0.01 * k + 0.001 * lab); cams.append(cam)
+        f.det_boxes, f.det_labels = np.asarray(boxes, np.float32), np.asarray(labels, np.int64)
+        f.det_scores, f.det_cam_idx = np.asarray(scores, np.float32), np.asarray(cams, np.int64)
+        frames.append(f)
+    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    eng.pts_factor = 64.0                       # a point is a member of up to 40 frustums here
+    plan = eng.plan(frames)
+    assert plan["max_cands"] == 240
+    res, n = _check_against_oracle(eng, frames, params)
+    assert n > 200
+    per_tile = res["cand_npts"].sum() / plan["n_tiles"]
+    assert per_tile > 1280, per_tile           # more members per tile than the list holds (csrc: kCullList)
+
+
+def test_sector_table_only_skips_cameras_that_cannot_see_the_point():
+    """Stage 1 projects a point only into the cameras its azimuth sector lists (csrc: sector_sees).  The table
+    must be a superset of the truth: with the table switched off (every camera for every point) stage 1 must
+    give the same members, and both must equal the oracle -- on a frame salted with the points the table could
+    get wrong: behind a camera on the thin tube that still lands on the image through the depth clamp, closer to
+    the sensor than the table's minimum radius, far above / below it, exactly on sector borders."""
+    from findnpropagate_b200 import _lib
+    cfg = synth.SynthConfig("sect", 16, 720, 1, 8, 4, 6, 1)
+    params = synth.seeker_params(cfg)
+    sf = synth.make_frame(3, cfg)
+    extra = []
+    for c in range(6):
+        L = sf.lidar2image[c][:3].astype(np.float64)
+        for t in np.linspace(0.3, 70.0, 160):           # wz = -t: behind camera c, wx and wy inside [0, 1600e-5) x [0, 900e-5)
+            for a, b in ((0.005, 0.004), (0.0, 0.0), (0.0155, 0.0085), (0.012, 0.001)):
+                extra.append(np.linalg.solve(L[:, :3], np.array([a, b, -t]) - L[:, 3]))
+    rng = np.random.default_rng(11)
+    near = rng.uniform(-3.5, 3.5, (600, 3)); near[:, 2] = rng.uniform(-2, 2, 600)            # inside the minimum radius
+    tall = rng.uniform(-40, 40, (600, 3)); tall[:, 2] = rng.choice([-30.0, 17.0, 16.0, -16.0, 60.0], 600)
+    r = rng.uniform(3.0, 60.0, 400)
+    ang = rng.choice(np.arctan2(np.arange(17) / 16.0, 1 - np.arange(17) / 16.0), 400) * rng.choice([1, -1], 400) \
+        + rng.choice([0, np.pi], 400)                                                         # exactly on sector borders
+    border = np.stack([r * np.cos(ang), r * np.sin(ang), rng.uniform(-2, 1, 400)], 1)
+    axes = np.array([[5, 0, 0], [-5, 0, 0], [0, 5, 0], [0, -5, 0], [-0.0, 7, 0], [7, -0.0, 0], [3, 0, 0], [0, 3, 0]], float)
+    add = np.concatenate([np.asarray(extra), near, tall, border, axes]).astype(np.float32)
+    pts = np.concatenate([sf.points, np.concatenate([add, np.zeros((add.shape[0], 2), np.float32)], 1)]).astype(np.float32)
+    fi = _frame_from_synth(sf)
+    fi.points = pts
+    boxes, labels, scores, cams = [fi.det_boxes], [fi.det_labels], [fi.det_scores], [fi.det_cam_idx]
+    for c in range(6):      # one box over the whole image of every camera: every on-image point is a member
+        boxes.append(np.array([[0, 0, 1600, 900]], np.float32)); labels.append(np.array([1 + c])); scores.append(np.array([0.9], np.float32))
+        cams.append(np.array([c]))
+    fi.det_boxes, fi.det_labels = np.concatenate(boxes).astype(np.float32), np.concatenate(labels).astype(np.int64)
+    fi.det_scores, fi.det_cam_idx = np.concatenate(scores).astype(np.float32), np.concatenate(cams).astype(np.int64)
+    out = {}
+    try:
+        for mode in (1, 0):
+            assert _lib.lib.fnp_set_option(b"cull_sectors", mode) == 0
+            eng = SeekerEngine(params, device="cuda:0", debug=True)
+            eng.pts_factor = 8.0
+            if mode == 1:
+                res, n = _check_against_oracle(eng, [fi], params)
+                assert n >= 6
+            plan = eng.plan([fi])
+            h = eng.execute(plan, eng.upload_points([fi]))
+            r_ = eng.finish(h)
+            d_ = eng.debug_views(h)
+            v_ = r_["cand_valid"]
+            out[mode] = (r_["cand_npts"].copy(), d_["frustum_idx"].copy(), d_["frustum_pts"].copy(), d_["counts"].copy(),
+                         v_.copy(), r_["cand_boxes"][v_].copy(), r_["cand_count"][v_].copy())
+    finally:
+        _lib.lib.fnp_set_option(b"cull_sectors", 1)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+    # the salted points did reach frustums (among them points BEHIND their camera)
+    n_base = sf.points.shape[0]
+    assert (out[1][1] >= n_base).sum() > 300
+    assert _lib.lib.fnp_set_option(b"no_such_option", 1) != 0
+
+
 def test_full_size_properties_cfg2():
     """cfg2 (300k points, 60 boxes, H = 768): properties that do not need the slow oracle on
     every hypothesis -- run twice = identical; membership ordered/unique; counts equal the

@@ -25,18 +25,22 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defs=(), out=None):
+    """defs / out: A/B builds with other compile-time constants (-DNAME=value) into another file; a process picks
+    one with FNP_LIB_PATH (see _lib.py)."""
+    if out is None and not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defs] + ["-o", out or SO] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libfnp_sm100.so")
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defs=defs, out=outs[0] if outs else None))

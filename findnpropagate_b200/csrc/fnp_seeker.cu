@@ -59,7 +59,15 @@ constexpr float kCellInv = 1.0f / kCellPx;
 __host__ __device__ inline int cell_cols(float img_w) { return (int)((img_w + kCellPx - 1) / kCellPx); }
 __host__ __device__ inline int cell_rows(float img_h) { return (int)((img_h + kCellPx - 1) / kCellPx); }
 
-constexpr int kCullList = 1280;      // member entries a tile can hold in shared memory (typical: ~300)
+// measured on 256 cfg2 frames (profiles/r02g_*): 5 CTAs/SM x 1280 entries 1.29 ms; 4 CTAs 1.49, 6 CTAs (40 registers,
+// spills) 1.39, a 768-entry list 1.49 (more tiles take the direct pass), 6 CTAs x 768 entries 1.60
+#ifndef FNP_CULL_LIST
+#define FNP_CULL_LIST 1280
+#endif
+#ifndef FNP_CULL_MIN_CTAS
+#define FNP_CULL_MIN_CTAS 5
+#endif
+constexpr int kCullList = FNP_CULL_LIST;      // member entries a tile can hold in shared memory (typical: ~300)
 
 struct alignas(16) CullSmem {
     float cam[6][24];       // by camera index
@@ -314,7 +322,7 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
 //   3. the list is flushed to the reserved slots by full warps.
 // A tile whose members do not fit the list (kCullList) repeats the membership pass with direct writes.
 template <int W>
-__global__ void __launch_bounds__(kCullThreads, 5) cull_kernel(const fnp_seeker_batch b, const float img_w,
+__global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(const fnp_seeker_batch b, const float img_w,
                                                             const float img_h, const int n_cu, const int n_cv,
                                                             const int use_sectors)
 {
@@ -450,6 +458,9 @@ constexpr int kSelBits = 11, kSelBins = 1 << kSelBits;
 constexpr int kSelList = 512;      // keys finished by rank counting
 constexpr int kStatsCache = 4096;  // depth keys cached in shared memory
 constexpr int kStatsThreads = 256;
+#ifndef FNP_STATS_MIN_CTAS
+#define FNP_STATS_MIN_CTAS 4      // 64 registers: 4 CTAs per SM (3 at the natural 79 registers: 0.50 -> 0.43 ms per 256 cfg2 frames)
+#endif
 
 struct SelSmem {
     unsigned hist[kSelBins];
@@ -639,7 +650,7 @@ __device__ float block_quantile(const FrustumPages &pts, SelSmem &S, bool cached
     return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), bv);
 }
 
-__global__ void __launch_bounds__(kStatsThreads) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+__global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ SelSmem S;
     __shared__ float s_red[8][8];
@@ -1754,14 +1765,12 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
 
 // Tuning / test switches (fnp_set_option): not part of the stable ABI.
 static int g_opt_cull_sectors = 1;      // stage 1 consults the per-frame sector table (0: every camera for every point)
-static int g_opt_sweep_variant = 0;
 
 extern "C" int fnp_set_option(const char *name, int value)
 {
     if (!name) return FNP_EINVAL;
     const std::string n(name);
     if (n == "cull_sectors") { g_opt_cull_sectors = value; return FNP_OK; }
-    if (n == "sweep_variant") { g_opt_sweep_variant = value; return FNP_OK; }
     return FNP_EINVAL;
 }
 

@@ -255,6 +255,7 @@ class FrustumProposerOG(nn.Module):
                 preds_paths = _cfg_get(model_cfg, 'PREDS_PATHS', [preds_path + "%s.json" % c for c in camera_names])
                 self.image_detector = PreprocessedDetector(preds_paths, class_names=class_names)
         self.engine = SeekerEngine(p, device=device, box_format=self.box_fmt)
+        self._cal_cache = {}
         self.anchors = torch.tensor(__import__('findnpropagate_b200.seeker', fromlist=['ANCHORS']).ANCHORS,
                                     dtype=torch.float32, device=self.engine.device)
         self.base_boxes = self.engine.base_boxes
@@ -271,9 +272,6 @@ class FrustumProposerOG(nn.Module):
         if 'img_aug_matrix' in batch_dict:
             raise NotImplementedError("img_aug_matrix (image_calibrate) is disabled in the shipped config")
         B = int(batch_dict['batch_size'])
-        aug = self._np(batch_dict['lidar_aug_matrix']).reshape(B, 4, 4)
-        if not np.array_equal(aug, np.broadcast_to(np.eye(4, dtype=aug.dtype), aug.shape)):
-            raise NotImplementedError("lidar_aug_matrix must be the identity (augmentation is disabled on this path)")
         det_boxes, det_labels, det_scores, det_batch_idx, det_cam_idx = self.image_detector(batch_dict)
         pts = batch_dict['points']
         dev = self.engine.device
@@ -298,14 +296,40 @@ class FrustumProposerOG(nn.Module):
             stride, xyz_offset = 3, 0
         else:
             pts = pts.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-            bidx = pts[:, 0].contiguous()
-            bounds = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32)).cpu().numpy()
-            if not bool((bidx[1:] >= bidx[:-1]).all()) if bidx.numel() > 1 else False:
-                raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+            if B == 1:
+                # the reference's operating point (tools/extract_pseudo_labels.py:36 asserts batch size 1): one
+                # frame, every row belongs to it -- no device round trip for the frame bounds
+                bounds = np.array([0, int(pts.shape[0])], np.int64)
+            else:
+                bidx = pts[:, 0].contiguous()
+                q = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32))
+                ordered = (bidx[1:] >= bidx[:-1]).all() if bidx.numel() > 1 else torch.ones((), dtype=torch.bool, device=dev)
+                got = torch.cat([q, ordered.reshape(1).to(q.dtype)]).cpu().numpy()      # one device round trip
+                if not got[-1]:
+                    raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+                bounds = got[:-1]
             stride, xyz_offset = int(pts.shape[1]), 1
         from .seeker import camera_matrices
-        cam_mats = camera_matrices(self._np(batch_dict['lidar2image']), self._np(batch_dict['camera2lidar']),
-                                   self._np(batch_dict['camera_intrinsics']))
+        cal = [batch_dict['lidar2image'], batch_dict['camera2lidar'], batch_dict['camera_intrinsics']]
+        aug = batch_dict['lidar_aug_matrix']
+        if all(isinstance(c, torch.Tensor) and c.is_cuda for c in cal + [aug]):
+            # four small device tensors: one concatenation, one copy back
+            flat = torch.cat([c.reshape(B, -1).to(torch.float32) for c in cal + [aug]], dim=1).cpu().numpy()
+            cal = [flat[:, 96 * i:96 * (i + 1)].reshape(B, 6, 4, 4) for i in range(3)]
+            aug = flat[:, 288:304]
+        else:
+            cal = [self._np(c) for c in cal]
+            aug = self._np(aug)
+        aug = aug.reshape(B, 4, 4)
+        if not np.array_equal(aug, np.broadcast_to(np.eye(4, dtype=aug.dtype), aug.shape)):
+            raise NotImplementedError("lidar_aug_matrix must be the identity (augmentation is disabled on this path)")
+        key = b"".join(np.ascontiguousarray(c, np.float32).tobytes() for c in cal)
+        cam_mats = self._cal_cache.get(key)
+        if cam_mats is None:          # calibration repeats from frame to frame within a scene
+            cam_mats = camera_matrices(*cal)
+            if len(self._cal_cache) > 256:
+                self._cal_cache.clear()
+            self._cal_cache[key] = cam_mats
         plan = self.engine.plan_arrays(
             bounds.astype(np.int64), stride, xyz_offset, cam_mats, self._np(det_boxes).astype(np.float32).reshape(-1, 4),
             self._np(det_labels).astype(np.int64), self._np(det_scores).astype(np.float32),

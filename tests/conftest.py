@@ -26,3 +26,4 @@ def ref_ops():
         return build_ref.load("roiaware_pool3d_cuda"), build_ref.load("iou3d_nms_cuda")
     except ImportError as e:  # pragma: no cover
         pytest.skip(str(e))
+

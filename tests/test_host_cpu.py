@@ -239,3 +239,28 @@ def test_cpu_op_box_constants_reproduce_the_reference_cpu_op(ref_ops):
     got = ~(np.abs(sz) > prep[:, None, 3]) & (np.abs(lxx) <= prep[:, None, 6]) & (np.abs(lyy) <= prep[:, None, 7])
     assert np.array_equal(got.astype(np.int32), want.numpy()), int((got.astype(np.int32) != want.numpy()).sum())
     assert want.numpy().sum() > 2000
+
+
+def test_shipped_yaml_params_equal_the_hard_coded_ones():
+    """MODEL.DENSE_HEAD.PARAMS of the reference's tools/cfgs/nuscenes_box_seeker_proposals.yaml against
+    synth.seeker_params (the option set every test and the bench run), the head's constructor defaults
+    (frustum_proposals_v1.py:146-148) filling the keys the YAML leaves out.  Needs the reference tree: runs in the
+    build container, skipped on the GPU box."""
+    import yaml
+    from findnpropagate_b200.seeker import DEFAULTS, resolve_params
+    path = "/root/reference/tools/cfgs/nuscenes_box_seeker_proposals.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    head = yaml.safe_load(open(path))["MODEL"]["DENSE_HEAD"]
+    assert head["NAME"] == "FrustumProposerOG" and head["PREDS_PATH"] == "PreprocessedGLIP" and head["BOX_FORMAT"] == "xyxy"
+    shipped = head["PARAMS"]
+    cfg1 = synth.CONFIGS["cfg1"]                     # BASELINE.json configs[0]: the shipped grid
+    mine = synth.seeker_params(cfg1)
+    for k, v in shipped.items():
+        assert mine[k] == v, (k, mine[k], v)
+    # keys the YAML omits fall back to the constructor defaults, as in the reference (:167-196)
+    for k in ("num_mags", "num_rotations"):
+        assert k not in shipped and mine[k] == DEFAULTS[k]
+    full = resolve_params(shipped)
+    assert (full["num_mags"], full["num_rotations"], full["num_sizes"]) == (cfg1.num_mags, cfg1.num_rotations, cfg1.num_sizes)
+    assert full["max_dist"] == 50 and full["topk"] == 1

@@ -393,3 +393,47 @@ def test_pseudo_loader_bev_nms_and_nms_dispatcher(ref_ops, tmp_path):
     assert np.array_equal(sel.cpu().numpy(), kept) and np.array_equal(sel_scores.cpu().numpy(), scores[kept])
     ps, pl, pb = model_nms_utils.multi_classes_nms(torch.stack([ts, 1 - ts], 1), tb, cfg, score_thresh=0.5)
     assert ps.shape[0] == pl.shape[0] == pb.shape[0] and set(pl.cpu().tolist()) <= {0, 1}
+
+
+def test_gt_database_creation_equals_the_reference_procedure(ref_ops, tmp_path):
+    """Row f4: create_groundtruth_database (nuscenes_dataset.py:346-390) -- frames batched into one
+    fnp_points_in_boxes launch -- against the reference's procedure run frame by frame with the reference's own
+    compiled kernel: the same .bin files byte for byte, the same db-info entries."""
+    import pickle
+    from findnpropagate_b200 import gt_database, synth
+    ref_rp, _ = ref_ops
+    cfg = synth.SynthConfig("gtdb", 16, 720, 1, 8, 4, 6, 1)
+    sf = [synth.make_frame(i, cfg) for i in range(5)]
+    sf[2].gt_boxes = sf[2].gt_boxes[:0]                       # a frame without GT
+    infos = synth.write_nuscenes_tree(str(tmp_path / "nusc"), sf)
+    used = ["car", "pedestrian", "truck"]
+    got = gt_database.create_groundtruth_database(tmp_path / "nusc", infos, used_classes=used, max_sweeps=1, batch_frames=2)
+    db_dir = tmp_path / "nusc" / "gt_database_1sweeps_withvelo"
+    n_files, n_pts = 0, 0
+    want = {}
+    for idx, (f, info) in enumerate(zip(sf, infos)):
+        pts = np.fromfile(str(tmp_path / "nusc" / info["lidar_path"]), np.float32).reshape(-1, 5)[:, :4]
+        pts = np.concatenate([pts, np.zeros((pts.shape[0], 1), np.float32)], 1)              # get_lidar_with_sweeps: + time lag
+        gt = info["gt_boxes"]
+        out = torch.full((1, pts.shape[0]), -1, dtype=torch.int32, device=DEV)
+        if gt.shape[0]:
+            ref_rp.points_in_boxes_gpu(torch.from_numpy(gt[None, :, :7]).float().to(DEV).contiguous(),
+                                       torch.from_numpy(pts[None, :, :3]).float().to(DEV).contiguous(), out)
+        box_of_pt = out.long().squeeze(0).cpu().numpy()
+        for i in range(gt.shape[0]):
+            name = info["gt_names"][i]
+            exp = pts[box_of_pt == i].copy()
+            exp[:, :3] -= gt[i, :3]
+            path = db_dir / ("%s_%s_%d.bin" % (idx, name, i))
+            assert path.exists() and np.fromfile(str(path), np.float32).tobytes() == exp.tobytes()
+            n_files += 1
+            n_pts += exp.shape[0]
+            if name in used:
+                want.setdefault(name, []).append((str(path.relative_to(tmp_path / "nusc")), idx, i, exp.shape[0]))
+    assert n_files == sum(i["gt_boxes"].shape[0] for i in infos) == len(list(db_dir.iterdir())) and n_pts > 100
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert [(d["path"], d["image_idx"], d["gt_idx"], d["num_points_in_gt"]) for d in got[name]] == want[name]
+        assert all(np.array_equal(d["box3d_lidar"], infos[d["image_idx"]]["gt_boxes"][d["gt_idx"]]) for d in got[name])
+    with open(tmp_path / "nusc" / "nuscenes_dbinfos_1sweeps_withvelo.pkl", "rb") as fh:
+        assert sorted(pickle.load(fh)) == sorted(want)

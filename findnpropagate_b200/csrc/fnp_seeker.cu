@@ -164,10 +164,10 @@ __device__ bool sector_sees(const float *__restrict__ L, const int s, const floa
 
 // One CTA per (frame, camera rank): cell -> candidates of that rank whose box may contain a
 // pixel of the cell.  Conservative (a superset); the exact test follows in cull_kernel.
-template <int W>
 __global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch b, const int n_cu, const int n_cv,
                                                          const float img_w, const float img_h)
 {
+    const int W = b.mask_words;
     extern __shared__ unsigned s_cells[];                 // [n_cu * n_cv][W]
     const int frame = blockIdx.x / 6, r = blockIdx.x % 6;
     const int n_cells = n_cu * n_cv;
@@ -243,7 +243,7 @@ __device__ __forceinline__ void store_member(const fnp_seeker_batch &b, const in
 // rank among the tile's members of that candidate from a shared-memory atomic and
 //   DIRECT == false: is appended to the tile's member list (unprojected point, candidate, rank);
 //   DIRECT == true : is written to its final place at once (s_base[] = the tile's reservation).
-template <bool DIRECT, int W>
+template <bool DIRECT>
 __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem &S, const float4 *s_box, int *s_cnt,
                                              const int *s_base, float4 *s_ent, int *s_key, int *s_row,
                                              const float (&x)[kPtsPerThread], const float (&y)[kPtsPerThread],
@@ -252,6 +252,7 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
                                              const float img_h, const int n_cu, const int n_cv, const bool use_sectors)
 {
     const int tid = threadIdx.x;
+    const int W = b.mask_words;          // words of a cell's candidate mask: 1 .. 32 (up to 1024 candidates per frame)
     // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
     const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
     const int n_cells = n_cu * n_cv;
@@ -284,7 +285,6 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
             const unsigned *cm = b.cell_masks + (((size_t)frame * 6 + r) * n_cells + cell) * W;
             bool have = false;
             float X = 0.f, Y = 0.f, Z = 0.f;
-#pragma unroll
             for (int w = 0; w < W; w++) {
                 unsigned m = __ldg(cm + w);
                 while (m) {
@@ -321,7 +321,6 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
 //      point indices; the reservation that contains the first slot of a page takes that page from the pool;
 //   3. the list is flushed to the reserved slots by full warps.
 // A tile whose members do not fit the list (kCullList) repeats the membership pass with direct writes.
-template <int W>
 __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(const fnp_seeker_batch b, const float img_w,
                                                             const float img_h, const int n_cu, const int n_cv,
                                                             const int use_sectors)
@@ -336,6 +335,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     int *s_cnt = s_row + kCullList;                                                      // [Cmax] members of a candidate in this tile
     int *s_base = s_cnt + Cmax;                                                          // [Cmax] first reserved slot
 
+    const int W = b.mask_words;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
     const int frame = b.tile_frame[tile];
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     }
     __syncthreads();
 
-    cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+    cull_members<false>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
                            n_cu, n_cv, use_sectors != 0);
     __syncthreads();
     const int n_list = S.n_list;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
         // the ranks are handed out again, any assignment of a candidate's members to its reserved slots will do
         for (int j = tid; j < nc; j += kCullThreads) s_cnt[j] = 0;
         __syncthreads();
-        cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+        cull_members<true>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
                               n_cu, n_cv, use_sectors != 0);
     }
 }
@@ -1779,17 +1779,16 @@ static size_t cull_smem(const fnp_seeker_batch *b)
     return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 + 4) + (size_t)kCullList * (16 + 4 + 4) + 16;
 }
 
-template <int W>
-static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
+static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st, const int W)
 {
     const int n_cu = cell_cols(cfg->img_w), n_cv = cell_rows(cfg->img_h);
     const size_t sa = cull_smem(b), sc = (size_t)n_cu * n_cv * W * 4;
     if (sa > 200 * 1024 || sc > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
-    cudaFuncSetAttribute(cell_table_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
+    cudaFuncSetAttribute(cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cell_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
     cudaMemsetAsync(b->cell_masks + (size_t)b->n_frames * 6 * n_cu * n_cv * W, 0, (size_t)b->n_frames * kSectors * 4, st);
-    cell_table_kernel<W><<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h);
-    cull_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
+    cell_table_kernel<<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h);
+    cull_kernel<<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
     cull_finish_kernel<<<1, 32, 0, st>>>(*b);
     return FNP_OK;
 }
@@ -1805,7 +1804,7 @@ extern "C" size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_fr
 extern "C" int fnp_seeker_mask_words(int max_cands_per_frame)
 {
     const int w = divup(max_cands_per_frame > 0 ? max_cands_per_frame : 1, 32);
-    return w <= 1 ? 1 : w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : -1;
+    return w <= 1 ? 1 : w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1;
 }
 
 extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, void *stream)
@@ -1827,13 +1826,8 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
     cudaMemsetAsync(b->cand_npts, 0, sizeof(int32_t) * (size_t)b->n_cands, st);
     cudaMemsetAsync(b->page_tab, 0, sizeof(int32_t) * (size_t)b->n_cands * (size_t)b->page_tab_stride, st);
     const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
-    if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 256 candidates in one frame
-    switch (W) {
-        case 1: rc = launch_cull<1>(cfg, b, st); break;
-        case 2: rc = launch_cull<2>(cfg, b, st); break;
-        case 4: rc = launch_cull<4>(cfg, b, st); break;
-        default: rc = launch_cull<8>(cfg, b, st); break;
-    }
+    if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 1024 candidates in one frame
+    rc = launch_cull(cfg, b, st, W);
     if (rc) return rc;
     FNP_LAUNCH_CHECK();
     return FNP_OK;

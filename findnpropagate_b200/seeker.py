@@ -165,6 +165,35 @@ class _Arena:
         return t
 
 
+class _FrameResults:
+    """Per-frame results of a batch as a read-only sequence: frame b -> dict(pred_boxes (K,7) f32, pred_scores (K) f32,
+    pred_labels (K) int32[, nms_keep (K) bool]) -- the reference's per-frame output (frustum_proposals_v1.py:1554-1573).
+    The dicts are views of the batch's compacted arrays, made when a frame is asked for: a 256-frame batch whose
+    consumer only wants the packed arrays (the frame-sharded exchange) pays nothing per frame."""
+
+    def __init__(self, boxes, scores, labels, keep, start):
+        self._b, self._s, self._l, self._k, self._st = boxes, scores, labels, keep, start
+
+    def __len__(self):
+        return len(self._st) - 1
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        lo, hi = int(self._st[b]), int(self._st[b + 1])
+        d = dict(pred_boxes=self._b[lo:hi], pred_scores=self._s[lo:hi], pred_labels=self._l[lo:hi])
+        if self._k is not None:
+            d["nms_keep"] = self._k[lo:hi]
+        return d
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self)))
+
+
 def _align(x, a=256):
     return (x + a - 1) // a * a
 
@@ -470,7 +499,7 @@ class SeekerEngine:
             Cmax = max(plan["max_cands"], 1)
             W = _lib.lib.fnp_seeker_mask_words(Cmax)
             if W < 0:
-                raise ValueError("more than 256 candidate frustums in one frame (%d) are not supported" % Cmax)
+                raise ValueError("more than 1024 candidate frustums in one frame (%d) are not supported" % Cmax)
             sizes = dict(
                 page_tab=4 * max(F, 1) * tab_stride, cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
                 frustum_pts=4 * planes * cap,
@@ -603,14 +632,7 @@ class SeekerEngine:
         c_boxes, c_scores = boxes[idx], plan["cand_score"][cand_of]
         c_labels = plan["cand_label"][cand_of].astype(np.int32)
         c_keep = raw[handle["off_keep"]:handle["off_keep"] + FT][idx].astype(bool) if handle["has_nms"] else None
-        st = np.searchsorted(idx, fcs * T).tolist()
-        frames = []
-        for b in range(B):
-            d = dict(pred_boxes=c_boxes[st[b]:st[b + 1]], pred_scores=c_scores[st[b]:st[b + 1]],
-                     pred_labels=c_labels[st[b]:st[b + 1]])
-            if c_keep is not None:
-                d["nms_keep"] = c_keep[st[b]:st[b + 1]]
-            frames.append(d)
+        frames = _FrameResults(c_boxes, c_scores, c_labels, c_keep, np.searchsorted(idx, fcs * T))
         # per-candidate views: the best proposal of each (slot 0); cand_topk has every slot
         res = dict(frames=frames, cand_valid=ok[::T].copy(), cand_best=best[::T].copy(), cand_score2=score[::T].copy(),
                    cand_count=count[::T].copy(), cand_npts=npts.copy(), cand_nvalid=nvalid.copy(),

@@ -235,7 +235,8 @@ typedef struct fnp_seeker_batch {
 #define FNP_SWEEP_MIN_MAGS 16
 #define FNP_SWEEP_COL_FLOATS 20
 /* Words of the per-point candidate mask for a batch whose busiest frame has that many
- * candidates: 1, 2, 4 or 8 (-1: more than 256 candidates per frame are not supported). */
+ * candidates: 1, 2, 4, 8, 16 or 32 (-1: more than 1024 candidates per frame are not supported -- the limit of
+ * the stage-4 NMS, FNP_SEG_NMS_MAX). */
 int fnp_seeker_mask_words(int max_cands_per_frame);
 /* Bytes of fnp_seeker_batch.cell_masks for a batch (0 on bad arguments). */
 size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_frames, int max_cands_per_frame);

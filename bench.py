@@ -655,7 +655,7 @@ def run_ours(a):
                       "solves one depth range per (point, column) pair instead of testing every (point, hypothesis) pair"
                       if score_mode == "sweep" else
                       "stage 2b, direct kernel: bound by the SM's ALU/FMA pipes, not by HBM (DESIGN.md section 4)"),
-        "cull": roof("cull", "fnp::cull_stage_kernel", cull_ms,
+        "cull": roof("cull", "fnp::cull_kernel", cull_ms,
                      "stage 1 (projection + frustum cull + ordered compaction), timed through fnp_seeker_cull (all its "
                      "launches); HBM-bound by design, instruction-issue-bound as measured"),
     }

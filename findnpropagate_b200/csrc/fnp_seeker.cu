@@ -243,7 +243,7 @@ __device__ __forceinline__ void store_member(const fnp_seeker_batch &b, const in
 // rank among the tile's members of that candidate from a shared-memory atomic and
 //   DIRECT == false: is appended to the tile's member list (unprojected point, candidate, rank);
 //   DIRECT == true : is written to its final place at once (s_base[] = the tile's reservation).
-template <bool DIRECT>
+template <bool DIRECT, int W>
 __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem &S, const float4 *s_box, int *s_cnt,
                                              const int *s_base, float4 *s_ent, int *s_key, int *s_row,
                                              const float (&x)[kPtsPerThread], const float (&y)[kPtsPerThread],
@@ -252,7 +252,6 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
                                              const float img_h, const int n_cu, const int n_cv, const bool use_sectors)
 {
     const int tid = threadIdx.x;
-    const int W = b.mask_words;          // words of a cell's candidate mask: 1 .. 32 (up to 1024 candidates per frame)
     // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
     const float w_hi = __fmul_rn(img_w, 1.0001f), h_hi = __fmul_rn(img_h, 1.0001f);
     const int n_cells = n_cu * n_cv;
@@ -285,7 +284,8 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
             const unsigned *cm = b.cell_masks + (((size_t)frame * 6 + r) * n_cells + cell) * W;
             bool have = false;
             float X = 0.f, Y = 0.f, Z = 0.f;
-            for (int w = 0; w < W; w++) {
+#pragma unroll
+            for (int w = 0; w < W; w++) {      // W words of the cell's candidate mask (W * 32 >= candidates of the busiest frame)
                 unsigned m = __ldg(cm + w);
                 while (m) {
                     const int jb = __ffs(m) - 1;
@@ -321,6 +321,7 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
 //      point indices; the reservation that contains the first slot of a page takes that page from the pool;
 //   3. the list is flushed to the reserved slots by full warps.
 // A tile whose members do not fit the list (kCullList) repeats the membership pass with direct writes.
+template <int W>
 __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(const fnp_seeker_batch b, const float img_w,
                                                             const float img_h, const int n_cu, const int n_cv,
                                                             const int use_sectors)
@@ -335,7 +336,6 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     int *s_cnt = s_row + kCullList;                                                      // [Cmax] members of a candidate in this tile
     int *s_base = s_cnt + Cmax;                                                          // [Cmax] first reserved slot
 
-    const int W = b.mask_words;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
     const int frame = b.tile_frame[tile];
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     }
     __syncthreads();
 
-    cull_members<false>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+    cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
                            n_cu, n_cv, use_sectors != 0);
     __syncthreads();
     const int n_list = S.n_list;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
         // the ranks are handed out again, any assignment of a candidate's members to its reserved slots will do
         for (int j = tid; j < nc; j += kCullThreads) s_cnt[j] = 0;
         __syncthreads();
-        cull_members<true>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
+        cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
                               n_cu, n_cv, use_sectors != 0);
     }
 }
@@ -1321,10 +1321,10 @@ __host__ __device__ inline int sweep_queue_cap(int SP, int J)
 }
 
 // Dynamic shared memory of sweep_score_kernel for split_points SP, H = M*J hypotheses, J columns.
-__host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J, int n_buffers = 2)
+__host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
 {
-    return (size_t)n_buffers * ((size_t)J * sizeof(SweepCol) + (size_t)SP * 12) + (size_t)H * 4 +
-           (size_t)sweep_queue_cap(SP, J) * 8 + (size_t)((H + 3) & ~3) * 2 + 32 + 16;
+    return (size_t)J * sizeof(SweepCol) + (size_t)SP * 12 + (size_t)H * 4 + (size_t)sweep_queue_cap(SP, J) * 8 +
+           (size_t)((H + 3) & ~3) * 2 + 16;
 }
 
 // Persistent CTAs pull (frustum, point split) items.  Per item:
@@ -1339,26 +1339,17 @@ __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J, int n_b
 #ifndef FNP_SWEEP_MIN_CTAS
 #define FNP_SWEEP_MIN_CTAS 4
 #endif
-// TMA = true: the split's pages (3 KB each) and the column parameters arrive by bulk copies (cp.async.bulk +
-// mbarrier complete_tx; SASS: UBLKCP) into one of two buffers, issued by one thread for the NEXT work item while
-// the CTA sweeps the current one; the item counter is read one item ahead too, so an item costs four CTA-wide
-// barriers instead of seven and no thread ever waits for a global load of points.
-// TMA = false: round 1's staging (every thread copies with LDG + STS after fetching the item), kept for A/B runs.
-template <bool TMA>
 __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int H = J * M, SP = b.split_points;
     const int QCAP = sweep_queue_cap(SP, J);
-    constexpr int NB = TMA ? 2 : 1;                                            // buffers of points + column parameters
-    SweepCol *s_col0 = reinterpret_cast<SweepCol *>(s_dyn);                     // [NB][J]   (80 B each: 16 B aligned)
-    uint2 *s_q = reinterpret_cast<uint2 *>(s_col0 + NB * J);                    // [QCAP] uncertain-step queue
-    float *s_pts0 = reinterpret_cast<float *>(s_q + QCAP);                      // [NB][SP / 256][x | y | z][256]: the split's pages
-    int *s_diff = reinterpret_cast<int *>(s_pts0 + NB * 3 * SP);                // [J][M] difference array, then counts
+    SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
+    uint2 *s_q = reinterpret_cast<uint2 *>(s_col + J);                          // [QCAP] uncertain-step queue
+    float *s_pts = reinterpret_cast<float *>(s_q + QCAP);                       // [SP / 256][x | y | z][256]: the split's pages
+    int *s_diff = reinterpret_cast<int *>(s_pts + 3 * SP);                      // [J][M] difference array, then counts
     short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
     int *s_ctl = reinterpret_cast<int *>(s_slot + ((H + 3) & ~3));              // [0] item [1] next piece [2] queue size [3] queue head
-                                                                                // [4], [5] item of buffer 0 / 1 (TMA)
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ctl + 8);                  // [2] mbarriers (TMA)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -1366,61 +1357,24 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
     const int n_items = b.status[2];
     auto red = [](int *p, int v) { atomicAdd(p, v); };
 
-    // one thread: bulk copies of work item `id` into buffer `buf`
-    auto issue = [&](const int id, const int buf) {
-        const int4 it = reinterpret_cast<const int4 *>(b.items)[id];
-        const int f = it.x, p0 = it.z * SP;
-        const int n = min(b.cand_npts[f], p0 + SP) - p0;
-        const int n_pg = (n + kPage - 1) / kPage;
-        const int *tab = b.page_tab + (size_t)f * b.page_tab_stride + p0 / kPage;
-        const uint32_t col_bytes = (uint32_t)J * (uint32_t)sizeof(SweepCol);
-        mbar_expect_tx(&s_bar[buf], col_bytes + (uint32_t)n_pg * 3u * kPage * 4u);
-        tma_load_1d(s_col0 + buf * J, b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS, col_bytes, &s_bar[buf]);
-        for (int q = 0; q < n_pg; q++)
-            tma_load_1d(s_pts0 + (size_t)buf * 3 * SP + q * 3 * kPage,
-                        b.frustum_pts + (size_t)(tab[q] - 1) * (size_t)(b.page_planes * kPage), 3u * kPage * 4u, &s_bar[buf]);
-    };
-    if (TMA) {
+    for (;;) {
+        __syncthreads();
         if (tid == 0) {
-            mbar_init(&s_bar[0], 1);
-            mbar_init(&s_bar[1], 1);
-            mbar_fence_init();
-            const int first = atomicAdd(&b.status[4], 1);
-            s_ctl[4] = first;
-            if (first < n_items) issue(first, 0);
+            s_ctl[0] = atomicAdd(&b.status[4], 1);
+            s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0;
         }
         __syncthreads();
-    }
-
-    for (int k = 0;; k++) {
-        const int buf = TMA ? (k & 1) : 0;
-        if (!TMA) {
-            __syncthreads();
-            if (tid == 0) {
-                s_ctl[0] = atomicAdd(&b.status[4], 1);
-                s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0;
-            }
-            __syncthreads();
-        }
-        const int item_id = TMA ? s_ctl[4 + buf] : s_ctl[0];
+        const int item_id = s_ctl[0];
         if (item_id >= n_items) break;
-        if (TMA && tid == 0) {      // one item ahead: its number, its copies (the other buffer was released by the barrier
-            s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0;         // that ended the previous item)
-            const int nxt = atomicAdd(&b.status[4], 1);
-            s_ctl[4 + (buf ^ 1)] = nxt;
-            if (nxt < n_items) issue(nxt, buf ^ 1);
-        }
         const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, -, split, -
         const int f = item.x, split = item.z;
         const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
         const int p0 = split * SP;
         const int n = min(npts, p0 + SP) - p0;
         const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
-        SweepCol *s_col = s_col0 + buf * J;
-        float *s_pts = s_pts0 + (size_t)buf * 3 * SP;
 
         // ---- stage
-        if (!TMA) {
+        {
             const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
             float4 *dst = reinterpret_cast<float4 *>(s_col);
             for (int i = tid; i < J * (FNP_SWEEP_COL_FLOATS / 4); i += kSweepThreads) dst[i] = __ldg(src + i);
@@ -1433,14 +1387,13 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                 const float4 *page = reinterpret_cast<const float4 *>(b.frustum_pts + (size_t)(tab[q] - 1) * (size_t)(b.page_planes * kPage));
                 reinterpret_cast<float4 *>(s_pts)[i] = __ldg(page + (i - q * kVec));
             }
+            for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
         }
-        for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
         __syncthreads();
         {
             const int *hidx = b.hyp_index + (size_t)f * H;
             for (int r = tid; r < nv; r += kSweepThreads) s_slot[hidx[r]] = (short)r;
         }
-        if (TMA) mbar_wait(&s_bar[buf], (unsigned)(k >> 1) & 1u);
         __syncthreads();
 
         // ---- sweep
@@ -1578,7 +1531,6 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
                 if (cnt) atomicAdd(out + r, cnt);      // RED.ADD: the splits of a frustum add up in any order
             }
         }
-        if (TMA) __syncthreads();      // everyone is done with this item's buffer, queue and tables
     }
 }
 
@@ -1813,14 +1765,12 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
 
 // Tuning / test switches (fnp_set_option): not part of the stable ABI.
 static int g_opt_cull_sectors = 1;      // stage 1 consults the per-frame sector table (0: every camera for every point)
-static int g_opt_sweep_tma = 1;         // the sweep kernel stages its points with TMA bulk copies, one item ahead (0: LDG + STS)
 
 extern "C" int fnp_set_option(const char *name, int value)
 {
     if (!name) return FNP_EINVAL;
     const std::string n(name);
     if (n == "cull_sectors") { g_opt_cull_sectors = value; return FNP_OK; }
-    if (n == "sweep_tma") { g_opt_sweep_tma = value; return FNP_OK; }
     return FNP_EINVAL;
 }
 
@@ -1829,16 +1779,17 @@ static size_t cull_smem(const fnp_seeker_batch *b)
     return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 + 4) + (size_t)kCullList * (16 + 4 + 4) + 16;
 }
 
-static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st, const int W)
+template <int W>
+static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
 {
     const int n_cu = cell_cols(cfg->img_w), n_cv = cell_rows(cfg->img_h);
     const size_t sa = cull_smem(b), sc = (size_t)n_cu * n_cv * W * 4;
     if (sa > 200 * 1024 || sc > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cull_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
     cudaFuncSetAttribute(cell_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
     cudaMemsetAsync(b->cell_masks + (size_t)b->n_frames * 6 * n_cu * n_cv * W, 0, (size_t)b->n_frames * kSectors * 4, st);
     cell_table_kernel<<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h);
-    cull_kernel<<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
+    cull_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
     cull_finish_kernel<<<1, 32, 0, st>>>(*b);
     return FNP_OK;
 }
@@ -1877,7 +1828,14 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
     cudaMemsetAsync(b->page_tab, 0, sizeof(int32_t) * (size_t)b->n_cands * (size_t)b->page_tab_stride, st);
     const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
     if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 1024 candidates in one frame
-    rc = launch_cull(cfg, b, st, W);
+    switch (W) {      // the words of a cell's candidate mask are a compile-time constant of the membership loop
+        case 1: rc = launch_cull<1>(cfg, b, st); break;
+        case 2: rc = launch_cull<2>(cfg, b, st); break;
+        case 4: rc = launch_cull<4>(cfg, b, st); break;
+        case 8: rc = launch_cull<8>(cfg, b, st); break;
+        case 16: rc = launch_cull<16>(cfg, b, st); break;
+        default: rc = launch_cull<32>(cfg, b, st); break;
+    }
     if (rc) return rc;
     FNP_LAUNCH_CHECK();
     return FNP_OK;
@@ -1949,19 +1907,17 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     if (b->max_items > 0) {
         // persistent CTAs: a whole number of CTAs per SM (148 SMs on B200), capped by the item capacity
         if (sweep) {
-            const int V = g_opt_sweep_tma ? 1 : 0;
-            const size_t smem_v = sweep_smem_bytes(b->split_points, H, J, V ? 2 : 1);
-            static size_t smem_set[2][64] = {{0}};
-            auto kern = V ? sweep_score_kernel<true> : sweep_score_kernel<false>;
-            if (dev < 0 || dev >= 64 || smem_v > smem_set[V][dev]) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
-                if (dev >= 0 && dev < 64) smem_set[V][dev] = smem_v;
+            const size_t smem = sweep_smem_bytes(b->split_points, H, J);
+            static size_t smem_set[64] = {0};
+            if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
+                cudaFuncSetAttribute(sweep_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (dev >= 0 && dev < 64) smem_set[dev] = smem;
             }
             int per_sm = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepThreads, smem_v);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_score_kernel, kSweepThreads, smem);
             if (per_sm < 1) return FNP_EINVAL;
             const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;
-            kern<<<grid, kSweepThreads, smem_v, st>>>(*b, J, M);
+            sweep_score_kernel<<<grid, kSweepThreads, smem, st>>>(*b, J, M);
         } else {
             const int per_sm = 6;
             const int grid = b->max_items < n_sms * per_sm ? b->max_items : n_sms * per_sm;

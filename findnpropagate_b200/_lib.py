@@ -68,7 +68,9 @@ class HostPlanOut(C.Structure):
                 ("reserved", C.c_int32), ("total_rows", C.c_int64)]
 
 
-CULL_TILE = 1024
+lib.fnp_seeker_cull_tile.restype = C.c_int
+lib.fnp_seeker_cull_tile.argtypes = []
+CULL_TILE = int(lib.fnp_seeker_cull_tile())
 PAGE_POINTS = 256
 SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
 SEEKER_MULT, SEEKER_OCCL_MULT, SEEKER_MULTICAM_IOU = 1, 2, 4
@@ -149,7 +151,7 @@ EXPORTED = [
     "fnp_seeker_score", "fnp_seeker_score_mode", "fnp_seeker_occlusion", "fnp_seeker_select", "fnp_seeker_run", "fnp_seg_nms_rotated", "fnp_seeker_mask_words", "fnp_seeker_cell_mask_bytes",
     "fnp_recall_counters", "fnp_host_select_candidates", "fnp_host_pack_xyz", "fnp_host_pack_xyz_begin",
     "fnp_host_pack_wait", "fnp_host_nms_order", "fnp_host_pack_xyz_multi_begin", "fnp_host_plan_sizes", "fnp_host_plan",
-    "fnp_points_in_boxes_matrix", "fnp_host_prep_boxes_cpu", "fnp_boxes_iou3d", "fnp_boxes_aligned_iou3d", "fnp_set_option",
+    "fnp_points_in_boxes_matrix", "fnp_host_prep_boxes_cpu", "fnp_boxes_iou3d", "fnp_boxes_aligned_iou3d", "fnp_set_option", "fnp_seeker_cull_tile",
 ]
 
 

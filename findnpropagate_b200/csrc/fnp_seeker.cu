@@ -15,9 +15,11 @@
 namespace fnp {
 
 constexpr int kCullThreads = 256;                       // one point per thread per sub-tile
-constexpr int kCullSub = FNP_CULL_TILE / kCullThreads;  // sub-tiles of one CTA tile
+constexpr int kCullSubAll = FNP_CULL_TILE / kCullThreads;  // sub-tiles (256 rows) of one CTA tile
+constexpr int kCullSub = 4;                                // sub-tiles a thread holds in registers at a time (one pass)
+constexpr int kCullPasses = kCullSubAll / kCullSub;        // passes over the tile: all passes share one reservation round
 constexpr int kStatsFloats = 40;
-static_assert(FNP_CULL_TILE % kCullThreads == 0, "tile must be a whole number of sub-tiles");
+static_assert(FNP_CULL_TILE % (kCullThreads * kCullSub) == 0, "tile must be a whole number of passes");
 
 // ======================================================================================
 // Frustum point storage: pages.
@@ -249,7 +251,8 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
                                              const float (&x)[kPtsPerThread], const float (&y)[kPtsPerThread],
                                              const float (&z)[kPtsPerThread], const bool (&live)[kPtsPerThread],
                                              const int frame, const int c0, const int row0, const float img_w,
-                                             const float img_h, const int n_cu, const int n_cv, const bool use_sectors)
+                                             const float img_h, const int n_cu, const int n_cv, const bool use_sectors,
+                                             int *n_list, const int list_cap)
 {
     const int tid = threadIdx.x;
     // conservative off-image bounds (see the exactness note in DESIGN.md, stage 1)
@@ -302,8 +305,8 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
                     if (DIRECT) {
                         store_member(b, c0 + j, s_base[j] + rank, X, Y, Z, d, row);
                     } else {
-                        const int e = atomicAdd(&S.n_list, 1);
-                        if (e < kCullList) {
+                        const int e = atomicAdd(n_list, 1);
+                        if (e < list_cap) {
                             s_ent[e] = make_float4(X, Y, Z, d);
                             s_key[e] = (j << 16) | rank;
                             s_row[e] = row;
@@ -314,6 +317,9 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
         }
     }
 }
+
+__device__ __forceinline__ void reserve_range(const fnp_seeker_batch &b, const int f, const int c, int *base_out,
+                                              const int n_pages_cap);
 
 // Stage 1 proper: one CTA per 1024-point tile; reads every point ONCE.
 //   1. membership pass -> member list in shared memory, per-candidate populations;
@@ -346,20 +352,23 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     const int nc = b.frame_cand_start[frame + 1] - c0;
     if (nc == 0) return;
 
-    // ---- my points (issued first: the loads overlap the per-CTA setup)
+    // ---- my points of the first pass (issued first: the loads overlap the per-CTA setup)
     const int stride = b.point_stride;
     float x[kPtsPerThread], y[kPtsPerThread], z[kPtsPerThread];
     bool live[kPtsPerThread];
+    auto load_pass = [&](const int pass) {
 #pragma unroll
-    for (int s = 0; s < kPtsPerThread; s++) {
-        const int row = row0 + s * kCullThreads + tid;
-        live[s] = row < frame_rows;
-        x[s] = y[s] = z[s] = 0.f;
-        if (live[s]) {
-            const float *p = b.points + (size_t)(frow + row) * stride + b.xyz_offset;
-            x[s] = __ldg(p); y[s] = __ldg(p + 1); z[s] = __ldg(p + 2);
+        for (int s = 0; s < kPtsPerThread; s++) {
+            const int row = row0 + (pass * kCullSub + s) * kCullThreads + tid;
+            live[s] = row < frame_rows;
+            x[s] = y[s] = z[s] = 0.f;
+            if (live[s]) {
+                const float *p = b.points + (size_t)(frow + row) * stride + b.xyz_offset;
+                x[s] = __ldg(p); y[s] = __ldg(p + 1); z[s] = __ldg(p + 2);
+            }
         }
-    }
+    };
+    load_pass(0);
 
     // ---- per-CTA setup
     if (tid < 6 * 24) (&S.cam[0][0])[tid] = b.cam_mats[(size_t)frame * 144 + tid];
@@ -376,8 +385,11 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     }
     __syncthreads();
 
-    cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
-                           n_cu, n_cv, use_sectors != 0);
+    for (int pass = 0; pass < kCullPasses; pass++) {      // all passes of the tile share one list and one reservation round
+        if (pass) load_pass(pass);
+        cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
+                               row0 + pass * kCullSub * kCullThreads, img_w, img_h, n_cu, n_cv, use_sectors != 0, &S.n_list, kCullList);
+    }
     __syncthreads();
     const int n_list = S.n_list;
     if (n_list == 0) return;
@@ -387,19 +399,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
     for (int j = tid; j < nc; j += kCullThreads) {
         const int c = s_cnt[j];
         if (c == 0) continue;
-        const int f = c0 + j;
-        const int base = atomicAdd(&b.cand_npts[f], c);
-        s_base[j] = base;
-        int *tab = b.page_tab + (size_t)f * b.page_tab_stride;
-        for (int k = (base + kPage - 1) / kPage; k * kPage < base + c; k++) {
-            const int pg = atomicAdd(&b.status[5], 1);
-            int val = pg + 1;
-            if (pg >= n_pages_cap || k >= b.page_tab_stride) { val = -1; atomicOr(&b.status[0], 1); }
-            if (k < b.page_tab_stride) {
-                __threadfence();
-                atomicExch(&tab[k], val);
-            }
-        }
+        reserve_range(b, c0 + j, c, &s_base[j], n_pages_cap);
     }
     __syncthreads();
 
@@ -416,8 +416,25 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
         // the ranks are handed out again, any assignment of a candidate's members to its reserved slots will do
         for (int j = tid; j < nc; j += kCullThreads) s_cnt[j] = 0;
         __syncthreads();
-        cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0, row0, img_w, img_h,
-                              n_cu, n_cv, use_sectors != 0);
+        for (int pass = 0; pass < kCullPasses; pass++) {
+            if (kCullPasses > 1) load_pass(pass);
+            cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
+                                  row0 + pass * kCullSub * kCullThreads, img_w, img_h, n_cu, n_cv, use_sectors != 0, &S.n_list, kCullList);
+        }
+    }
+}
+
+__device__ __forceinline__ void reserve_range(const fnp_seeker_batch &b, const int f, const int c, int *base_out,
+                                              const int n_pages_cap)
+{
+    const int base = atomicAdd(&b.cand_npts[f], c);
+    *base_out = base;
+    int *tab = b.page_tab + (size_t)f * b.page_tab_stride;
+    for (int k = (base + kPage - 1) / kPage; k * kPage < base + c; k++) {      // pages whose first slot is in the range
+        const int pg = atomicAdd(&b.status[5], 1);
+        int val = pg + 1;
+        if (pg >= n_pages_cap || k >= b.page_tab_stride) { val = -1; atomicOr(&b.status[0], 1); }
+        if (k < b.page_tab_stride) atomicExch(&tab[k], val);
     }
 }
 
@@ -1801,6 +1818,8 @@ extern "C" size_t fnp_seeker_cell_mask_bytes(const fnp_seeker_cfg *cfg, int n_fr
     // per (frame, camera rank, cell) W words, then the 64-entry sector table of every frame
     return (size_t)n_frames * 6 * cell_cols(cfg->img_w) * cell_rows(cfg->img_h) * W * 4 + (size_t)n_frames * kSectors * 4;
 }
+
+extern "C" int fnp_seeker_cull_tile(void) { return FNP_CULL_TILE; }
 
 extern "C" int fnp_seeker_mask_words(int max_cands_per_frame)
 {

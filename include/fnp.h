@@ -217,7 +217,9 @@ typedef struct fnp_seeker_batch {
                                         topk > 1 (needs H <= 32768)                          */
 } fnp_seeker_batch;
 
-#define FNP_CULL_TILE 1024
+#ifndef FNP_CULL_TILE
+#define FNP_CULL_TILE 1024      /* rows of a stage-1 point tile (one CTA); fnp_seeker_cull_tile() reports the built value */
+#endif
 #define FNP_PAGE_POINTS 256
 /* Scoring modes (fnp_seeker_batch.score_mode).  Both produce the same counts, bit for bit.
  *   DIRECT: every valid hypothesis tests every frustum point (P_f * nv_f in-box predicates).
@@ -234,6 +236,8 @@ typedef struct fnp_seeker_batch {
 #define FNP_SCORE_SWEEP 2
 #define FNP_SWEEP_MIN_MAGS 16
 #define FNP_SWEEP_COL_FLOATS 20
+/* Rows of a stage-1 point tile in this build of the library (the host's tile table must use it). */
+int fnp_seeker_cull_tile(void);
 /* Words of the per-point candidate mask for a batch whose busiest frame has that many
  * candidates: 1, 2, 4, 8, 16 or 32 (-1: more than 1024 candidates per frame are not supported -- the limit of
  * the stage-4 NMS, FNP_SEG_NMS_MAX). */

@@ -479,7 +479,7 @@ constexpr int kStatsThreads = 256;
 #define FNP_STATS_MIN_CTAS 4      // 64 registers: 4 CTAs per SM (3 at the natural 79 registers: 0.50 -> 0.43 ms per 256 cfg2 frames)
 #endif
 
-struct SelSmem {
+struct alignas(16) SelSmem {
     unsigned hist[kSelBins];
     unsigned list[kSelList];
     unsigned key[kStatsCache];
@@ -705,12 +705,20 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
                 const int p = (k0 + u) * kPage + i4;            // first of the vector's four points
                 if (k0 + u >= n_pg || p >= n) continue;
                 const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                if (p + 3 < n) {                                // a whole vector (all but the frustum's last one)
+                    lo = fminf(fminf(lo, e[0]), fminf(fminf(e[1], e[2]), e[3]));
+                    hi = fmaxf(fmaxf(hi, e[0]), fmaxf(fmaxf(e[1], e[2]), e[3]));
+                    if (cached && plane == 3)
+                        *reinterpret_cast<uint4 *>(&S.key[p]) = make_uint4(__float_as_uint(e[0]), __float_as_uint(e[1]),
+                                                                           __float_as_uint(e[2]), __float_as_uint(e[3]));
+                } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if (p + c < n) {                            // the tail of the last page is not initialised
-                        lo = fminf(lo, e[c]); hi = fmaxf(hi, e[c]);
-                        if (cached && plane == 3) S.key[p + c] = __float_as_uint(e[c]);
-                    }
+                    for (int c = 0; c < 4; c++)
+                        if (p + c < n) {                        // the tail of the last page is not initialised
+                            lo = fminf(lo, e[c]); hi = fmaxf(hi, e[c]);
+                            if (cached && plane == 3) S.key[p + c] = __float_as_uint(e[c]);
+                        }
+                }
             }
         }
         lo = warp_min(lo);

@@ -142,3 +142,93 @@ def test_reference_head_on_gpu_cfg1(ref):
 def test_reference_head_on_gpu_cfg2(ref):
     st = _compare(ref, "cfg2", [0])
     print("REFERENCE-GPU cfg2 x1:", st)
+
+
+def _kitti_frame(index):
+    """A KITTI-shaped frame: points in front of the sensor, P2 / R0 / Tr_velo2cam, x-y-w-h 2D boxes of the visible
+    synthetic objects, labels 1..7 (the KITTI head's seven anchors)."""
+    cfg = synth.SynthConfig("kitti", 32, 900, 1, 12, 4, 6, 1)
+    f = synth.make_frame(index, cfg)
+    pts = f.points[f.points[:, 0] > 1.0][:, :4].copy()
+    V2C = np.array([[0.0, -1.0, 0.0, 0.004], [0.0, 0.0, -1.0, -0.076], [1.0, 0.0, 0.0, -0.272]], np.float32)
+    a = 0.01
+    R0 = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    P2 = np.array([[721.54, 0, 609.56, 44.857], [0, 721.54, 172.85, 0.2163], [0, 0, 1, 0.002746]], np.float32)
+    boxes, labels, scores = [], [], []
+    rng = np.random.default_rng(index)
+    for g in f.gt_boxes:
+        if g[0] < 4 or abs(g[1]) > g[0]:
+            continue
+        c = synth._box_corners(g[None, :7].astype(np.float64))[0]
+        rect = (np.c_[c, np.ones(8)] @ (np.vstack([V2C, [0, 0, 0, 1]]).T))[:, :3] @ R0.T
+        img = np.c_[rect, np.ones(8)] @ P2.T
+        u, v = img[:, 0] / rect[:, 2], img[:, 1] / rect[:, 2]
+        x1, x2 = np.clip(u.min(), 0, 1242), np.clip(u.max(), 0, 1242)
+        y1, y2 = np.clip(v.min(), 0, 375), np.clip(v.max(), 0, 375)
+        if x2 - x1 < 8 or y2 - y1 < 8:
+            continue
+        boxes.append([x1, y1, x2 - x1, y2 - y1])
+        labels.append(1 + int(rng.integers(0, 7)))
+        scores.append(float(rng.uniform(0.5, 0.9)))
+    return (pts, {'P2': P2, 'R0': R0, 'Tr_velo2cam': V2C}, np.asarray(boxes, np.float32).reshape(-1, 4),
+            np.asarray(labels, np.int64), np.asarray(scores, np.float32))
+
+
+def test_kitti_head_runs_on_the_drop_in_ops(ref):
+    """The KITTI single-camera head (frustum_proposals_v1_kitti.py) is not rebuilt as fused stages, but
+    its two native call sites -- ONE batched first-match points_in_boxes_gpu per frustum (:571) and nms_normal_gpu
+    (:596) -- are on the drop-in boundary.  The reference's own KITTI head, source unmodified, runs here twice on the
+    same frames: on the reference's compiled kernels and on findnpropagate_b200.pcdet_ops; proposals, labels and scores
+    must be identical, bit for bit."""
+    import contextlib
+    import io
+    import sys as _sys
+    from findnpropagate_b200.pcdet_ops import iou3d_nms_utils as our_iou, roiaware_pool3d_utils as our_rp
+    mod = ref.load("cuda", head_file="frustum_proposals_v1_kitti.py")
+    Calibration = _sys.modules["pcdet.utils.calibration_kitti"].Calibration       # imported by the head
+    frames = [_kitti_frame(i) for i in range(3)]
+    state = {}
+
+    class Feeder:
+        def __call__(self, bd):
+            pts, calib, boxes, labels, scores = state["frame"]
+            z = torch.zeros(len(boxes), dtype=torch.long)
+            return torch.from_numpy(boxes.copy()), torch.from_numpy(labels), torch.from_numpy(scores), z, z.clone()
+    mod.PreprocessedDetector = lambda paths, class_names=None: Feeder()
+    params = dict(lq=0.0, uq=0.25, cq=1.0, iou_w=1.0, nms_normal=1.0, dst_w=0.2, dns_w=1.0, min_cam_iou=0.1, score_thr=0.45,
+                  nms_2d=0.4, nms_3d=0.0, clamp_bottom=1, num_sizes=1, num_mags=8, num_rotations=6, topk=2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        head = mod.FrustumProposerOGKITTI(model_cfg=ref.AttrDict(PARAMS=params, PREDS_PATH="unused.json"), class_names=None)
+    head.eval()
+    ref_rp, ref_iou = mod.roiaware_pool3d_utils, mod.iou3d_nms_utils
+    calls = {"pib": 0, "nms": 0}
+
+    class CountingRP:
+        @staticmethod
+        def points_in_boxes_gpu(points, boxes):
+            calls["pib"] += 1
+            return our_rp.points_in_boxes_gpu(points, boxes)
+
+    class CountingIoU:
+        @staticmethod
+        def nms_normal_gpu(boxes, scores, thresh, **kw):
+            calls["nms"] += 1
+            return our_iou.nms_normal_gpu(boxes, scores, thresh, **kw)
+    total = 0
+    try:
+        for fr in frames:
+            state["frame"] = fr
+            outs = []
+            for ops in ((ref_rp, ref_iou), (CountingRP, CountingIoU)):
+                mod.roiaware_pool3d_utils, mod.iou3d_nms_utils = ops
+                bd = dict(batch_size=1, calib=[Calibration(fr[1])],
+                          points=torch.from_numpy(np.c_[np.zeros(len(fr[0]), np.float32), fr[0]]).cuda())
+                with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                    outs.append([o.cpu() for o in head.get_proposals(bd)])
+            for a, b in zip(*outs):
+                assert a.shape == b.shape and torch.equal(a, b)
+            total += int(outs[0][0].shape[0])
+    finally:
+        mod.roiaware_pool3d_utils, mod.iou3d_nms_utils = ref_rp, ref_iou
+    assert total >= 4 and calls["pib"] >= 3 and calls["nms"] == calls["pib"]
+    print("KITTI head on the drop-in ops: %d proposals over %d frames, %d frustums scored" % (total, len(frames), calls["pib"]))

@@ -1335,6 +1335,20 @@ constexpr int kSweepThreads = FNP_SWEEP_THREADS;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kSweepChunk = kPage;   // points per (column, chunk) warp item = one page
 
+#ifndef FNP_SWEEP_V1
+// Entries (point | column << 16, packed steps) of a WARP's uncertain-step queue.  A piece (256 points of one column)
+// pushes at most 256; a warp drains its queue before a piece that might not fit.
+#ifndef FNP_SWEEP_QUEUE
+#define FNP_SWEEP_QUEUE 384
+#endif
+constexpr int kSweepQueue = FNP_SWEEP_QUEUE;
+static_assert(kSweepQueue >= kSweepChunk, "a piece must fit an empty queue");
+__host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
+{
+    return (size_t)J * sizeof(SweepCol) + (size_t)kSweepWarps * kSweepQueue * 8 + (size_t)SP * 12 + (size_t)H * 4 +
+           (size_t)((H + 3) & ~3) * 2 + 16 + 128;      // + one scratch word per lane
+}
+#else
 // Entries of the uncertain-step queue of a CTA: (point | column << 16, packed steps).
 __host__ __device__ inline int sweep_queue_cap(int SP, int J)
 {
@@ -1349,10 +1363,11 @@ __host__ __device__ inline int sweep_queue_cap(int SP, int J)
 __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
 {
     return (size_t)J * sizeof(SweepCol) + (size_t)SP * 12 + (size_t)H * 4 + (size_t)sweep_queue_cap(SP, J) * 8 +
-           (size_t)((H + 3) & ~3) * 2 + 16;
+           (size_t)((H + 3) & ~3) * 2 + 16 + 128;
 }
+#endif
 
-// Persistent CTAs pull (frustum, point split) items.  Per item:
+// (FNP_SWEEP_V1) Persistent CTAs pull (frustum, point split) items.  Per item:
 //   stage   column parameters, the split's points as SoA, cleared difference arrays, slot table;
 //   sweep   warps pull (column, 256-point chunk) pieces off a shared counter; per point one range
 //           solve (sweep_solve), the definite range into the column's difference array
@@ -1364,6 +1379,216 @@ __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
 #ifndef FNP_SWEEP_MIN_CTAS
 #define FNP_SWEEP_MIN_CTAS 4
 #endif
+
+#ifndef FNP_SWEEP_V1
+// A point that lies in no hypothesis of any column: the tail of a split's last page is filled with it, so that the
+// sweep needs no "is this lane's point live" predicate (its possible range is empty in every column: one of
+// U, V is >= 0.7e18, far beyond any centre, and 1e18 / slope stays finite).
+#define FNP_SWEEP_FAR 1e18f
+
+// *addr += v in shared memory, unconditionally (the caller points lanes that have nothing to add at their own scratch
+// word: ptxas turns a predicated RED back into a branch around it, five instructions instead of two)
+__device__ __forceinline__ void red_shared(const unsigned addr, const int v)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Exact predicates of `qn` queued entries of one warp (its own queue region `q`): expanded to single depth steps and
+// spread evenly over the lanes -- every lane takes one step at a time, whichever point and column it belongs to.
+__device__ __noinline__ void sweep_drain(const uint2 *q, const int qn, const SweepCol *s_col, const float *s_pts, int *s_diff,
+                                         const short *s_slot, const float *prep_f, const int J, const int M)
+{
+    const int lane = threadIdx.x & 31;
+    auto red = [](int *p, int v) { atomicAdd(p, v); };
+    for (int qb = 0; qb < qn; qb += 32) {
+        uint2 ent = make_uint2(0u, 0u);
+        if (qb + lane < qn) ent = q[qb + lane];
+        const int cnt = sweep_packed_count(ent.y);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            // owner = first lane whose inclusive prefix exceeds t
+            int own = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, own + step - 1);
+                if (v <= t) own += step;
+            }
+            own = min(own, 31);
+            const unsigned e0 = __shfl_sync(0xffffffffu, ent.x, own);
+            const unsigned e1 = __shfl_sync(0xffffffffu, ent.y, own);
+            const int first = __shfl_sync(0xffffffffu, incl - cnt, own);
+            if (t < total) {
+                const int i = (int)(e0 & 0xffffu), j = (int)(e0 >> 16);
+                const float4 rot = *reinterpret_cast<const float4 *>(&s_col[j].cosa);     // cosa, sina, tx, ty
+                const int m0 = s_col[j].m0, D = s_col[j].m1 - m0;
+                const float *pp = s_pts + (i >> 8) * (3 * kPage) + (i & (kPage - 1));
+                sweep_exact_step_col(pp[0], pp[kPage], pp[2 * kPage], sweep_packed_step(e1, t - first), D, s_diff + j * M + m0,
+                                     s_slot + m0 * J + j, J, prep_f, rot.x, rot.y, rot.z, rot.w, red);
+            }
+        }
+    }
+}
+
+// Persistent CTAs pull (frustum, point split) items.  Per item:
+//   stage   column parameters, the split's pages (x, y, z planes as they lie in the pool), cleared difference arrays,
+//           slot table;
+//   sweep   warps pull (column, 256-point chunk) pieces off a shared counter; per point one range solve
+//           (sweep_solve) and the branch-free bookkeeping of sweep_emit: the definite range as two unconditional
+//           shared-memory REDs (lanes with nothing to add aim at their own scratch word), the uncertain steps --
+//           ~9 % of the pairs have any -- as one entry into the WARP's own queue region (ballot + popc, no atomic);
+//           a warp drains its queue (sweep_drain) when the next piece might not fit and when the pieces run out;
+//   scan    prefix sum over the depth steps of every column, one integer RED per valid hypothesis
+//           into row f of `counts`.
+__global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int H = J * M, SP = b.split_points;
+    SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
+    uint2 *s_q = reinterpret_cast<uint2 *>(s_col + J);                          // [warps][kSweepQueue] uncertain-step queues
+    float *s_pts = reinterpret_cast<float *>(s_q + kSweepWarps * kSweepQueue);  // [SP / 256][x | y | z][256]: the split's pages
+    int *s_diff = reinterpret_cast<int *>(s_pts + 3 * SP);                      // [J][M] difference array, then counts
+    short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
+    int *s_ctl = reinterpret_cast<int *>(s_slot + ((H + 3) & ~3));              // [0] item [1] next piece [4..35] scratch
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (b.status[0] & 2) return;
+    const int n_items = b.status[2];
+    uint2 *q_w = s_q + warp * kSweepQueue;                                      // this warp's queue region
+    const unsigned scratch_addr = smem_u32(s_ctl + 4 + lane);                   // this lane's scratch word (its own bank)
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_ctl[0] = atomicAdd(&b.status[4], 1);
+            s_ctl[1] = 0;
+        }
+        __syncthreads();
+        const int item_id = s_ctl[0];
+        if (item_id >= n_items) break;
+        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, -, split, -
+        const int f = item.x, split = item.z;
+        const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
+        const int p0 = split * SP;
+        const int n = min(npts, p0 + SP) - p0;
+        const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
+
+        // ---- stage
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
+            float4 *dst = reinterpret_cast<float4 *>(s_col);
+            for (int i = tid; i < J * (FNP_SWEEP_COL_FLOATS / 4); i += kSweepThreads) dst[i] = __ldg(src + i);
+            // the x, y, z planes of the split's pages, as they lie in the pool (coalesced, no transposition); slots past
+            // the split's last point (the unwritten tail of the last page) become far points
+            const int *tab = b.page_tab + (size_t)f * b.page_tab_stride + p0 / kPage;
+            const int n_pg = (n + kPage - 1) / kPage;
+            constexpr int kVec = 3 * kPage / 4;        // 16-byte vectors of a page's x, y, z planes
+            for (int i = tid; i < n_pg * kVec; i += kSweepThreads) {
+                const int q = i / kVec, v = i - q * kVec;
+                const float4 *page = reinterpret_cast<const float4 *>(b.frustum_pts + (size_t)(tab[q] - 1) * (size_t)(b.page_planes * kPage));
+                float4 val = __ldg(page + v);
+                const int first = q * kPage + 4 * (v & (kPage / 4 - 1));      // point index of val.x
+                if (first + 3 >= n) {
+                    const float pad = v < kPage / 4 ? FNP_SWEEP_FAR : 0.f;    // x plane: far; y, z planes: 0
+                    if (first >= n) val.x = pad;
+                    if (first + 1 >= n) val.y = pad;
+                    if (first + 2 >= n) val.z = pad;
+                    val.w = pad;
+                }
+                reinterpret_cast<float4 *>(s_pts)[i] = val;
+            }
+            for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
+        }
+        __syncthreads();
+        {
+            const int *hidx = b.hyp_index + (size_t)f * H;
+            for (int r = tid; r < nv; r += kSweepThreads) s_slot[hidx[r]] = (short)r;
+        }
+        __syncthreads();
+
+        // ---- sweep
+        const int n_chunks = (n + kSweepChunk - 1) / kSweepChunk;
+        const int n_pieces = J * n_chunks;
+        int qn = 0;                                  // entries in this warp's queue (warp-uniform)
+        for (;;) {
+            int piece = 0;
+            if (lane == 0) piece = atomicAdd(&s_ctl[1], 1);
+            piece = __shfl_sync(0xffffffffu, piece, 0);
+            const bool done = piece >= n_pieces;
+            if (done || qn + kSweepChunk > kSweepQueue) {      // out of pieces, or the next piece might not fit
+                sweep_drain(q_w, qn, s_col, s_pts, s_diff, s_slot, prep_f, J, M);
+                qn = 0;
+            }
+            if (done) break;
+            const int j = piece % J, ch = piece / J;
+            const SweepCol c = s_col[j];            // warp-uniform: lives in registers for the whole piece
+            if (c.m1 < c.m0) continue;
+            const int D = c.m1 - c.m0;
+            int *diff = s_diff + j * M + c.m0;       // indexed by dm = m - m0
+            const unsigned diff_addr = smem_u32(diff);
+            int base_cnt = 0;
+            const int n_pass = (min(n - ch * kSweepChunk, kSweepChunk) + 63) >> 6;   // 64 points per pass
+            const float *px = s_pts + ch * (3 * kPage) + lane;
+            unsigned key = (unsigned)(ch * kSweepChunk + lane) | ((unsigned)j << 16);
+            // two points per lane and pass: the two range solves are independent instruction chains
+            for (int pass = 0; pass < n_pass; pass++, px += 64, key += 64) {
+                const float xa = px[0], ya = px[kPage], za = px[2 * kPage];
+                const float xb = px[32], yb = px[kPage + 32], zb = px[2 * kPage + 32];
+                const SweepRanges ra = sweep_solve(c, xa, ya, za);
+                const SweepRanges rb = sweep_solve(c, xb, yb, zb);
+                const SweepEmit ea = sweep_emit(ra, D), eb = sweep_emit(rb, D);
+                red_shared(ea.add_lo ? diff_addr + 4u * (unsigned)ra.a : scratch_addr, 1);
+                red_shared(ea.add_hi ? diff_addr + 4u * (unsigned)ra.e + 4u : scratch_addr, -1);
+                red_shared(eb.add_lo ? diff_addr + 4u * (unsigned)rb.a : scratch_addr, 1);
+                red_shared(eb.add_hi ? diff_addr + 4u * (unsigned)rb.e + 4u : scratch_addr, -1);
+                base_cnt += (int)ea.from_zero + (int)eb.from_zero;
+                const unsigned mka = __ballot_sync(0xffffffffu, ea.uncertain), mkb = __ballot_sync(0xffffffffu, eb.uncertain);
+                if (ea.uncertain) q_w[qn + __popc(mka & lt_mask)] = make_uint2(key, ea.packed);
+                qn += __popc(mka);
+                if (eb.uncertain) q_w[qn + __popc(mkb & lt_mask)] = make_uint2(key + 32u, eb.packed);
+                qn += __popc(mkb);
+            }
+            base_cnt = __reduce_add_sync(0xffffffffu, base_cnt);
+            if (lane == 0 && base_cnt) atomicAdd(diff, base_cnt);   // ranges that start at the column's first step
+        }
+        __syncthreads();
+
+        // ---- prefix sum over the depth steps of every column (warp per column, in place)
+        for (int j = warp; j < J; j += kSweepWarps) {
+            int carry = 0;
+            for (int mb = 0; mb < M; mb += 32) {
+                const int m = mb + lane;
+                int v = m < M ? s_diff[j * M + m] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += t;
+                }
+                v += carry;
+                if (m < M) s_diff[j * M + m] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        int *out = b.counts + (size_t)f * H;
+        for (int h = tid; h < H; h += kSweepThreads) {
+            const int r = s_slot[h];
+            if (r >= 0) {
+                const int m = h / J, j = h - m * J;
+                const int cnt = s_diff[j * M + m];
+                if (cnt) atomicAdd(out + r, cnt);      // RED.ADD: the splits of a frustum add up in any order
+            }
+        }
+    }
+}
+#else   // FNP_SWEEP_V1: the kernel before the branch-free rewrite (A/B builds)
 __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -1558,6 +1783,7 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
         }
     }
 }
+#endif
 
 // ======================================================================================
 // Stage 3: score + greedy argmax

@@ -216,6 +216,39 @@ FNP_HD int sweep_uncertain_step(unsigned w, int k)
     return k < n1 ? (int)(w & 0xffu) + k : (int)((w >> 16) & 0xffu) + (k - n1);
 }
 
+// ---------------------------------------------------------------------------------------
+// Second form of the bookkeeping after sweep_solve (sweep_score_kernel since round 2, session 3): branch-free.
+//   definite range [a, e] (if a <= e):  +1 at a unless a == 0 (those are summed per warp), -1 at e + 1 unless e == D;
+//   uncertain steps: [A, a2 - 1] and [e2 + 1, B] with (a2, e2) = (a, e) when there is a definite range and
+//   (B + 1, B) otherwise -- one formula for both cases; packed as four bytes A | a2 << 8 | e2 << 16 | B << 24
+//   (all in [0, 255]: the sweep mode needs M <= 255, and a2 <= B + 1 <= D + 1 <= M).
+// ---------------------------------------------------------------------------------------
+struct SweepEmit {
+    bool add_lo, add_hi, from_zero, uncertain;   // +1 at a; -1 at e + 1; range starts at step 0; has uncertain steps
+    unsigned packed;                              // valid when uncertain
+};
+
+FNP_HD SweepEmit sweep_emit(const SweepRanges &r, const int D)
+{
+    SweepEmit o;
+    const bool def = r.a <= r.e;
+    o.add_lo = def && r.a != 0;
+    o.add_hi = def && r.e < D;
+    o.from_zero = def && r.a == 0;
+    const unsigned a2 = def ? (unsigned)r.a : (unsigned)r.B + 1u, e2 = def ? (unsigned)r.e : (unsigned)r.B;
+    const unsigned n_unc = (a2 - (unsigned)r.A) + ((unsigned)r.B - e2);
+    o.uncertain = (r.A <= r.B) && n_unc != 0u;
+    o.packed = (unsigned)r.A | (a2 << 8) | (e2 << 16) | ((unsigned)r.B << 24);
+    return o;
+}
+FNP_HD int sweep_packed_count(unsigned w) { return (int)(((w >> 8) & 0xffu) - (w & 0xffu)) + (int)((w >> 24) - ((w >> 16) & 0xffu)); }
+// k-th uncertain step (0 <= k < count) of a packed word
+FNP_HD int sweep_packed_step(unsigned w, int k)
+{
+    const int A = (int)(w & 0xffu), n1 = (int)((w >> 8) & 0xffu) - A;
+    return k < n1 ? A + k : (int)((w >> 16) & 0xffu) + 1 + (k - n1);
+}
+
 // Exact predicate of point (x, y, z) against the hypothesis at depth step m0 + dm of column j.
 // `slot_col` = slot table of the column (slot_col[dm * J], -1: not a valid hypothesis), diff = the
 // column's difference array indexed by dm, D = m1 - m0.  add(ptr, v): *ptr += v.

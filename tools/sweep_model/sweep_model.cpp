@@ -1,5 +1,5 @@
 // Host model of the depth-sweep scoring kernel (FNP_SCORE_SWEEP): runs the SAME functions the
-// device kernels call (findnpropagate_b200/csrc/fnp_sweep.cuh: sweep_col_build, sweep_solve, sweep_pack_uncertain, sweep_exact_step,
+// device kernels call (findnpropagate_b200/csrc/fnp_sweep.cuh: sweep_col_build, sweep_solve, sweep_emit, sweep_exact_step_col,
 // in_box) serially on the CPU, next to the brute-force count with in_box(), so that the range
 // logic can be checked without a GPU (tests/test_sweep_model_cpu.py).  Test infrastructure; not
 // part of the product library.
@@ -98,15 +98,18 @@ extern "C" int sweep_model_counts(const float *pts, int n, const float *prep, co
             for (int i = 0; i < np; i++) {
                 const float *p = pts + (size_t)(p0 + i) * 3;
                 const SweepRanges r = sweep_solve(c, p[0], p[1], p[2]);
-                base += sweep_add_definite(r, D, d, add);
+                // the device kernel's bookkeeping (sweep_emit): unconditional adds, lanes without one aim at a scratch word
+                const SweepEmit e = sweep_emit(r, D);
+                if (e.add_lo) add(d + r.a, 1);
+                if (e.add_hi) add(d + r.e + 1, -1);
+                base += e.from_zero ? 1 : 0;
                 // the device queues (point, column, packed steps) and drains the queue densely; the
-                // arithmetic per queued step is sweep_uncertain_step + sweep_exact_step, as here
-                const unsigned w = sweep_pack_uncertain(r);
-                const int cnt = sweep_uncertain_count(w);
+                // arithmetic per queued step is sweep_packed_step + sweep_exact_step_col, as here
+                const int cnt = e.uncertain ? sweep_packed_count(e.packed) : 0;
                 for (int k = 0; k < cnt; k++)
-                    sweep_exact_step_col(p[0], p[1], p[2], sweep_uncertain_step(w, k), D, d, sl, J, prep, c.cosa, c.sina, c.tx, c.ty, add);
+                    sweep_exact_step_col(p[0], p[1], p[2], sweep_packed_step(e.packed, k), D, d, sl, J, prep, c.cosa, c.sina, c.tx, c.ty, add);
                 stats[5] += (r.a <= r.e);
-                stats[6] += (w != 0);
+                stats[6] += e.uncertain ? 1 : 0;
                 stats[2]++;
             }
             d[0] += base;

@@ -369,7 +369,6 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
         }
     };
     load_pass(0);
-
     // ---- per-CTA setup
     if (tid < 6 * 24) (&S.cam[0][0])[tid] = b.cam_mats[(size_t)frame * 144 + tid];
     for (int j = tid; j < nc; j += kCullThreads) { s_box[j] = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j]; s_cnt[j] = 0; }

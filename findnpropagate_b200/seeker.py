@@ -489,12 +489,11 @@ class SeekerEngine:
             else:
                 # point splits small enough to balance the persistent CTAs (measured on cfg2, 32 frames,
                 # direct kernel: 2048 -> 0.737 ms, 512 -> 0.666 ms, 256 -> 0.663 ms), large enough to amortise
-                # an item; the sweep kernel stages a whole split in shared memory and has its best time at
-                # 1024 (128 cfg2 frames: 512 -> 1.28 ms, 1024 -> 1.20 ms, 2048 -> 1.37 ms)
+                # an item; the sweep kernel stages a whole split in shared memory: 256 cfg2 frames per step, whole
+                # step / score stage alone: 512 -> 4.02 / 1.83 ms, 1024 -> 3.80 / 1.64, 1536 -> 3.73 / 1.60,
+                # 2048 -> 3.69 / 1.62 (profiles/r02s_ab_sweep_split_and_queue.txt; round 1's kernel was best at 1024)
                 sp = plan["total_rows"] // (self.n_sms * 128)
                 sp = int(min(2048, max(256, 1 << max(sp, 1).bit_length() - 1)))
-                if self.M >= _lib.SWEEP_MIN_MAGS and self.score_mode != _lib.SCORE_DIRECT:
-                    sp = min(sp, 1024)
             max_items = (cap // sp + F + 1) * chunks
             Cmax = max(plan["max_cands"], 1)
             W = _lib.lib.fnp_seeker_mask_words(Cmax)

@@ -586,10 +586,15 @@ __device__ void select_pair(const FrustumPages &pts, SelSmem &S, bool cached, in
         }
         __syncthreads();
         const unsigned B = S.misc[0], below = S.misc[1], cB = S.misc[2];
+        {   // nearest non-empty bin above B: the first one per thread, then per warp, one atomic per warp
+            unsigned mine = kSelBins;
 #pragma unroll
-        for (int j = 0; j < kSelBins / kStatsThreads; j++) {
-            const unsigned bin = tid * (kSelBins / kStatsThreads) + j;
-            if (bin > B && c[j]) atomicMin(&S.misc[3], bin);
+            for (int j = kSelBins / kStatsThreads - 1; j >= 0; j--) {
+                const unsigned bin = tid * (kSelBins / kStatsThreads) + j;
+                if (bin > B && c[j]) mine = bin;
+            }
+            mine = __reduce_min_sync(0xffffffffu, mine);
+            if (lane == 0 && mine < (unsigned)kSelBins) atomicMin(&S.misc[3], mine);
         }
         __syncthreads();
         const unsigned Bn = S.misc[3];
@@ -645,6 +650,120 @@ __device__ void select_pair(const FrustumPages &pts, SelSmem &S, bool cached, in
         shift = max(0, shift - kSelBits);
         __syncthreads();
     }
+}
+
+// Two ranks k1 <= k2 at once, first level only: ONE histogram pass and ONE collect pass serve both (the near and the
+// far depth quantile of a frustum).  Returns false -- nothing decided, the caller runs select_pair per rank -- when the
+// bins are too crowded to finish by rank counting.  v[0], v[1] = keys of rank k1, k1 + 1; v[2], v[3] = k2, k2 + 1.
+__device__ bool select_two(const FrustumPages &pts, SelSmem &S, bool cached, int n, int k1, int k2, unsigned kmin,
+                           unsigned kmax, float (&v)[4])
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    if (kmin == kmax) { v[0] = v[1] = v[2] = v[3] = __uint_as_float(kmin); return true; }
+    const int shift = max(0, (32 - __clz(kmax - kmin)) - kSelBits);
+    for (int i = tid; i < kSelBins; i += nt) S.hist[i] = 0;
+    unsigned *m2 = S.list + kSelList - 8;      // the second rank's misc[] (the lists stay below this tail)
+    if (tid == 0) { S.misc[3] = kSelBins; S.misc[4] = 0; S.misc[5] = 0xffffffffu; m2[3] = kSelBins; m2[4] = 0; m2[5] = 0xffffffffu; }
+    __syncthreads();
+    for_each_key(pts, S, cached, n, [&](unsigned key) { atomicAdd(&S.hist[((key - kmin) >> shift) & (kSelBins - 1)], 1u); });
+    __syncthreads();
+    unsigned c[kSelBins / kStatsThreads], local = 0;
+#pragma unroll
+    for (int j = 0; j < kSelBins / kStatsThreads; j++) { c[j] = S.hist[tid * (kSelBins / kStatsThreads) + j]; local += c[j]; }
+    unsigned inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) S.warp_sum[warp] = inc;
+    __syncthreads();
+    unsigned excl = inc - local;
+    for (int w = 0; w < warp; w++) excl += S.warp_sum[w];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const unsigned rank = (unsigned)(r ? k2 : k1);
+        unsigned *mm = r ? m2 : S.misc;
+        if (rank >= excl && rank < excl + local) {
+            unsigned acc = excl;
+#pragma unroll
+            for (int j = 0; j < kSelBins / kStatsThreads; j++) {
+                if (rank >= acc && rank < acc + c[j]) { mm[0] = tid * (kSelBins / kStatsThreads) + j; mm[1] = acc; mm[2] = c[j]; }
+                acc += c[j];
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned B1 = S.misc[0], below1 = S.misc[1], c1 = S.misc[2], B2 = m2[0], below2 = m2[1], c2 = m2[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {      // nearest non-empty bin above each
+        const unsigned B = r ? B2 : B1;
+        unsigned mine = kSelBins;
+#pragma unroll
+        for (int j = kSelBins / kStatsThreads - 1; j >= 0; j--) {
+            const unsigned bin = tid * (kSelBins / kStatsThreads) + j;
+            if (bin > B && c[j]) mine = bin;
+        }
+        mine = __reduce_min_sync(0xffffffffu, mine);
+        if (lane == 0 && mine < (unsigned)kSelBins) atomicMin(r ? &m2[3] : &S.misc[3], mine);
+    }
+    __syncthreads();
+    const unsigned Bn1 = S.misc[3], Bn2 = m2[3];
+    const int r1 = k1 - (int)below1, r2 = k2 - (int)below2;
+    const bool sec1 = (unsigned)(r1 + 1) < c1, sec2 = (unsigned)(r2 + 1) < c2;       // rank + 1 in the same bin
+    const bool nx1 = Bn1 < (unsigned)kSelBins, nx2 = Bn2 < (unsigned)kSelBins;
+    if (shift == 0) {                          // a bin is one exact key
+        v[0] = __uint_as_float(kmin + B1);
+        v[1] = sec1 ? v[0] : nx1 ? __uint_as_float(kmin + Bn1) : v[0];
+        v[2] = __uint_as_float(kmin + B2);
+        v[3] = sec2 ? v[2] : nx2 ? __uint_as_float(kmin + Bn2) : v[2];
+        __syncthreads();
+        return true;
+    }
+    const bool same = B1 == B2;
+    if ((same ? c1 : c1 + c2) > (unsigned)(kSelList - 16)) { __syncthreads(); return false; }
+    // ---- collect: list 1 grows from S.list[0], list 2 (if it is another bin) from S.list[c1]
+    unsigned n1 = 0xffffffffu, n2 = 0xffffffffu;
+    for_each_key(pts, S, cached, n, [&](unsigned key) {
+        const unsigned digit = ((key - kmin) >> shift) & (kSelBins - 1);
+        if (digit == B1) S.list[atomicAdd(&S.misc[4], 1u)] = key;
+        else if (digit == B2) S.list[c1 + atomicAdd(&m2[4], 1u)] = key;
+        if (!sec1 && nx1 && digit == Bn1) n1 = min(n1, key);
+        if (!sec2 && nx2 && digit == Bn2) n2 = min(n2, key);
+    });
+    n1 = __reduce_min_sync(0xffffffffu, n1);
+    n2 = __reduce_min_sync(0xffffffffu, n2);
+    if (lane == 0 && n1 != 0xffffffffu) atomicMin(&S.misc[5], n1);
+    if (lane == 0 && n2 != 0xffffffffu) atomicMin(&m2[5], n2);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const unsigned *lst = (r && !same) ? S.list + c1 : S.list;
+        const int m = (int)((r && !same) ? c2 : c1), rank = r ? r2 : r1;
+        const bool sec = r ? sec2 : sec1;
+        unsigned *mm = r ? m2 : S.misc;
+        for (int e = tid; e < m; e += nt) {
+            const unsigned key = lst[e];
+            int lt = 0, le = 0;
+            for (int j = 0; j < m; j++) { const unsigned o = lst[j]; lt += o < key; le += o <= key; }
+            if (lt <= rank && rank < le) mm[6] = key;               // same value from every writer
+            if (sec && lt <= rank + 1 && rank + 1 < le) mm[7] = key;
+        }
+    }
+    __syncthreads();
+    v[0] = __uint_as_float(S.misc[6]);
+    v[1] = sec1 ? __uint_as_float(S.misc[7]) : nx1 ? __uint_as_float(S.misc[5]) : v[0];
+    v[2] = __uint_as_float(m2[6]);
+    v[3] = sec2 ? __uint_as_float(m2[7]) : nx2 ? __uint_as_float(m2[5]) : v[2];
+    __syncthreads();
+    return true;
+}
+
+// The interpolation of torch.quantile given the two order statistics around the position
+__device__ __forceinline__ float quantile_lerp(float a, float bv, float w)
+{
+    const float diff = __fsub_rn(bv, a);
+    return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), bv);
 }
 
 // torch.quantile(depth, q), linear interpolation (ATen Sorting.cpp quantile_compute + lerp)
@@ -733,11 +852,30 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
     __syncthreads();
 
     // ---- depth quantiles (frustum_proposals_v1.py:616-648)
-    const float qmin = block_quantile(pts, S, cached, n, cfg.lq, mn[3], mx[3]);
-    // search_depth (:619-623): the far end of the frustum is the near quantile + depth
-    const float qmax = (cfg.search_depth > 0.f) ? __fadd_rn(qmin, cfg.search_depth)
-                                                : block_quantile(pts, S, cached, n, cfg.uq, mn[3], mx[3]);
-    const float qc = block_quantile(pts, S, cached, n, cfg.cq, mn[3], mx[3]);
+    float qmin = 0.f, qmax = 0.f;
+    bool both = false;
+    if (!(cfg.search_depth > 0.f)) {
+        // near and far quantile from one histogram pass and one collect pass when neither is an end of the range
+        const float p1 = __fmul_rn(cfg.lq, (float)(n - 1)), p2 = __fmul_rn(cfg.uq, (float)(n - 1));
+        const int klo1 = (int)floorf(p1), khi1 = (int)ceilf(p1), klo2 = (int)floorf(p2), khi2 = (int)ceilf(p2);
+        if (khi1 != 0 && klo1 != n - 1 && khi2 != 0 && klo2 != n - 1 && klo1 <= klo2) {
+            float v[4];
+            both = select_two(pts, S, cached, n, klo1, klo2, __float_as_uint(mn[3]), __float_as_uint(mx[3]), v);
+            if (both) {
+                qmin = quantile_lerp(v[0], khi1 == klo1 ? v[0] : v[1], __fsub_rn(p1, floorf(p1)));
+                qmax = quantile_lerp(v[2], khi2 == klo2 ? v[2] : v[3], __fsub_rn(p2, floorf(p2)));
+            }
+        }
+    }
+    if (!both) {
+        qmin = block_quantile(pts, S, cached, n, cfg.lq, mn[3], mx[3]);
+        // search_depth (:619-623): the far end of the frustum is the near quantile + depth
+        qmax = (cfg.search_depth > 0.f) ? __fadd_rn(qmin, cfg.search_depth)
+                                        : block_quantile(pts, S, cached, n, cfg.uq, mn[3], mx[3]);
+    }
+    // the centre quantile only feeds weighted_centre_xyz (:631-636), which only the distance term reads
+    const bool want_wc = b.hyp_dist != nullptr;
+    const float qc = want_wc ? block_quantile(pts, S, cached, n, cfg.cq, mn[3], mx[3]) : 0.f;
     const float dmax = fminf(qmax, cfg.max_dist);
     const float dmin = fmaxf(qmin, cfg.frustum_min);
 
@@ -779,8 +917,9 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
             for (int a = 0; a < 3; a++) s_geo[3 + a] = __fmul_rn(__fdiv_rn(s_geo[3 + a], nv), cfg.search_depth);
         }
         // weighted_centre_xyz (:631-636): the 2D box centre at the cq depth quantile, unprojected
-        unproject(cm + 12, cm + 21, __fmul_rn(__fadd_rn(bx[0], bx[2]), 0.5f), __fmul_rn(__fadd_rn(bx[1], bx[3]), 0.5f), qc,
-                  st[10], st[11], st[12]);
+        if (want_wc)
+            unproject(cm + 12, cm + 21, __fmul_rn(__fadd_rn(bx[0], bx[2]), 0.5f), __fmul_rn(__fadd_rn(bx[1], bx[3]), 0.5f), qc,
+                      st[10], st[11], st[12]);
         st[0] = dmin; st[1] = dmax; st[2] = qc;
         for (int a = 0; a < 3; a++) { st[3 + a] = mn[a]; st[6 + a] = mx[a]; }
         st[9] = (float)n;
@@ -825,8 +964,13 @@ __device__ __forceinline__ float view_iou(const float *__restrict__ L, const flo
 
 // EXTRAS = false is the shipped configuration (single-view IoU, no hyp_dist): the optional terms are
 // compiled out so that they cost the hot path no registers.
+// the shipped instance at 64 registers (8 CTAs per SM, 32 B of spills): 0.448 -> 0.429 ms per 256 cfg2 frames; 7 CTAs 0.435,
+// 5 CTAs 0.489 (profiles/r02u_ab_hypotheses_occupancy.txt)
+#ifndef FNP_HYP_MIN_CTAS
+#define FNP_HYP_MIN_CTAS 8
+#endif
 template <bool EXTRAS>
-__global__ void __launch_bounds__(128) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
+__global__ void __launch_bounds__(128, EXTRAS ? 4 : FNP_HYP_MIN_CTAS) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ int s_wcnt[4];
     __shared__ int s_base;

@@ -178,7 +178,9 @@ typedef struct fnp_seeker_batch {
     float *cand_stats;               /* (F,40): [0]dmin [1]dmax [2]dcentre [3..5]pmin [6..8]pmax
                                         [9]n_points [10..12] weighted_centre_xyz [13]/[14] min/max of
                                         hyp_dist over the hypotheses within max_dist
-                                        [16..39] clamped frustum corners (8,3)  */
+                                        [16..39] clamped frustum corners (8,3).  [2] and [10..14] are
+                                        formed only when hyp_dist != NULL (the distance term is their
+                                        only reader; without it the cq quantile is not selected)  */
     float *centres;                  /* (F,M,3) */
     float *hyp_prep;                 /* (F,H,8) compacted valid hypotheses, H = M*J:
                                         cx,cy,cz,hz, cosa,sina,tx,ty                       */

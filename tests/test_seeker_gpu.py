@@ -558,6 +558,27 @@ def test_optional_score_terms_vs_oracle(opts, override, mode):
         assert r2["recall"] == exp
 
 
+@pytest.mark.parametrize("cfg_name,quant,n_frames", [
+    ("cfg1", dict(lq=0.336, uq=0.356, cq=0.46, dst_w=0.226), 3),      # the KITTI head's defaults (frustum_proposals_v1_kitti.py:41)
+    ("cfg1", dict(lq=0.1, uq=0.9, cq=0.5), 3),                          # far apart: two bins, two lists
+    ("cfg1", dict(lq=0.5, uq=0.5, cq=0.0, dst_w=0.1), 2),               # the same rank twice
+    ("cfg1", dict(lq=0.0, uq=1.0, cq=1.0), 2),                          # both ends trivial
+    ("cfg2", dict(lq=0.05, uq=0.3, cq=0.7, dst_w=0.2), 1),              # frustums of > 4096 points stream their depth planes
+])
+def test_interior_depth_quantiles_vs_oracle(cfg_name, quant, n_frames):
+    """torch.quantile at interior positions (frustum_proposals_v1.py:616-648): the near and the far quantile come from
+    ONE histogram pass and ONE collect pass of the radix select (select_two), the centre quantile -- selected only
+    when the distance term reads it -- from the single-rank select; dmin / dmax / weighted centre and everything
+    downstream bit-exact against the oracle.  The shipped YAML (lq 0, uq 0.25, cq 1) needs one interior rank only."""
+    cfg = synth.CONFIGS[cfg_name]
+    params = synth.seeker_params(cfg)
+    params.update(quant)
+    frames = [_frame_from_synth(synth.make_frame(10 + i, cfg)) for i in range(n_frames)]
+    eng = SeekerEngine(params, device="cuda:0", debug=True)
+    res, n = _check_against_oracle(eng, frames, params)
+    assert n > 10
+
+
 def test_optional_score_terms_full_size_frame():
     """The same on a cfg2 frame (BASELINE.json configs[1]: ~322k points, 58 frustums of up to 1e4 points,
     768 hypotheses each): occl_kernel runs several point tiles and hypothesis blocks per frustum, the

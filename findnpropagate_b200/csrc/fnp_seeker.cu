@@ -785,18 +785,11 @@ __device__ float block_quantile(const FrustumPages &pts, SelSmem &S, bool cached
     return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), bv);
 }
 
-struct StatsSmem {
-    SelSmem S;
-    float red[8][8];
-    float geo[16];  // close[3], vec[3]
-};
-
-// One CTA (kStatsThreads threads) per frustum; every thread of the block calls this.
-__device__ __forceinline__ void stats_body(const fnp_seeker_batch &b, const fnp_seeker_cfg &cfg, StatsSmem &SS)
+__global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
-    SelSmem &S = SS.S;
-    float (&s_red)[8][8] = SS.red;
-    float (&s_geo)[16] = SS.geo;
+    __shared__ SelSmem S;
+    __shared__ float s_red[8][8];
+    __shared__ float s_geo[16];  // close[3], vec[3]
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = b.cand_npts[f];
@@ -941,12 +934,6 @@ __device__ __forceinline__ void stats_body(const fnp_seeker_batch &b, const fnp_
     }
 }
 
-__global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
-{
-    __shared__ StatsSmem SS;
-    stats_body(b, cfg, SS);
-}
-
 // ======================================================================================
 // Stage 2a: hypotheses
 // ======================================================================================
@@ -982,20 +969,12 @@ __device__ __forceinline__ float view_iou(const float *__restrict__ L, const flo
 #ifndef FNP_HYP_MIN_CTAS
 #define FNP_HYP_MIN_CTAS 8
 #endif
-struct HypSmem {
-    int wcnt[8];
-    int base;
-    float dmm[8][2];
-};
-
-// One CTA (128 or 256 threads) per frustum; every thread of the block calls this.
 template <bool EXTRAS>
-__device__ __forceinline__ void hyp_body(const fnp_seeker_batch &b, const fnp_seeker_cfg &cfg, HypSmem &HS)
+__global__ void __launch_bounds__(128, EXTRAS ? 4 : FNP_HYP_MIN_CTAS) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
-    int (&s_wcnt)[8] = HS.wcnt;
-    int &s_base = HS.base;
-    float (&s_dmm)[8][2] = HS.dmm;
-    const int n_warps = blockDim.x >> 5;
+    __shared__ int s_wcnt[4];
+    __shared__ int s_base;
+    __shared__ float s_dmm[4][2];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int J = cfg.num_yaw_size, M = cfg.num_mags, H = J * M;
@@ -1110,11 +1089,7 @@ __device__ __forceinline__ void hyp_body(const fnp_seeker_batch &b, const fnp_se
             if (want_dist) b.hyp_dist[(size_t)f * H + r] = dist;
         }
         __syncthreads();
-        if (tid == 0) {
-            int tot = base;
-            for (int w = 0; w < n_warps; w++) tot += s_wcnt[w];
-            s_base = tot;
-        }
+        if (tid == 0) s_base = base + s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
         __syncthreads();
     }
     if (tid == 0) b.hyp_nvalid[f] = s_base;
@@ -1125,32 +1100,11 @@ __device__ __forceinline__ void hyp_body(const fnp_seeker_batch &b, const fnp_se
         __syncthreads();
         if (tid == 0) {
             float *st = b.cand_stats + (size_t)f * kStatsFloats;
-            float lo = s_dmm[0][0], hi = s_dmm[0][1];
-            for (int w = 1; w < n_warps; w++) { lo = fminf(lo, s_dmm[w][0]); hi = fmaxf(hi, s_dmm[w][1]); }
-            st[13] = lo;
-            st[14] = hi;
+            st[13] = fminf(fminf(s_dmm[0][0], s_dmm[1][0]), fminf(s_dmm[2][0], s_dmm[3][0]));
+            st[14] = fmaxf(fmaxf(s_dmm[0][1], s_dmm[1][1]), fmaxf(s_dmm[2][1], s_dmm[3][1]));
         }
     }
 }
-
-template <bool EXTRAS>
-__global__ void __launch_bounds__(128, EXTRAS ? 4 : FNP_HYP_MIN_CTAS) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
-{
-    __shared__ HypSmem HS;
-    hyp_body<EXTRAS>(b, cfg, HS);
-}
-
-// Stages 1b + 2a of a frustum in one CTA (the shipped configuration: no optional terms): the latency-bound selection
-// phase of some CTAs runs under the arithmetic of the hypothesis phase of others on the same SM.
-__global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_hyp_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
-{
-    __shared__ StatsSmem SS;
-    __shared__ HypSmem HS;
-    stats_body(b, cfg, SS);
-    __syncthreads();             // the centre line (global memory) written above is read by every thread below
-    hyp_body<false>(b, cfg, HS);
-}
-
 
 // ======================================================================================
 // Stage 2b: scoring -- per-hypothesis point counts
@@ -2205,14 +2159,12 @@ static int check_batch(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b)
 
 // Tuning / test switches (fnp_set_option): not part of the stable ABI.
 static int g_opt_cull_sectors = 1;      // stage 1 consults the per-frame sector table (0: every camera for every point)
-static int g_opt_fuse_stats_hyp = 1;    // fnp_seeker_run: stages 1b + 2a of a frustum in one CTA (shipped configuration)
 
 extern "C" int fnp_set_option(const char *name, int value)
 {
     if (!name) return FNP_EINVAL;
     const std::string n(name);
     if (n == "cull_sectors") { g_opt_cull_sectors = value; return FNP_OK; }
-    if (n == "fuse_stats_hyp") { g_opt_fuse_stats_hyp = value; return FNP_OK; }
     return FNP_EINVAL;
 }
 
@@ -2415,13 +2367,8 @@ extern "C" int fnp_seeker_run(const fnp_seeker_cfg *cfg, const fnp_seeker_batch 
 {
     int rc;
     if ((rc = fnp_seeker_cull(cfg, b, stream))) return rc;
-    if (g_opt_fuse_stats_hyp && b->n_cands > 0 && !((cfg->flags & FNP_SEEKER_MULTICAM_IOU) || b->hyp_dist)) {
-        stats_hyp_kernel<<<b->n_cands, kStatsThreads, 0, (cudaStream_t)stream>>>(*b, *cfg);
-        FNP_LAUNCH_CHECK();
-    } else {
-        if ((rc = fnp_seeker_frustum_stats(cfg, b, stream))) return rc;
-        if ((rc = fnp_seeker_hypotheses(cfg, b, stream))) return rc;
-    }
+    if ((rc = fnp_seeker_frustum_stats(cfg, b, stream))) return rc;
+    if ((rc = fnp_seeker_hypotheses(cfg, b, stream))) return rc;
     if ((rc = fnp_seeker_score(cfg, b, stream))) return rc;
     if ((rc = fnp_seeker_occlusion(cfg, b, stream))) return rc;
     return fnp_seeker_select(cfg, b, stream);

@@ -28,7 +28,7 @@ class SeekerCfg(C.Structure):
                 ("cq", _f), ("frustum_min", _f), ("max_dist", _f), ("min_cam_iou", _f),
                 ("dns_w", _f), ("iou_w", _f),
                 ("dst_w", _f), ("ego_w", _f), ("occl_w", _f), ("search_depth", _f), ("flags", C.c_int32),
-                ("topk", C.c_int32), ("nms_normal", _f)]
+                ("topk", C.c_int32), ("nms_normal", _f), ("variant", C.c_int32)]
 
 
 class SeekerBatch(C.Structure):
@@ -73,6 +73,7 @@ lib.fnp_seeker_cull_tile.argtypes = []
 CULL_TILE = int(lib.fnp_seeker_cull_tile())
 PAGE_POINTS = 256
 SCORE_AUTO, SCORE_DIRECT, SCORE_SWEEP = 0, 1, 2
+VARIANT_NUSCENES, VARIANT_KITTI = 0, 1
 SEEKER_MULT, SEEKER_OCCL_MULT, SEEKER_MULTICAM_IOU = 1, 2, 4
 SWEEP_MIN_MAGS = 16
 SWEEP_COL_FLOATS = 20

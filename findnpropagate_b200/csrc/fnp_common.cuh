@@ -126,6 +126,47 @@ __device__ __forceinline__ void unproject(const float *__restrict__ C, const flo
 }
 
 // ---------------------------------------------------------------------------------------
+// KITTI calibration (pcdet/utils/calibration_kitti.py:128-216, CalibrationTorch) for FNP_VARIANT_KITTI.
+// K = the 48 floats of the frame (include/fnp.h): M1 (4,3) | P2T (4,3) | cu cv fu fv tx ty | Minv (4,4).
+// [x y z 1] @ M (4,C), column c: torch's matmul accumulates k = 0..3 as one fma chain on B200 for >= 33 rows,
+// and rounds every product on its own below that (tools/probe_kitti.py); `chain` selects the order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot4h(const float *__restrict__ M, const int c, const int C, const float x, const float y,
+                                       const float z, const bool chain = true)
+{
+    if (chain) {
+        float acc = __fmul_rn(x, M[c]);
+        acc = __fmaf_rn(y, M[C + c], acc);
+        acc = __fmaf_rn(z, M[2 * C + c], acc);
+        return __fadd_rn(acc, M[3 * C + c]);                      // fma(1, m, acc)
+    }
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, M[c]), __fmul_rn(y, M[C + c])), __fmul_rn(z, M[2 * C + c])), M[3 * C + c]);
+}
+
+// lidar_to_img (:196-203): rect = [p 1] @ M1, hom = [rect 1] @ P2T, (u, v) = hom.xy / rect.z, depth = hom.z - P2T[3][2].
+// No clamp and no on-image test in this head (frustum_proposals_v1_kitti.py:693-700).
+__device__ __forceinline__ void project_kitti(const float *__restrict__ K, const float x, const float y, const float z,
+                                              float &u, float &v, float &d)
+{
+    const float r0 = dot4h(K, 0, 3, x, y, z), r1 = dot4h(K, 1, 3, x, y, z), r2 = dot4h(K, 2, 3, x, y, z);
+    const float h0 = dot4h(K + 12, 0, 3, r0, r1, r2), h1 = dot4h(K + 12, 1, 3, r0, r1, r2), h2 = dot4h(K + 12, 2, 3, r0, r1, r2);
+    u = __fdiv_rn(h0, r2);
+    v = __fdiv_rn(h1, r2);
+    d = __fsub_rn(h2, K[12 + 9 + 2]);
+}
+
+// img_to_rect (:205-216) then rect_to_lidar (:151-169): x = ((u - cu) d) / fu + tx, y likewise, [x y d 1] @ Minv
+__device__ __forceinline__ void unproject_kitti(const float *__restrict__ K, const float u, const float v, const float d,
+                                                float &x, float &y, float &z, const bool chain = true)
+{
+    const float xr = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(u, K[24]), d), K[26]), K[28]);
+    const float yr = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(v, K[25]), d), K[27]), K[29]);
+    x = dot4h(K + 32, 0, 4, xr, yr, d, chain);
+    y = dot4h(K + 32, 1, 4, xr, yr, d, chain);
+    z = dot4h(K + 32, 2, 4, xr, yr, d, chain);
+}
+
+// ---------------------------------------------------------------------------------------
 // mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -167,7 +167,7 @@ __device__ bool sector_sees(const float *__restrict__ L, const int s, const floa
 // One CTA per (frame, camera rank): cell -> candidates of that rank whose box may contain a
 // pixel of the cell.  Conservative (a superset); the exact test follows in cull_kernel.
 __global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch b, const int n_cu, const int n_cv,
-                                                         const float img_w, const float img_h)
+                                                         const float img_w, const float img_h, const int kitti)
 {
     const int W = b.mask_words;
     extern __shared__ unsigned s_cells[];                 // [n_cu * n_cv][W]
@@ -182,17 +182,21 @@ __global__ void __launch_bounds__(128) cell_table_kernel(const fnp_seeker_batch 
         const float4 bx = reinterpret_cast<const float4 *>(b.cand_box2d)[c0 + j];
         if (!(bx.z > bx.x) || !(bx.w > bx.y)) continue;   // empty (or NaN) box: no point can match
         // cell cu covers u in [64 cu, 64 cu + 64); a member has x1 <= u < x2
-        const int cu0 = max(0, (int)floorf(fmaxf(bx.x, 0.f) * kCellInv));
-        const int cu1 = min(n_cu - 1, (int)floorf(fminf(bx.z, 65536.f) * kCellInv));
-        const int cv0 = max(0, (int)floorf(fmaxf(bx.y, 0.f) * kCellInv));
-        const int cv1 = min(n_cv - 1, (int)floorf(fminf(bx.w, 65536.f) * kCellInv));
+        int cu0 = max(0, (int)floorf(fmaxf(bx.x, 0.f) * kCellInv));
+        int cu1 = min(n_cu - 1, (int)floorf(fminf(bx.z, 65536.f) * kCellInv));
+        int cv0 = max(0, (int)floorf(fmaxf(bx.y, 0.f) * kCellInv));
+        int cv1 = min(n_cv - 1, (int)floorf(fminf(bx.w, 65536.f) * kCellInv));
+        if (kitti) {   // no on-image test in that head: a point beyond the grid looks up the nearest border cell
+            cu0 = min(cu0, n_cu - 1); cv0 = min(cv0, n_cv - 1);
+            cu1 = max(cu1, 0); cv1 = max(cv1, 0);
+        }
         for (int cv = cv0; cv <= cv1; cv++)
             for (int cu = cu0; cu <= cu1; cu++) atomicOr(&s_cells[(cv * n_cu + cu) * W + (j >> 5)], 1u << (j & 31));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_cells * W; i += blockDim.x) out[i] = s_cells[i];
     // sector table of the frame (after the cell masks of all frames; zeroed by the host call): bit r of entry s
-    if (hi > lo && (int)threadIdx.x < kSectors) {
+    if (hi > lo && (int)threadIdx.x < kSectors && !kitti) {
         unsigned *sect = b.cell_masks + (size_t)b.n_frames * 6 * n_cells * W + (size_t)frame * kSectors;
         const float *L = b.cam_mats + ((size_t)frame * 6 + kImageOrder[r]) * 24;
         if (sector_sees(L, threadIdx.x, img_w, img_h)) atomicOr(&sect[threadIdx.x], 1u << r);
@@ -245,7 +249,7 @@ __device__ __forceinline__ void store_member(const fnp_seeker_batch &b, const in
 // rank among the tile's members of that candidate from a shared-memory atomic and
 //   DIRECT == false: is appended to the tile's member list (unprojected point, candidate, rank);
 //   DIRECT == true : is written to its final place at once (s_base[] = the tile's reservation).
-template <bool DIRECT, int W>
+template <bool DIRECT, int W, bool KITTI>
 __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem &S, const float4 *s_box, int *s_cnt,
                                              const int *s_base, float4 *s_ent, int *s_key, int *s_row,
                                              const float (&x)[kPtsPerThread], const float (&y)[kPtsPerThread],
@@ -273,17 +277,26 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
             const int r = __ffs(todo) - 1;
             todo &= todo - 1;
             const float *L = S.cam[kImageOrder[r]];
-            const float wx = __fadd_rn(dot3(L + 0, x[s], y[s], z[s]), L[3]);
-            const float wy = __fadd_rn(dot3(L + 4, x[s], y[s], z[s]), L[7]);
-            const float wz = __fadd_rn(dot3(L + 8, x[s], y[s], z[s]), L[11]);
-            const float d = fminf(fmaxf(wz, 1e-5f), 1e5f);
-            // cheap, division-free "certainly off this image" test
-            const bool off = (wx < -1e-30f) | (wy < -1e-30f) | (wx > __fmul_rn(w_hi, d)) | (wy > __fmul_rn(h_hi, d));
-            if (!live[s] | off) continue;
-            // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
-            const float u = __fdiv_rn(wx, d), v = __fdiv_rn(wy, d);
-            if (!((v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f))) continue;
-            const int cell = min((int)(v * kCellInv), n_cv - 1) * n_cu + min((int)(u * kCellInv), n_cu - 1);
+            float u, v, d;
+            int cell;
+            if (KITTI) {
+                // FrustumProposerOGKITTI: the two-step calibration, no depth clamp, every point "on the image"
+                if (!live[s]) continue;
+                project_kitti(&S.cam[0][0], x[s], y[s], z[s], u, v, d);
+                cell = min(max(__float2int_rz(v * kCellInv), 0), n_cv - 1) * n_cu + min(max(__float2int_rz(u * kCellInv), 0), n_cu - 1);
+            } else {
+                const float wx = __fadd_rn(dot3(L + 0, x[s], y[s], z[s]), L[3]);
+                const float wy = __fadd_rn(dot3(L + 4, x[s], y[s], z[s]), L[7]);
+                const float wz = __fadd_rn(dot3(L + 8, x[s], y[s], z[s]), L[11]);
+                d = fminf(fmaxf(wz, 1e-5f), 1e5f);
+                // cheap, division-free "certainly off this image" test
+                const bool off = (wx < -1e-30f) | (wy < -1e-30f) | (wx > __fmul_rn(w_hi, d)) | (wy > __fmul_rn(h_hi, d));
+                if (!live[s] | off) continue;
+                // exact path: the reference's u, v (IEEE division) and on-image / in-box tests
+                u = __fdiv_rn(wx, d); v = __fdiv_rn(wy, d);
+                if (!((v < img_h) & (v >= 0.f) & (u < img_w) & (u >= 0.f))) continue;
+                cell = min((int)(v * kCellInv), n_cv - 1) * n_cu + min((int)(u * kCellInv), n_cu - 1);
+            }
             const unsigned *cm = b.cell_masks + (((size_t)frame * 6 + r) * n_cells + cell) * W;
             bool have = false;
             float X = 0.f, Y = 0.f, Z = 0.f;
@@ -297,7 +310,8 @@ __device__ __forceinline__ void cull_members(const fnp_seeker_batch &b, CullSmem
                     const float4 bx = s_box[j];
                     if (!((v < bx.w) & (v >= bx.y) & (u < bx.z) & (u >= bx.x))) continue;
                     if (!have) {     // the reference tests unproject(project(p)) (:812-815): one per (point, camera)
-                        unproject(L + 12, L + 21, u, v, d, X, Y, Z);
+                        if (KITTI) unproject_kitti(&S.cam[0][0], u, v, d, X, Y, Z);
+                        else unproject(L + 12, L + 21, u, v, d, X, Y, Z);
                         have = true;
                     }
                     const int rank = atomicAdd(&s_cnt[j], 1);
@@ -327,7 +341,7 @@ __device__ __forceinline__ void reserve_range(const fnp_seeker_batch &b, const i
 //      point indices; the reservation that contains the first slot of a page takes that page from the pool;
 //   3. the list is flushed to the reserved slots by full warps.
 // A tile whose members do not fit the list (kCullList) repeats the membership pass with direct writes.
-template <int W>
+template <int W, bool KITTI>
 __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(const fnp_seeker_batch b, const float img_w,
                                                             const float img_h, const int n_cu, const int n_cv,
                                                             const int use_sectors)
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
 
     for (int pass = 0; pass < kCullPasses; pass++) {      // all passes of the tile share one list and one reservation round
         if (pass) load_pass(pass);
-        cull_members<false, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
+        cull_members<false, W, KITTI>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
                                row0 + pass * kCullSub * kCullThreads, img_w, img_h, n_cu, n_cv, use_sectors != 0, &S.n_list, kCullList);
     }
     __syncthreads();
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(kCullThreads, FNP_CULL_MIN_CTAS) cull_kernel(c
         __syncthreads();
         for (int pass = 0; pass < kCullPasses; pass++) {
             if (kCullPasses > 1) load_pass(pass);
-            cull_members<true, W>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
+            cull_members<true, W, KITTI>(b, S, s_box, s_cnt, s_base, s_ent, s_key, s_row, x, y, z, live, frame, c0,
                                   row0 + pass * kCullSub * kCullThreads, img_w, img_h, n_cu, n_cv, use_sectors != 0, &S.n_list, kCullList);
         }
     }
@@ -881,6 +895,7 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
 
     if (tid == 0) {
         const int frame = b.cand_frame[f];
+        const bool kitti = cfg.variant == FNP_VARIANT_KITTI;
         const float *cm = b.cam_mats + ((size_t)frame * 6 + b.cand_cam[f]) * 24;
         const float *bx = b.cand_box2d + (size_t)f * 4;
         const float lo[3] = {bx[0], bx[1], dmin}, hi[3] = {bx[2], bx[3], dmax};
@@ -894,7 +909,9 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
                 const float cen = __fmul_rn(__fadd_rn(hi[a], lo[a]), 0.5f);
                 uvd[a] = __fadd_rn(__fmul_rn(whl, tpl[k][a] * 0.5f), cen);
             }
-            unproject(cm + 12, cm + 21, uvd[0], uvd[1], uvd[2], c[k][0], c[k][1], c[k][2]);
+            // KITTI variant: the (8,4)@(4,4) matmul of rect_to_lidar rounds every product on its own (fewer than 33 rows)
+            if (kitti) unproject_kitti(b.cam_mats + (size_t)frame * 144, uvd[0], uvd[1], uvd[2], c[k][0], c[k][1], c[k][2], false);
+            else unproject(cm + 12, cm + 21, uvd[0], uvd[1], uvd[2], c[k][0], c[k][1], c[k][2]);
         }
         if (cfg.clamp_bottom > 0) {
             for (int a = 0; a < 3; a++) {
@@ -917,9 +934,11 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
             for (int a = 0; a < 3; a++) s_geo[3 + a] = __fmul_rn(__fdiv_rn(s_geo[3 + a], nv), cfg.search_depth);
         }
         // weighted_centre_xyz (:631-636): the 2D box centre at the cq depth quantile, unprojected
-        if (want_wc)
-            unproject(cm + 12, cm + 21, __fmul_rn(__fadd_rn(bx[0], bx[2]), 0.5f), __fmul_rn(__fadd_rn(bx[1], bx[3]), 0.5f), qc,
-                      st[10], st[11], st[12]);
+        if (want_wc) {
+            const float uc = __fmul_rn(__fadd_rn(bx[0], bx[2]), 0.5f), vc = __fmul_rn(__fadd_rn(bx[1], bx[3]), 0.5f);
+            if (kitti) unproject_kitti(b.cam_mats + (size_t)frame * 144, uc, vc, qc, st[10], st[11], st[12], false);
+            else unproject(cm + 12, cm + 21, uc, vc, qc, st[10], st[11], st[12]);
+        }
         st[0] = dmin; st[1] = dmax; st[2] = qc;
         for (int a = 0; a < 3; a++) { st[3 + a] = mn[a]; st[6 + a] = mx[a]; }
         st[9] = (float)n;
@@ -938,6 +957,7 @@ __global__ void __launch_bounds__(kStatsThreads, FNP_STATS_MIN_CTAS) stats_kerne
 // Stage 2a: hypotheses
 // ======================================================================================
 // 2D IoU of the image-plane bounding box of the 8 shifted corners with a 2D box (calc_iou, :1392-1411)
+template <bool KITTI = false>
 __device__ __forceinline__ float view_iou(const float *__restrict__ L, const float4 box2d, const float (&cor)[8][3],
                                           const float (&shift)[3], const float img_w, const float img_h)
 {
@@ -947,8 +967,11 @@ __device__ __forceinline__ float view_iou(const float *__restrict__ L, const flo
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         float u, v, d;
-        project(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]),
-                __fadd_rn(cor[k][2], shift[2]), img_w, img_h, u, v, d);
+        if (KITTI)
+            project_kitti(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]), __fadd_rn(cor[k][2], shift[2]), u, v, d);
+        else
+            project(L, __fadd_rn(cor[k][0], shift[0]), __fadd_rn(cor[k][1], shift[1]),
+                    __fadd_rn(cor[k][2], shift[2]), img_w, img_h, u, v, d);
         u = fminf(fmaxf(u, 0.f), img_w);
         v = fminf(fmaxf(v, 0.f), img_h);
         x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
@@ -969,7 +992,7 @@ __device__ __forceinline__ float view_iou(const float *__restrict__ L, const flo
 #ifndef FNP_HYP_MIN_CTAS
 #define FNP_HYP_MIN_CTAS 8
 #endif
-template <bool EXTRAS>
+template <bool EXTRAS, bool KITTI = false>
 __global__ void __launch_bounds__(128, EXTRAS ? 4 : FNP_HYP_MIN_CTAS) hypotheses_kernel(const fnp_seeker_batch b, const fnp_seeker_cfg cfg)
 {
     __shared__ int s_wcnt[4];
@@ -1043,7 +1066,7 @@ __global__ void __launch_bounds__(128, EXTRAS ? 4 : FNP_HYP_MIN_CTAS) hypotheses
 #pragma unroll
             for (int a = 3; a < 7; a++) box[a] = __ldg(bb + a);
             const bool near_enough = norm3(front[0], front[1], front[2]) < cfg.max_dist;
-            if (!multicam) iou = view_iou(L, box2d, cor, shift, cfg.img_w, cfg.img_h);
+            if (!multicam) iou = view_iou<KITTI>(L, box2d, cor, shift, cfg.img_w, cfg.img_h);
             else {
                 // multicam_ious (:1413-1429): every candidate of the frame with points and the same label
                 // (this one included), summed in candidate order, over (number of non-zero IoUs + 1e-6)
@@ -1929,6 +1952,34 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
 #endif
 
 // ======================================================================================
+// Stage 2b, KITTI variant: ONE batched first-match points_in_boxes_gpu over the valid hypotheses of a frustum
+// (frustum_proposals_v1_kitti.py:644-648; roiaware_pool3d_kernel.cu:313-359): a point counts for the FIRST hypothesis,
+// in compacted order, that contains it.  CTA per (frustum, 4096-point split); every thread walks the hypotheses of
+// its point until the first hit (the hypotheses are read by all lanes at once: L1 broadcast).
+// ======================================================================================
+constexpr int kFmThreads = 256, kFmSplit = 4096;
+__global__ void __launch_bounds__(kFmThreads) firstmatch_kernel(const fnp_seeker_batch b, const int H)
+{
+    const int f = blockIdx.x;
+    const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
+    if (nv <= 0 || npts <= 0 || (b.status[0] & 2)) return;
+    const int p0 = blockIdx.y * kFmSplit;
+    if (p0 >= npts) return;
+    const int p1 = min(npts, p0 + kFmSplit);
+    int *cnt = b.counts + (size_t)f * H;
+    for (int i = p0 + (int)threadIdx.x; i < p1; i += kFmThreads) {
+        const float *pg = page_of(b, f, i >> 8) + (i & (kPage - 1));
+        const float x = pg[0], y = pg[kPage], z = pg[2 * kPage];
+        for (int r = 0; r < nv; r++) {
+            if (in_box(x, y, z, load_prep(b.hyp_prep, (size_t)f * H + r))) {
+                atomicAdd(cnt + r, 1);
+                break;
+            }
+        }
+    }
+}
+
+// ======================================================================================
 // Stage 3: score + greedy argmax
 // ======================================================================================
 // Optional stage 2c: n_far of every compacted hypothesis = frustum points whose norm exceeds the norm of
@@ -2050,7 +2101,7 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
     const int *cbase = b.counts + (size_t)f * H;
     const float *pbase = b.hyp_prep + (size_t)f * H * 8;
     const bool mult = EXTRAS && (cfg.flags & FNP_SEEKER_MULT) != 0, occl_mult = EXTRAS && (cfg.flags & FNP_SEEKER_OCCL_MULT) != 0;
-    const bool use_dist = EXTRAS && ((cfg.dst_w != 0.f) || mult);
+    const bool use_dist = EXTRAS && ((cfg.dst_w != 0.f) || mult || cfg.variant == FNP_VARIANT_KITTI);
     const bool use_fail = EXTRAS && ((cfg.occl_w > 0.f) || occl_mult);
     const bool use_ego = EXTRAS && cfg.ego_w > 0.f;
     const bool use_occl_w = EXTRAS && cfg.occl_w > 0.f;
@@ -2058,14 +2109,25 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
     const int *nfar = use_fail ? b.hyp_nfar + (size_t)f * H : nullptr;
     // the reference's occlusion score: n_far * n_out (a (P,1) & (P,) broadcast, :453), stored as float
 #define FNP_FAIL(r) __ll2float_rn((long long)nfar[r] * (npts - (long long)cbase[r]))
-    int mxi = 0;
+    // FrustumProposerOGKITTI (frustum_proposals_v1_kitti.py:650-654): first-match counts over their SUM, and
+    // score = dns_w + density + iou_w iou + dst_w dists_ranked
+    const bool kitti = EXTRAS && cfg.variant == FNP_VARIANT_KITTI;
+    int mxi = 0, sumi = 0;
     float fmx = 0.f, emx = 0.f;
     for (int r = tid; r < nv; r += blockDim.x) {
         mxi = max(mxi, cbase[r]);
+        sumi += cbase[r];
         if (use_fail) fmx = fmaxf(fmx, FNP_FAIL(r));
         if (use_ego) emx = fmaxf(emx, norm3(pbase[r * 8], pbase[r * 8 + 1], pbase[r * 8 + 2]));
     }
-    const float den = __fadd_rn(block_max128((float)mxi, s_f, lane, warp), 1e-8f);
+    float den = __fadd_rn(block_max128((float)mxi, s_f, lane, warp), 1e-8f);
+    if (kitti) {      // integer-valued floats: the sum is exact in any order (below 2^24 points)
+        sumi = __reduce_add_sync(0xffffffffu, sumi);
+        if (lane == 0) s_i[warp] = sumi;
+        __syncthreads();
+        den = __fadd_rn((float)(s_i[0] + s_i[1] + s_i[2] + s_i[3]), 1e-8f);
+        __syncthreads();
+    }
     float fden = 1.f, dmin = 0.f, dden = 1.f;
     if (use_fail) fden = __fadd_rn(block_max128(fmx, s_f, lane, warp), 1e-6f);
     if (use_ego) emx = block_max128(emx, s_f, lane, warp);
@@ -2082,7 +2144,9 @@ __global__ void __launch_bounds__(128) select_kernel(const fnp_seeker_batch b, c
         const float iou = b.hyp_iou[(size_t)f * H + r];
         const float dr = use_dist ? __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(b.hyp_dist[(size_t)f * H + r], dmin), dden)) : 1.0f;
         float sc;
-        if (mult)
+        if (kitti)
+            sc = __fadd_rn(__fadd_rn(__fadd_rn(cfg.dns_w, dens), __fmul_rn(cfg.iou_w, iou)), __fmul_rn(dr, cfg.dst_w));
+        else if (mult)
             sc = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(dens, cfg.dns_w), iou), cfg.iou_w), dr), cfg.dst_w);
         else {
             sc = __fadd_rn(__fmul_rn(dens, cfg.dns_w), __fmul_rn(iou, cfg.iou_w));
@@ -2173,17 +2237,19 @@ static size_t cull_smem(const fnp_seeker_batch *b)
     return sizeof(CullSmem) + (size_t)b->max_cands_per_frame * (16 + 4 + 4) + (size_t)kCullList * (16 + 4 + 4) + 16;
 }
 
-template <int W>
+template <int W, bool KITTI>
 static int launch_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch *b, cudaStream_t st)
 {
     const int n_cu = cell_cols(cfg->img_w), n_cv = cell_rows(cfg->img_h);
     const size_t sa = cull_smem(b), sc = (size_t)n_cu * n_cv * W * 4;
     if (sa > 200 * 1024 || sc > 200 * 1024) return FNP_EINVAL;
-    cudaFuncSetAttribute(cull_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    cudaFuncSetAttribute(cull_kernel<W, KITTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
     cudaFuncSetAttribute(cell_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc);
     cudaMemsetAsync(b->cell_masks + (size_t)b->n_frames * 6 * n_cu * n_cv * W, 0, (size_t)b->n_frames * kSectors * 4, st);
-    cell_table_kernel<<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h);
-    cull_kernel<W><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv, g_opt_cull_sectors);
+    cell_table_kernel<<<b->n_frames * 6, 128, sc, st>>>(*b, n_cu, n_cv, cfg->img_w, cfg->img_h, KITTI ? 1 : 0);
+    // the azimuth-sector table is built from lidar2image: not in the KITTI variant (one camera anyway)
+    cull_kernel<W, KITTI><<<b->n_tiles, kCullThreads, sa, st>>>(*b, cfg->img_w, cfg->img_h, n_cu, n_cv,
+                                                               KITTI ? 0 : g_opt_cull_sectors);
     cull_finish_kernel<<<1, 32, 0, st>>>(*b);
     return FNP_OK;
 }
@@ -2224,13 +2290,21 @@ extern "C" int fnp_seeker_cull(const fnp_seeker_cfg *cfg, const fnp_seeker_batch
     cudaMemsetAsync(b->page_tab, 0, sizeof(int32_t) * (size_t)b->n_cands * (size_t)b->page_tab_stride, st);
     const int W = fnp_seeker_mask_words(b->max_cands_per_frame);
     if (W < 0 || W != b->mask_words) return FNP_EINVAL;   // more than 1024 candidates in one frame
+    if (cfg->variant == FNP_VARIANT_KITTI) {      // up to 128 candidates per frame in this variant
+        switch (W) {
+            case 1: rc = launch_cull<1, true>(cfg, b, st); break;
+            case 2: rc = launch_cull<2, true>(cfg, b, st); break;
+            case 4: rc = launch_cull<4, true>(cfg, b, st); break;
+            default: rc = FNP_EINVAL; break;
+        }
+    } else
     switch (W) {      // the words of a cell's candidate mask are a compile-time constant of the membership loop
-        case 1: rc = launch_cull<1>(cfg, b, st); break;
-        case 2: rc = launch_cull<2>(cfg, b, st); break;
-        case 4: rc = launch_cull<4>(cfg, b, st); break;
-        case 8: rc = launch_cull<8>(cfg, b, st); break;
-        case 16: rc = launch_cull<16>(cfg, b, st); break;
-        default: rc = launch_cull<32>(cfg, b, st); break;
+        case 1: rc = launch_cull<1, false>(cfg, b, st); break;
+        case 2: rc = launch_cull<2, false>(cfg, b, st); break;
+        case 4: rc = launch_cull<4, false>(cfg, b, st); break;
+        case 8: rc = launch_cull<8, false>(cfg, b, st); break;
+        case 16: rc = launch_cull<16, false>(cfg, b, st); break;
+        default: rc = launch_cull<32, false>(cfg, b, st); break;
     }
     if (rc) return rc;
     FNP_LAUNCH_CHECK();
@@ -2252,7 +2326,10 @@ extern "C" int fnp_seeker_hypotheses(const fnp_seeker_cfg *cfg, const fnp_seeker
     int rc = check_batch(cfg, b);
     if (rc) return rc;
     if (b->n_cands == 0) return FNP_OK;
-    if ((cfg->flags & FNP_SEEKER_MULTICAM_IOU) || b->hyp_dist)
+    if (cfg->variant == FNP_VARIANT_KITTI) {
+        if (!b->hyp_dist || (cfg->flags & FNP_SEEKER_MULTICAM_IOU)) return FNP_EINVAL;   // this head always ranks distances
+        hypotheses_kernel<true, true><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
+    } else if ((cfg->flags & FNP_SEEKER_MULTICAM_IOU) || b->hyp_dist)
         hypotheses_kernel<true><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
     else
         hypotheses_kernel<false><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
@@ -2283,6 +2360,15 @@ extern "C" int fnp_seeker_score(const fnp_seeker_cfg *cfg, const fnp_seeker_batc
     const int J = cfg->num_yaw_size, M = cfg->num_mags, H = M * J;
     cudaStream_t st = (cudaStream_t)stream;
     if (!b->items || !b->cand_item_start || !b->counts) return FNP_EINVAL;
+    if (cfg->variant == FNP_VARIANT_KITTI) {      // first-match counts: its own kernel, no work items
+        cudaMemsetAsync(b->counts, 0, sizeof(int32_t) * (size_t)b->n_cands * H, st);
+        // a frustum holds at most the rows of the largest frame: page_tab_stride pages
+        int rows = (int)(((long long)b->page_tab_stride * kPage + kFmSplit - 1) / kFmSplit);
+        rows = rows < 1 ? 1 : rows > 65535 ? 65535 : rows;
+        firstmatch_kernel<<<dim3(b->n_cands, rows), kFmThreads, 0, st>>>(*b, H);
+        FNP_LAUNCH_CHECK();
+        return FNP_OK;
+    }
     const int mode = resolve_score_mode(cfg, b);
     if (mode < 0) return FNP_EINVAL;
     const int sweep = mode == FNP_SCORE_SWEEP;
@@ -2337,11 +2423,13 @@ extern "C" int fnp_seeker_select(const fnp_seeker_cfg *cfg, const fnp_seeker_bat
 {
     int rc = check_batch(cfg, b);
     if (rc) return rc;
-    if (((cfg->dst_w != 0.f) || (cfg->flags & FNP_SEEKER_MULT)) && !b->hyp_dist) return FNP_EINVAL;
+    const bool kitti = cfg->variant == FNP_VARIANT_KITTI;
+    if (kitti && (cfg->flags != 0 || cfg->ego_w > 0.f || cfg->occl_w > 0.f)) return FNP_EINVAL;   // not terms of that head's score
+    if (((cfg->dst_w != 0.f) || (cfg->flags & FNP_SEEKER_MULT) || kitti) && !b->hyp_dist) return FNP_EINVAL;
     if (((cfg->occl_w > 0.f) || (cfg->flags & FNP_SEEKER_OCCL_MULT)) && !b->hyp_nfar) return FNP_EINVAL;
     if (cfg->topk > 1 && (!b->hyp_score || cfg->num_yaw_size * cfg->num_mags > kSelectMaxTopkH)) return FNP_EINVAL;
     if (b->n_cands == 0) return FNP_OK;
-    const bool extras = cfg->dst_w != 0.f || cfg->ego_w > 0.f || cfg->occl_w > 0.f || cfg->flags != 0 || cfg->topk > 1;
+    const bool extras = cfg->dst_w != 0.f || cfg->ego_w > 0.f || cfg->occl_w > 0.f || cfg->flags != 0 || cfg->topk > 1 || kitti;
     if (extras)
         select_kernel<true><<<b->n_cands, 128, 0, (cudaStream_t)stream>>>(*b, *cfg);
     else

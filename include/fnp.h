@@ -125,7 +125,21 @@ typedef struct fnp_seeker_cfg {
     int32_t topk;            /* proposals per frustum (:1040-1046); 0 and 1 both mean the single best one  */
     float nms_normal;        /* axis-aligned BEV IoU threshold of the per-frustum NMS (:1030); only matters
                                 for topk > 1 (the first survivor is the arg-max whatever the threshold)    */
+    int32_t variant;         /* FNP_VARIANT_NUSCENES (FrustumProposerOG, frustum_proposals_v1.py) or
+                                FNP_VARIANT_KITTI (FrustumProposerOGKITTI, frustum_proposals_v1_kitti.py:38):
+                                KITTI calibration arithmetic (calibration_kitti.py:128-216), no on-image test,
+                                first-match point counts normalised by their sum, additive score (:646-654)  */
 } fnp_seeker_cfg;
+
+#define FNP_VARIANT_NUSCENES 0
+#define FNP_VARIANT_KITTI 1
+/* FNP_VARIANT_KITTI: one camera (index 0); the 144 floats of a frame in cam_mats hold
+ *   [0..11]  M1  = V2C.T @ R0.T, (4,3) row-major      (lidar_to_rect, calibration_kitti.py:171-182)
+ *   [12..23] P2T = P2.T, (4,3) row-major               (rect_to_img, :184-194)
+ *   [24..29] cu, cv, fu, fv, tx, ty                    (img_to_rect, :205-216)
+ *   [32..47] Minv = inverse((R0_ext @ V2C_ext).T), (4,4) row-major   (rect_to_lidar, :151-169)
+ * each formed by the caller with the reference's own torch calls.  The matmuls are restated in the
+ * accumulation order torch uses on B200 for >= 33 rows (tools/probe_kitti.py): an fma chain over k = 0..3. */
 
 #define FNP_SEEKER_MULT 1          /* MODEL.DENSE_HEAD.MULT: product of the score terms (:998-999)             */
 #define FNP_SEEKER_OCCL_MULT 2     /* OCCL_MULT: score = density * iou * occlusion fail score (:1022-1026)      */

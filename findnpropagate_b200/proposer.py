@@ -363,3 +363,105 @@ class FrustumProposerOG(nn.Module):
         batch_dict['final_box_dicts'] = self.get_bboxes(batch_dict)
         assert not self.training, "not trainable!"
         return batch_dict
+
+
+class FrustumProposerOGKITTI(nn.Module):
+    """The KITTI single-camera Greedy Box Seeker head with the reference's constructor signature and
+    ``get_proposals`` / ``get_bboxes`` / ``forward`` contract (frustum_proposals_v1_kitti.py:38-48, 292-690, 709-740),
+    on the fused stages in their KITTI variant (include/fnp.h FNP_VARIANT_KITTI): CalibrationTorch's two-step
+    projection without an on-image test, x-y-w-h boxes, seven anchors, max_dist 70, ONE batched first-match
+    ``points_in_boxes_gpu`` per frustum, densities over their sum, ``score = dns_w + density + iou_w iou + dst_w dist``,
+    ``nms_normal`` + ``topk``.  ``batch_dict``: ``points`` (N, 1+3+) with the batch index in column 0, ``calib`` a list
+    of objects with ``P2``, ``R0``, ``V2C`` (pcdet.utils.calibration_kitti.Calibration), ``batch_size``."""
+
+    def __init__(self, model_cfg=None, input_channels=None, num_class=None, class_names=None, grid_size=None,
+                 point_cloud_range=None, voxel_size=None, predict_boxes_when_training=True,
+                 lq=0.336, uq=0.356, iou_w=0.95, dst_w=0.226, dns_w=0.05, min_cam_iou=0.3, size_min=0.957,
+                 size_max=1.2, ry_min=0.0, ry_max=torch.pi, cq=0.46, num_mags=6, max_dist=70, num_sizes=4,
+                 num_rotations=10, topk=1, nms_2d=0.7, nms_3d=1.0, score_thr=0.1, nms_normal=0.7, clamp_bottom=0,
+                 image_detector=None, device=None):
+        super().__init__()
+        p = dict(lq=lq, uq=uq, iou_w=iou_w, dst_w=dst_w, dns_w=dns_w, min_cam_iou=min_cam_iou, size_min=size_min,
+                 size_max=size_max, ry_min=ry_min, ry_max=float(ry_max), cq=cq, num_mags=num_mags, max_dist=max_dist,
+                 num_sizes=num_sizes, num_rotations=num_rotations, topk=topk, nms_2d=nms_2d, nms_3d=nms_3d,
+                 score_thr=score_thr, nms_normal=nms_normal, clamp_bottom=0)      # the argument is ignored (:62)
+        params = _cfg_get(model_cfg, 'PARAMS')
+        if params is not None:                       # PARAMS override the defaults (:68-98)
+            for k in list(DEFAULTS) + ['aln_w', 'ego_w', 'occl_w', 'rand_center', 'search_depth']:
+                if k in params:
+                    p[k] = params[k]
+        if _cfg_get(model_cfg, 'SAVE_BLEND', False):
+            raise NotImplementedError("SAVE_BLEND (Blender visualisation dumps) is outside the Box Seeker path")
+        assert p['nms_3d'] == 0, 'DO NOT USE!'          # the reference's own assertion (:114)
+        # aln_w / ego_w / occl_w and the MULT / OCCL_MULT / MULTICAM_IOU switches are read by that constructor and never
+        # used by its get_proposals: ignored here as there
+        p['aln_w'] = p['ego_w'] = p['occl_w'] = 0
+        self.params = p
+        self.image_size = [900, 1600]
+        self.topk, self.score_thr, self.max_dist = p['topk'], p['score_thr'], p['max_dist']
+        self.num_mags, self.num_sizes, self.num_rotations = p['num_mags'], p['num_sizes'], p['num_rotations']
+        if image_detector is not None:
+            self.image_detector = image_detector
+        else:
+            preds_path = _cfg_get(model_cfg, 'PREDS_PATH', '/home/uqdetche/GLIP/OWL_PREDEFINED_MMDETCOCO_val_kitti.coco.json')
+            self.image_detector = PreprocessedDetector([preds_path], class_names=class_names)
+        self.engine = SeekerEngine(p, device=device, box_format='xywh', variant='kitti')
+        self.base_boxes = self.engine.base_boxes
+        self.base_corners = self.engine.base_corners
+
+    def get_proposals(self, batch_dict):
+        """-> (proposal_boxes (K,7) f32 on the GPU, frust_labels (K) int64 CPU, frust_scores (K) f32 CPU,
+        frust_batch_idx (K) int64 CPU), as frustum_proposals_v1_kitti.py:676-690."""
+        from .seeker import KittiFrameInput
+        B = int(batch_dict['batch_size'])
+        det_boxes, det_labels, det_scores, det_batch_idx, det_cam_idx = self.image_detector(batch_dict)
+        det_boxes, det_labels = FrustumProposerOG._np(det_boxes), FrustumProposerOG._np(det_labels)
+        det_scores, det_batch_idx = FrustumProposerOG._np(det_scores), FrustumProposerOG._np(det_batch_idx)
+        det_cam_idx = FrustumProposerOG._np(det_cam_idx)
+        pts = batch_dict['points']
+        dev = self.engine.device
+        if isinstance(pts, np.ndarray):
+            pts = torch.from_numpy(np.ascontiguousarray(pts, np.float32))
+        pts = pts.to(dev, dtype=torch.float32).contiguous()
+        bidx = pts[:, 0].contiguous()
+        if bidx.numel() > 1 and not bool((bidx[1:] >= bidx[:-1]).all()):
+            raise ValueError("batch_dict['points'] must be grouped by batch index (collate_batch order)")
+        bounds = torch.searchsorted(bidx, torch.arange(B + 1, device=dev, dtype=torch.float32)).cpu().numpy()
+        frames = []
+        for b in range(B):
+            cal = batch_dict['calib'][b]
+            m = (det_batch_idx == b) & (det_cam_idx == 0)           # c = 0 only (:336-337)
+            n = int(bounds[b + 1] - bounds[b])
+            frames.append(KittiFrameInput(points=np.empty((n, int(pts.shape[1])), np.float32), P2=cal.P2, R0=cal.R0, V2C=cal.V2C,
+                                          det_boxes=det_boxes[m], det_labels=det_labels[m], det_scores=det_scores[m],
+                                          device=str(dev)))
+        plan = self.engine.plan(frames, xyz_offset=1, stride=int(pts.shape[1]))
+        while True:
+            h = self.engine.execute(plan, pts)
+            try:
+                res = self.engine.finish(h)
+                break
+            except OverflowError as e:
+                self.engine.pts_factor = max(self.engine.pts_factor * 1.5,
+                                             1.25 * int(e.args[0]) / max(plan["total_rows"], 1))
+        boxes, labels, scores, bi = [], [], [], []
+        for b, fr in enumerate(res["frames"]):
+            boxes.append(fr["pred_boxes"]); labels.append(fr["pred_labels"]); scores.append(fr["pred_scores"])
+            bi.append(np.full(fr["pred_labels"].shape[0], b, np.int64))
+        proposal_boxes = torch.from_numpy(np.concatenate(boxes).reshape(-1, 7)).to(dev)
+        return (proposal_boxes, torch.from_numpy(np.concatenate(labels).astype(np.int64)),
+                torch.from_numpy(np.concatenate(scores).astype(np.float32)), torch.from_numpy(np.concatenate(bi)))
+
+    def get_bboxes(self, batch_dict):
+        boxes, labels, scores, bidx = self.get_proposals(batch_dict)
+        ret = []
+        for k in range(batch_dict['batch_size']):
+            mask = (bidx == k)
+            ret.append(dict(pred_boxes=boxes[mask.to(boxes.device)], pred_scores=scores[mask],
+                            pred_labels=labels[mask].int()))
+        return ret
+
+    def forward(self, batch_dict):
+        batch_dict['final_box_dicts'] = self.get_bboxes(batch_dict)
+        assert not self.training, "not trainable!"
+        return batch_dict

@@ -32,6 +32,10 @@ ANCHORS = [[4.63, 1.97, 1.74], [6.93, 2.51, 2.84], [6.37, 2.85, 3.19], [10.5, 2.
            [0.73, 0.67, 1.77], [0.41, 0.41, 1.07]]          # frustum_proposals_v1.py:270-281
 IMAGE_SIZE = (900, 1600)                                     # frustum_proposals_v1.py:203
 FRUSTUM_MIN = 2.0                                            # frustum_proposals_v1.py:240
+# FrustumProposerOGKITTI (frustum_proposals_v1_kitti.py:157-166): car, tram, truck, van, person sitting, cyclist,
+# pedestrian; same constructor defaults except max_dist = 70 (:44); image_size and frustum_min as above (:108, :141)
+ANCHORS_KITTI = [[3.9, 1.6, 1.56], [6.37, 2.85, 3.19], [6.93, 2.51, 2.84], [6.93, 2.51, 2.84], [0.8, 0.6, 1.73],
+                 [1.76, 0.6, 1.73], [0.8, 0.6, 1.73]]
 
 # constructor defaults, frustum_proposals_v1.py:146-148
 DEFAULTS = dict(lq=0.336, uq=0.356, iou_w=0.95, dst_w=0.226, dns_w=0.05, min_cam_iou=0.3,
@@ -46,11 +50,15 @@ RECALL_PER_THRESH = ["rcnn", "rcnn_3known", "rcnn_6known", "rcnn_4unknown", "rcn
 FLAG_KEYS = ("MULT", "OCCL_MULT", "MULTICAM_IOU")     # MODEL.DENSE_HEAD switches, frustum_proposals_v1.py:154-156
 
 
-def resolve_params(params: Optional[dict]) -> dict:
+def resolve_params(params: Optional[dict], variant: str = "nuscenes") -> dict:
     """PARAMS of the head (frustum_proposals_v1.py:167-195) over the constructor defaults.  Besides the
     shipped option set, the optional terms of SURVEY.md 8 row f3 are supported: dst_w, ego_w, occl_w,
-    search_depth and the switches MULT / OCCL_MULT / MULTICAM_IOU (keys of the same dict)."""
+    search_depth and the switches MULT / OCCL_MULT / MULTICAM_IOU (keys of the same dict).
+    variant "kitti": FrustumProposerOGKITTI (frustum_proposals_v1_kitti.py:38-98), whose score has the density, IoU
+    and distance terms only."""
     p = dict(DEFAULTS)
+    if variant == "kitti":
+        p["max_dist"] = 70
     p.update(ego_w=0, occl_w=0, aln_w=0, rand_center=False, search_depth=None)      # :160-165
     p.update({k: False for k in FLAG_KEYS})
     if params:
@@ -66,16 +74,20 @@ def resolve_params(params: Optional[dict]) -> dict:
         unsupported.append("rand_center (torch.randn centres: not reproducible in the reference)")
     if p["search_depth"] is not None and not p["search_depth"] > 0:
         unsupported.append("search_depth <= 0")
+    if variant == "kitti":
+        for k in ("ego_w", "occl_w") + FLAG_KEYS:      # read by that constructor, never used in its score (:650-654)
+            if p.get(k):
+                unsupported.append("%s with the KITTI head (not a term of its score)" % k)
     if unsupported:
         raise NotImplementedError("Box Seeker options outside the supported set: " + ", ".join(unsupported))
     return p
 
 
-def build_tables(p: dict):
+def build_tables(p: dict, anchors=None):
     """base_boxes (A,J,7), base_corners (A,J,8,3) -- the constructor tables of
     frustum_proposals_v1.py:282-298 (+ box_utils.boxes_to_corners_3d, box_utils.py:28-52),
     built with the same torch calls on the host."""
-    anchors = torch.tensor(ANCHORS, dtype=torch.float32)
+    anchors = torch.tensor(ANCHORS if anchors is None else anchors, dtype=torch.float32)
     A, R, S = anchors.shape[0], int(p["num_rotations"]), int(p["num_sizes"])
     size_variations = torch.linspace(p["size_min"], p["size_max"], steps=S)
     base_rotations = torch.linspace(p["ry_min"], p["ry_max"], steps=R)
@@ -145,6 +157,59 @@ class FrameInput:
         return self._prep
 
 
+def kitti_camera_block(P2, R0, V2C, device):
+    """The 144 floats of a frame for FNP_VARIANT_KITTI (include/fnp.h): M1 = V2C.T @ R0.T | P2.T | cu cv fu fv tx ty |
+    inverse((R0_ext @ V2C_ext).T) -- formed with the calls CalibrationTorch makes (calibration_kitti.py:128-169), on
+    the device the reference forms them on, so that the bits are its bits."""
+    P2 = torch.as_tensor(np.asarray(P2, np.float32), device=device)
+    R0 = torch.as_tensor(np.asarray(R0, np.float32), device=device)
+    V2C = torch.as_tensor(np.asarray(V2C, np.float32), device=device)
+    m1 = V2C.T @ R0.T                                                   # (4,3)
+    cu, cv, fu, fv = P2[0, 2], P2[1, 2], P2[0, 0], P2[1, 1]
+    tx, ty = P2[0, 3] / (-fu), P2[1, 3] / (-fv)
+    r0e = torch.cat((torch.cat((R0, R0.new_zeros((3, 1))), dim=1), R0.new_zeros((1, 4))), dim=0)
+    r0e[3, 3] = 1
+    v2ce = torch.cat((V2C, V2C.new_zeros((1, 4))), dim=0)
+    v2ce[3, 3] = 1
+    minv = torch.inverse(torch.matmul(r0e, v2ce).T)                     # (4,4)
+    out = torch.zeros(144, dtype=torch.float32, device=device)
+    out[0:12] = m1.reshape(-1)
+    out[12:24] = P2.T.reshape(-1)
+    out[24:30] = torch.stack((cu, cv, fu, fv, tx, ty))
+    out[32:48] = minv.reshape(-1)
+    return out.cpu().numpy().reshape(6, 24)
+
+
+@dataclass
+class KittiFrameInput:
+    """One KITTI frame for SeekerEngine(variant="kitti"): LiDAR points, the calibration (P2 (3,4), R0 (3,3),
+    Tr_velo2cam (3,4) -- pcdet.utils.calibration_kitti.Calibration) and the 2D detections of the one camera as
+    x, y, w, h boxes (PreprocessedDetector on one COCO result file, frustum_proposals_v1_kitti.py:150)."""
+    points: np.ndarray            # (N, C>=3) f32
+    P2: np.ndarray
+    R0: np.ndarray
+    V2C: np.ndarray
+    det_boxes: np.ndarray         # (D,4) x, y, w, h
+    det_labels: np.ndarray        # (D,) 1..7
+    det_scores: np.ndarray        # (D,)
+    gt_boxes: Optional[np.ndarray] = None
+    device: str = "cuda"
+    _prep: Optional[dict] = None
+
+    def prepare(self):
+        if self._prep is None:
+            boxes = np.ascontiguousarray(self.det_boxes, np.float32).reshape(-1, 4)
+            labels = np.ascontiguousarray(self.det_labels, np.int64).reshape(-1)
+            scores = np.ascontiguousarray(self.det_scores, np.float32).reshape(-1)
+            cam = np.zeros(scores.shape[0], np.int64)                   # c = 0 (:336)
+            cm = np.ascontiguousarray(kitti_camera_block(self.P2, self.R0, self.V2C, self.device), np.float32)
+            rec = _lib.HostFrame(n_rows=int(self.points.shape[0]), det_boxes=boxes.ctypes.data, det_labels=labels.ctypes.data,
+                                 det_scores=scores.ctypes.data, det_cam=cam.ctypes.data, cam_mats=cm.ctypes.data,
+                                 n_dets=int(scores.shape[0]), reserved=0)
+            self._prep = dict(blob=bytes(rec), keep=(boxes, labels, scores, cam, cm))
+        return self._prep
+
+
 class _Arena:
     """Grow-only device/pinned scratch so that steady-state batches allocate nothing."""
 
@@ -202,16 +267,18 @@ class SeekerEngine:
     """Batched Box Seeker on one GPU."""
 
     def __init__(self, params=None, device=None, debug=False, split_points=None, score_mode="auto", box_format="xyxy",
-                 host_cache=True):
+                 host_cache=True, variant="nuscenes"):
         if not torch.cuda.is_available():
             raise RuntimeError("findnpropagate_b200.SeekerEngine needs a CUDA device (no CPU fallback)")
-        self.p = resolve_params(params)
+        assert variant in ("nuscenes", "kitti")
+        self.variant = variant
+        self.p = resolve_params(params, variant)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.debug = debug
         self.M = max(int(self.p["num_mags"]), 1)
         self.J = int(self.p["num_rotations"]) * int(self.p["num_sizes"])
         self.H = self.M * self.J
-        bb, bc = build_tables(self.p)
+        bb, bc = build_tables(self.p, ANCHORS_KITTI if variant == "kitti" else None)
         self.base_boxes_host, self.base_corners_host = bb, bc
         self.base_boxes = bb.to(self.device)
         self.base_corners = bc.to(self.device)
@@ -226,10 +293,11 @@ class SeekerEngine:
             search_depth=float(self.p["search_depth"] or 0),
             flags=(_lib.SEEKER_MULT if self.p["MULT"] else 0) | (_lib.SEEKER_OCCL_MULT if self.p["OCCL_MULT"] else 0)
             | (_lib.SEEKER_MULTICAM_IOU if self.p["MULTICAM_IOU"] else 0),
-            topk=int(self.p["topk"]), nms_normal=float(self.p["nms_normal"]))
+            topk=int(self.p["topk"]), nms_normal=float(self.p["nms_normal"]),
+            variant=_lib.VARIANT_KITTI if variant == "kitti" else _lib.VARIANT_NUSCENES)
         self.T = int(self.p["topk"])       # proposal slots per candidate frustum (NMS order), :1040-1046
         # workspaces of the optional score terms (include/fnp.h: hyp_dist, hyp_nfar)
-        self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"])
+        self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"]) or variant == "kitti"   # that head always ranks distances
         self.use_occl = self.cfg.occl_w > 0 or bool(self.p["OCCL_MULT"])
         self.arena = _Arena(self.device)
         self.fixed_split_points = split_points

@@ -261,3 +261,56 @@ def test_kitti_head_runs_on_the_drop_in_ops(ref):
     assert twins <= total // 4
     print("KITTI head on the drop-in ops: %d proposals over %d frames, %d frustums scored, %d tied twins in the other order"
           % (total, len(frames), calls["pib"], twins))
+
+
+@pytest.mark.parametrize("override", [dict(), dict(topk=1, nms_normal=0.7, dst_w=0.226, dns_w=0.05, iou_w=0.95, lq=0.336, uq=0.356, cq=0.46,
+                                                   num_mags=6, num_rotations=10, num_sizes=4, min_cam_iou=0.3, clamp_bottom=0)])
+def test_kitti_head_fused_stages_vs_reference_head(ref, override):
+    """The KITTI head as fused stages (include/fnp.h FNP_VARIANT_KITTI; proposer.FrustumProposerOGKITTI) next to the
+    reference's own FrustumProposerOGKITTI.get_proposals (frustum_proposals_v1_kitti.py:292-690, source unmodified, its
+    kernels compiled for sm_100a) on the same KITTI-shaped frames: identical K, labels and 2D scores; box coordinates
+    within 1e-5 * max(|value|, 1 m) modulo the yaw 0 / pi twin (tied scores; counted).  The reference's calibration
+    matmuls round differently below 33 rows (tools/probe_kitti.py), so the last ulp of a small frustum's points can
+    differ: boxes are compared at the tolerance the north star states, not bit for bit."""
+    import contextlib
+    import io
+    import sys as _sys
+    from findnpropagate_b200 import proposer
+    mod = ref.load("cuda", head_file="frustum_proposals_v1_kitti.py")
+    Calibration = _sys.modules["pcdet.utils.calibration_kitti"].Calibration
+    frames = [_kitti_frame(i) for i in range(4)]
+    state = {}
+
+    class Feeder:
+        def __call__(self, bd):
+            pts, calib, boxes, labels, scores = state["frame"]
+            z = torch.zeros(len(boxes), dtype=torch.long)
+            return torch.from_numpy(boxes.copy()), torch.from_numpy(labels), torch.from_numpy(scores), z, z.clone()
+    mod.PreprocessedDetector = lambda paths, class_names=None: Feeder()
+    params = dict(lq=0.0, uq=0.25, cq=1.0, iou_w=1.0, nms_normal=1.0, dst_w=0.2, dns_w=1.0, min_cam_iou=0.1, score_thr=0.45,
+                  nms_2d=0.4, nms_3d=0.0, clamp_bottom=1, num_sizes=1, num_mags=8, num_rotations=6, topk=2)
+    params.update(override)
+    with contextlib.redirect_stdout(io.StringIO()):
+        head = mod.FrustumProposerOGKITTI(model_cfg=ref.AttrDict(PARAMS=params, PREDS_PATH="unused.json"), class_names=None)
+    head.eval()
+    ours = proposer.FrustumProposerOGKITTI(model_cfg=dict(PARAMS=params), image_detector=Feeder(), device="cuda:0")
+    total = twins = 0
+    for fr in frames:
+        state["frame"] = fr
+        pts = torch.from_numpy(np.c_[np.zeros(len(fr[0]), np.float32), fr[0]]).cuda()
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            r = [o.cpu() for o in head.get_proposals(dict(batch_size=1, calib=[Calibration(fr[1])], points=pts))]
+        o = [x.cpu() for x in ours.get_proposals(dict(batch_size=1, calib=[Calibration(fr[1])], points=pts))]
+        assert r[0].shape == o[0].shape, (r[0].shape, o[0].shape)
+        assert torch.equal(r[1], o[1]) and torch.equal(r[2], o[2]) and torch.equal(r[3], o[3])
+        a, b = r[0].numpy(), o[0].numpy()
+        for k in range(a.shape[0]):
+            tol = TOL * np.maximum(np.abs(a[k]), 1.0)
+            if np.all(np.abs(a[k] - b[k]) <= tol):
+                continue
+            d = a[k] - b[k]
+            assert abs(abs(d[6]) - np.pi) < 1e-5 and np.all(np.abs(d[:6]) <= 1e-4), (k, a[k], b[k])     # the yaw 0 / pi twin
+            twins += 1
+        total += a.shape[0]
+    assert total >= 4 and twins <= total // 3, (total, twins)
+    print("KITTI fused stages vs reference head: %d proposals over %d frames, %d yaw twins" % (total, len(frames), twins))

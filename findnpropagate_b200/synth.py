@@ -323,3 +323,33 @@ def write_nuscenes_tree(root, frames):
                           gt_names=np.array([CLASS_NAMES[int(c) - 1] for c in gt[:, -1]]),
                           num_lidar_pts=np.full(gt.shape[0], 10)))
     return infos
+
+
+def make_kitti_frame(index):
+    """A KITTI-shaped frame: points in front of the sensor, P2 / R0 / Tr_velo2cam, x-y-w-h 2D boxes of the visible
+    synthetic objects, labels 1..7 (the KITTI head's seven anchors)."""
+    cfg = SynthConfig("kitti", 32, 900, 1, 12, 4, 6, 1)
+    f = make_frame(index, cfg)
+    pts = f.points[f.points[:, 0] > 1.0][:, :4].copy()
+    V2C = np.array([[0.0, -1.0, 0.0, 0.004], [0.0, 0.0, -1.0, -0.076], [1.0, 0.0, 0.0, -0.272]], np.float32)
+    a = 0.01
+    R0 = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    P2 = np.array([[721.54, 0, 609.56, 44.857], [0, 721.54, 172.85, 0.2163], [0, 0, 1, 0.002746]], np.float32)
+    boxes, labels, scores = [], [], []
+    rng = np.random.default_rng(index)
+    for g in f.gt_boxes:
+        if g[0] < 4 or abs(g[1]) > g[0]:
+            continue
+        c = _box_corners(g[None, :7].astype(np.float64))[0]
+        rect = (np.c_[c, np.ones(8)] @ (np.vstack([V2C, [0, 0, 0, 1]]).T))[:, :3] @ R0.T
+        img = np.c_[rect, np.ones(8)] @ P2.T
+        u, v = img[:, 0] / rect[:, 2], img[:, 1] / rect[:, 2]
+        x1, x2 = np.clip(u.min(), 0, 1242), np.clip(u.max(), 0, 1242)
+        y1, y2 = np.clip(v.min(), 0, 375), np.clip(v.max(), 0, 375)
+        if x2 - x1 < 8 or y2 - y1 < 8:
+            continue
+        boxes.append([x1, y1, x2 - x1, y2 - y1])
+        labels.append(1 + int(rng.integers(0, 7)))
+        scores.append(float(rng.uniform(0.5, 0.9)))
+    return (pts, {'P2': P2, 'R0': R0, 'Tr_velo2cam': V2C}, np.asarray(boxes, np.float32).reshape(-1, 4),
+            np.asarray(labels, np.int64), np.asarray(scores, np.float32))

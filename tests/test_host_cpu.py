@@ -26,8 +26,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from findnpropagate_b200 import _lib
-    # 21 x 4-byte fields, in the header's order
-    assert ctypes.sizeof(_lib.SeekerCfg) == 84
+    # 22 x 4-byte fields, in the header's order
+    assert ctypes.sizeof(_lib.SeekerCfg) == 88
     hdr = open(os.path.join(ROOT, "include", "fnp.h")).read()
     cbody = hdr[hdr.index("typedef struct fnp_seeker_cfg"):hdr.index("} fnp_seeker_cfg;")]
     cbody = re.sub(r"/\*.*?\*/", "", cbody, flags=re.S)

@@ -1,0 +1,108 @@
+"""The KITTI single-camera head as fused stages (include/fnp.h FNP_VARIANT_KITTI) against fixtures made
+by the reference's own FrustumProposerOGKITTI (tools/gen_golden_kitti.py: frustum_proposals_v1_kitti.py run through the
+namespace stubs of tools/ref_seeker.py on the CPU, its two native ops emulated by the oracle).  The reference head on the
+GPU, side by side on the same frames, is in tests/test_reference_gpu.py.
+
+CPU torch (MKL sgemm, cdist) rounds the calibration matmuls and the distance term differently from the device in the last
+ulp, so: K / labels / 2D scores identical; boxes within 1e-5 * max(|value|, 1 m) modulo the yaw 0 / pi twin; per frustum
+the same points (1e-5), the same valid hypotheses (boxes 1e-5), first-match counts equal except where a point lies on a
+face (reported, bounded), second-stage scores within 1e-4."""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "kitti_*.npz")))
+TOL = 1e-5
+
+
+def test_kitti_fixtures_exist():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_kitti_prior_tables_equal_the_reference_constructor(path):
+    """base_boxes / base_corners of the seven KITTI anchors (frustum_proposals_v1_kitti.py:157-183): same torch calls on
+    the host, bit for bit; options that are no term of that head's score are refused."""
+    from findnpropagate_b200 import seeker
+    g = np.load(path)
+    p = seeker.resolve_params(json.loads(str(g["params"])), "kitti")
+    assert p["max_dist"] == 70
+    bb, bc = seeker.build_tables(p, seeker.ANCHORS_KITTI)
+    assert np.array_equal(bb.numpy().view(np.uint32), g["base_boxes"].view(np.uint32))
+    assert np.array_equal(bc.numpy().view(np.uint32), g["base_corners"].view(np.uint32))
+    for bad in (dict(ego_w=0.2), dict(occl_w=0.1), dict(MULT=True)):
+        with pytest.raises(NotImplementedError):
+            seeker.resolve_params(dict(json.loads(str(g["params"])), **bad), "kitti")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN)
+def test_kitti_fused_stages_vs_reference_golden(path):
+    from findnpropagate_b200.seeker import KittiFrameInput, SeekerEngine
+    g = np.load(path)
+    params = json.loads(str(g["params"]))
+    eng = SeekerEngine(params, device="cuda:0", debug=True, box_format="xywh", variant="kitti")
+    fi = KittiFrameInput(points=g["points"], P2=g["P2"], R0=g["R0"], V2C=g["V2C"], det_boxes=g["det_boxes"],
+                         det_labels=g["det_labels"], det_scores=g["det_scores"], device="cuda:0")
+    plan = eng.plan([fi])
+    h = eng.execute(plan, eng.upload_points([fi]))
+    res = eng.finish(h)
+    dbg = eng.debug_views(h)
+    fr = res["frames"][0]
+    # ---- the head's outputs
+    assert fr["pred_boxes"].shape == g["ref_boxes"].shape
+    assert np.array_equal(fr["pred_labels"], g["ref_labels"]) and np.array_equal(fr["pred_scores"], g["ref_scores"])
+    twins = 0
+    for k in range(g["ref_boxes"].shape[0]):
+        a, b = g["ref_boxes"][k], fr["pred_boxes"][k]
+        if np.all(np.abs(a - b) <= TOL * np.maximum(np.abs(a), 1.0)):
+            continue
+        d = a - b
+        assert abs(abs(d[6]) - np.pi) < 1e-5 and np.all(np.abs(d[:6]) <= 1e-4), (k, a, b)
+        twins += 1
+    assert twins <= max(1, g["ref_boxes"].shape[0] // 3)
+    # ---- per frustum, what went through the reference's two native call sites
+    scored = [f for f in range(plan["F"]) if res["cand_npts"][f] > 0 and res["cand_nvalid"][f] > 0]
+    assert len(scored) == int(g["n_frustums"])
+    stats = dict(hyp=0, counts_equal=0, max_count_diff=0, pts_bit_equal=0, pts=0)
+    T = eng.T
+    for k, f in enumerate(scored):
+        pts = g["f%d_points" % k]
+        p0, p1 = dbg["pt_start"][f], dbg["pt_start"][f + 1]
+        assert p1 - p0 == pts.shape[0]
+        ours = dbg["frustum_pts"][p0:p1, :3]
+        assert np.allclose(ours, pts, rtol=TOL, atol=1e-5)
+        stats["pts"] += pts.size
+        stats["pts_bit_equal"] += int((ours.view(np.uint32) == pts.view(np.uint32)).sum())
+        nv = int(res["cand_nvalid"][f])
+        boxes = g["f%d_boxes" % k]
+        assert nv == boxes.shape[0]
+        hb = dbg["hyp_boxes"][f][dbg["hyp_index"][f, :nv]]
+        assert np.allclose(hb, boxes, rtol=TOL, atol=1e-5)
+        first = g["f%d_first" % k]
+        cnt = np.bincount(first[first >= 0], minlength=nv)[:nv]
+        mine = dbg["counts"][f, :nv]
+        stats["hyp"] += nv
+        stats["counts_equal"] += int((cnt == mine).sum())
+        stats["max_count_diff"] = max(stats["max_count_diff"], int(np.abs(cnt - mine).max()))
+        assert mine.sum() <= pts.shape[0]
+        # the keep order of the reference (stable descending sort, nms_normal): our proposal slots hold its first T
+        keep = g["f%d_keep" % k][:T]
+        bests = res["cand_topk"]["best"][f] if T > 1 else np.array([res["cand_best"][f]])
+        score2 = res["cand_topk"]["score2"][f] if T > 1 else np.array([res["cand_score2"][f]])
+        sc = g["f%d_scores" % k]
+        assert int((bests >= 0).sum()) == len(keep)
+        for slot, kk in enumerate(keep):   # the same hypothesis, or one tied with it within the rounding of the scores
+            assert abs(float(sc[kk]) - float(score2[slot])) <= 1e-4, (f, slot, sc[kk], score2[slot])
+            if int(bests[slot]) != int(kk):
+                assert abs(float(sc[kk]) - float(sc[int(bests[slot])])) <= 1e-4, (f, slot, kk, bests[slot])
+    assert stats["counts_equal"] >= 0.97 * stats["hyp"] and stats["max_count_diff"] <= 3, stats
+    print("KITTI golden %s: %s, %d twins" % (os.path.basename(path), stats, twins))

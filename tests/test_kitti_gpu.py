@@ -100,9 +100,63 @@ def test_kitti_fused_stages_vs_reference_golden(path):
         score2 = res["cand_topk"]["score2"][f] if T > 1 else np.array([res["cand_score2"][f]])
         sc = g["f%d_scores" % k]
         assert int((bests >= 0).sum()) == len(keep)
+        # a point on a face that flips (last ulp of the CPU reference's points) moves a density by 1 / sum of the counts
+        stol = 1e-4 + 2.0 * float(np.abs(cnt - mine).max()) / max(float(cnt.sum()), 1.0)
+        # dists_ranked = 1 - (d - dmin) / (dmax - dmin + 1e-8): torch.cdist takes its matmul form above 25 rows, whose
+        # rounding is backend-defined (|a|^2 + |b|^2 - 2ab at 50 m: ~3e-4 m); a narrow range of distances amplifies it
+        st = dbg["stats"][f]
+        stol += min(1.0, 2.0 * 3e-4 / max(float(st[14] - st[13]), 1e-8)) * abs(float(params.get("dst_w", 0.226)))
         for slot, kk in enumerate(keep):   # the same hypothesis, or one tied with it within the rounding of the scores
-            assert abs(float(sc[kk]) - float(score2[slot])) <= 1e-4, (f, slot, sc[kk], score2[slot])
+            assert abs(float(sc[kk]) - float(score2[slot])) <= stol, (f, slot, sc[kk], score2[slot], stol)
             if int(bests[slot]) != int(kk):
-                assert abs(float(sc[kk]) - float(sc[int(bests[slot])])) <= 1e-4, (f, slot, kk, bests[slot])
+                assert abs(float(sc[kk]) - float(sc[int(bests[slot])])) <= stol, (f, slot, kk, bests[slot])
     assert stats["counts_equal"] >= 0.97 * stats["hyp"] and stats["max_count_diff"] <= 3, stats
     print("KITTI golden %s: %s, %d twins" % (os.path.basename(path), stats, twins))
+
+
+@pytest.mark.gpu
+def test_kitti_batch_of_frames_equals_frame_by_frame_and_head_contract():
+    """A batch of KITTI frames through the engine is the frames one by one, bit for bit (boxes, second-stage scores,
+    counts), whatever the order of a frustum's points; and proposer.FrustumProposerOGKITTI returns the reference head's
+    four outputs (frustum_proposals_v1_kitti.py:676-690: boxes on the GPU, labels / 2D scores / batch index on the CPU)
+    for a collated batch of two frames."""
+    from findnpropagate_b200 import proposer, synth
+    from findnpropagate_b200.seeker import KittiFrameInput, SeekerEngine
+    params = dict(nms_3d=0.0, score_thr=0.45, nms_2d=0.4, topk=2, nms_normal=0.6, num_mags=7, clamp_bottom=1)
+    raw = [synth.make_kitti_frame(i) for i in range(4)]
+    fis = [KittiFrameInput(points=f[0], P2=f[1]["P2"], R0=f[1]["R0"], V2C=f[1]["Tr_velo2cam"], det_boxes=f[2], det_labels=f[3],
+                           det_scores=f[4], device="cuda:0") for f in raw]
+    eng = SeekerEngine(params, device="cuda:0", box_format="xywh", variant="kitti")
+    whole = eng.run(fis)
+    n = 0
+    for b, fi in enumerate(fis):
+        one = eng.run([fi])
+        for k in ("pred_boxes", "pred_scores", "pred_labels"):
+            assert np.array_equal(one["frames"][0][k], whole["frames"][b][k]), (b, k)
+        n += one["frames"][0]["pred_boxes"].shape[0]
+    assert n >= 6
+
+    class Cal:
+        def __init__(self, d):
+            self.P2, self.R0, self.V2C = d["P2"], d["R0"], d["Tr_velo2cam"]
+
+    class Feeder:
+        def __call__(self, bd):
+            boxes = np.concatenate([raw[0][2], raw[1][2]])
+            labels = np.concatenate([raw[0][3], raw[1][3]])
+            scores = np.concatenate([raw[0][4], raw[1][4]])
+            bidx = np.concatenate([np.zeros(len(raw[0][2]), np.int64), np.ones(len(raw[1][2]), np.int64)])
+            return (torch.from_numpy(boxes), torch.from_numpy(labels), torch.from_numpy(scores), torch.from_numpy(bidx),
+                    torch.zeros(len(bidx), dtype=torch.long))
+    head = proposer.FrustumProposerOGKITTI(model_cfg=dict(PARAMS=params), image_detector=Feeder(), device="cuda:0")
+    pts = np.concatenate([np.c_[np.full(len(raw[b][0]), b, np.float32), raw[b][0]] for b in range(2)])
+    bd = dict(batch_size=2, calib=[Cal(raw[0][1]), Cal(raw[1][1])], points=torch.from_numpy(pts).cuda())
+    boxes, labels, scores, bidx = head.get_proposals(bd)
+    assert boxes.is_cuda and boxes.dtype == torch.float32 and not labels.is_cuda and labels.dtype == torch.int64
+    assert scores.dtype == torch.float32 and bidx.dtype == torch.int64
+    for b in range(2):
+        m = (bidx == b).numpy()
+        assert np.array_equal(boxes.cpu().numpy()[m], whole["frames"][b]["pred_boxes"])
+        assert np.array_equal(labels.numpy()[m], whole["frames"][b]["pred_labels"].astype(np.int64))
+    out = head.forward(dict(bd))
+    assert len(out["final_box_dicts"]) == 2 and out["final_box_dicts"][0]["pred_labels"].dtype == torch.int32

@@ -158,5 +158,6 @@ def test_kitti_batch_of_frames_equals_frame_by_frame_and_head_contract():
         m = (bidx == b).numpy()
         assert np.array_equal(boxes.cpu().numpy()[m], whole["frames"][b]["pred_boxes"])
         assert np.array_equal(labels.numpy()[m], whole["frames"][b]["pred_labels"].astype(np.int64))
+    head.eval()                      # forward asserts it, as the reference does (:714)
     out = head.forward(dict(bd))
     assert len(out["final_box_dicts"]) == 2 and out["final_box_dicts"][0]["pred_labels"].dtype == torch.int32

@@ -63,6 +63,10 @@ def resolve_params(params: Optional[dict], variant: str = "nuscenes") -> dict:
     p.update({k: False for k in FLAG_KEYS})
     if params:
         p.update(params)
+    # rand_center (:844-847; frustum_proposals_v1_kitti.py:568-571): the hypothesis centres of a frustum are
+    # weighted_centre_xyz + torch.randn((num_mags, 3)) drawn from the device's default generator, one draw per frustum
+    # with points, in frustum order -- reproduced draw for draw (same generator, same shapes, same order), so a run
+    # seeded like the reference's gives the reference's centres.
     unsupported = []
     if int(p["topk"]) < 1:
         unsupported.append("topk < 1")
@@ -70,8 +74,8 @@ def resolve_params(params: Optional[dict], variant: str = "nuscenes") -> dict:
         unsupported.append("nms_3d != 0 (the reference asserts it too, :209)")
     if p.get("aln_w"):
         unsupported.append("aln_w (torch.pca_lowrank draws a random projection: not reproducible in the reference)")
-    if p.get("rand_center"):
-        unsupported.append("rand_center (torch.randn centres: not reproducible in the reference)")
+    if p.get("rand_center") and int(p["num_mags"]) < 1:
+        unsupported.append("rand_center with num_mags < 1")
     if p["search_depth"] is not None and not p["search_depth"] > 0:
         unsupported.append("search_depth <= 0")
     if variant == "kitti":
@@ -297,12 +301,16 @@ class SeekerEngine:
             variant=_lib.VARIANT_KITTI if variant == "kitti" else _lib.VARIANT_NUSCENES)
         self.T = int(self.p["topk"])       # proposal slots per candidate frustum (NMS order), :1040-1046
         # workspaces of the optional score terms (include/fnp.h: hyp_dist, hyp_nfar)
-        self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"]) or variant == "kitti"   # that head always ranks distances
+        self.rand_center = bool(self.p.get("rand_center"))
+        # the KITTI head always ranks distances; rand_center needs the weighted centre, which rides on the same workspace
+        self.use_dist = self.cfg.dst_w != 0 or bool(self.p["MULT"]) or variant == "kitti" or self.rand_center
         self.use_occl = self.cfg.occl_w > 0 or bool(self.p["OCCL_MULT"])
         self.arena = _Arena(self.device)
         self.fixed_split_points = split_points
         # "auto" | "direct" | "sweep": which stage-2b kernel counts the points (same counts either way)
         self.score_mode = {"auto": _lib.SCORE_AUTO, "direct": _lib.SCORE_DIRECT, "sweep": _lib.SCORE_SWEEP}[score_mode]
+        if self.rand_center:      # random centres are no line: the depth sweep would only take exact predicates
+            self.score_mode = _lib.SCORE_DIRECT
         self.last_score_mode = None
         # MODEL.DENSE_HEAD.BOX_FORMAT (frustum_proposals_v1.py:252,597-601): 'xyxy', anything else means
         # x, y, w, h -- the 2D NMS runs on the raw numbers (as in the reference), the corner x+w, y+h is
@@ -618,8 +626,12 @@ class SeekerEngine:
                 counts=ptr["counts"], score_mode=self.score_mode, sweep_cols=ptr["sweep_cols"],
                 out_boxes=o_boxes, out_score=o_score, out_best=o_best, out_count=o_count, status=o_status,
                 hyp_dist=ptr.get("hyp_dist"), hyp_nfar=ptr.get("hyp_nfar"), hyp_score=ptr.get("hyp_score"))
-            rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
-            _lib.check(rc, "fnp_seeker_run")
+            if self.rand_center and F and plan["n_tiles"]:
+                self._run_rand_center(b, stream, F, M, out_dev[40 * FT:40 * FT + 4 * F].view(torch.int32),
+                                      self.arena.bufs["cand_stats" + sfx], self.arena.bufs["centres" + sfx])
+            else:
+                rc = _lib.lib.fnp_seeker_run(C.byref(self.cfg), C.byref(b), stream)
+                _lib.check(rc, "fnp_seeker_run")
             mode = _lib.lib.fnp_seeker_score_mode(C.byref(self.cfg), C.byref(b))
             self.last_score_mode = {_lib.SCORE_DIRECT: "direct", _lib.SCORE_SWEEP: "sweep"}.get(mode)
             self.launches += (9 + (mode == _lib.SCORE_SWEEP) + self.use_occl) if F and plan["n_tiles"] else 0
@@ -720,6 +732,23 @@ class SeekerEngine:
             for j, k in enumerate(RECALL_PER_THRESH):
                 d["%s_%s" % (k, th)] = int(counters[5 + 5 * t + j])
         return d
+
+    def _run_rand_center(self, b, stream, F, M, npts_dev, stats_buf, centres_buf):
+        """The stages one by one, with the reference's random centres put in between (rand_center): after stage 1b the
+        population and the weighted centre of every frustum are known; the host then draws torch.randn((M, 3)) per
+        frustum WITH points, in frustum order, exactly as frustum_proposals_v1.py:844-847 does, and overwrites the
+        centre line.  One device round trip per batch: an option for experiments, not for throughput."""
+        L, cfg = _lib.lib, C.byref(self.cfg)
+        _lib.check(L.fnp_seeker_cull(cfg, C.byref(b), stream), "fnp_seeker_cull")
+        _lib.check(L.fnp_seeker_frustum_stats(cfg, C.byref(b), stream), "fnp_seeker_frustum_stats")
+
+        npts = npts_dev.cpu().numpy()                                                   # synchronises
+        stats = stats_buf[:4 * F * _lib.STATS_FLOATS].view(torch.float32).view(F, _lib.STATS_FLOATS)
+        centres = centres_buf[:12 * F * M].view(torch.float32).view(F, M, 3)
+        for f in np.flatnonzero(npts > 0):
+            centres[f] = stats[f, 10:13].reshape(1, 3) + torch.randn((M, 3), dtype=torch.float32, device=self.device)
+        for name in ("fnp_seeker_hypotheses", "fnp_seeker_score", "fnp_seeker_occlusion", "fnp_seeker_select"):
+            _lib.check(getattr(L, name)(cfg, C.byref(b), stream), name)
 
     def run(self, frames: List[FrameInput], points_dev=None, nms_thresh=None, with_recall=False, xyz_offset=0):
         """Plan + H2D + execute + finish for a list of frames; grows the frustum-point

@@ -105,7 +105,7 @@ def test_unsupported_options_raise():
     from findnpropagate_b200 import seeker
     with pytest.raises(NotImplementedError):
         seeker.resolve_params(dict(topk=0, nms_3d=0, dst_w=0))
-    for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(nms_3d=0.5), dict(search_depth=0.0)):
+    for bad in (dict(aln_w=0.1), dict(nms_3d=0.5), dict(search_depth=0.0)):
         with pytest.raises(NotImplementedError):
             seeker.resolve_params(dict(dict(nms_3d=0), **bad))
     # the optional terms of SURVEY.md 8 row f3 are accepted

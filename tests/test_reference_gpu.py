@@ -288,3 +288,82 @@ def test_kitti_head_fused_stages_vs_reference_head(ref, override):
         total += a.shape[0]
     assert total >= 4 and twins <= total // 3, (total, twins)
     print("KITTI fused stages vs reference head: %d proposals over %d frames, %d yaw twins" % (total, len(frames), twins))
+
+
+def _boxes_close_modulo_twins(a, b):
+    twins = 0
+    assert a.shape == b.shape, (a.shape, b.shape)
+    for k in range(a.shape[0]):
+        if np.all(np.abs(a[k] - b[k]) <= TOL * np.maximum(np.abs(a[k]), 1.0)):
+            continue
+        d = a[k] - b[k]
+        assert abs(abs(d[6]) - np.pi) < 1e-5 and np.all(np.abs(d[:6]) <= 1e-4), (k, a[k], b[k])
+        twins += 1
+    return twins
+
+
+def test_rand_center_reproduces_the_reference_draw_for_draw(ref):
+    """PARAMS rand_center (frustum_proposals_v1.py:844-847): the hypothesis centres of a frustum are weighted_centre_xyz +
+    torch.randn((num_mags, 3)) from the device's default generator.  The engine draws the same shapes from the same
+    generator in the same order (one draw per frustum with points, frustum order), so seeded like the reference it forms
+    the reference's centres: identical K / labels / scores, boxes within 1e-5 modulo yaw twins, on the reference's own
+    head run on this GPU -- nuScenes head and KITTI head."""
+    import contextlib
+    import io
+    import sys as _sys
+    from findnpropagate_b200 import proposer
+    cfg = synth.CONFIGS["cfg1"]
+    params = dict(synth.seeker_params(cfg), rand_center=True, num_mags=6)
+    total = twins = 0
+    for i in (0, 1):
+        fr = synth.make_frame(i, cfg)
+        torch.manual_seed(1234 + i)
+        with contextlib.redirect_stdout(io.StringIO()):
+            rb, rl, rs, _, _, _ = ref.run([fr], params, capture=False, device="cuda")
+        head = proposer.FrustumProposerOG(model_cfg=dict(PARAMS=params), image_detector=proposer.SyntheticGLIP([fr]), device="cuda:0")
+        bd = synth.collate([fr])
+        for k, v in list(bd.items()):
+            if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+                bd[k] = torch.from_numpy(v).float().cuda()
+        torch.manual_seed(1234 + i)
+        ob, ol, os_, _ = head.get_proposals(bd)
+        assert np.array_equal(rl, ol.numpy()) and np.array_equal(rs, os_.numpy())
+        twins += _boxes_close_modulo_twins(rb, ob.cpu().numpy())
+        total += rb.shape[0]
+    assert total >= 6 and twins <= total // 3
+    # the reference draws anew on every call: another seed gives other boxes (the option is live)
+    torch.manual_seed(99)
+    ob2 = head.get_proposals(bd)[0].cpu().numpy()
+    assert ob2.shape != ob.shape or not np.allclose(ob2, ob.cpu().numpy(), atol=1e-3)
+
+    # ---- the KITTI head (frustum_proposals_v1_kitti.py:568-571)
+    mod = ref.load("cuda", head_file="frustum_proposals_v1_kitti.py")
+    Calibration = _sys.modules["pcdet.utils.calibration_kitti"].Calibration
+    state = {}
+
+    class Feeder:
+        def __call__(self, bd):
+            pts, calib, boxes, labels, scores = state["frame"]
+            z = torch.zeros(len(boxes), dtype=torch.long)
+            return torch.from_numpy(boxes.copy()), torch.from_numpy(labels), torch.from_numpy(scores), z, z.clone()
+    mod.PreprocessedDetector = lambda paths, class_names=None: Feeder()
+    kp = dict(nms_3d=0.0, score_thr=0.45, nms_2d=0.4, rand_center=True, num_mags=8, clamp_bottom=1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        khead = mod.FrustumProposerOGKITTI(model_cfg=ref.AttrDict(PARAMS=kp, PREDS_PATH="unused.json"), class_names=None)
+    khead.eval()
+    ours = proposer.FrustumProposerOGKITTI(model_cfg=dict(PARAMS=kp), image_detector=Feeder(), device="cuda:0")
+    ktotal = ktwins = 0
+    for i in (0, 1):
+        fr = synth.make_kitti_frame(i)
+        state["frame"] = fr
+        pts = torch.from_numpy(np.c_[np.zeros(len(fr[0]), np.float32), fr[0]]).cuda()
+        torch.manual_seed(77 + i)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            r = [o.cpu() for o in khead.get_proposals(dict(batch_size=1, calib=[Calibration(fr[1])], points=pts))]
+        torch.manual_seed(77 + i)
+        o = [x.cpu() for x in ours.get_proposals(dict(batch_size=1, calib=[Calibration(fr[1])], points=pts))]
+        assert torch.equal(r[1], o[1]) and torch.equal(r[2], o[2])
+        ktwins += _boxes_close_modulo_twins(r[0].numpy(), o[0].numpy())
+        ktotal += r[0].shape[0]
+    assert ktotal >= 2 and ktwins <= max(1, ktotal // 3)
+    print("rand_center: nuScenes head %d proposals (%d twins), KITTI head %d proposals (%d twins)" % (total, twins, ktotal, ktwins))

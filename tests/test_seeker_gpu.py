@@ -595,7 +595,7 @@ def test_optional_score_terms_full_size_frame():
 
 
 def test_unsupported_options_raise():
-    for bad in (dict(aln_w=0.1), dict(rand_center=True), dict(topk=0), dict(nms_3d=0.5), dict(search_depth=0.0)):
+    for bad in (dict(aln_w=0.1), dict(topk=0), dict(nms_3d=0.5), dict(search_depth=0.0)):
         with pytest.raises(NotImplementedError):
             SeekerEngine(dict(synth.seeker_params(synth.CONFIGS["tiny"]), **bad), device="cuda:0")
 

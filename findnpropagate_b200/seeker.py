@@ -73,7 +73,8 @@ def resolve_params(params: Optional[dict], variant: str = "nuscenes") -> dict:
     if p["nms_3d"] != 0:
         unsupported.append("nms_3d != 0 (the reference asserts it too, :209)")
     if p.get("aln_w"):
-        unsupported.append("aln_w (torch.pca_lowrank draws a random projection: not reproducible in the reference)")
+        unsupported.append("aln_w (it cannot run in the reference either: frustum_proposals_v1.py:987 indexes the (P,3) points "
+                           "with a (1,P) mask and raises IndexError as soon as a hypothesis holds more than 3 points)")
     if p.get("rand_center") and int(p["num_mags"]) < 1:
         unsupported.append("rand_center with num_mags < 1")
     if p["search_depth"] is not None and not p["search_depth"] > 0:

@@ -264,3 +264,20 @@ def test_shipped_yaml_params_equal_the_hard_coded_ones():
     full = resolve_params(shipped)
     assert (full["num_mags"], full["num_rotations"], full["num_sizes"]) == (cfg1.num_mags, cfg1.num_rotations, cfg1.num_sizes)
     assert full["max_dist"] == 50 and full["topk"] == 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pcdet"), reason="needs the reference tree (build container only)")
+def test_aln_w_raises_in_the_reference_itself():
+    """PARAMS aln_w is refused by this build (seeker.resolve_params) because it cannot run in the reference:
+    frustum_proposals_v1.py:987 indexes the (P,3) frustum points with a (1,P) mask.  The reference head (CPU run of
+    tools/ref_seeker.py, own process: it registers the reference modules globally) raises IndexError."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]\n"
+            "import ref_seeker\nfrom findnpropagate_b200 import synth\n"
+            "cfg = synth.CONFIGS['tiny']\n"
+            "try:\n    ref_seeker.run([synth.make_frame(0, cfg)], dict(synth.seeker_params(cfg), aln_w=0.1), capture=False)\n"
+            "    print('RAN')\nexcept IndexError as e:\n    print('INDEXERROR', e)\n") % (
+        os.path.join(ROOT, "tools"), ROOT, os.path.join(ROOT, "oracle"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300).stdout
+    assert "INDEXERROR" in out and "shape of the mask" in out, out

@@ -79,6 +79,17 @@ def lib():
         L.fnp_o_hypotheses_ex.restype = None
         L.fnp_o_hypotheses_ex.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _f, _f, _f, _f,
                                           C.c_int, _fp, _fp, _fp, _fp, _fp, _bp, _bp, _fp]
+        L.fnp_o_project_kitti.restype = None
+        L.fnp_o_project_kitti.argtypes = [_fp, _f, _f, _f, _fp]
+        L.fnp_o_unproject_kitti.restype = None
+        L.fnp_o_unproject_kitti.argtypes = [_fp, _f, _f, _f, C.c_int, _fp]
+        L.fnp_o_frustum_cull_kitti.restype = C.c_int
+        L.fnp_o_frustum_cull_kitti.argtypes = [_fp, C.c_int, C.c_int, _fp, _fp, _ip, _fp, _fp]
+        L.fnp_o_centre_line_kitti.restype = None
+        L.fnp_o_centre_line_kitti.argtypes = [_fp, _f, _f, _fp, _fp, _fp, C.c_int, _fp, C.c_int, _f, _fp, _fp]
+        L.fnp_o_hypotheses_kitti.restype = None
+        L.fnp_o_hypotheses_kitti.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _f, _f, _f, _f, _fp,
+                                             _fp, _fp, _bp, _bp, _fp]
         L.fnp_o_occl_fail.restype = None
         L.fnp_o_occl_fail.argtypes = [C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _ip]
         L.fnp_o_select_ex.restype = C.c_int
@@ -327,3 +338,50 @@ def select(counts, iou, valid, dns_w=1.0, iou_w=1.0):
     h = lib().fnp_o_select(_p(counts, _ip), _p(iou), _p(valid, _bp), counts.shape[0],
                            np.float32(dns_w), np.float32(iou_w), C.byref(s))
     return h, np.float32(s.value)
+
+
+# ---------------------------------------------------------------- KITTI head (FrustumProposerOGKITTI)
+def frustum_cull_kitti(points, K, box2d):
+    """points (N,>=3), K (48,) calibration block -> idx (P,), uvd (P,3), xyz (P,3) of the points inside the 2D box
+    (no on-image test in that head)."""
+    points = _f32(points)
+    K, box2d = _f32(K).reshape(-1), _f32(box2d).reshape(-1)
+    N = points.shape[0]
+    idx = np.empty((N,), np.int32)
+    uvd = np.empty((N, 3), np.float32)
+    xyz = np.empty((N, 3), np.float32)
+    n = lib().fnp_o_frustum_cull_kitti(_p(points), N, points.shape[1], _p(K), _p(box2d), _p(idx, _ip), _p(uvd), _p(xyz))
+    return idx[:n].copy(), uvd[:n].copy(), xyz[:n].copy()
+
+
+def unproject_kitti(K, u, v, d, chain=False):
+    K = _f32(K).reshape(-1)
+    out = np.empty(3, np.float32)
+    lib().fnp_o_unproject_kitti(_p(K), np.float32(u), np.float32(v), np.float32(d), int(chain), _p(out))
+    return out
+
+
+def centre_line_kitti(box2d, dmin, dmax, K, pmin, pmax, clamp_bottom, mags, search_depth=None):
+    box2d, K, pmin, pmax, mags = (_f32(x).reshape(-1) for x in (box2d, K, pmin, pmax, mags))
+    M = mags.shape[0]
+    centres = np.empty((M, 3), np.float32)
+    corners = np.empty((8, 3), np.float32)
+    lib().fnp_o_centre_line_kitti(_p(box2d), np.float32(dmin), np.float32(dmax), _p(K), _p(pmin), _p(pmax),
+                                  int(clamp_bottom), _p(mags), M, np.float32(search_depth or 0.0), _p(centres), _p(corners))
+    return centres, corners
+
+
+def hypotheses_kitti(base_boxes, base_corners, centres, K, box2d, max_dist, min_iou, wc, img_w=1600.0, img_h=900.0):
+    base_boxes, base_corners, centres = _f32(base_boxes), _f32(base_corners), _f32(centres)
+    K, box2d, wcv = _f32(K).reshape(-1), _f32(box2d).reshape(-1), _f32(wc).reshape(-1)
+    J, M = base_boxes.shape[0], centres.shape[0]
+    H = J * M
+    boxes = np.empty((H, 7), np.float32)
+    iou = np.empty((H,), np.float32)
+    valid = np.empty((H,), np.uint8)
+    near = np.empty((H,), np.uint8)
+    dist = np.zeros((H,), np.float32)
+    lib().fnp_o_hypotheses_kitti(_p(base_boxes), _p(base_corners), J, _p(centres), M, _p(K), _p(box2d), img_w, img_h,
+                                 np.float32(max_dist), np.float32(min_iou), _p(wcv), _p(boxes), _p(iou), _p(valid, _bp),
+                                 _p(near, _bp), _p(dist))
+    return boxes, iou, valid.astype(bool), near.astype(bool), dist

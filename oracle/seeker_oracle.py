@@ -184,6 +184,103 @@ def seek_frame(points, lidar2image, camera2lidar, camera_intrinsics, dets, param
         frustums=inter)
 
 
+ANCHORS_KITTI = [[3.9, 1.6, 1.56], [6.37, 2.85, 3.19], [6.93, 2.51, 2.84], [6.93, 2.51, 2.84], [0.8, 0.6, 1.73],
+                 [1.76, 0.6, 1.73], [0.8, 0.6, 1.73]]      # frustum_proposals_v1_kitti.py:157-166
+
+
+def build_tables_kitti(params):
+    """The KITTI head's constructor tables (frustum_proposals_v1_kitti.py:167-183): the same torch calls as
+    build_tables over its seven anchors."""
+    global ANCHORS
+    saved, ANCHORS = ANCHORS, ANCHORS_KITTI
+    try:
+        return build_tables(dict(dict(max_dist=70), **params))
+    finally:
+        ANCHORS = saved
+
+
+def kitti_block(P2, R0, V2C):
+    """The 48-float calibration block of a KITTI frame (include/fnp.h, FNP_VARIANT_KITTI), formed with the calls
+    CalibrationTorch makes (calibration_kitti.py:128-169) -- on the host here; the GPU tests pass the block the engine
+    formed on the device, so that both sides read the same numbers."""
+    P2, R0, V2C = (torch.as_tensor(np.asarray(x, np.float32)) for x in (P2, R0, V2C))
+    m1 = V2C.T @ R0.T
+    cu, cv, fu, fv = P2[0, 2], P2[1, 2], P2[0, 0], P2[1, 1]
+    tx, ty = P2[0, 3] / (-fu), P2[1, 3] / (-fv)
+    r0e = torch.cat((torch.cat((R0, R0.new_zeros((3, 1))), dim=1), R0.new_zeros((1, 4))), dim=0)
+    r0e[3, 3] = 1
+    v2ce = torch.cat((V2C, V2C.new_zeros((1, 4))), dim=0)
+    v2ce[3, 3] = 1
+    minv = torch.inverse(torch.matmul(r0e, v2ce).T)
+    out = np.zeros(48, np.float32)
+    out[0:12] = m1.reshape(-1).numpy()
+    out[12:24] = P2.T.reshape(-1).numpy()
+    out[24:30] = torch.stack((cu, cv, fu, fv, tx, ty)).numpy()
+    out[32:48] = minv.reshape(-1).numpy()
+    return out
+
+
+def seek_frame_kitti(points, K, dets, params, tables=None, keep_intermediates=False):
+    """One frame of FrustumProposerOGKITTI.get_proposals (frustum_proposals_v1_kitti.py:292-690) restated on the C
+    oracle.  points (N,>=3) xyz first; K (48,) calibration block (kitti_block, or the engine's); dets = (boxes x-y-w-h,
+    labels 1..7, scores).  Differences from seek_frame: CalibrationTorch's projection without an on-image test, ONE
+    batched first-match points_in_boxes_gpu per frustum (:644-648), densities over their sum, score = dns_w + density +
+    iou_w iou + dst_w dists_ranked (:650-654), nms_normal + topk (:657-671)."""
+    p = dict(DEFAULTS); p.update(max_dist=70); p.update(params)
+    assert p["nms_3d"] == 0 and not p.get("rand_center")
+    topk = int(p["topk"])
+    dns_w, iou_w, dst_w = np.float32(p["dns_w"]), np.float32(p["iou_w"]), np.float32(p["dst_w"])
+    sdepth = p.get("search_depth")
+    base_boxes, base_corners = tables if tables is not None else build_tables_kitti(p)
+    mags = torch.linspace(0.0, 1.0, p["num_mags"]).numpy() if p["num_mags"] > 0 else np.zeros(1, np.float32)
+    max_dist = np.float32(p["max_dist"])
+    pts = np.ascontiguousarray(points, np.float32)
+    boxes2d, labels, scores = dets
+    cands = nms2d_candidates(boxes2d, labels, scores, np.zeros(len(scores), np.int64), p["nms_2d"], p["score_thr"], "xywh")
+    boxes_out, labels_out, scores_out, inter = [], [], [], []
+    for (c, box2d, label, score) in cands:
+        idx, uvd, xyz = O.frustum_cull_kitti(pts, K, box2d)
+        rec = dict(cam=c, box2d=box2d, label=label, score=score, n_points=int(idx.shape[0]))
+        if idx.shape[0] == 0:                       # :399-401
+            if keep_intermediates:
+                inter.append(rec)
+            continue
+        d = uvd[:, 2]
+        qmin = O.quantile(d, p["lq"])
+        qmax = O.quantile(d, p["uq"]) if sdepth is None else np.float32(qmin + np.float32(sdepth))
+        dmin = np.maximum(qmin, FRUSTUM_MIN)
+        dmax = np.minimum(qmax, max_dist)
+        # weighted_centre_xyz (:392-395): one row through rect_to_lidar -- the small-matrix rounding
+        wc = O.unproject_kitti(K, (box2d[0] + box2d[2]) / np.float32(2), (box2d[1] + box2d[3]) / np.float32(2),
+                               O.quantile(d, p["cq"]), chain=False)
+        centres, corners = O.centre_line_kitti(box2d, dmin, dmax, K, xyz.min(0), xyz.max(0), p["clamp_bottom"], mags,
+                                               search_depth=sdepth)
+        hb, iou, valid, near, dist = O.hypotheses_kitti(base_boxes[label - 1], base_corners[label - 1], centres, K, box2d,
+                                                        max_dist, p["min_cam_iou"], wc)
+        counts = np.zeros(hb.shape[0], np.int32)
+        sc = np.zeros(hb.shape[0], np.float32)
+        vi = np.flatnonzero(valid)
+        order = np.zeros(0, np.int64)
+        if vi.size:
+            first = O.points_in_boxes_gpu(xyz[None], hb[vi][None])[0]
+            counts[vi] = np.bincount(first[first >= 0], minlength=vi.size)[:vi.size]
+            cnt = counts[vi].astype(np.float32)
+            dens = cnt / np.float32(cnt.sum(dtype=np.float32) + np.float32(1e-8))
+            dn = dist[near]                          # dists_ranked is normalised over the hypotheses within max_dist (:620-622)
+            dr = np.float32(1) - (dist[vi] - dn.min()) / np.float32((dn.max() - dn.min()) + np.float32(1e-8))
+            sc[vi] = ((dns_w + dens) + iou_w * iou[vi]) + dr * dst_w
+            order = vi[O.nms_normal(hb[vi], sc[vi], p["nms_normal"])[:topk]]
+        rec.update(idx=idx, uvd=uvd, xyz=xyz, dmin=dmin, dmax=dmax, wc=wc, centres=centres, corners=corners, hyp_boxes=hb,
+                   iou=iou, valid=valid, near=near, dist=dist, counts=counts, scores=sc, topk=order,
+                   best=int(order[0]) if order.size else -1)
+        if keep_intermediates:
+            inter.append(rec)
+        for hh in order:
+            boxes_out.append(hb[hh]); labels_out.append(label); scores_out.append(score)
+    return dict(pred_boxes=np.asarray(boxes_out, np.float32).reshape(-1, 7), pred_labels=np.asarray(labels_out, np.int32),
+                pred_scores=np.asarray(scores_out, np.float32), frustums=inter)
+
+
 def recall_record(pred_boxes, gt_boxes, thresh_list=(0.3, 0.5, 0.7)):
     """Detector3DTemplate.generate_recall_record restated
     (pcdet/models/detectors/detector3d_template.py:315-399) for one frame; returns the

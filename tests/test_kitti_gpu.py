@@ -18,6 +18,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "kitti_*.npz")))
 TOL = 1e-5
@@ -41,6 +42,107 @@ def test_kitti_prior_tables_equal_the_reference_constructor(path):
     for bad in (dict(ego_w=0.2), dict(occl_w=0.1), dict(MULT=True)):
         with pytest.raises(NotImplementedError):
             seeker.resolve_params(dict(json.loads(str(g["params"])), **bad), "kitti")
+
+
+def _twins(a, b):
+    n = 0
+    assert a.shape == b.shape, (a.shape, b.shape)
+    for k in range(a.shape[0]):
+        if np.all(np.abs(a[k] - b[k]) <= TOL * np.maximum(np.abs(a[k]), 1.0)):
+            continue
+        d = a[k] - b[k]
+        assert abs(abs(d[6]) - np.pi) < 1e-5 and np.all(np.abs(d[:6]) <= 1e-4), (k, a[k], b[k])
+        n += 1
+    return n
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_kitti_oracle_vs_reference_golden(path):
+    """The CPU oracle of the KITTI variant (oracle/seeker_oracle.seek_frame_kitti on fnp_oracle.c: fnp_o_project_kitti,
+    fnp_o_unproject_kitti, fnp_o_frustum_cull_kitti, fnp_o_centre_line_kitti, fnp_o_hypotheses_kitti) against what the
+    reference's own KITTI head produced: K / labels / 2D scores identical, boxes within 1e-5 modulo yaw twins; per
+    scored frustum the same points and valid hypotheses (1e-5) and the same first-match counts."""
+    import seeker_oracle as SO
+    g = np.load(path)
+    params = json.loads(str(g["params"]))
+    K = SO.kitti_block(g["P2"], g["R0"], g["V2C"])
+    o = SO.seek_frame_kitti(g["points"], K, (g["det_boxes"], g["det_labels"], g["det_scores"]), params, keep_intermediates=True)
+    assert np.array_equal(o["pred_labels"], g["ref_labels"]) and np.array_equal(o["pred_scores"], g["ref_scores"])
+    assert _twins(g["ref_boxes"], o["pred_boxes"]) <= max(1, g["ref_boxes"].shape[0] // 3)
+    scored = [r for r in o["frustums"] if r["n_points"] > 0 and r["valid"].any()]
+    assert len(scored) == int(g["n_frustums"])
+    for k, r in enumerate(scored):
+        assert np.allclose(r["xyz"], g["f%d_points" % k], rtol=TOL, atol=1e-5)
+        assert np.allclose(r["hyp_boxes"][r["valid"]], g["f%d_boxes" % k], rtol=TOL, atol=1e-5)
+        first = g["f%d_first" % k]
+        nv = int(r["valid"].sum())
+        assert np.array_equal(r["counts"][r["valid"]], np.bincount(first[first >= 0], minlength=nv)[:nv])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,override", [(0, None), (1, None), (3, dict(topk=3, nms_normal=0.5, num_mags=12, clamp_bottom=1)),
+                                            (5, dict(lq=0.1, uq=0.6, cq=0.5, search_depth=6.0, num_rotations=7))])
+def test_kitti_fused_stages_bit_exact_vs_oracle(seed, override):
+    """Every intermediate of the KITTI variant against the CPU oracle on the calibration block the engine formed on the
+    device: frustum membership (as ordered index lists), the unprojected points and depths, dmin / dmax, weighted centre,
+    frustum corners, centre line, hypothesis boxes / IoU / validity / distances, first-match counts, second-stage
+    scores, proposal slots and the head's outputs -- bit for bit."""
+    import seeker_oracle as SO
+    from findnpropagate_b200 import synth
+    from findnpropagate_b200.seeker import KittiFrameInput, SeekerEngine
+    params = dict(nms_3d=0.0, score_thr=0.45, nms_2d=0.4)
+    if override:
+        params.update(override)
+    raw = [synth.make_kitti_frame(seed + i) for i in range(2)]
+    fis = [KittiFrameInput(points=f[0], P2=f[1]["P2"], R0=f[1]["R0"], V2C=f[1]["Tr_velo2cam"], det_boxes=f[2], det_labels=f[3],
+                           det_scores=f[4], device="cuda:0") for f in raw]
+    eng = SeekerEngine(params, device="cuda:0", debug=True, box_format="xywh", variant="kitti")
+    plan = eng.plan(fis)
+    h = eng.execute(plan, eng.upload_points(fis))
+    res = eng.finish(h)
+    dbg = eng.debug_views(h)
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    T, fcs, n_checked = eng.T, plan["frame_cand_start"], 0
+    tables = (eng.base_boxes_host.numpy(), eng.base_corners_host.numpy())
+    for b, f in enumerate(raw):
+        K = plan["cam_mats"][b].reshape(-1)[:48].copy()
+        ora = SO.seek_frame_kitti(f[0], K, (f[2], f[3], f[4]), params, tables=tables, keep_intermediates=True)
+        assert len(ora["frustums"]) == fcs[b + 1] - fcs[b]
+        for j, rec in enumerate(ora["frustums"]):
+            fi = fcs[b] + j
+            assert res["cand_npts"][fi] == rec["n_points"]
+            if rec["n_points"] == 0:
+                continue
+            p0, p1 = dbg["pt_start"][fi], dbg["pt_start"][fi + 1]
+            assert np.array_equal(dbg["frustum_idx"][p0:p1], rec["idx"])
+            assert np.array_equal(bits(dbg["frustum_pts"][p0:p1, :3]), bits(rec["xyz"]))
+            assert np.array_equal(bits(dbg["frustum_pts"][p0:p1, 3]), bits(rec["uvd"][:, 2]))
+            st = dbg["stats"][fi]
+            assert st[0].tobytes() == np.float32(rec["dmin"]).tobytes() and st[1].tobytes() == np.float32(rec["dmax"]).tobytes()
+            assert np.array_equal(bits(st[10:13]), bits(rec["wc"]))
+            assert np.array_equal(bits(st[16:40].reshape(8, 3)), bits(rec["corners"]))
+            assert np.array_equal(bits(dbg["centres"][fi]), bits(rec["centres"]))
+            assert np.array_equal(dbg["hyp_valid"][fi], rec["valid"])
+            assert np.array_equal(bits(dbg["hyp_boxes"][fi]), bits(rec["hyp_boxes"]))
+            assert np.array_equal(bits(dbg["hyp_iou"][fi]), bits(rec["iou"]))
+            nv = int(rec["valid"].sum())
+            assert res["cand_nvalid"][fi] == nv
+            vi = np.flatnonzero(rec["valid"])
+            assert np.array_equal(dbg["hyp_index"][fi, :nv], vi)
+            assert np.array_equal(bits(dbg["hyp_dist"][fi, :nv]), bits(rec["dist"][vi]))
+            assert np.array_equal(dbg["counts"][fi, :nv], rec["counts"][vi])
+            bests = res["cand_topk"]["best"][fi] if T > 1 else np.array([res["cand_best"][fi]])
+            score2 = res["cand_topk"]["score2"][fi] if T > 1 else np.array([res["cand_score2"][fi]])
+            want = list(rec["topk"])
+            assert int((bests >= 0).sum()) == len(want)
+            for slot, hh in enumerate(want):
+                assert int(dbg["hyp_index"][fi, int(bests[slot])]) == int(hh)
+                assert np.float32(score2[slot]).tobytes() == np.float32(rec["scores"][hh]).tobytes()
+            n_checked += 1
+        fr = res["frames"][b]
+        assert np.array_equal(bits(fr["pred_boxes"]), bits(ora["pred_boxes"]))
+        assert np.array_equal(fr["pred_labels"], ora["pred_labels"]) and np.array_equal(fr["pred_scores"], ora["pred_scores"])
+    assert n_checked >= 4
 
 
 @pytest.mark.gpu

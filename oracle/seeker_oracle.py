@@ -6,6 +6,7 @@ pcdet/models/dense_heads/frustum_proposals_v1.py:523-1067) on top of the C oracl
 tools/cfgs/nuscenes_box_seeker_proposals.yaml:83 (no img/lidar augmentation, nms_3d = 0),
 plus the optional terms of SURVEY.md 8 row f3: dst_w, ego_w, occl_w, search_depth and the flags
 MULT, OCCL_MULT, MULTICAM_IOU (passed as keys of `params`), topk > 1 with nms_normal.
+seek_frame_kitti restates FrustumProposerOGKITTI.get_proposals (frustum_proposals_v1_kitti.py:292-690) the same way.
 
 Never imported by the product package.  Used by tests/ (as the checker of the CUDA
 pipeline), tools/gen_golden.py and the CPU-baseline legs of bench.py.

@@ -576,6 +576,8 @@ class SeekerEngine:
             W = _lib.lib.fnp_seeker_mask_words(Cmax)
             if W < 0:
                 raise ValueError("more than 1024 candidate frustums in one frame (%d) are not supported" % Cmax)
+            if self.variant == "kitti" and W > 4:
+                raise ValueError("the KITTI variant takes up to 128 candidate frustums per frame (%d)" % Cmax)
             sizes = dict(
                 page_tab=4 * max(F, 1) * tab_stride, cell_masks=_lib.lib.fnp_seeker_cell_mask_bytes(C.byref(self.cfg), B, Cmax),
                 frustum_pts=4 * planes * cap,

@@ -263,3 +263,35 @@ def test_kitti_batch_of_frames_equals_frame_by_frame_and_head_contract():
     head.eval()                      # forward asserts it, as the reference does (:714)
     out = head.forward(dict(bd))
     assert len(out["final_box_dicts"]) == 2 and out["final_box_dicts"][0]["pred_labels"].dtype == torch.int32
+
+
+@pytest.mark.gpu
+def test_kitti_edge_cases():
+    """No detections, no points in any box, a frame without points, and more candidates than the variant takes."""
+    from findnpropagate_b200 import synth
+    from findnpropagate_b200.seeker import KittiFrameInput, SeekerEngine
+    f = synth.make_kitti_frame(0)
+    cal = dict(P2=f[1]["P2"], R0=f[1]["R0"], V2C=f[1]["Tr_velo2cam"], device="cuda:0")
+    eng = SeekerEngine(dict(nms_3d=0.0, score_thr=0.45, nms_2d=0.4), device="cuda:0", box_format="xywh", variant="kitti")
+    none = KittiFrameInput(points=f[0], det_boxes=np.zeros((0, 4), np.float32), det_labels=np.zeros(0, np.int64),
+                           det_scores=np.zeros(0, np.float32), **cal)
+    r = eng.run([none])
+    assert r["frames"][0]["pred_boxes"].shape == (0, 7)
+    # boxes that no point projects into (a corner of the image above the horizon of the synthetic scene)
+    far = KittiFrameInput(points=f[0], det_boxes=np.array([[1500.0, 0.0, 20.0, 5.0]], np.float32), det_labels=np.array([1]),
+                          det_scores=np.array([0.9], np.float32), **cal)
+    r = eng.run([far, none])
+    assert r["cand_npts"].tolist() == [0] and r["frames"][0]["pred_boxes"].shape == (0, 7) and len(r["frames"]) == 2
+    empty = KittiFrameInput(points=np.zeros((0, 4), np.float32), det_boxes=f[2], det_labels=f[3], det_scores=f[4], **cal)
+    full = KittiFrameInput(points=f[0], det_boxes=f[2], det_labels=f[3], det_scores=f[4], **cal)
+    r = eng.run([empty, full])
+    alone = eng.run([full])
+    assert r["frames"][0]["pred_boxes"].shape == (0, 7)
+    assert np.array_equal(r["frames"][1]["pred_boxes"], alone["frames"][0]["pred_boxes"]) and alone["frames"][0]["pred_boxes"].shape[0] > 0
+    many = 140
+    rng = np.random.default_rng(0)
+    bx = np.c_[rng.uniform(0, 1100, many), rng.uniform(0, 300, many), rng.uniform(20, 100, many), rng.uniform(20, 60, many)].astype(np.float32)
+    crowd = KittiFrameInput(points=f[0], det_boxes=bx, det_labels=rng.integers(1, 8, many), det_scores=np.full(many, 0.9, np.float32), **cal)
+    eng2 = SeekerEngine(dict(nms_3d=0.0, score_thr=0.45, nms_2d=1.0), device="cuda:0", box_format="xywh", variant="kitti")
+    with pytest.raises(ValueError):
+        eng2.run([crowd])

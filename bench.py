@@ -499,7 +499,13 @@ def run_ours(a):
         for k in range(steps):
             step(k, resident, prev, nf_of(k), nf_of(k + 1) if k + 1 < steps else None)
         last = drain(prev)
+        ms_pre = 0.0
         if world > 1:
+            # this rank's own time up to the exchange (the ranks leave the timed region together, through the collective:
+            # the per-rank totals below are equal by construction, these are not)
+            for st in comp + [copy_stream]:
+                st.synchronize()
+            ms_pre = 1e3 * (time.perf_counter() - t_host)
             t_x = time.perf_counter()
             g = gather_results()
             torch.cuda.synchronize()
@@ -516,6 +522,9 @@ def run_ours(a):
             every = torch.empty(world, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(every, t)
             ms_by_rank[("resident" if resident else "e2e")] = [round(float(x) / steps, 4) for x in every.tolist()]
+            t = torch.tensor([ms_pre], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(every, t)
+            ms_by_rank[("resident" if resident else "e2e") + "_before_exchange"] = [round(float(x) / steps, 4) for x in every.tolist()]
             ms = float(every.max().item())
             dist.barrier()
         host_ms = {k: 1e3 * (eng.host_s[k] - h0[k]) / steps for k in h0}

@@ -1501,7 +1501,6 @@ constexpr int kSweepThreads = FNP_SWEEP_THREADS;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kSweepChunk = kPage;   // points per (column, chunk) warp item = one page
 
-#ifndef FNP_SWEEP_V1
 // Entries (point | column << 16, packed steps) of a WARP's uncertain-step queue.  A piece (256 points of one column)
 // pushes at most 256; a warp drains its queue before a piece that might not fit.
 #ifndef FNP_SWEEP_QUEUE
@@ -1514,39 +1513,11 @@ __host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
     return (size_t)J * sizeof(SweepCol) + (size_t)kSweepWarps * kSweepQueue * 8 + (size_t)SP * 12 + (size_t)H * 4 +
            (size_t)((H + 3) & ~3) * 2 + 16 + 128;      // + one scratch word per lane
 }
-#else
-// Entries of the uncertain-step queue of a CTA: (point | column << 16, packed steps).
-__host__ __device__ inline int sweep_queue_cap(int SP, int J)
-{
-    // a quarter of the (point, column) pairs (~13 % have an entry on cfg2).  Measured on 128 cfg2 frames,
-    // SP = 1024: a queue twice this size costs one resident CTA per SM and 19 % of the kernel's time,
-    // more than the exact predicates taken in place when the queue is full.
-    const int want = (SP * J / 4 + 31) & ~31;
-    return want < 512 ? 512 : want > 4096 ? 4096 : want;
-}
 
-// Dynamic shared memory of sweep_score_kernel for split_points SP, H = M*J hypotheses, J columns.
-__host__ __device__ inline size_t sweep_smem_bytes(int SP, int H, int J)
-{
-    return (size_t)J * sizeof(SweepCol) + (size_t)SP * 12 + (size_t)H * 4 + (size_t)sweep_queue_cap(SP, J) * 8 +
-           (size_t)((H + 3) & ~3) * 2 + 16 + 128;
-}
-#endif
-
-// (FNP_SWEEP_V1) Persistent CTAs pull (frustum, point split) items.  Per item:
-//   stage   column parameters, the split's points as SoA, cleared difference arrays, slot table;
-//   sweep   warps pull (column, 256-point chunk) pieces off a shared counter; per point one range
-//           solve (sweep_solve), the definite range into the column's difference array
-//           (shared-memory RED), the uncertain steps -- if any -- as one entry into the CTA's queue;
-//   drain   the queue is expanded to single depth steps and spread evenly over the lanes: every
-//           lane takes one exact predicate at a time, whichever point and column it belongs to;
-//   scan    prefix sum over the depth steps of every column, one integer RED per valid hypothesis
-//           into row f of `counts`.
 #ifndef FNP_SWEEP_MIN_CTAS
 #define FNP_SWEEP_MIN_CTAS 4
 #endif
 
-#ifndef FNP_SWEEP_V1
 // A point that lies in no hypothesis of any column: the tail of a split's last page is filled with it, so that the
 // sweep needs no "is this lane's point live" predicate (its possible range is empty in every column: one of
 // U, V is >= 0.7e18, far beyond any centre, and 1e18 / slope stays finite).
@@ -1754,202 +1725,6 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
         }
     }
 }
-#else   // FNP_SWEEP_V1: the kernel before the branch-free rewrite (A/B builds)
-__global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score_kernel(const fnp_seeker_batch b, const int J, const int M)
-{
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    const int H = J * M, SP = b.split_points;
-    const int QCAP = sweep_queue_cap(SP, J);
-    SweepCol *s_col = reinterpret_cast<SweepCol *>(s_dyn);                      // [J]   (80 B each: 16 B aligned)
-    uint2 *s_q = reinterpret_cast<uint2 *>(s_col + J);                          // [QCAP] uncertain-step queue
-    float *s_pts = reinterpret_cast<float *>(s_q + QCAP);                       // [SP / 256][x | y | z][256]: the split's pages
-    int *s_diff = reinterpret_cast<int *>(s_pts + 3 * SP);                      // [J][M] difference array, then counts
-    short *s_slot = reinterpret_cast<short *>(s_diff + H);                      // [H] compacted slot of hypothesis h, -1
-    int *s_ctl = reinterpret_cast<int *>(s_slot + ((H + 3) & ~3));              // [0] item [1] next piece [2] queue size [3] queue head
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    if (b.status[0] & 2) return;
-    const int n_items = b.status[2];
-    auto red = [](int *p, int v) { atomicAdd(p, v); };
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            s_ctl[0] = atomicAdd(&b.status[4], 1);
-            s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0;
-        }
-        __syncthreads();
-        const int item_id = s_ctl[0];
-        if (item_id >= n_items) break;
-        const int4 item = reinterpret_cast<const int4 *>(b.items)[item_id];   // frustum, -, split, -
-        const int f = item.x, split = item.z;
-        const int nv = b.hyp_nvalid[f], npts = b.cand_npts[f];
-        const int p0 = split * SP;
-        const int n = min(npts, p0 + SP) - p0;
-        const float *prep_f = b.hyp_prep + (size_t)f * H * 8;
-
-        // ---- stage
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(b.sweep_cols + (size_t)f * J * FNP_SWEEP_COL_FLOATS);
-            float4 *dst = reinterpret_cast<float4 *>(s_col);
-            for (int i = tid; i < J * (FNP_SWEEP_COL_FLOATS / 4); i += kSweepThreads) dst[i] = __ldg(src + i);
-            // the x, y, z planes of the split's pages, as they lie in the pool (coalesced, no transposition)
-            const int *tab = b.page_tab + (size_t)f * b.page_tab_stride + p0 / kPage;
-            const int n_pg = (n + kPage - 1) / kPage;
-            constexpr int kVec = 3 * kPage / 4;        // 16-byte vectors of a page's x, y, z planes
-            for (int i = tid; i < n_pg * kVec; i += kSweepThreads) {
-                const int q = i / kVec;
-                const float4 *page = reinterpret_cast<const float4 *>(b.frustum_pts + (size_t)(tab[q] - 1) * (size_t)(b.page_planes * kPage));
-                reinterpret_cast<float4 *>(s_pts)[i] = __ldg(page + (i - q * kVec));
-            }
-            for (int h = tid; h < H; h += kSweepThreads) { s_diff[h] = 0; s_slot[h] = -1; }
-        }
-        __syncthreads();
-        {
-            const int *hidx = b.hyp_index + (size_t)f * H;
-            for (int r = tid; r < nv; r += kSweepThreads) s_slot[hidx[r]] = (short)r;
-        }
-        __syncthreads();
-
-        // ---- sweep
-        const int n_chunks = (n + kSweepChunk - 1) / kSweepChunk;
-        const int n_pieces = J * n_chunks;
-        for (;;) {
-            int piece = 0;
-            if (lane == 0) piece = atomicAdd(&s_ctl[1], 1);
-            piece = __shfl_sync(0xffffffffu, piece, 0);
-            if (piece >= n_pieces) break;
-            const int j = piece % J, ch = piece / J;
-            const SweepCol c = s_col[j];            // warp-uniform: lives in registers for the whole piece
-            if (c.m1 < c.m0) continue;
-            const int D = c.m1 - c.m0;
-            int *diff = s_diff + j * M + c.m0;       // indexed by dm = m - m0
-            const short *slot_col = s_slot + c.m0 * J + j;
-            int base_cnt = 0;
-            const int i_end = min(n, (ch + 1) * kSweepChunk);
-            const float *pg = s_pts + ch * (3 * kPage) - ch * kSweepChunk;   // chunk ch is page ch: x of point i at pg[i]
-            // two points per lane and pass: the two range solves are independent instruction chains
-            for (int i0 = ch * kSweepChunk; i0 < i_end; i0 += 64) {
-                int ia = i0 + lane, ib = i0 + 32 + lane;
-                const bool live_a = ia < i_end, live_b = ib < i_end;
-                ia = min(ia, i_end - 1); ib = min(ib, i_end - 1);
-                const float xa = pg[ia], ya = pg[kPage + ia], za = pg[2 * kPage + ia];
-                const float xb = pg[ib], yb = pg[kPage + ib], zb = pg[2 * kPage + ib];
-                const SweepRanges ra = sweep_solve(c, xa, ya, za);
-                const SweepRanges rb = sweep_solve(c, xb, yb, zb);
-                unsigned wa = 0, wb = 0;
-                if (live_a) {
-                    base_cnt += sweep_add_definite(ra, D, diff, red);
-                    wa = sweep_pack_uncertain(ra);
-                }
-                if (live_b) {
-                    base_cnt += sweep_add_definite(rb, D, diff, red);
-                    wb = sweep_pack_uncertain(rb);
-                }
-                const unsigned mka = __ballot_sync(0xffffffffu, wa != 0u), mkb = __ballot_sync(0xffffffffu, wb != 0u);
-                if (mka | mkb) {
-                    const int na = __popc(mka);
-                    int qb = 0;
-                    if (lane == 0) qb = atomicAdd(&s_ctl[2], na + __popc(mkb));
-                    qb = __shfl_sync(0xffffffffu, qb, 0);
-                    const int qa = qb + __popc(mka & lt_mask), qbb = qb + na + __popc(mkb & lt_mask);
-                    if (wa) {
-                        if (qa < QCAP) {
-                            s_q[qa] = make_uint2((unsigned)ia | ((unsigned)j << 16), wa);
-                        } else {   // queue full: take the exact predicates here
-                            const int cnt = sweep_uncertain_count(wa);
-                            for (int k = 0; k < cnt; k++)
-                                sweep_exact_step_col(xa, ya, za, sweep_uncertain_step(wa, k), D, diff, slot_col, J, prep_f, c.cosa, c.sina, c.tx, c.ty, red);
-                        }
-                    }
-                    if (wb) {
-                        if (qbb < QCAP) {
-                            s_q[qbb] = make_uint2((unsigned)ib | ((unsigned)j << 16), wb);
-                        } else {
-                            const int cnt = sweep_uncertain_count(wb);
-                            for (int k = 0; k < cnt; k++)
-                                sweep_exact_step_col(xb, yb, zb, sweep_uncertain_step(wb, k), D, diff, slot_col, J, prep_f, c.cosa, c.sina, c.tx, c.ty, red);
-                        }
-                    }
-                }
-            }
-            base_cnt = __reduce_add_sync(0xffffffffu, base_cnt);
-            if (lane == 0 && base_cnt) atomicAdd(diff, base_cnt);   // ranges that start at the column's first step
-        }
-        __syncthreads();
-
-        // ---- drain: 32 queue entries per warp at a time, expanded to steps, one step per lane and pass
-        const int qn = min(s_ctl[2], QCAP);
-        for (;;) {
-            int qb = 0;
-            if (lane == 0) qb = atomicAdd(&s_ctl[3], 32);
-            qb = __shfl_sync(0xffffffffu, qb, 0);
-            if (qb >= qn) break;
-            uint2 ent = make_uint2(0u, 0u);
-            if (qb + lane < qn) ent = s_q[qb + lane];
-            const int cnt = sweep_uncertain_count(ent.y);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                // owner = first lane whose inclusive prefix exceeds t
-                int own = 0;
-#pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, incl, own + step - 1);
-                    if (v <= t) own += step;
-                }
-                own = min(own, 31);
-                const unsigned e0 = __shfl_sync(0xffffffffu, ent.x, own);
-                const unsigned e1 = __shfl_sync(0xffffffffu, ent.y, own);
-                const int first = __shfl_sync(0xffffffffu, incl - cnt, own);
-                if (t < total) {
-                    const int i = (int)(e0 & 0xffffu), j = (int)(e0 >> 16);
-                    const float4 rot = *reinterpret_cast<const float4 *>(&s_col[j].cosa);     // cosa, sina, tx, ty
-                    const int m0 = s_col[j].m0, D = s_col[j].m1 - m0;
-                    const float *pp = s_pts + (i >> 8) * (3 * kPage) + (i & (kPage - 1));
-                    sweep_exact_step_col(pp[0], pp[kPage], pp[2 * kPage], sweep_uncertain_step(e1, t - first), D, s_diff + j * M + m0,
-                                         s_slot + m0 * J + j, J, prep_f, rot.x, rot.y, rot.z, rot.w, red);
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- prefix sum over the depth steps of every column (warp per column, in place)
-        for (int j = warp; j < J; j += kSweepWarps) {
-            int carry = 0;
-            for (int mb = 0; mb < M; mb += 32) {
-                const int m = mb + lane;
-                int v = m < M ? s_diff[j * M + m] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v += t;
-                }
-                v += carry;
-                if (m < M) s_diff[j * M + m] = v;
-                carry = __shfl_sync(0xffffffffu, v, 31);
-            }
-        }
-        __syncthreads();
-        int *out = b.counts + (size_t)f * H;
-        for (int h = tid; h < H; h += kSweepThreads) {
-            const int r = s_slot[h];
-            if (r >= 0) {
-                const int m = h / J, j = h - m * J;
-                const int cnt = s_diff[j * M + m];
-                if (cnt) atomicAdd(out + r, cnt);      // RED.ADD: the splits of a frustum add up in any order
-            }
-        }
-    }
-}
-#endif
 
 // ======================================================================================
 // Stage 2b, KITTI variant: ONE batched first-match points_in_boxes_gpu over the valid hypotheses of a frustum

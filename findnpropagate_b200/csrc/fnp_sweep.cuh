@@ -198,26 +198,8 @@ FNP_HD SweepRanges sweep_solve(const SweepCol &c, const float x, const float y, 
     return r;
 }
 
-// The depth steps that are possible but not definite take the exact predicate.  They are
-// [A, a-1] and [e+1, B], or all of [A, B] when there is no definite range; packed as
-// (first step, count) x 2 in one word (8 bits each: the sweep mode needs M <= 255); 0 = none.
-FNP_HD unsigned sweep_pack_uncertain(const SweepRanges &r)
-{
-    if (r.A > r.B) return 0u;
-    if (r.a > r.e) return (unsigned)r.A | ((unsigned)(r.B - r.A + 1) << 8);
-    if (r.a == r.A && r.e == r.B) return 0u;      // everything possible is definite
-    return (unsigned)r.A | ((unsigned)(r.a - r.A) << 8) | ((unsigned)(r.e + 1) << 16) | ((unsigned)(r.B - r.e) << 24);
-}
-FNP_HD int sweep_uncertain_count(unsigned w) { return (int)((w >> 8) & 0xffu) + (int)(w >> 24); }
-// k-th uncertain step (0 <= k < count) of a packed word
-FNP_HD int sweep_uncertain_step(unsigned w, int k)
-{
-    const int n1 = (int)((w >> 8) & 0xffu);
-    return k < n1 ? (int)(w & 0xffu) + k : (int)((w >> 16) & 0xffu) + (k - n1);
-}
-
 // ---------------------------------------------------------------------------------------
-// Second form of the bookkeeping after sweep_solve (sweep_score_kernel since round 2, session 3): branch-free.
+// The bookkeeping after sweep_solve, branch-free (sweep_score_kernel since round 2, session 3).
 //   definite range [a, e] (if a <= e):  +1 at a unless a == 0 (those are summed per warp), -1 at e + 1 unless e == D;
 //   uncertain steps: [A, a2 - 1] and [e2 + 1, B] with (a2, e2) = (a, e) when there is a definite range and
 //   (B + 1, B) otherwise -- one formula for both cases; packed as four bytes A | a2 << 8 | e2 << 16 | B << 24
@@ -249,27 +231,12 @@ FNP_HD int sweep_packed_step(unsigned w, int k)
     return k < n1 ? A + k : (int)((w >> 16) & 0xffu) + 1 + (k - n1);
 }
 
-// Exact predicate of point (x, y, z) against the hypothesis at depth step m0 + dm of column j.
-// `slot_col` = slot table of the column (slot_col[dm * J], -1: not a valid hypothesis), diff = the
-// column's difference array indexed by dm, D = m1 - m0.  add(ptr, v): *ptr += v.
-template <class Add>
-FNP_HD void sweep_exact_step(const float x, const float y, const float z, const int dm, const int D, int *diff,
-                             const short *slot_col, const int J, const float *prep_f, Add add)
-{
-    const int r = slot_col[dm * J];
-    if (r < 0) return;
-#ifdef FNP_SWEEP_MODEL
-    g_exact_tests++;   // host model only: how many exact predicates the sweep takes
-#endif
-    if (in_box(x, y, z, load_prep(prep_f, (size_t)r))) {
-        add(diff + dm, 1);
-        if (dm < D) add(diff + dm + 1, -1);
-    }
-}
-
-// The same with the column's shared parameters supplied by the caller (cosa, sina, tx, ty are equal, bit for
+// Exact predicate of point (x, y, z) against the hypothesis at depth step m0 + dm of column j, the column's shared
+// parameters supplied by the caller (cosa, sina, tx, ty are equal, bit for
 // bit, for all hypotheses of a column: prep_box computes them from the same row of the prior table), so that
 // only the 16 bytes {cx, cy, cz, hz} of the hypothesis are loaded.
+// `slot_col` = slot table of the column (slot_col[dm * J], -1: not a valid hypothesis), diff = the
+// column's difference array indexed by dm, D = m1 - m0.  add(ptr, v): *ptr += v.
 template <class Add>
 FNP_HD void sweep_exact_step_col(const float x, const float y, const float z, const int dm, const int D, int *diff,
                                  const short *slot_col, const int J, const float *prep_f, const float cosa,
@@ -288,18 +255,6 @@ FNP_HD void sweep_exact_step_col(const float x, const float y, const float z, co
         add(diff + dm, 1);
         if (dm < D) add(diff + dm + 1, -1);
     }
-}
-
-// Definite range into the difference array.  Returns 1 if it starts at dm = 0 (the caller sums
-// these per warp and adds them to diff[0] once), else 0.
-template <class Add>
-FNP_HD int sweep_add_definite(const SweepRanges &r, const int D, int *diff, Add add)
-{
-    if (r.a > r.e) return 0;
-    if (r.e < D) add(diff + r.e + 1, -1);
-    if (r.a == 0) return 1;
-    add(diff + r.a, 1);
-    return 0;
 }
 
 }  // namespace fnp

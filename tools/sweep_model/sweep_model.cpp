@@ -13,7 +13,7 @@
 
 struct float4 { float x, y, z, w; };
 #define FNP_SWEEP_MODEL 1
-static long long g_exact_tests = 0;   // incremented by sweep_exact_step under FNP_SWEEP_MODEL
+static long long g_exact_tests = 0;   // incremented by sweep_exact_step_col under FNP_SWEEP_MODEL
 #include "../../findnpropagate_b200/csrc/fnp_sweep.cuh"
 
 using namespace fnp;

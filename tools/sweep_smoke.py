@@ -10,17 +10,20 @@ sys.path.insert(0, ROOT)
 from findnpropagate_b200 import synth  # noqa: E402
 from findnpropagate_b200.seeker import FrameInput, SeekerEngine  # noqa: E402
 
-cfg = synth.CONFIGS["cfg1"]
-params = dict(synth.seeker_params(cfg), num_mags=24)
+# argv[1] = "cfg2": one full-size frame (frustums of thousands of points: the warp queues fill and drain in place
+# several times per item); default: two cfg1 frames with a deeper grid, split into 256-point items
+big = len(sys.argv) > 1 and sys.argv[1] == "cfg2"
+cfg = synth.CONFIGS["cfg2" if big else "cfg1"]
+params = synth.seeker_params(cfg) if big else dict(synth.seeker_params(cfg), num_mags=24)
 frames = []
-for i in range(2):
+for i in range(1 if big else 2):
     f = synth.make_frame(i, cfg)
     frames.append(FrameInput(points=f.points, lidar2image=f.lidar2image, camera2lidar=f.camera2lidar,
                              camera_intrinsics=f.camera_intrinsics, det_boxes=f.det_boxes, det_labels=f.det_labels,
                              det_scores=f.det_scores, det_cam_idx=f.det_cam_idx, gt_boxes=f.gt_boxes))
 out = {}
 for mode in ("direct", "sweep"):
-    eng = SeekerEngine(params, device="cuda:0", score_mode=mode, split_points=256)
+    eng = SeekerEngine(params, device="cuda:0", score_mode=mode, split_points=None if big else 256)
     out[mode] = eng.run(frames, nms_thresh=0.1, with_recall=True)
     assert eng.last_score_mode == mode
 v = out["direct"]["cand_valid"]

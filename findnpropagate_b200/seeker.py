@@ -162,10 +162,25 @@ class FrameInput:
         return self._prep
 
 
+_KITTI_BLOCKS = {}      # calibration repeats from frame to frame (it is fixed per drive): block by content
+
+
 def kitti_camera_block(P2, R0, V2C, device):
     """The 144 floats of a frame for FNP_VARIANT_KITTI (include/fnp.h): M1 = V2C.T @ R0.T | P2.T | cu cv fu fv tx ty |
     inverse((R0_ext @ V2C_ext).T) -- formed with the calls CalibrationTorch makes (calibration_kitti.py:128-169), on
     the device the reference forms them on, so that the bits are its bits."""
+    key = (str(device), np.asarray(P2, np.float32).tobytes(), np.asarray(R0, np.float32).tobytes(),
+           np.asarray(V2C, np.float32).tobytes())
+    hit = _KITTI_BLOCKS.get(key)
+    if hit is not None:
+        return hit
+    if len(_KITTI_BLOCKS) > 256:
+        _KITTI_BLOCKS.clear()
+    _KITTI_BLOCKS[key] = out = _kitti_camera_block(P2, R0, V2C, device)
+    return out
+
+
+def _kitti_camera_block(P2, R0, V2C, device):
     P2 = torch.as_tensor(np.asarray(P2, np.float32), device=device)
     R0 = torch.as_tensor(np.asarray(R0, np.float32), device=device)
     V2C = torch.as_tensor(np.asarray(V2C, np.float32), device=device)

@@ -1537,6 +1537,7 @@ __device__ __noinline__ void sweep_drain(const uint2 *q, const int qn, const Swe
 {
     const int lane = threadIdx.x & 31;
     auto red = [](int *p, int v) { atomicAdd(p, v); };
+    __syncwarp();      // the entries were written by other lanes of this warp: order their stores before the loads below
     for (int qb = 0; qb < qn; qb += 32) {
         uint2 ent = make_uint2(0u, 0u);
         if (qb + lane < qn) ent = q[qb + lane];
@@ -1661,6 +1662,7 @@ __global__ void __launch_bounds__(kSweepThreads, FNP_SWEEP_MIN_CTAS) sweep_score
             const bool done = piece >= n_pieces;
             if (done || qn + kSweepChunk > kSweepQueue) {      // out of pieces, or the next piece might not fit
                 sweep_drain(q_w, qn, s_col, s_pts, s_diff, s_slot, prep_f, J, M);
+                __syncwarp();      // ... and the loads above before the next piece's stores into the same region
                 qn = 0;
             }
             if (done) break;

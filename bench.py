@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU (BASELINE.json configs[2]: batches of 256 frames)")
+    ap.add_argument("--pool-offset", type=int, default=0, help="weak scaling: rank r works on block r + offset of the synthetic "
+                    "frames (diagnosis of per-rank differences: which block is more work)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames per rank (weak scaling) / in the pool (--total-frames)")
     ap.add_argument("--total-frames", type=int, default=0,
                     help="strong scaling, BASELINE.json configs[3]: this many frames in all, sharded rank::world "
@@ -332,7 +334,7 @@ def run_ours(a):
     else:
         # weak scaling: the same NUMBER of frames per rank and step, but every rank works on its own D distinct
         # synthetic frames (indices rank D .. rank D + D - 1)
-        pool, params = make_frames(a.config, rank * D, D, str(dev))
+        pool, params = make_frames(a.config, (rank + a.pool_offset) * D, D, str(dev))
         n_steps, tail = a.steps, B
 
         def content(r, j):
@@ -544,7 +546,7 @@ def run_ours(a):
             elif r == rank:
                 fr = [pool[j % D] for j in pos]
             else:
-                fr = [make_frames(a.config, r * D + (j % D), 1, str(dev))[0][0] for j in pos]
+                fr = [make_frames(a.config, (r + a.pool_offset) * D + (j % D), 1, str(dev))[0][0] for j in pos]
             res = chk.run(fr, nms_thresh=0.1, with_recall=True)
             cnt = gathered["allc"][r, 0]
             off = np.concatenate([[0], np.cumsum(cnt)])

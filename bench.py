@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU (BASELINE.json configs[2]: batches of 256 frames)")
     ap.add_argument("--pool-offset", type=int, default=0, help="weak scaling: rank r works on block r + offset of the synthetic "
                     "frames (diagnosis of per-rank differences: which block is more work)")
-    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames per rank (weak scaling) / in the pool (--total-frames)")
+    ap.add_argument("--distinct", type=int, default=256, help="distinct synthetic frames per rank (weak scaling) / in the pool (--total-frames)")
     ap.add_argument("--total-frames", type=int, default=0,
                     help="strong scaling, BASELINE.json configs[3]: this many frames in all, sharded rank::world "
                          "(6019 = the nuScenes val sweep); steps = ceil(shard / frames), --steps is ignored")
